@@ -1,0 +1,270 @@
+/* ssr_b200.h -- C ABI of the B200-native partitioned-convolution engine.
+ *
+ * Drop-in boundary for ONE path of the SoundScape Renderer: the apf::conv
+ * uniformly-partitioned overlap-save convolution engine and the per-block step
+ * of the Binaural / BRS / Generic renderers that drive it.  Citations are
+ * file:line in the reference tree (SoundScapeRenderer/ssr-pre-0.4.0).
+ *
+ * Conventions
+ *  - plain C, opaque handles, plain pointers and sizes; no C++ / torch types.
+ *  - every function returns SSR_OK (0) or a negative ssr_status; nothing throws
+ *    across this boundary.  ssr_last_error() returns the message of the last
+ *    failure on the calling thread.  The C++ facade
+ *    (ssr-pre-0.4.0_b200/cpp/apf/convolver.h) rethrows the reference's exception
+ *    types (std::logic_error, apf/apf/convolver.h:163-166).
+ *  - there is NO CPU fallback: every compute entry point runs CUDA kernels for
+ *    sm_100a and fails with SSR_ERR_CUDA when no device is usable.
+ *  - "block" = audio block size B (samples); a partition spectrum is B complex
+ *    bins = 2B floats (8 KiB at B = 1024), resident in HBM.
+ *  - host result pointers are owned by the engine (pinned memory) and stay
+ *    valid until the next call that produces a result for the same object.
+ *  - threading: one engine is used by one host thread at a time (the reference
+ *    gives the same guarantee per convolver object, apf/apf/convolver.h:53 and
+ *    the list barrier apf/apf/mimoprocessor.h:476-482).
+ */
+#ifndef SSR_B200_H
+#define SSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSR_B200_ABI_VERSION 1
+
+typedef enum ssr_status
+{
+  SSR_OK = 0,
+  SSR_ERR_INVALID = -1,      /* bad argument / precondition (reference: assert) */
+  SSR_ERR_BLOCK_SIZE = -2,   /* "Convolver: block size must be a multiple of 8!"
+                                (apf/apf/convolver.h:163-166) */
+  SSR_ERR_UNSUPPORTED = -3,  /* block size not a power of two in [8, 4096] */
+  SSR_ERR_CUDA = -4,         /* CUDA runtime failure / no device */
+  SSR_ERR_NOMEM = -5,
+  SSR_ERR_STATE = -6,        /* call order violated */
+  SSR_ERR_FILE = -7          /* IR set shape mismatch (apf/apf/sndfiletools.h:48-87,
+                                src/binauralrenderer.h:124-128, src/brsrenderer.h:101-105) */
+} ssr_status;
+
+typedef struct ssr_engine ssr_engine;
+typedef struct ssr_filterset ssr_filterset;
+typedef struct ssr_input ssr_input;
+typedef struct ssr_output ssr_output;
+typedef struct ssr_renderer ssr_renderer;
+
+const char* ssr_last_error(void);
+int ssr_abi_version(void);
+
+/* ------------------------------------------------------------------ engine */
+
+typedef struct ssr_engine_config
+{
+  int device;        /* CUDA device ordinal */
+  int block_size;    /* B; reference parameter "block_size" (apf/apf/pointer_policy.h:75) */
+  int sample_rate;   /* reference parameter "sample_rate" (pointer_policy.h:74) */
+  void* stream;      /* cudaStream_t to run on, or NULL for an engine-owned stream */
+  int mac_variant;   /* 0 = default; see DESIGN.md (1 = register-prefetch, 2 = bulk-copy staged) */
+  int reserved[7];
+} ssr_engine_config;
+
+/* replaces: apf::MimoProcessor construction for this path
+ * (apf/apf/mimoprocessor.h:406-425) + per-object FFTW plan creation
+ * (apf/apf/convolver.h:176-181, 421-423). */
+int ssr_engine_create(const ssr_engine_config* cfg, ssr_engine** out);
+void ssr_engine_destroy(ssr_engine* e);
+int ssr_engine_block_size(const ssr_engine* e);
+/* Blocks until all queued device work of this engine has finished. */
+int ssr_engine_synchronize(ssr_engine* e);
+
+typedef struct ssr_engine_stats
+{
+  /* accumulated since the last reset, device time from CUDA events (ms) */
+  double ms_fft;          /* forward transforms of input blocks */
+  double ms_mac;          /* spectral multiply-accumulate kernel */
+  double ms_ifft;         /* inverse transform + crossfade epilogue */
+  double ms_total;        /* first kernel start -> last kernel end */
+  uint64_t blocks;        /* timed block steps */
+  uint64_t mac_launches;  /* kernel launches, by kind */
+  uint64_t fft_launches;
+  uint64_t ifft_launches;
+  uint64_t mac_bytes;     /* ALGORITHMIC bytes of the timed MAC launches:
+                             8*B * (H partitions read + X partitions + accumulators written)
+                             = SURVEY 8(d) formula */
+  uint64_t mac_terms;     /* partition-MACs (8*B flops each at 8 flops / complex MAC) */
+  uint64_t h2d_bytes, d2h_bytes;
+  int timing_enabled;
+  int reserved[7];
+} ssr_engine_stats;
+
+int ssr_engine_set_timing(ssr_engine* e, int enabled);  /* per-stage CUDA events */
+int ssr_engine_get_stats(ssr_engine* e, ssr_engine_stats* out, int reset);
+
+/* ------------------------------------------------------------- filter sets */
+
+/* A set of `channels` filters, each `partitions` partition spectra, resident in
+ * HBM (north_star item 1).  Replaces apf::conv::Filter and containers of them
+ * (apf/apf/convolver.h:100-117; hrtf_set_t src/binauralrenderer.h:72,
+ * brtf_set_t src/brsrenderer.h:213).  A new set is all "zero"-flagged, like
+ * Filter(block, partitions) (convolver.h:103-107). */
+int ssr_filterset_create(ssr_engine* e, int channels, int partitions, ssr_filterset** out);
+void ssr_filterset_destroy(ssr_filterset* fs);
+int ssr_filterset_channels(const ssr_filterset* fs);
+int ssr_filterset_partitions(const ssr_filterset* fs);
+
+/* Transform `frames` taps of every channel: channel c, tap t is
+ * data[t * frame_stride + c * channel_stride]  (libsndfile readf layout =
+ * frame_stride = channels, channel_stride = 1, the apf::fixed_matrix "slices",
+ * apf/apf/container.h:357-364).  Equals Transform::prepare_filter per channel
+ * (apf/apf/convolver.h:190-231): chunks of <= B taps, zero-padded to 2B,
+ * forward FFT; partitions beyond the taps stay zero-flagged.  `first_channel`
+ * selects where in the set the `channels` channels of `data` are stored. */
+int ssr_filterset_load_time(ssr_filterset* fs, int first_channel, int channels,
+                            const float* data, long frames,
+                            long frame_stride, long channel_stride);
+
+/* = TransformBase::prepare_partition (convolver.h:209-231) for one partition. */
+int ssr_filterset_set_partition_time(ssr_filterset* fs, int channel, int partition,
+                                     const float* taps, int n);
+
+/* Deterministic synthetic IRs generated ON THE DEVICE (no host copy), see
+ * DESIGN.md "synthetic workload": tap t of channel c is
+ * u(seed, c, t) * envelope[t] * scale, u uniform in [-1, 1).  The same generator
+ * exists on the host as ssr_synth_ir() for parity tests. */
+int ssr_filterset_generate(ssr_filterset* fs, int first_channel, int channels, long taps,
+                           uint64_t seed, uint64_t channel_id_offset,
+                           const float* envelope, float scale);
+void ssr_synth_ir(uint64_t seed, uint64_t channel_id, long taps, const float* envelope,
+                  float scale, float* out);
+/* same generator for signal blocks: uniform [-1, 1) */
+void ssr_synth_uniform(uint64_t seed, uint64_t stream_id, uint64_t first_index, long n, float* out);
+
+/* dst[dch] = (1 - t) * a[ach] + t * b[bch], honouring zero flags and unequal
+ * partition counts = apf::conv::transform_nested with the lerp of
+ * src/binauralrenderer.h:372-377 (convolver.h:773-817). */
+int ssr_filterset_lerp(ssr_filterset* dst, int dch, const ssr_filterset* a, int ach,
+                       const ssr_filterset* b, int bch, float t);
+
+/* Parity / debug: copies one partition spectrum to the host in the REFERENCE's
+ * "sorted halfcomplex" layout (convolver.h:236-268), 2B floats; *zero receives
+ * the zero flag. */
+int ssr_filterset_download(ssr_filterset* fs, int channel, int partition,
+                           float* sorted_out, int* zero);
+
+/* ------------------------------------------- Level 1: apf::conv class API */
+
+/* = apf::conv::Input(block, partitions) (convolver.h:296-318) */
+int ssr_input_create(ssr_engine* e, int partitions, ssr_input** out);
+void ssr_input_destroy(ssr_input* in);
+int ssr_input_partitions(const ssr_input* in);
+/* = Input::add_block (convolver.h:324-375): B host floats; H2D + forward FFT
+ * are queued asynchronously. */
+int ssr_input_add_block(ssr_input* in, const float* x);
+/* parity / debug: spectrum `p` blocks ago (0 = newest) in the reference layout */
+int ssr_input_download(ssr_input* in, int p, float* sorted_out);
+
+typedef enum ssr_output_kind { SSR_OUTPUT_DYNAMIC = 0, SSR_OUTPUT_STATIC = 1 } ssr_output_kind;
+
+/* = apf::conv::Output(input) / StaticOutput(input, ...) (convolver.h:618-634,
+ * 705-726).  Starts with every partition "empty" (convolver.h:415-417). */
+int ssr_output_create(ssr_input* in, ssr_output_kind kind, ssr_output** out);
+void ssr_output_destroy(ssr_output* o);
+/* = StaticOutput::_set_filter (convolver.h:729-739) */
+int ssr_output_bind_static(ssr_output* o, const ssr_filterset* fs, int channel);
+/* = Output::set_filter / queues_empty / rotate_queues (convolver.h:642-699) */
+int ssr_output_set_filter(ssr_output* o, const ssr_filterset* fs, int channel);
+int ssr_output_queues_empty(const ssr_output* o);  /* 1 / 0 */
+int ssr_output_rotate_queues(ssr_output* o);
+/* = OutputBase::convolve(weight) (convolver.h:435-465).  *result points at B
+ * floats (engine-owned pinned memory), valid until the next convolve() on `o`. */
+int ssr_output_convolve(ssr_output* o, float weight, const float** result);
+
+/* ------------------------- Level 2: renderer block step (the batched path) */
+
+typedef enum ssr_renderer_kind
+{
+  SSR_RENDERER_GENERIC = 0,   /* src/genericrenderer.h */
+  SSR_RENDERER_BINAURAL = 1,  /* src/binauralrenderer.h */
+  SSR_RENDERER_BRS = 2        /* src/brsrenderer.h */
+} ssr_renderer_kind;
+
+typedef struct ssr_renderer_config
+{
+  ssr_renderer_kind kind;
+  int outputs;                       /* Generic: loudspeakers M (total); Binaural / BRS: must be 2 */
+  int output_first, output_count;    /* Generic sharding by output channel:
+                                        this engine renders outputs [first, first+count);
+                                        count = 0 means all */
+  float master_volume_correction_db; /* "master_volume_correction" (src/rendererbase.h:234-235) */
+  int reserved[8];
+} ssr_renderer_config;
+
+int ssr_renderer_create(ssr_engine* e, const ssr_renderer_config* cfg, ssr_renderer** out);
+void ssr_renderer_destroy(ssr_renderer* r);
+
+/* Binaural: = BinauralRenderer::_load_hrtfs (src/binauralrenderer.h:117-169).
+ * data is frames x channels interleaved (libsndfile readf); channels must be
+ * even (else SSR_ERR_FILE "Number of channels in HRIR file must be a multiple
+ * of 2!"); hrir_size = 0 means all frames. */
+int ssr_renderer_load_hrirs(ssr_renderer* r, const float* data, long frames, int channels,
+                            long hrir_size);
+/* synthetic HRIR set generated on the device (bench workloads) */
+int ssr_renderer_generate_hrirs(ssr_renderer* r, int channels, long taps, uint64_t seed,
+                                const float* envelope, float scale);
+
+/* = RendererBase::add_source (src/rendererbase.h:247-287) with the Source
+ * constructors of the three renderers:
+ *   Generic  (src/genericrenderer.h:88-120): ir = frames x M interleaved, channels
+ *            must equal the renderer's TOTAL outputs (SSR_ERR_FILE otherwise);
+ *   BRS      (src/brsrenderer.h:90-139): ir = frames x (2*angles);
+ *   Binaural (src/binauralrenderer.h:235-259): ir must be NULL.
+ * Returns the new source id in *id. */
+int ssr_renderer_add_source(ssr_renderer* r, const float* ir, long frames, int channels, int* id);
+/* synthetic IR set for a source generated on the device (Generic / BRS) */
+int ssr_renderer_add_source_synthetic(ssr_renderer* r, long taps, int channels, uint64_t seed,
+                                      uint64_t channel_id_offset, const float* envelope,
+                                      float scale, int* id);
+int ssr_renderer_rem_source(ssr_renderer* r, int id);
+int ssr_renderer_sources(const ssr_renderer* r);
+
+/* per-source control inputs (src/rendererbase.h:419-423) */
+int ssr_source_set_gain(ssr_renderer* r, int id, float gain);
+int ssr_source_set_mute(ssr_renderer* r, int id, int mute);
+int ssr_source_set_position(ssr_renderer* r, int id, float x, float y);
+int ssr_source_set_model(ssr_renderer* r, int id, int plane);  /* 0 point, 1 plane */
+
+/* global control inputs (RendererBase::State, src/rendererbase.h:84-103) */
+int ssr_renderer_set_reference_position(ssr_renderer* r, float x, float y);
+int ssr_renderer_set_reference_orientation(ssr_renderer* r, float azimuth_deg);
+int ssr_renderer_set_reference_offset_position(ssr_renderer* r, float x, float y);
+int ssr_renderer_set_reference_offset_orientation(ssr_renderer* r, float azimuth_deg);
+int ssr_renderer_set_master_volume(ssr_renderer* r, float v);
+int ssr_renderer_set_processing(ssr_renderer* r, int on);
+int ssr_renderer_set_amplitude_reference_distance(ssr_renderer* r, float d);
+
+/* One audio block = apf::pointer_policy<float*>::audio_callback(n, in, out)
+ * (apf/apf/pointer_policy.h:58,112-122): `in` has one pointer per source (in
+ * add order), `out` one per LOCAL output; each points at B host floats.
+ * H2D, forward FFT, MAC, inverse FFT + crossfade + source sum, D2H; returns
+ * when `out` is filled. */
+int ssr_renderer_process(ssr_renderer* r, int n, const float* const* in, float* const* out);
+
+/* Same step on DEVICE buffers, asynchronous on the engine's stream: d_in is
+ * sources x B floats, d_out is local_outputs x B floats (both contiguous).
+ * Used by the multi-GPU driver, which owns the buffers and the NCCL gather. */
+int ssr_renderer_process_device(ssr_renderer* r, const float* d_in, float* d_out);
+
+/* Pipelined host variant: queues the block and returns immediately; the result
+ * of block t is delivered by ssr_renderer_wait().  Lets block t+1's H2D overlap
+ * block t's compute (north_star item 5: CUDA-stream pipeline). */
+int ssr_renderer_submit(ssr_renderer* r, int n, const float* const* in);
+int ssr_renderer_wait(ssr_renderer* r, float* const* out);
+
+int ssr_renderer_local_outputs(const ssr_renderer* r);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SSR_B200_H */

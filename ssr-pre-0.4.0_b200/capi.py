@@ -1,0 +1,421 @@
+"""ctypes binding of lib/libssr_b200.so (see include/ssr_b200.h for the contract)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libssr_b200.so")
+
+SSR_OK = 0
+SSR_ERR_INVALID, SSR_ERR_BLOCK_SIZE, SSR_ERR_UNSUPPORTED = -1, -2, -3
+SSR_ERR_CUDA, SSR_ERR_NOMEM, SSR_ERR_STATE, SSR_ERR_FILE = -4, -5, -6, -7
+OUTPUT_DYNAMIC, OUTPUT_STATIC = 0, 1
+GENERIC, BINAURAL, BRS = 0, 1, 2
+
+_f32p = C.POINTER(C.c_float)
+_pp = C.POINTER(_f32p)
+
+
+class EngineConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("block_size", C.c_int), ("sample_rate", C.c_int),
+                ("stream", C.c_void_p), ("mac_variant", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class EngineStats(C.Structure):
+    _fields_ = [("ms_fft", C.c_double), ("ms_mac", C.c_double), ("ms_ifft", C.c_double),
+                ("ms_total", C.c_double), ("blocks", C.c_uint64), ("mac_launches", C.c_uint64),
+                ("fft_launches", C.c_uint64), ("ifft_launches", C.c_uint64),
+                ("mac_bytes", C.c_uint64), ("mac_terms", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("timing_enabled", C.c_int), ("reserved", C.c_int * 7)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class RendererConfig(C.Structure):
+    _fields_ = [("kind", C.c_int), ("outputs", C.c_int), ("output_first", C.c_int),
+                ("output_count", C.c_int), ("master_volume_correction_db", C.c_float),
+                ("reserved", C.c_int * 8)]
+
+
+class SsrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/ssr_b200.h declares
+SIGNATURES = {
+    "ssr_last_error": (C.c_char_p, []),
+    "ssr_abi_version": (C.c_int, []),
+    "ssr_engine_create": (C.c_int, [C.POINTER(EngineConfig), C.POINTER(C.c_void_p)]),
+    "ssr_engine_destroy": (None, [C.c_void_p]),
+    "ssr_engine_block_size": (C.c_int, [C.c_void_p]),
+    "ssr_engine_synchronize": (C.c_int, [C.c_void_p]),
+    "ssr_engine_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssr_engine_get_stats": (C.c_int, [C.c_void_p, C.POINTER(EngineStats), C.c_int]),
+    "ssr_filterset_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "ssr_filterset_destroy": (None, [C.c_void_p]),
+    "ssr_filterset_channels": (C.c_int, [C.c_void_p]),
+    "ssr_filterset_partitions": (C.c_int, [C.c_void_p]),
+    "ssr_filterset_load_time": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_long, C.c_long, C.c_long]),
+    "ssr_filterset_set_partition_time": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]),
+    "ssr_filterset_generate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_uint64, C.c_uint64, _f32p, C.c_float]),
+    "ssr_synth_ir": (None, [C.c_uint64, C.c_uint64, C.c_long, _f32p, C.c_float, _f32p]),
+    "ssr_synth_uniform": (None, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_long, _f32p]),
+    "ssr_filterset_lerp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float]),
+    "ssr_filterset_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]),
+    "ssr_input_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ssr_input_destroy": (None, [C.c_void_p]),
+    "ssr_input_partitions": (C.c_int, [C.c_void_p]),
+    "ssr_input_add_block": (C.c_int, [C.c_void_p, _f32p]),
+    "ssr_input_download": (C.c_int, [C.c_void_p, C.c_int, _f32p]),
+    "ssr_output_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ssr_output_destroy": (None, [C.c_void_p]),
+    "ssr_output_bind_static": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ssr_output_set_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ssr_output_queues_empty": (C.c_int, [C.c_void_p]),
+    "ssr_output_rotate_queues": (C.c_int, [C.c_void_p]),
+    "ssr_output_convolve": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(_f32p)]),
+    "ssr_renderer_create": (C.c_int, [C.c_void_p, C.POINTER(RendererConfig), C.POINTER(C.c_void_p)]),
+    "ssr_renderer_destroy": (None, [C.c_void_p]),
+    "ssr_renderer_load_hrirs": (C.c_int, [C.c_void_p, _f32p, C.c_long, C.c_int, C.c_long]),
+    "ssr_renderer_generate_hrirs": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_uint64, _f32p, C.c_float]),
+    "ssr_renderer_add_source": (C.c_int, [C.c_void_p, _f32p, C.c_long, C.c_int, C.POINTER(C.c_int)]),
+    "ssr_renderer_add_source_synthetic": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_uint64, C.c_uint64, _f32p, C.c_float, C.POINTER(C.c_int)]),
+    "ssr_renderer_rem_source": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssr_renderer_sources": (C.c_int, [C.c_void_p]),
+    "ssr_source_set_gain": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
+    "ssr_source_set_mute": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ssr_source_set_position": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float]),
+    "ssr_source_set_model": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ssr_renderer_set_reference_position": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "ssr_renderer_set_reference_orientation": (C.c_int, [C.c_void_p, C.c_float]),
+    "ssr_renderer_set_reference_offset_position": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "ssr_renderer_set_reference_offset_orientation": (C.c_int, [C.c_void_p, C.c_float]),
+    "ssr_renderer_set_master_volume": (C.c_int, [C.c_void_p, C.c_float]),
+    "ssr_renderer_set_processing": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssr_renderer_set_amplitude_reference_distance": (C.c_int, [C.c_void_p, C.c_float]),
+    "ssr_renderer_process": (C.c_int, [C.c_void_p, C.c_int, _pp, _pp]),
+    "ssr_renderer_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_renderer_submit": (C.c_int, [C.c_void_p, C.c_int, _pp]),
+    "ssr_renderer_wait": (C.c_int, [C.c_void_p, _pp]),
+    "ssr_renderer_local_outputs": (C.c_int, [C.c_void_p]),
+}
+
+
+def lib():
+    """Loads libssr_b200.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+            "(make -C ssr-pre-0.4.0_b200). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != SSR_OK:
+        raise SsrError(rc, lib().ssr_last_error().decode())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(_f32p) if a is not None else _f32p()
+
+
+def min_partitions(block: int, taps: int) -> int:
+    return (taps + block - 1) // block
+
+
+def synth_ir(seed: int, channel_id: int, taps: int, envelope: Optional[np.ndarray], scale: float) -> np.ndarray:
+    out = np.empty(taps, np.float32)
+    env = None if envelope is None else _f32(envelope)
+    lib().ssr_synth_ir(seed, channel_id, taps, _ptr(env), scale, _ptr(out))
+    return out
+
+
+def synth_uniform(seed: int, stream_id: int, first_index: int, n: int) -> np.ndarray:
+    out = np.empty(n, np.float32)
+    lib().ssr_synth_uniform(seed, stream_id, first_index, n, _ptr(out))
+    return out
+
+
+class Engine:
+    def __init__(self, block_size: int, sample_rate: int = 48000, device: int = 0,
+                 stream: int = 0, mac_variant: int = 0):
+        cfg = EngineConfig(device=device, block_size=block_size, sample_rate=sample_rate,
+                           stream=stream or None, mac_variant=mac_variant)
+        h = C.c_void_p()
+        _check(lib().ssr_engine_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.block_size = block_size
+
+    def synchronize(self):
+        _check(lib().ssr_engine_synchronize(self.h))
+
+    def set_timing(self, on: bool):
+        _check(lib().ssr_engine_set_timing(self.h, int(on)))
+
+    def stats(self, reset: bool = False) -> dict:
+        st = EngineStats()
+        _check(lib().ssr_engine_get_stats(self.h, C.byref(st), int(reset)))
+        return st.as_dict()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ssr_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+class FilterSet:
+    def __init__(self, engine: Engine, channels: int, partitions: int):
+        self.engine = engine
+        h = C.c_void_p()
+        _check(lib().ssr_filterset_create(engine.h, channels, partitions, C.byref(h)))
+        self.h = h
+        self.channels, self.partitions = channels, partitions
+
+    @classmethod
+    def from_time(cls, engine: Engine, frames_by_channels, partitions: int = 0) -> "FilterSet":
+        """frames_by_channels: (frames, channels), the libsndfile readf layout."""
+        a = _f32(frames_by_channels)
+        if a.ndim == 1:
+            a = a[:, None]
+        P = partitions or min_partitions(engine.block_size, a.shape[0])
+        fs = cls(engine, a.shape[1], P)
+        fs.load_time(a)
+        return fs
+
+    def load_time(self, frames_by_channels, first_channel: int = 0):
+        a = _f32(frames_by_channels)
+        _check(lib().ssr_filterset_load_time(self.h, first_channel, a.shape[1], _ptr(a),
+                                             a.shape[0], a.shape[1], 1))
+
+    def set_partition_time(self, channel: int, partition: int, taps):
+        t = _f32(taps)
+        _check(lib().ssr_filterset_set_partition_time(self.h, channel, partition, _ptr(t), t.size))
+
+    def generate(self, taps: int, seed: int, envelope=None, scale: float = 1.0,
+                 first_channel: int = 0, channels: int = 0, channel_id_offset: int = 0):
+        env = None if envelope is None else _f32(envelope)
+        _check(lib().ssr_filterset_generate(self.h, first_channel, channels or self.channels, taps,
+                                            seed, channel_id_offset, _ptr(env), scale))
+
+    def lerp_from(self, dch: int, a: "FilterSet", ach: int, b: "FilterSet", bch: int, t: float):
+        _check(lib().ssr_filterset_lerp(self.h, dch, a.h, ach, b.h, bch, t))
+
+    def download(self, channel: int, partition: int):
+        out = np.empty(2 * self.engine.block_size, np.float32)
+        z = C.c_int()
+        _check(lib().ssr_filterset_download(self.h, channel, partition, _ptr(out), C.byref(z)))
+        return out, bool(z.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ssr_filterset_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Input:
+    """apf::conv::Input"""
+
+    def __init__(self, engine: Engine, partitions: int):
+        self.engine = engine
+        h = C.c_void_p()
+        _check(lib().ssr_input_create(engine.h, partitions, C.byref(h)))
+        self.h = h
+        self.partitions = partitions
+
+    def add_block(self, x):
+        x = _f32(x)
+        assert x.size == self.engine.block_size
+        _check(lib().ssr_input_add_block(self.h, _ptr(x)))
+
+    def download(self, p: int) -> np.ndarray:
+        out = np.empty(2 * self.engine.block_size, np.float32)
+        _check(lib().ssr_input_download(self.h, p, _ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ssr_input_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+class _OutBase:
+    def convolve(self, weight: float = 1.0) -> np.ndarray:
+        res = _f32p()
+        _check(lib().ssr_output_convolve(self.h, weight, C.byref(res)))
+        return np.ctypeslib.as_array(res, shape=(self.inp.engine.block_size,)).copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ssr_output_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Output(_OutBase):
+    """apf::conv::Output"""
+
+    def __init__(self, inp: Input):
+        self.inp = inp
+        self._keep = []
+        h = C.c_void_p()
+        _check(lib().ssr_output_create(inp.h, OUTPUT_DYNAMIC, C.byref(h)))
+        self.h = h
+
+    def set_filter(self, fs: FilterSet, channel: int = 0):
+        self._keep.append(fs)
+        _check(lib().ssr_output_set_filter(self.h, fs.h, channel))
+
+    def queues_empty(self) -> bool:
+        return bool(lib().ssr_output_queues_empty(self.h))
+
+    def rotate_queues(self):
+        _check(lib().ssr_output_rotate_queues(self.h))
+
+
+class StaticOutput(_OutBase):
+    """apf::conv::StaticOutput"""
+
+    def __init__(self, inp: Input, taps=None, fs: Optional[FilterSet] = None, channel: int = 0):
+        self.inp = inp
+        if fs is None:
+            # Filter(block, first, last, input.partitions()) (convolver.h:713-714)
+            fs = FilterSet.from_time(inp.engine, _f32(taps).reshape(-1, 1), inp.partitions)
+        self._keep = fs
+        h = C.c_void_p()
+        _check(lib().ssr_output_create(inp.h, OUTPUT_STATIC, C.byref(h)))
+        self.h = h
+        _check(lib().ssr_output_bind_static(self.h, fs.h, channel))
+
+
+class Renderer:
+    def __init__(self, engine: Engine, kind: int, outputs: int = 2, output_first: int = 0,
+                 output_count: int = 0, master_volume_correction_db: float = 0.0):
+        self.engine = engine
+        self.kind = kind
+        cfg = RendererConfig(kind=kind, outputs=outputs, output_first=output_first,
+                             output_count=output_count,
+                             master_volume_correction_db=master_volume_correction_db)
+        h = C.c_void_p()
+        _check(lib().ssr_renderer_create(engine.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    @property
+    def local_outputs(self) -> int:
+        return lib().ssr_renderer_local_outputs(self.h)
+
+    @property
+    def n_sources(self) -> int:
+        return lib().ssr_renderer_sources(self.h)
+
+    def load_hrirs(self, frames_by_channels, hrir_size: int = 0):
+        a = _f32(frames_by_channels)
+        _check(lib().ssr_renderer_load_hrirs(self.h, _ptr(a), a.shape[0], a.shape[1], hrir_size))
+
+    def generate_hrirs(self, channels: int, taps: int, seed: int, envelope=None, scale: float = 1.0):
+        env = None if envelope is None else _f32(envelope)
+        _check(lib().ssr_renderer_generate_hrirs(self.h, channels, taps, seed, _ptr(env), scale))
+
+    def add_source(self, ir=None) -> int:
+        sid = C.c_int()
+        if ir is None:
+            _check(lib().ssr_renderer_add_source(self.h, _f32p(), 0, 0, C.byref(sid)))
+        else:
+            a = _f32(ir)
+            _check(lib().ssr_renderer_add_source(self.h, _ptr(a), a.shape[0], a.shape[1], C.byref(sid)))
+        return sid.value
+
+    def add_source_synthetic(self, taps: int, channels: int, seed: int, channel_id_offset: int = 0,
+                             envelope=None, scale: float = 1.0) -> int:
+        sid = C.c_int()
+        env = None if envelope is None else _f32(envelope)
+        _check(lib().ssr_renderer_add_source_synthetic(self.h, taps, channels, seed, channel_id_offset,
+                                                       _ptr(env), scale, C.byref(sid)))
+        return sid.value
+
+    def rem_source(self, sid: int):
+        _check(lib().ssr_renderer_rem_source(self.h, sid))
+
+    def set_gain(self, sid, v): _check(lib().ssr_source_set_gain(self.h, sid, v))
+    def set_mute(self, sid, v): _check(lib().ssr_source_set_mute(self.h, sid, int(v)))
+    def set_position(self, sid, x, y): _check(lib().ssr_source_set_position(self.h, sid, x, y))
+    def set_model(self, sid, plane): _check(lib().ssr_source_set_model(self.h, sid, int(plane)))
+    def set_reference_position(self, x, y): _check(lib().ssr_renderer_set_reference_position(self.h, x, y))
+    def set_reference_orientation(self, az): _check(lib().ssr_renderer_set_reference_orientation(self.h, az))
+    def set_reference_offset_position(self, x, y): _check(lib().ssr_renderer_set_reference_offset_position(self.h, x, y))
+    def set_reference_offset_orientation(self, az): _check(lib().ssr_renderer_set_reference_offset_orientation(self.h, az))
+    def set_master_volume(self, v): _check(lib().ssr_renderer_set_master_volume(self.h, v))
+    def set_processing(self, on): _check(lib().ssr_renderer_set_processing(self.h, int(on)))
+    def set_amplitude_reference_distance(self, d): _check(lib().ssr_renderer_set_amplitude_reference_distance(self.h, d))
+
+    def _ptr_arrays(self, x: np.ndarray, y: np.ndarray):
+        ins = (_f32p * max(1, x.shape[0]))(*[x[i].ctypes.data_as(_f32p) for i in range(x.shape[0])])
+        outs = (_f32p * y.shape[0])(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
+        return ins, outs
+
+    def process(self, x) -> np.ndarray:
+        """x: (sources, B) host floats -> (local_outputs, B); = audio_callback."""
+        B = self.engine.block_size
+        x = _f32(x).reshape(-1, B)
+        y = np.empty((self.local_outputs, B), np.float32)
+        ins, outs = self._ptr_arrays(x, y)
+        _check(lib().ssr_renderer_process(self.h, B, ins, outs))
+        return y
+
+    def submit(self, x):
+        B = self.engine.block_size
+        x = _f32(x).reshape(-1, B)
+        ins = (_f32p * max(1, x.shape[0]))(*[x[i].ctypes.data_as(_f32p) for i in range(x.shape[0])])
+        _check(lib().ssr_renderer_submit(self.h, B, ins))
+
+    def wait(self) -> np.ndarray:
+        B = self.engine.block_size
+        y = np.empty((self.local_outputs, B), np.float32)
+        outs = (_f32p * y.shape[0])(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
+        _check(lib().ssr_renderer_wait(self.h, outs))
+        return y
+
+    def process_device(self, d_in_ptr: int, d_out_ptr: int):
+        _check(lib().ssr_renderer_process_device(self.h, d_in_ptr, d_out_ptr))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ssr_renderer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

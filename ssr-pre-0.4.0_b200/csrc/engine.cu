@@ -1,0 +1,619 @@
+// engine.cu -- engine core: device resources, launches, filter sets, Level-1 objects.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace ssr_b200
+{
+
+using namespace ssrk;
+
+// ------------------------------------------------------------------ MacPlan
+void MacPlan::make_work(int slots)
+{
+  work.host.clear();
+  npartials = 0;
+  const int G = int(groups.size());
+  long total = 0;
+  for (auto& g : groups) total += g.term_end - g.term_begin;
+  if (G == 0) return;
+  const long avg = std::max<long>(1, (total + G - 1) / G);
+  // pick the split count S (per average group) that minimises
+  //   waves(G*S) * (chunk length + fixed cost of a CTA in term units)
+  const long c0 = 2;
+  long bestS = 1; double best = 1e300;
+  const long Smax = std::min<long>(avg, 512);
+  for (long S = 1; S <= Smax; ++S)
+  {
+    const long ctas = long(G) * S;
+    const long waves = (ctas + slots - 1) / slots;
+    const long chunk = (avg + S - 1) / S;
+    const double cost = double(waves) * double(chunk + c0);
+    if (cost < best - 1e-9) { best = cost; bestS = S; }
+  }
+  const long chunk = std::max<long>(1, (avg + bestS - 1) / bestS);
+  for (auto& g : groups)
+  {
+    const int n = g.term_end - g.term_begin;
+    int S = std::max(1, int((n + chunk - 1) / chunk));
+    g.partial_first = npartials;
+    g.nsplit = S;
+    for (int s = 0; s < S; ++s)
+    {
+      const int b = g.term_begin + int((long(n) * s) / S);
+      const int e = g.term_begin + int((long(n) * (s + 1)) / S);
+      work.host.push_back(make_int4(b, e, npartials + s, 0));
+    }
+    npartials += S;
+  }
+}
+
+// ------------------------------------------------------------------ Engine
+static int mac_nv(int B) { return B >= 1024 ? 2 : 1; }
+static int mac_ktiles(int B) { return B > 1024 ? B / 1024 : 1; }
+
+template<int MT, int NV> static void* mac_fn() { return (void*)mac_kernel<MT, NV>; }
+
+static void* mac_kernel_ptr(int MT, int NV)
+{
+  if (NV == 2)
+  {
+    if (MT == 1) return mac_fn<1, 2>();
+    if (MT == 2) return mac_fn<2, 2>();
+    return mac_fn<4, 2>();
+  }
+  if (MT == 1) return mac_fn<1, 1>();
+  if (MT == 2) return mac_fn<2, 1>();
+  return mac_fn<4, 1>();
+}
+
+Engine::Engine(const ssr_engine_config& cfg)
+  : device(cfg.device), B(cfg.block_size), sample_rate(cfg.sample_rate)
+  , mac_variant(cfg.mac_variant), stream(nullptr), own_stream(false)
+{
+  if (B <= 0 || B % 8 != 0)
+    throw Error(SSR_ERR_BLOCK_SIZE, "Convolver: block size must be a multiple of 8!");
+  if ((B & (B - 1)) != 0 || B > 4096)
+    throw Error(SSR_ERR_UNSUPPORTED,
+        "ssr_b200: block size must be a power of two in [8, 4096]");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    throw Error(SSR_ERR_CUDA, std::string("ssr_b200: no CUDA device usable (")
+        + cudaGetErrorString(err) + "); this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) throw Error(SSR_ERR_INVALID, "ssr_b200: bad device ordinal");
+  use_device();
+  cudaDeviceProp prop;
+  SSR_CUDA(cudaGetDeviceProperties(&prop, device));
+  sm_count = prop.multiProcessorCount;
+  if (cfg.stream) stream = static_cast<cudaStream_t>(cfg.stream);
+  else { SSR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+
+  // twiddles exp(-2 pi i k / 2B), computed in double
+  const int n = 2 * B;
+  std::vector<float2> htw(n);
+  for (int k = 0; k < n; ++k)
+  {
+    const double a = -2.0 * M_PI * double(k) / double(n);
+    htw[k] = make_float2(float(std::cos(a)), float(std::sin(a)));
+  }
+  tw.resize(n);
+  SSR_CUDA(cudaMemcpy(tw.ptr, htw.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+
+  // raised-cosine crossfade, same float expression as the reference
+  // (apf/apf/math.h:254-259 with period 2B, apf/apf/combine_channels.h:481-497)
+  std::vector<float> w(B + 1), fo(B), fi(B);
+  const float period = float(2 * B);
+  const float pi_f = float(M_PI);
+  for (int i = 0; i <= B; ++i) w[i] = std::cos(float(i) * 2 * pi_f / period) * 0.5f + 0.5f;
+  for (int i = 0; i < B; ++i) { fo[i] = w[i]; fi[i] = w[B - i]; }
+  fade_out.resize(B); fade_in.resize(B);
+  SSR_CUDA(cudaMemcpy(fade_out.ptr, fo.data(), B * sizeof(float), cudaMemcpyHostToDevice));
+  SSR_CUDA(cudaMemcpy(fade_in.ptr, fi.data(), B * sizeof(float), cudaMemcpyHostToDevice));
+
+  zero_part.resize(B);
+  SSR_CUDA(cudaMemset(zero_part.ptr, 0, B * sizeof(float2)));
+
+  d_xring.resize(kMaxInputs); d_xparts.resize(kMaxInputs); d_heads.resize(kMaxInputs);
+  SSR_CUDA(cudaMemset(d_xring.ptr, 0, kMaxInputs * sizeof(void*)));
+  SSR_CUDA(cudaMemset(d_xparts.ptr, 0, kMaxInputs * sizeof(int)));
+  SSR_CUDA(cudaMemset(d_heads.ptr, 0, kMaxInputs * sizeof(int)));
+
+  const size_t fft_smem = size_t(2) * B * sizeof(float2);
+  if (fft_smem > 48 * 1024)
+  {
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+  }
+  SSR_CUDA(cudaDeviceSynchronize());
+}
+
+Engine::~Engine()
+{
+  cudaSetDevice(device);
+  cudaStreamSynchronize(stream);
+  for (auto& p : pending) for (auto& ev : p.ev) cudaEventDestroy(ev);
+  for (auto& p : free_events) for (auto& ev : p.ev) cudaEventDestroy(ev);
+  if (own_stream) cudaStreamDestroy(stream);
+}
+
+int Engine::register_input(Input* in)
+{
+  int id = -1;
+  for (size_t i = 0; i < inputs.size(); ++i) if (!inputs[i]) { id = int(i); break; }
+  if (id < 0)
+  {
+    if (int(inputs.size()) >= kMaxInputs) throw Error(SSR_ERR_NOMEM, "ssr_b200: too many inputs");
+    id = int(inputs.size());
+    inputs.push_back(nullptr);
+  }
+  inputs[id] = in;
+  const float4* ring = reinterpret_cast<const float4*>(in->ring.ptr);
+  const int parts = in->P, zero = 0;
+  SSR_CUDA(cudaMemcpyAsync(d_xring.ptr + id, &ring, sizeof(ring), cudaMemcpyHostToDevice, stream));
+  SSR_CUDA(cudaMemcpyAsync(d_xparts.ptr + id, &parts, sizeof(int), cudaMemcpyHostToDevice, stream));
+  SSR_CUDA(cudaMemcpyAsync(d_heads.ptr + id, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
+  sync();  // the sources above are stack variables
+  return id;
+}
+
+void Engine::unregister_input(int id)
+{
+  if (id >= 0 && id < int(inputs.size())) inputs[id] = nullptr;
+}
+
+int Engine::mac_slots() const
+{
+  int occ = 0;
+  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &occ, mac_kernel<4, 2>, kThreads, 0);
+  if (err != cudaSuccess || occ < 1) occ = 1;
+  return sm_count * occ;
+}
+
+void Engine::launch_fwd(const FwdJob* d_jobs, int njobs)
+{
+  if (njobs <= 0) return;
+  const size_t smem = size_t(2) * B * sizeof(float2);
+  fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr);
+  SSR_CUDA(cudaGetLastError());
+  if (cur) cur->fft_launches++;
+}
+
+void Engine::ensure_partials(size_t nspectra)
+{
+  const size_t need = nspectra * size_t(B / 2);
+  if (need > partials.count)
+  {
+    sync();  // previous launches may still read the old buffer
+    partials.resize(need + need / 4);
+  }
+}
+
+void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset)
+{
+  const int nwork = int(plan.work.uploaded);
+  if (nwork == 0) return;
+  MacParams p;
+  p.term_meta = plan.meta.dev.ptr;
+  p.term_h = plan.hptr.dev.ptr;
+  p.work = plan.work.dev.ptr;
+  p.wtab = wtab.ptr;
+  p.xring = d_xring.ptr;
+  p.xparts = d_xparts.ptr;
+  p.heads = d_heads.ptr;
+  p.partials = partials.ptr;
+  p.B = B;
+  p.wtab_offset = wtab_offset;
+  p.partial_offset = partial_offset;
+  void* fn = mac_kernel_ptr(plan.MT, mac_nv(B));
+  void* args[] = { &p };
+  dim3 grid(nwork, mac_ktiles(B), 1);
+  SSR_CUDA(cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, stream));
+  if (cur) cur->mac_launches++;
+}
+
+void Engine::launch_inv(const InvPlan& plan)
+{
+  const int njobs = int(plan.jobs.uploaded);
+  if (njobs == 0) return;
+  const size_t smem = size_t(2) * B * sizeof(float2);
+  inv_fft_kernel<<<njobs, kThreads, smem, stream>>>(plan.jobs.dev.ptr, plan.entries.dev.ptr,
+      reinterpret_cast<const float2*>(partials.ptr), B, tw.ptr, fade_out.ptr, fade_in.ptr);
+  SSR_CUDA(cudaGetLastError());
+  if (cur) cur->ifft_launches++;
+}
+
+void Engine::upload_weights(const float* w, size_t n)
+{
+  if (n == 0) return;
+  if (n > wtab.count) { sync(); wtab.resize(n + 64); }
+  // small and latency critical: a pageable-source async copy is staged by the
+  // driver at call time, so `w` may be reused immediately
+  SSR_CUDA(cudaMemcpyAsync(wtab.ptr, w, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+}
+
+void Engine::stage_begin()
+{
+  if (!timing) { cur = nullptr; return; }
+  StageEvents se{};
+  if (!free_events.empty()) { se = free_events.back(); free_events.pop_back(); }
+  else for (auto& ev : se.ev) SSR_CUDA(cudaEventCreate(&ev));
+  se.mac_bytes = 0; se.mac_terms = 0; se.mac_launches = se.fft_launches = se.ifft_launches = 0;
+  pending.push_back(se);
+  cur = &pending.back();
+  SSR_CUDA(cudaEventRecord(cur->ev[0], stream));
+}
+
+void Engine::stage_mark(int i) { if (cur) SSR_CUDA(cudaEventRecord(cur->ev[i], stream)); }
+
+void Engine::stage_end()
+{
+  cur = nullptr;
+  if (pending.size() > 4096) fold_stats();
+}
+
+void Engine::fold_stats()
+{
+  if (pending.empty()) return;
+  sync();
+  for (auto& p : pending)
+  {
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, p.ev[0], p.ev[1]);
+    cudaEventElapsedTime(&b, p.ev[1], p.ev[2]);
+    cudaEventElapsedTime(&c, p.ev[2], p.ev[3]);
+    cudaEventElapsedTime(&d, p.ev[0], p.ev[3]);
+    stats.ms_fft += a; stats.ms_mac += b; stats.ms_ifft += c; stats.ms_total += d;
+    stats.blocks++;
+    stats.mac_launches += p.mac_launches; stats.fft_launches += p.fft_launches;
+    stats.ifft_launches += p.ifft_launches;
+    stats.mac_bytes += p.mac_bytes; stats.mac_terms += p.mac_terms;
+    free_events.push_back(p);
+  }
+  pending.clear();
+}
+
+// ------------------------------------------------------------------ FilterSet
+FilterSet::FilterSet(Engine* e_, int channels_, int partitions_)
+  : e(e_), channels(channels_), partitions(partitions_)
+{
+  if (channels <= 0 || partitions <= 0) throw Error(SSR_ERR_INVALID, "ssr_b200: empty filter set");
+  e->use_device();
+  data.resize(size_t(channels) * partitions * e->B);
+  valid.assign(channels, 0);
+  flags.assign(size_t(channels) * partitions, 0);
+}
+
+static void run_fwd_jobs(Engine* e, std::vector<FwdJob>& jobs)
+{
+  // chunked so the job table stays small
+  const size_t chunk = 1 << 16;
+  DeviceArray<FwdJob> d(std::min(chunk, jobs.size()));
+  for (size_t off = 0; off < jobs.size(); off += chunk)
+  {
+    const size_t n = std::min(chunk, jobs.size() - off);
+    SSR_CUDA(cudaMemcpyAsync(d.ptr, jobs.data() + off, n * sizeof(FwdJob),
+          cudaMemcpyHostToDevice, e->stream));
+    e->launch_fwd(d.ptr, int(n));
+    e->sync();
+  }
+}
+
+void FilterSet::load_time(int first_channel, int nch, const float* host, long frames,
+                          long frame_stride, long channel_stride)
+{
+  if (first_channel < 0 || nch <= 0 || first_channel + nch > channels || frames < 0 || !host)
+    throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_load_time: bad arguments");
+  e->use_device();
+  const int B = e->B;
+  // extent of the host array touched
+  const long extent = (frames > 0)
+    ? (frames - 1) * frame_stride + (nch - 1) * channel_stride + 1 : 0;
+  DeviceArray<float> d_time{static_cast<size_t>(std::max<long>(extent, 1))};
+  if (extent > 0)
+    SSR_CUDA(cudaMemcpyAsync(d_time.ptr, host, size_t(extent) * sizeof(float),
+          cudaMemcpyHostToDevice, e->stream));
+  const int nvalid = int(std::min<long>(partitions, (frames + B - 1) / B));
+  std::vector<FwdJob> jobs;
+  jobs.reserve(size_t(nch) * nvalid);
+  for (int c = 0; c < nch; ++c)
+  {
+    const int ch = first_channel + c;
+    valid[ch] = nvalid;
+    for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
+    for (int p = 0; p < nvalid; ++p)
+    {
+      FwdJob j{};
+      j.first.ptr = d_time.ptr + c * channel_stride + long(p) * B * frame_stride;
+      j.first.stride = frame_stride;
+      j.first.count = int(std::min<long>(B, frames - long(p) * B));
+      j.second.ptr = nullptr; j.second.count = 0; j.second.stride = 1;
+      j.dst = part(ch, p);
+      jobs.push_back(j);
+    }
+  }
+  run_fwd_jobs(e, jobs);
+  e->sync();
+}
+
+void FilterSet::set_partition_time(int ch, int p, const float* taps, int n)
+{
+  if (ch < 0 || ch >= channels || p < 0 || p >= partitions || n < 0 || n > e->B)
+    throw Error(SSR_ERR_INVALID, "ssr_b200: set_partition_time: bad arguments");
+  e->use_device();
+  if (n == 0)
+  {
+    // chunk == 0 -> zero flag, no FFT (convolver.h:218-221)
+    flags[size_t(ch) * partitions + p] = 0;
+    return;
+  }
+  DeviceArray<float> d{size_t(n)};
+  SSR_CUDA(cudaMemcpyAsync(d.ptr, taps, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  std::vector<FwdJob> jobs(1);
+  jobs[0] = FwdJob{};
+  jobs[0].first.ptr = d.ptr; jobs[0].first.stride = 1; jobs[0].first.count = n;
+  jobs[0].second.stride = 1;
+  jobs[0].dst = part(ch, p);
+  run_fwd_jobs(e, jobs);
+  flags[size_t(ch) * partitions + p] = 1;
+  valid[ch] = std::max(valid[ch], p + 1);
+}
+
+void FilterSet::generate(int first_channel, int nch, long taps, uint64_t seed, uint64_t id_offset,
+                         const float* envelope, float scale)
+{
+  if (first_channel < 0 || nch <= 0 || first_channel + nch > channels || taps <= 0)
+    throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_generate: bad arguments");
+  e->use_device();
+  const int B = e->B;
+  DeviceArray<float> d_env;
+  if (envelope)
+  {
+    d_env.resize(size_t(taps));
+    SSR_CUDA(cudaMemcpyAsync(d_env.ptr, envelope, size_t(taps) * sizeof(float),
+          cudaMemcpyHostToDevice, e->stream));
+  }
+  const int nvalid = int(std::min<long>(partitions, (taps + B - 1) / B));
+  std::vector<FwdJob> jobs;
+  const size_t batch_channels = std::max<size_t>(1, (size_t(1) << 16) / size_t(nvalid));
+  for (int c0 = 0; c0 < nch; c0 += int(batch_channels))
+  {
+    const int c1 = int(std::min<size_t>(nch, c0 + batch_channels));
+    jobs.clear();
+    for (int c = c0; c < c1; ++c)
+    {
+      const int ch = first_channel + c;
+      valid[ch] = nvalid;
+      for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
+      const uint64_t key = synth_key(seed, id_offset + uint64_t(c));
+      for (int p = 0; p < nvalid; ++p)
+      {
+        FwdJob j{};
+        j.first.ptr = d_env.ptr;
+        j.first.stride = 1;
+        j.first.count = int(std::min<long>(B, taps - long(p) * B));
+        j.first.synth = 1;
+        j.first.key = key;
+        j.first.first_index = uint64_t(p) * B;
+        j.first.scale = scale;
+        j.second.stride = 1;
+        j.dst = part(ch, p);
+        jobs.push_back(j);
+      }
+    }
+    run_fwd_jobs(e, jobs);
+  }
+  e->sync();
+}
+
+void FilterSet::lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t)
+{
+  if (dch < 0 || dch >= channels || ach < 0 || ach >= a.channels || bch < 0 || bch >= b.channels)
+    throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_lerp: bad channel");
+  e->use_device();
+  std::vector<LerpJob> jobs;
+  for (int p = 0; p < partitions; ++p)
+  {
+    const float2* pa = a.part_or_null(ach, p);
+    const float2* pb = b.part_or_null(bch, p);
+    if (!pa && !pb) { flags[size_t(dch) * partitions + p] = 0; continue; }
+    flags[size_t(dch) * partitions + p] = 1;
+    jobs.push_back({reinterpret_cast<const float4*>(pa), reinterpret_cast<const float4*>(pb),
+        reinterpret_cast<float4*>(part(dch, p))});
+  }
+  if (jobs.empty()) return;
+  DeviceArray<LerpJob> d(jobs.size());
+  SSR_CUDA(cudaMemcpyAsync(d.ptr, jobs.data(), jobs.size() * sizeof(LerpJob),
+        cudaMemcpyHostToDevice, e->stream));
+  lerp_kernel<<<int(jobs.size()), kThreads, 0, e->stream>>>(d.ptr, e->B / 2, 1.0f - t, t);
+  SSR_CUDA(cudaGetLastError());
+  e->sync();  // `jobs` / `d` go out of scope
+}
+
+// packed complex -> the reference's sorted halfcomplex layout (convolver.h:236-268):
+// group g of 8 floats = [Re X_{4g..4g+3} | Im X_{4g..4g+3}], slot 4 of group 0 = Re X_B
+static void packed_to_sorted(const float2* packed, int B, float* sorted)
+{
+  for (int k = 0; k < B; ++k)
+  {
+    const int g = k >> 2, j = k & 3;
+    sorted[8 * g + j] = packed[k].x;
+    sorted[8 * g + 4 + j] = packed[k].y;
+  }
+}
+
+void FilterSet::download(int ch, int p, float* sorted_out, int* zero)
+{
+  if (ch < 0 || ch >= channels || p < 0 || p >= partitions)
+    throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_download: bad index");
+  e->use_device();
+  const int B = e->B;
+  const bool z = !flags[size_t(ch) * partitions + p];
+  if (zero) *zero = z ? 1 : 0;
+  if (z) { std::fill(sorted_out, sorted_out + 2 * B, 0.0f); return; }
+  std::vector<float2> tmp(B);
+  e->sync();
+  SSR_CUDA(cudaMemcpy(tmp.data(), part(ch, p), B * sizeof(float2), cudaMemcpyDeviceToHost));
+  packed_to_sorted(tmp.data(), B, sorted_out);
+}
+
+// ------------------------------------------------------------------ FilterPtrTable
+FilterPtrTable::FilterPtrTable(int partitions)
+  : P(partitions), ptrs(partitions, nullptr)
+{
+  for (int i = 0; i + 1 < P; ++i) queues.emplace_back(size_t(i + 1), Slot{nullptr, false});
+  qstart.assign(queues.size(), 0);
+}
+
+void FilterPtrTable::set_static(const FilterSet& fs, int ch)
+{
+  for (int p = 0; p < P; ++p) ptrs[p] = fs.part_or_null(ch, p);  // missing -> empty
+}
+
+void FilterPtrTable::set_filter(const FilterSet& fs, int ch)
+{
+  // first partition immediately; partition i+1 at the tail of queue i
+  if (fs.partitions > 0) ptrs[0] = fs.part_or_null(ch, 0);
+  for (size_t i = 0; i < queues.size(); ++i)
+  {
+    auto& q = queues[i];
+    const size_t last = (size_t(qstart[i]) + i) % q.size();
+    q[last] = Slot{fs.part_or_null(ch, int(i) + 1), true};  // beyond the filter -> empty
+  }
+}
+
+bool FilterPtrTable::queues_empty() const
+{
+  if (queues.empty()) return true;
+  for (auto& s : queues.back()) if (s.set) return false;
+  return true;
+}
+
+void FilterPtrTable::rotate_queues()
+{
+  for (size_t i = 0; i < queues.size(); ++i)
+  {
+    auto& q = queues[i];
+    Slot& front = q[qstart[i]];
+    if (front.set) ptrs[i + 1] = front.ptr;
+    front = Slot{nullptr, false};  // becomes the new back
+    qstart[i] = int((size_t(qstart[i]) + 1) % q.size());
+  }
+}
+
+bool FilterPtrTable::references(const float2* lo, const float2* hi) const
+{
+  for (auto p : ptrs) if (p >= lo && p < hi) return true;
+  for (auto& q : queues) for (auto& s : q) if (s.set && s.ptr >= lo && s.ptr < hi) return true;
+  return false;
+}
+
+// ------------------------------------------------------------------ Input
+Input::Input(Engine* e_, int partitions)
+  : e(e_), id(-1), P(partitions)
+{
+  if (partitions <= 0) throw Error(SSR_ERR_INVALID, "ssr_b200: Input needs partitions > 0");
+  e->use_device();
+  const int B = e->B;
+  ring.resize(size_t(P) * B);
+  prev.resize(B); cur.resize(B);
+  stage.resize(B);
+  SSR_CUDA(cudaMemsetAsync(ring.ptr, 0, size_t(P) * B * sizeof(float2), e->stream));
+  SSR_CUDA(cudaMemsetAsync(prev.ptr, 0, B * sizeof(float), e->stream));
+  id = e->register_input(this);
+  job.host.assign(1, make_job(cur.ptr));
+  job.upload(e->stream);
+  e->sync();
+}
+
+Input::~Input() { e->unregister_input(id); }
+
+FwdJob Input::make_job(const float* d_cur)
+{
+  FwdJob j{};
+  j.first.ptr = prev.ptr; j.first.stride = 1; j.first.count = e->B;
+  j.second.ptr = d_cur; j.second.stride = 1; j.second.count = e->B;
+  j.dst = nullptr;
+  j.ring = ring.ptr;
+  j.head = e->d_heads.ptr + id;
+  j.parts = P;
+  j.save_second = prev.ptr;
+  return j;
+}
+
+void Input::add_block(const float* x)
+{
+  e->use_device();
+  e->sync();  // the single staging buffer may still be in flight
+  std::memcpy(stage.ptr, x, e->B * sizeof(float));
+  SSR_CUDA(cudaMemcpyAsync(cur.ptr, stage.ptr, e->B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  e->stats.h2d_bytes += e->B * sizeof(float);
+  e->launch_fwd(job.dev.ptr, 1);
+}
+
+void Input::download(int p, float* sorted_out)
+{
+  if (p < 0 || p >= P) throw Error(SSR_ERR_INVALID, "ssr_b200: input_download: bad partition");
+  e->use_device();
+  e->sync();
+  int head = 0;
+  SSR_CUDA(cudaMemcpy(&head, e->d_heads.ptr + id, sizeof(int), cudaMemcpyDeviceToHost));
+  int slot = head - p; if (slot < 0) slot += P;
+  std::vector<float2> tmp(e->B);
+  SSR_CUDA(cudaMemcpy(tmp.data(), ring.ptr + size_t(slot) * e->B, e->B * sizeof(float2), cudaMemcpyDeviceToHost));
+  packed_to_sorted(tmp.data(), e->B, sorted_out);
+}
+
+// ------------------------------------------------------------------ Output
+Output::Output(Input* in_, ssr_output_kind kind_)
+  : in(in_), e(in_->e), kind(kind_), table(in_->P)
+{
+  e->use_device();
+  d_res.resize(e->B); h_res.resize(e->B);
+  mac.MT = 1;
+}
+
+const float* Output::convolve(float weight)
+{
+  e->use_device();
+  const int B = e->B;
+  mac.clear();
+  mac.begin_group();
+  for (int p = 0; p < table.P; ++p)
+  {
+    // zero-flagged partitions are skipped (convolver.h:561)
+    if (!table.ptrs[p]) continue;
+    const float4* h = reinterpret_cast<const float4*>(table.ptrs[p]);
+    mac.add_term(in->id, p, 0, &h);
+  }
+  mac.end_group();
+  const int nterms = int(mac.meta.host.size());
+  inv.clear();
+  if (nterms == 0 || weight == 0.0f)
+  {
+    // nothing contributed: the reference returns its zero-filled buffer
+    // without an IFFT (convolver.h:448-452)
+    inv.jobs.host.push_back({0, 0, d_res.ptr});
+  }
+  else
+  {
+    mac.make_work(e->mac_slots());
+    e->sync();  // staging tables of the previous call
+    mac.upload(e->stream);
+    e->ensure_partials(size_t(mac.npartials) * mac.MT);
+    e->upload_weights(&weight, 1);
+    e->launch_mac(mac, 0, 0);
+    inv.entries.host.push_back({0, mac.groups[0].nsplit, 1, 0, 0, 1.0f / float(2 * B)});
+    inv.jobs.host.push_back({0, 1, d_res.ptr});
+  }
+  inv.upload(e->stream);
+  e->launch_inv(inv);
+  SSR_CUDA(cudaMemcpyAsync(h_res.ptr, d_res.ptr, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  e->stats.d2h_bytes += B * sizeof(float);
+  e->sync();
+  return h_res.ptr;
+}
+
+}  // namespace ssr_b200

@@ -1,0 +1,343 @@
+// engine.hpp -- host side of the B200 partitioned-convolution engine.
+//
+// The classes here own HBM-resident spectra and build the small job tables the
+// kernels in kernels.cuh consume.  They mirror the reference's object model
+// (apf/apf/convolver.h: Filter / Input / Output / StaticOutput) but batch the
+// arithmetic: one launch handles every (source, output, partition) triple of a
+// block instead of one call per pair.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ssr_b200.h"
+#include "kernels.cuh"
+
+namespace ssr_b200
+{
+
+struct Error : std::runtime_error
+{
+  Error(int code_, const std::string& what) : std::runtime_error(what), code(code_) {}
+  int code;
+};
+
+#define SSR_CUDA(call) \
+  do { cudaError_t err__ = (call); if (err__ != cudaSuccess) \
+    throw ::ssr_b200::Error(SSR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+// ------------------------------------------------------------ memory helpers
+template<typename T>
+struct DeviceArray
+{
+  T* ptr = nullptr;
+  size_t count = 0;
+  DeviceArray() {}
+  explicit DeviceArray(size_t n) { resize(n); }
+  DeviceArray(const DeviceArray&) = delete;
+  DeviceArray& operator=(const DeviceArray&) = delete;
+  ~DeviceArray() { release(); }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; count = 0; }
+  void resize(size_t n)
+  {
+    release();
+    if (n == 0) return;
+    cudaError_t err = cudaMalloc(&ptr, n * sizeof(T));
+    if (err != cudaSuccess)
+      throw Error(err == cudaErrorMemoryAllocation ? SSR_ERR_NOMEM : SSR_ERR_CUDA,
+          std::string("cudaMalloc: ") + cudaGetErrorString(err));
+    count = n;
+  }
+  void ensure(size_t n) { if (n > count) resize(n + n / 2 + 16); }
+};
+
+template<typename T>
+struct PinnedArray
+{
+  T* ptr = nullptr;
+  size_t count = 0;
+  PinnedArray() {}
+  explicit PinnedArray(size_t n) { resize(n); }
+  PinnedArray(const PinnedArray&) = delete;
+  PinnedArray& operator=(const PinnedArray&) = delete;
+  ~PinnedArray() { release(); }
+  void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; count = 0; }
+  void resize(size_t n)
+  {
+    release();
+    if (n == 0) return;
+    SSR_CUDA(cudaMallocHost(&ptr, n * sizeof(T)));
+    count = n;
+  }
+  void ensure(size_t n) { if (n > count) resize(n + n / 2 + 16); }
+};
+
+// A host-built table mirrored on the device (pinned staging + async copy).
+template<typename T>
+struct Table
+{
+  std::vector<T> host;
+  PinnedArray<T> stage;
+  DeviceArray<T> dev;
+  size_t uploaded = 0;
+  void upload(cudaStream_t s)
+  {
+    uploaded = host.size();
+    if (host.empty()) return;
+    stage.ensure(host.size());
+    dev.ensure(host.size());
+    std::memcpy(stage.ptr, host.data(), host.size() * sizeof(T));
+    SSR_CUDA(cudaMemcpyAsync(dev.ptr, stage.ptr, host.size() * sizeof(T),
+          cudaMemcpyHostToDevice, s));
+  }
+};
+
+struct Engine;
+struct FilterSet;
+struct Input;
+
+// ------------------------------------------------------------ MAC plan
+// Rows of a group share their term sequence (and therefore every X load).
+struct MacPlan
+{
+  int MT = 1;
+  Table<ssrk::MacTermMeta> meta;
+  Table<const float4*> hptr;   // [nterms][MT]
+  Table<int4> work;            // one per CTA
+  int npartials = 0;           // partial spectra groups written per launch (= CTAs)
+  struct Group { int term_begin, term_end, partial_first, nsplit; };
+  std::vector<Group> groups;
+  void clear() { meta.host.clear(); hptr.host.clear(); work.host.clear(); groups.clear(); npartials = 0; }
+  int begin_group() { groups.push_back({int(meta.host.size()), 0, 0, 0}); return int(groups.size()) - 1; }
+  void add_term(int input, int p, int wslot, const float4* const* h)
+  {
+    meta.host.push_back({input, p, wslot, 0});
+    for (int j = 0; j < MT; ++j) hptr.host.push_back(h[j]);
+  }
+  void end_group() { groups.back().term_end = int(meta.host.size()); }
+  // split every group's terms into equal chunks; `slots` = CTAs resident at once
+  void make_work(int slots);
+  void upload(cudaStream_t s) { meta.upload(s); hptr.upload(s); work.upload(s); }
+};
+
+struct InvPlan
+{
+  Table<ssrk::InvJob> jobs;
+  Table<ssrk::InvEntry> entries;
+  void clear() { jobs.host.clear(); entries.host.clear(); }
+  void upload(cudaStream_t s) { jobs.upload(s); entries.upload(s); }
+};
+
+// ------------------------------------------------------------ engine
+struct StageEvents { cudaEvent_t ev[4]; uint64_t mac_bytes, mac_terms; int mac_launches, fft_launches, ifft_launches; };
+
+struct Engine
+{
+  explicit Engine(const ssr_engine_config& cfg);
+  ~Engine();
+
+  int device, B, sample_rate, sm_count, mac_variant;
+  cudaStream_t stream;
+  bool own_stream;
+
+  DeviceArray<float2> tw;          // exp(-2 pi i k / 2B), k in [0, 2B)
+  DeviceArray<float> fade_out, fade_in;
+  DeviceArray<float2> zero_part;   // B float2 of zeros ("empty partition", convolver.h:415)
+
+  // input registry (device tables indexed by input id)
+  static constexpr int kMaxInputs = 16384;
+  DeviceArray<const float4*> d_xring;
+  DeviceArray<int> d_xparts, d_heads;
+  std::vector<Input*> inputs;
+  int register_input(Input* in);
+  void unregister_input(int id);
+
+  DeviceArray<float> wtab;         // weight slots
+  PinnedArray<float> wtab_stage;
+  DeviceArray<float4> partials;
+
+  // launches (all asynchronous on `stream`)
+  void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs);
+  void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset);
+  void launch_inv(const InvPlan& plan);
+  void upload_weights(const float* w, size_t n);
+  void ensure_partials(size_t npartial_spectra);
+  int mac_slots() const;           // CTAs resident at once for the MAC kernel
+
+  // stats
+  bool timing = false;
+  ssr_engine_stats stats{};
+  std::vector<StageEvents> pending;
+  std::vector<StageEvents> free_events;
+  StageEvents* cur = nullptr;
+  void stage_begin();              // call before the first kernel of a block step
+  void stage_mark(int i);          // 1 after fft, 2 after mac, 3 after ifft
+  void stage_end();
+  void fold_stats();
+  void sync() { SSR_CUDA(cudaStreamSynchronize(stream)); }
+  void use_device() { SSR_CUDA(cudaSetDevice(device)); }
+};
+
+// ------------------------------------------------------------ filter sets
+struct FilterSet
+{
+  FilterSet(Engine* e, int channels, int partitions);
+  Engine* e;
+  int channels, partitions;
+  DeviceArray<float2> data;          // [channels][partitions][B]
+  std::vector<int> valid;            // per channel: partitions [0, valid) carry data
+  std::vector<uint8_t> flags;        // per (channel, partition): 1 = non-zero-flagged
+  const float2* part(int ch, int p) const { return data.ptr + (size_t(ch) * partitions + p) * e->B; }
+  float2* part(int ch, int p) { return data.ptr + (size_t(ch) * partitions + p) * e->B; }
+  // null for zero-flagged partitions (fft_node::zero, convolver.h:91-96)
+  const float2* part_or_null(int ch, int p) const
+  { return (p < partitions && flags[size_t(ch) * partitions + p]) ? part(ch, p) : nullptr; }
+  void load_time(int first_channel, int nch, const float* data, long frames,
+                 long frame_stride, long channel_stride);
+  void set_partition_time(int ch, int p, const float* taps, int n);
+  void generate(int first_channel, int nch, long taps, uint64_t seed, uint64_t id_offset,
+                const float* envelope, float scale);
+  void lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t);
+  void download(int ch, int p, float* sorted_out, int* zero);
+};
+
+// pointer table + staggered switch queues of one dynamic Output
+// (apf/apf/convolver.h:618-699); pointers are device addresses, null = empty
+struct FilterPtrTable
+{
+  explicit FilterPtrTable(int partitions);
+  int P;
+  std::vector<const float2*> ptrs;             // _filter_ptrs
+  // _queues[i] (i = 0..P-2) has i+1 slots; kept as rings so rotate is O(P)
+  struct Slot { const float2* ptr; bool set; };
+  std::vector<std::vector<Slot>> queues;
+  std::vector<int> qstart;
+  void set_static(const FilterSet& fs, int ch);    // StaticOutput::_set_filter :729-739
+  void set_filter(const FilterSet& fs, int ch);    // :642-658
+  bool queues_empty() const;                       // :666-677
+  void rotate_queues();                            // :683-699
+  bool references(const float2* lo, const float2* hi) const;
+};
+
+// ------------------------------------------------------------ Level 1 objects
+struct Input
+{
+  Input(Engine* e, int partitions);
+  ~Input();
+  Engine* e;
+  int id, P;
+  DeviceArray<float2> ring;          // [P][B]
+  DeviceArray<float> prev, cur;      // B floats each
+  PinnedArray<float> stage;
+  Table<ssrk::FwdJob> job;
+  ssrk::FwdJob make_job(const float* d_cur);
+  void add_block(const float* x);
+  void download(int p, float* sorted_out);
+};
+
+struct Output
+{
+  Output(Input* in, ssr_output_kind kind);
+  Input* in;
+  Engine* e;
+  ssr_output_kind kind;
+  FilterPtrTable table;
+  MacPlan mac;
+  InvPlan inv;
+  DeviceArray<float> d_res;
+  PinnedArray<float> h_res;
+  const float* convolve(float weight);
+};
+
+// ------------------------------------------------------------ Level 2
+template<typename T>
+struct BlockParameter  // apf::BlockParameter (apf/apf/misc.h:94-195)
+{
+  T current, old_value;
+  explicit BlockParameter(T v = T()) : current(v), old_value(v) {}
+  void assign(T v) { old_value = current; current = v; }
+  const T& get() const { return current; }
+  const T& old() const { return old_value; }
+  bool changed() const { return current != old_value; }
+  bool both_eq(T v) const { return current == v && old_value == v; }
+};
+
+enum Mode { NOTHING = 0, CONSTANT = 1, CHANGE = 2, FADE_IN = 3, FADE_OUT = 4 };
+
+struct Renderer
+{
+  Renderer(Engine* e, const ssr_renderer_config& cfg);
+  ~Renderer();
+
+  struct Source
+  {
+    int id;
+    std::unique_ptr<Input> input;
+    float gain = 1.0f; bool mute = false; float px = 0, py = 0; bool plane = false;
+    BlockParameter<float> weighting_factor{0.0f};
+    // generic
+    std::unique_ptr<FilterSet> irs;
+    BlockParameter<float> w{0.0f};
+    // brs / binaural
+    int angles = 0;
+    std::unique_ptr<FilterSet> brtf;
+    BlockParameter<float> bw{-1.0f};
+    BlockParameter<long> index{-1};
+    BlockParameter<float> interp{-1.0f};
+    std::vector<FilterPtrTable> chan;                 // 2 ears
+    std::vector<std::vector<std::unique_ptr<FilterSet>>> temp;  // per ear: pool of temporary_hrtf
+    Mode mode = NOTHING;
+  };
+
+  Engine* e;
+  ssr_renderer_config cfg;
+  int M_total, m_first, m_local;
+  std::vector<std::unique_ptr<Source>> sources;
+  int next_id = 1;
+
+  // RendererBase::State (src/rendererbase.h:84-103)
+  float ref_x = 0, ref_y = 0, ref_az = 0, off_x = 0, off_y = 0, off_az = 0;
+  float master_volume = 1.0f, amplitude_reference_distance = 3.0f, mvc = 1.0f;
+  bool processing = true;
+
+  // binaural
+  std::unique_ptr<FilterSet> hrtfs, neutral;
+  int angles = 0, partitions = 0;
+
+  // per-block plans
+  MacPlan static_mac;           // generic: built when the source list changes
+  bool static_dirty = true;
+  MacPlan dyn_mac[3];           // brs / binaural: const / old / new
+  InvPlan inv;
+  Table<ssrk::FwdJob> fwd;
+  std::vector<float> wtab_host;
+  DeviceArray<float> d_in, d_out;
+  PinnedArray<float> h_in, h_out;
+  int inv_key = -1;
+
+  Source* find(int id);
+  int add_source(std::unique_ptr<FilterSet> irs, int channels);
+  void rem_source(int id);
+  void base_weight(Source& s);
+  void step(const float* d_input, float* d_output);   // async on e->stream
+  void step_generic(const float* d_input, float* d_output);
+  void step_dynamic(const float* d_input, float* d_output);
+  void build_fwd(const float* d_input);
+  void process(int n, const float* const* in, float* const* out);
+  // pipelined
+  int outstanding = 0;
+  uint64_t submitted = 0;
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  void submit(int n, const float* const* in);
+  void wait(float* const* out);
+};
+
+}  // namespace ssr_b200

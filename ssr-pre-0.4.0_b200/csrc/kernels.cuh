@@ -1,0 +1,546 @@
+// kernels.cuh -- hand-written sm_100a kernels of the partitioned-convolution path.
+//
+//   fwd_fft_kernel   batched real->packed-complex FFT of [first half | second half]
+//                    (input blocks: [prev | cur]; filter partitions: [taps | 0]).
+//                    Replaces FFTW R2HC + _sort_coefficients
+//                    (apf/apf/convolver.h:144-148, 176-181, 209-268, 324-375).
+//   mac_kernel       frequency-domain delay-line complex multiply-accumulate
+//                    acc[row, k] = sum_terms w * X[n, p, k] * H[row, n, p, k].
+//                    Replaces _multiply_spectra / _multiply_partition_simd
+//                    (convolver.h:503-572).  HBM-bound, FP32 FMA, no tensor cores.
+//   inv_fft_kernel   sum of split partial accumulators + packed-complex->real
+//                    inverse FFT + 1/(2B) scale + keep-second-half + raised-cosine
+//                    crossfade + accumulate into the output block.  Replaces
+//                    _unsort_coefficients + FFTW HC2R + scaling
+//                    (convolver.h:448-463, 574-613) and
+//                    CombineChannelsCrossfadeCopy (apf/apf/combine_channels.h:
+//                    297-335, 366-403).
+//
+// Spectrum layout ("packed complex"): a partition spectrum is B float2;
+// element k (1 <= k < B) is bin k, element 0 is (Re X_0, Re X_B) -- DC and
+// Nyquist are both real.  The reference's "sorted halfcomplex" layout
+// (convolver.h:236-268) is only produced on download for parity checks.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ssrk
+{
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------- synthetic data
+// counter-based generator shared by host and device (bit-identical)
+__host__ __device__ inline uint64_t mix64(uint64_t z)
+{
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+
+__host__ __device__ inline uint64_t synth_key(uint64_t seed, uint64_t stream)
+{
+  return mix64(seed ^ mix64(stream + 0x9E3779B97F4A7C15ull));
+}
+
+// uniform in [-1, 1) on a 2^-23 grid: exact in float32 on host and device
+__host__ __device__ inline float synth_uniform(uint64_t key, uint64_t index)
+{
+  const uint64_t h = mix64(key + index * 0x9E3779B97F4A7C15ull);
+  return float(uint32_t(h >> 40)) * (1.0f / 8388608.0f) - 1.0f;
+}
+
+// ---------------------------------------------------------------- small helpers
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p)
+{
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------- FFT core
+// Complex FFT of size m (power of two) in shared memory, Stockham autosort,
+// radix-4 stages plus one radix-2 stage when log2(m) is odd.  `a` holds the
+// input; the result ends up in the returned buffer (a or b).  tw[i] =
+// exp(-2 pi i * i / (2m)), i in [0, 2m); INVERSE conjugates the twiddles.
+template<bool INVERSE>
+__device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
+                                            const float2* __restrict__ tw)
+{
+  const int t = threadIdx.x;
+  float2* src = a;
+  float2* dst = b;
+  int Ns = 1;
+  int rem = m;
+  while (rem > 1)
+  {
+    if ((rem & 3) == 0)
+    {
+      const int q = m >> 2;
+      // twiddle index step: e^{-2 pi i k / (4 Ns)} = tw[k * (2m / (4 Ns))]
+      const int tstep = (2 * m) / (4 * Ns);
+      for (int j = t; j < q; j += kThreads)
+      {
+        const int k = j & (Ns - 1);
+        float2 v0 = src[j];
+        float2 v1 = src[j + q];
+        float2 v2 = src[j + 2 * q];
+        float2 v3 = src[j + 3 * q];
+        if (Ns > 1)
+        {
+          float2 w1 = __ldg(&tw[k * tstep]);
+          float2 w2 = __ldg(&tw[2 * k * tstep]);
+          float2 w3 = __ldg(&tw[3 * k * tstep]);
+          if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+          v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
+        }
+        const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y);
+        const float2 d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+        const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y);
+        const float2 d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+        // forward: -i * d13 = (d13.y, -d13.x); inverse: +i * d13 = (-d13.y, d13.x)
+        const float2 r = INVERSE ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);
+        const int j0 = ((j - k) << 2) + k;
+        dst[j0]          = make_float2(s02.x + s13.x, s02.y + s13.y);
+        dst[j0 + Ns]     = make_float2(d02.x + r.x, d02.y + r.y);
+        dst[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+        dst[j0 + 3 * Ns] = make_float2(d02.x - r.x, d02.y - r.y);
+      }
+      Ns <<= 2; rem >>= 2;
+    }
+    else
+    {
+      const int q = m >> 1;
+      const int tstep = (2 * m) / (2 * Ns);
+      for (int j = t; j < q; j += kThreads)
+      {
+        const int k = j & (Ns - 1);
+        float2 v0 = src[j];
+        float2 v1 = src[j + q];
+        if (Ns > 1)
+        {
+          float2 w1 = __ldg(&tw[k * tstep]);
+          if (INVERSE) w1.y = -w1.y;
+          v1 = cmul(v1, w1);
+        }
+        const int j0 = ((j - k) << 1) + k;
+        dst[j0]      = make_float2(v0.x + v1.x, v0.y + v1.y);
+        dst[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+      }
+      Ns <<= 1; rem >>= 1;
+    }
+    __syncthreads();
+    float2* tmp = src; src = dst; dst = tmp;
+  }
+  return src;
+}
+
+// ---------------------------------------------------------------- forward
+struct FwdHalf
+{
+  const float* ptr;   // memory source (or envelope table when synth != 0), may be null = zeros
+  long stride;        // element stride (de-interleaving libsndfile frames x channels)
+  int count;          // valid samples (<= B); the rest is zero padding
+  int synth;          // 1: generate u(key, first_index + i) * ptr[env_offset + i] * scale
+  uint64_t key;
+  uint64_t first_index;
+  float scale;
+  int pad;
+};
+
+struct FwdJob
+{
+  FwdHalf first, second;
+  float2* dst;        // explicit destination spectrum, or null -> ring mode
+  float2* ring;       // ring base (parts x B float2)
+  int* head;          // ring head (device); advanced by this kernel
+  int parts;          // ring length
+  float* save_second; // if non-null: B floats <- second half (becomes "prev")
+};
+
+__device__ __forceinline__ float fwd_sample(const FwdHalf& h, int i)
+{
+  if (i >= h.count) return 0.0f;
+  if (h.synth)
+  {
+    const float u = synth_uniform(h.key, h.first_index + uint64_t(i));
+    const float env = h.ptr ? __ldg(h.ptr + h.first_index + i) : 1.0f;
+    return (u * env) * h.scale;
+  }
+  return h.ptr ? h.ptr[long(i) * h.stride] : 0.0f;
+}
+
+// One CTA per transform.  B = block size = complex FFT size; smem = 2 * B float2.
+__global__ void __launch_bounds__(kThreads)
+fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw)
+{
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B;
+  const FwdJob job = jobs[blockIdx.x];
+  const int t = threadIdx.x;
+  const int half = B >> 1;
+
+  int new_head = 0;
+  if (!job.dst)
+  {
+    new_head = *job.head + 1;
+    if (new_head >= job.parts) new_head = 0;
+  }
+
+  // z[j] = x[2j] + i x[2j+1], x = [first | second]
+  for (int j = t; j < B; j += kThreads)
+  {
+    float x0, x1;
+    if (j < half) { x0 = fwd_sample(job.first, 2 * j); x1 = fwd_sample(job.first, 2 * j + 1); }
+    else { x0 = fwd_sample(job.second, 2 * j - B); x1 = fwd_sample(job.second, 2 * j + 1 - B); }
+    a[j] = make_float2(x0, x1);
+  }
+  __syncthreads();
+
+  // all reads of `first` (= prev) are done: it may now be overwritten
+  if (job.save_second)
+  {
+    for (int j = t + half; j < B; j += kThreads)
+    {
+      const float2 v = a[j];
+      reinterpret_cast<float2*>(job.save_second)[j - half] = v;
+    }
+  }
+
+  const float2* z = fft_smem<false>(a, b, B, tw);
+
+  float2* dst = job.dst;
+  if (!dst) dst = job.ring + size_t(new_head) * B;
+
+  // split: X[k] = E[k] + w^k O[k], w = exp(-2 pi i / 2B)
+  for (int k = t; k <= half; k += kThreads)
+  {
+    if (k == 0)
+    {
+      const float2 z0 = z[0];
+      dst[0] = make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
+    }
+    else
+    {
+      const int k2 = B - k;
+      const float2 zk = z[k], zk2 = z[k2];
+      const float er = 0.5f * (zk.x + zk2.x), ei = 0.5f * (zk.y - zk2.y);
+      const float orr = 0.5f * (zk.y + zk2.y), oi = -0.5f * (zk.x - zk2.x);
+      const float2 w = __ldg(&tw[k]);
+      const float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;
+      dst[k] = make_float2(er + tr, ei + ti);
+      if (k2 != k) dst[k2] = make_float2(er - tr, -(ei - ti));
+    }
+  }
+
+  // Every thread read the old head before the first __syncthreads above, so
+  // thread 0 may publish the new one now.  No other CTA of this launch touches
+  // this ring; the next kernel in stream order (MAC) sees the new value.
+  if (!job.dst && t == 0) *job.head = new_head;
+}
+
+// ---------------------------------------------------------------- MAC
+// A "term" is one partition-MAC shared by the MT rows of a group:
+//   acc[row j] += w * X[input, partition p blocks ago] * H_j
+struct MacTermMeta { int input; int p; int wslot; int pad; };
+
+struct MacParams
+{
+  const MacTermMeta* term_meta;      // [nterms]
+  const float4* const* term_h;       // [nterms][MT] partition spectra (never null:
+                                     //  "empty" partitions point at a zero partition)
+  const int4* work;                  // per CTA: x = term_begin, y = term_end, z = partial index
+  const float* wtab;                 // weights by slot
+  const float4* const* xring;        // per input: ring base
+  const int* xparts;                 // per input: ring length
+  const int* heads;                  // per input: ring head
+  float4* partials;                  // [npartials][MT][B/2] float4
+  int B;
+  int wtab_offset;                   // added to wslot (selects the weight "kind")
+  int partial_offset;                // added to work.z
+};
+
+constexpr int kMacTile = 64;
+
+template<int MT, int NV>
+__global__ void __launch_bounds__(kThreads)
+mac_kernel(const MacParams p)
+{
+  __shared__ const float4* s_x[kMacTile];
+  __shared__ const float4* s_h[kMacTile][MT];
+  __shared__ float s_w[kMacTile];
+  __shared__ int s_count;
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int4 wk = p.work[blockIdx.x];
+  const int nvec = p.B >> 1;  // float4 per partition
+  // B > 1024: blockIdx.y selects a 1024-bin tile of the spectrum
+  const int tile_off = blockIdx.y * (NV * kThreads);
+  const int tt = tile_off + t;
+
+  float4 acc[MT][NV];
+  float nyq[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+  {
+    nyq[j] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  bool valid[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) valid[v] = (tt + v * kThreads) < nvec;
+
+  for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+  {
+    const int tile_n = min(kMacTile, wk.y - tb);
+    __syncthreads();  // previous tile fully consumed
+    if (t < 32)
+    {
+      // warp 0 stages the tile and compacts away terms with zero weight
+      int count = 0;
+      for (int base = 0; base < tile_n; base += 32)
+      {
+        const int i = base + lane;
+        bool ok = false;
+        MacTermMeta m; float w = 0.f;
+        if (i < tile_n)
+        {
+          m = p.term_meta[tb + i];
+          w = p.wtab[m.wslot + p.wtab_offset];
+          ok = (w != 0.0f);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (ok)
+        {
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          const int parts = p.xparts[m.input];
+          int slot = p.heads[m.input] - m.p;
+          if (slot < 0) slot += parts;
+          s_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
+          s_w[pos] = w;
+#pragma unroll
+          for (int j = 0; j < MT; ++j) s_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+        }
+        count += __popc(mask);
+      }
+      if (lane == 0) s_count = count;
+    }
+    __syncthreads();
+    const int n = s_count;
+
+    // software pipeline: loads of term i+1 are in flight while term i is consumed
+    float4 xb[2][NV];
+    float4 hb[2][MT][NV];
+
+#define SSR_MAC_LOAD(buf, i) \
+    { \
+      const float4* xp = s_x[i]; \
+      _Pragma("unroll") for (int v = 0; v < NV; ++v) \
+        if (valid[v]) xb[buf][v] = ldg_stream(xp + tt + v * kThreads); \
+      _Pragma("unroll") for (int j = 0; j < MT; ++j) \
+      { \
+        const float4* hp = s_h[i][j]; \
+        _Pragma("unroll") for (int v = 0; v < NV; ++v) \
+          if (valid[v]) hb[buf][j][v] = ldg_stream(hp + tt + v * kThreads); \
+      } \
+    }
+
+#define SSR_MAC_FMA(buf, i) \
+    { \
+      const float w = s_w[i]; \
+      _Pragma("unroll") for (int v = 0; v < NV; ++v) \
+      { \
+        if (valid[v]) \
+        { \
+          float4 x = xb[buf][v]; \
+          x.x *= w; x.y *= w; x.z *= w; x.w *= w; \
+          _Pragma("unroll") for (int j = 0; j < MT; ++j) \
+          { \
+            const float4 h = hb[buf][j][v]; \
+            acc[j][v].x = fmaf(x.x, h.x, acc[j][v].x); \
+            acc[j][v].x = fmaf(-x.y, h.y, acc[j][v].x); \
+            acc[j][v].y = fmaf(x.x, h.y, acc[j][v].y); \
+            acc[j][v].y = fmaf(x.y, h.x, acc[j][v].y); \
+            acc[j][v].z = fmaf(x.z, h.z, acc[j][v].z); \
+            acc[j][v].z = fmaf(-x.w, h.w, acc[j][v].z); \
+            acc[j][v].w = fmaf(x.z, h.w, acc[j][v].w); \
+            acc[j][v].w = fmaf(x.w, h.z, acc[j][v].w); \
+            if (v == 0 && tt == 0) nyq[j] = fmaf(x.y, h.y, nyq[j]); \
+          } \
+        } \
+      } \
+    }
+
+    if (n > 0) SSR_MAC_LOAD(0, 0)
+    int i = 0;
+    for (; i + 1 < n; i += 2)
+    {
+      SSR_MAC_LOAD(1, i + 1)
+      SSR_MAC_FMA(0, i)
+      if (i + 2 < n) SSR_MAC_LOAD(0, i + 2)
+      SSR_MAC_FMA(1, i + 1)
+    }
+    if (i < n) SSR_MAC_FMA(0, i)
+#undef SSR_MAC_LOAD
+#undef SSR_MAC_FMA
+  }
+
+  // bin 0 holds (DC, Nyquist), both real products (convolver.h:510-541):
+  // acc.x = sum(xr*hr - xi*hi) -> DC = acc.x + nyq ; Nyquist = nyq
+  if (tt == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < MT; ++j)
+    {
+      acc[j][0].x += nyq[j];
+      acc[j][0].y = nyq[j];
+    }
+  }
+
+  float4* out = p.partials + size_t(wk.z + p.partial_offset) * MT * nvec;
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (valid[v]) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
+}
+
+// ---------------------------------------------------------------- inverse
+struct InvEntry
+{
+  int part_first;   // first partial index
+  int part_count;   // number of partials to sum (split count of the group)
+  int part_stride;  // MT of the group
+  int part_row;     // row within the group
+  int fade;         // 0 none, 1 fade-out, 2 fade-in (combine_channels.h:297-335)
+  float scale;      // 1 / (2B) (convolver.h:458) [times a per-row weight]
+};
+
+struct InvJob
+{
+  int first_entry;
+  int n_entries;    // 0 -> output block is zeros (combine_channels.h:126-129)
+  float* out;       // B floats (device)
+};
+
+constexpr int kInvMaxRes = 8;  // B <= 4096: (B/2 float2) / 256 threads
+
+// One CTA per output block.
+__global__ void __launch_bounds__(kThreads)
+inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
+               const float2* __restrict__ partials, int B,
+               const float2* __restrict__ tw,
+               const float* __restrict__ fade_out, const float* __restrict__ fade_in)
+{
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B;
+  const InvJob job = jobs[blockIdx.x];
+  const int t = threadIdx.x;
+  const int half = B >> 1;
+
+  float2 res[kInvMaxRes];
+#pragma unroll
+  for (int q = 0; q < kInvMaxRes; ++q) res[q] = make_float2(0.f, 0.f);
+
+  for (int e = 0; e < job.n_entries; ++e)
+  {
+    const InvEntry en = entries[job.first_entry + e];
+    // A[k] = sum over split partials
+    for (int k = t; k < B; k += kThreads)
+    {
+      float2 s = make_float2(0.f, 0.f);
+      for (int c = 0; c < en.part_count; ++c)
+      {
+        const float2 v = partials[(size_t(en.part_first + c) * en.part_stride + en.part_row) * B + k];
+        s.x += v.x; s.y += v.y;
+      }
+      a[k] = s;
+    }
+    __syncthreads();
+    // Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k])
+    for (int k = t; k <= half; k += kThreads)
+    {
+      if (k == 0)
+      {
+        const float2 x0 = a[0];  // (DC, Nyquist)
+        b[0] = make_float2(x0.x + x0.y, x0.x - x0.y);
+      }
+      else
+      {
+        const int k2 = B - k;
+        const float2 xk = a[k], xk2 = a[k2];
+        const float er = xk.x + xk2.x, ei = xk.y - xk2.y;
+        const float dr = xk.x - xk2.x, di = xk.y + xk2.y;
+        float2 w = __ldg(&tw[k]);
+        w.y = -w.y;  // w^{-k}
+        const float tr = -(dr * w.y + di * w.x), ti = dr * w.x - di * w.y;
+        b[k] = make_float2(er + tr, ei + ti);
+        if (k2 != k) b[k2] = make_float2(er - tr, -(ei - ti));
+      }
+    }
+    __syncthreads();
+    const float2* z = fft_smem<true>(b, a, B, tw);
+    // keep the second half: time index i = 2j, 2j+1 with j >= B/2
+#pragma unroll
+    for (int q = 0; q < kInvMaxRes; ++q)
+    {
+      const int jj = t + q * kThreads;  // j - half
+      if (jj < half)
+      {
+        const float2 v = z[half + jj];
+        float f0 = en.scale, f1 = en.scale;
+        if (en.fade == 1) { f0 *= __ldg(fade_out + 2 * jj); f1 *= __ldg(fade_out + 2 * jj + 1); }
+        else if (en.fade == 2) { f0 *= __ldg(fade_in + 2 * jj); f1 *= __ldg(fade_in + 2 * jj + 1); }
+        res[q].x = fmaf(v.x, f0, res[q].x);
+        res[q].y = fmaf(v.y, f1, res[q].y);
+      }
+    }
+    __syncthreads();  // z (smem) is rewritten by the next entry
+  }
+
+#pragma unroll
+  for (int q = 0; q < kInvMaxRes; ++q)
+  {
+    const int jj = t + q * kThreads;
+    if (jj < half) reinterpret_cast<float2*>(job.out)[jj] = res[q];
+  }
+}
+
+// ---------------------------------------------------------------- elementwise
+// dst = ca * a + cb * b over one partition spectrum (transform_nested lerp,
+// convolver.h:773-817 with src/binauralrenderer.h:372-377); a / b may be null
+// (zero-flagged partition).  grid.x = partitions.
+struct LerpJob { const float4* a; const float4* b; float4* dst; };
+
+__global__ void __launch_bounds__(kThreads)
+lerp_kernel(const LerpJob* __restrict__ jobs, int nvec, float ca, float cb)
+{
+  const LerpJob job = jobs[blockIdx.x];
+  for (int i = threadIdx.x; i < nvec; i += kThreads)
+  {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (job.a) { const float4 v = job.a[i]; r.x = ca * v.x; r.y = ca * v.y; r.z = ca * v.z; r.w = ca * v.w; }
+    if (job.b)
+    {
+      const float4 v = job.b[i];
+      r.x = fmaf(cb, v.x, r.x); r.y = fmaf(cb, v.y, r.y);
+      r.z = fmaf(cb, v.z, r.z); r.w = fmaf(cb, v.w, r.w);
+    }
+    job.dst[i] = r;
+  }
+}
+
+}  // namespace ssrk

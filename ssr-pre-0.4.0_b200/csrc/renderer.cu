@@ -1,0 +1,504 @@
+// renderer.cu -- Level 2: the per-block step of the Generic / Binaural / BRS
+// renderers, batched into  forward FFT -> MAC -> inverse FFT + crossfade + sum.
+//
+// Host logic (weights, crossfade modes, filter index, staggered filter switch)
+// follows the reference exactly; arithmetic is moved to the kernels:
+//   src/rendererbase.h:386-407      weighting_factor
+//   src/genericrenderer.h:122-180   Generic source phase + RenderFunction::select
+//   src/brsrenderer.h:141-210       BRS source phase
+//   src/binauralrenderer.h:261-389  Binaural source phase
+//   apf/apf/combine_channels.h:89-130, 292-335, 366-403  crossfade combine
+// The reference evaluates every (source, output) pair in the time domain and adds
+// the results; here sources are summed in the frequency domain per accumulator
+// kind (constant / fade-out / fade-in) so only <= 3 inverse FFTs per output run.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace ssr_b200
+{
+
+using namespace ssrk;
+
+static constexpr int kGenericMT = 4;
+
+Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
+  : e(e_), cfg(c)
+{
+  e->use_device();
+  if (cfg.kind == SSR_RENDERER_GENERIC)
+  {
+    if (cfg.outputs <= 0) throw Error(SSR_ERR_INVALID, "ssr_b200: GenericRenderer needs outputs > 0");
+    M_total = cfg.outputs;
+    m_first = cfg.output_first;
+    m_local = cfg.output_count > 0 ? cfg.output_count : M_total - m_first;
+    if (m_first < 0 || m_local <= 0 || m_first + m_local > M_total)
+      throw Error(SSR_ERR_INVALID, "ssr_b200: bad output shard");
+  }
+  else
+  {
+    if (cfg.outputs != 0 && cfg.outputs != 2)
+      throw Error(SSR_ERR_INVALID, "ssr_b200: Binaural/BRS renderers have exactly 2 outputs");
+    M_total = 2; m_first = 0; m_local = 2;
+  }
+  // apf::math::dB2linear (src/rendererbase.h:234-235)
+  mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
+  static_mac.MT = kGenericMT;
+  for (auto& p : dyn_mac) p.MT = 2;
+  d_out.resize(size_t(m_local) * e->B);
+  h_out.resize(size_t(2) * m_local * e->B);
+}
+
+Renderer::~Renderer()
+{
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (auto ev : done) if (ev) cudaEventDestroy(ev);
+}
+
+Renderer::Source* Renderer::find(int id)
+{
+  for (auto& s : sources) if (s->id == id) return s.get();
+  throw Error(SSR_ERR_INVALID, "ssr_b200: no such source");
+}
+
+int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
+{
+  e->use_device();
+  e->sync();
+  auto s = std::unique_ptr<Source>(new Source);
+  s->id = next_id++;
+  if (cfg.kind == SSR_RENDERER_GENERIC)
+  {
+    s->irs = std::move(irs);
+    int P = 0;
+    for (int v : s->irs->valid) P = std::max(P, v);
+    // Input(block, min_partitions(block, frames)) (src/genericrenderer.h:109-110)
+    s->input.reset(new Input(e, s->irs->partitions));
+    (void)P; (void)channels;
+  }
+  else if (cfg.kind == SSR_RENDERER_BRS)
+  {
+    s->brtf = std::move(irs);
+    s->angles = channels / 2;
+    s->input.reset(new Input(e, s->brtf->partitions));
+    for (int i = 0; i < 2; ++i) s->chan.emplace_back(s->brtf->partitions);
+  }
+  else
+  {
+    if (!hrtfs) throw Error(SSR_ERR_STATE, "ssr_b200: BinauralRenderer: load HRIRs before adding sources");
+    s->input.reset(new Input(e, partitions));
+    for (int i = 0; i < 2; ++i) s->chan.emplace_back(partitions);
+    s->temp.resize(2);
+    s->bw = BlockParameter<float>(0.0f);  // _weight(0.0f) (src/binauralrenderer.h:245)
+  }
+  sources.push_back(std::move(s));
+  static_dirty = true;
+  fwd.host.clear();
+  return sources.back()->id;
+}
+
+void Renderer::rem_source(int id)
+{
+  e->use_device();
+  e->sync();
+  for (size_t i = 0; i < sources.size(); ++i)
+    if (sources[i]->id == id)
+    {
+      sources.erase(sources.begin() + i);
+      static_dirty = true;
+      fwd.host.clear();
+      return;
+    }
+  throw Error(SSR_ERR_INVALID, "ssr_b200: no such source");
+}
+
+// RendererBase::Source::Process (src/rendererbase.h:386-407)
+void Renderer::base_weight(Source& s)
+{
+  if (!processing || s.mute) s.weighting_factor.assign(0.0f);
+  else
+  {
+    float w = s.gain;
+    w *= master_volume;
+    w *= mvc;
+    s.weighting_factor.assign(w);
+  }
+}
+
+void Renderer::build_fwd(const float* d_input)
+{
+  const int N = int(sources.size());
+  bool rebuild = int(fwd.host.size()) != N;
+  if (!rebuild && N > 0 && fwd.host[0].second.ptr != d_input) rebuild = true;
+  if (!rebuild) return;
+  fwd.host.resize(N);
+  for (int n = 0; n < N; ++n) fwd.host[n] = sources[n]->input->make_job(d_input + size_t(n) * e->B);
+  fwd.upload(e->stream);
+}
+
+static Mode mode_from_weight(const BlockParameter<float>& f)
+{
+  // GenericRenderer::RenderFunction::select (src/genericrenderer.h:161-180)
+  if (f.both_eq(0.0f)) return NOTHING;
+  if (f.old() == 0.0f) return FADE_IN;
+  if (f.get() == 0.0f) return FADE_OUT;
+  if (!f.changed()) return CONSTANT;
+  return CHANGE;
+}
+
+void Renderer::step_generic(const float* d_input, float* d_output)
+{
+  const int N = int(sources.size());
+  const int B = e->B;
+  wtab_host.assign(size_t(3) * std::max(N, 1), 0.0f);
+  bool kind_active[3] = {false, false, false};
+  uint64_t active_parts[3] = {0, 0, 0};
+  for (int n = 0; n < N; ++n)
+  {
+    Source& s = *sources[n];
+    base_weight(s);
+    s.w.assign(s.weighting_factor.get());  // src/genericrenderer.h:124
+    s.mode = mode_from_weight(s.w);
+    const uint64_t parts = uint64_t(s.irs->valid.empty() ? 0 : s.irs->valid[0]);
+    if (s.mode == CONSTANT) { wtab_host[n] = s.w.get(); kind_active[0] = true; active_parts[0] += parts; }
+    if (s.mode == CHANGE || s.mode == FADE_OUT) { wtab_host[N + n] = s.w.old(); kind_active[1] = true; active_parts[1] += parts; }
+    if (s.mode == CHANGE || s.mode == FADE_IN) { wtab_host[2 * N + n] = s.w.get(); kind_active[2] = true; active_parts[2] += parts; }
+  }
+
+  if (static_dirty)
+  {
+    e->sync();
+    static_mac.clear();
+    const float4* zero = reinterpret_cast<const float4*>(e->zero_part.ptr);
+    for (int m0 = 0; m0 < m_local; m0 += kGenericMT)
+    {
+      static_mac.begin_group();
+      for (int n = 0; n < N; ++n)
+      {
+        Source& s = *sources[n];
+        const int P = s.irs->partitions;
+        for (int p = 0; p < P; ++p)
+        {
+          const float4* h[kGenericMT];
+          bool any = false;
+          for (int j = 0; j < kGenericMT; ++j)
+          {
+            const float2* ptr = (m0 + j < m_local) ? s.irs->part_or_null(m0 + j, p) : nullptr;
+            h[j] = ptr ? reinterpret_cast<const float4*>(ptr) : zero;
+            any |= (ptr != nullptr);
+          }
+          if (any) static_mac.add_term(s.input->id, p, n, h);
+        }
+      }
+      static_mac.end_group();
+    }
+    static_mac.make_work(e->mac_slots());
+    static_mac.upload(e->stream);
+    e->ensure_partials(size_t(3) * static_mac.npartials * static_mac.MT);
+    static_dirty = false;
+    inv_key = -1;
+  }
+
+  const int key = (kind_active[0] ? 1 : 0) | (kind_active[1] ? 2 : 0) | (kind_active[2] ? 4 : 0);
+  if (key != inv_key || (inv.jobs.host.size() && inv.jobs.host[0].out != d_output))
+  {
+    e->sync();
+    inv.clear();
+    const float scale = 1.0f / float(2 * B);
+    for (int m = 0; m < m_local; ++m)
+    {
+      const int g = m / kGenericMT, row = m % kGenericMT;
+      const auto& grp = static_mac.groups[g];
+      InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(m) * B};
+      for (int k = 0; k < 3; ++k)
+      {
+        if (!kind_active[k]) continue;
+        inv.entries.host.push_back({k * static_mac.npartials + grp.partial_first, grp.nsplit,
+            kGenericMT, row, k, scale});
+        job.n_entries++;
+      }
+      inv.jobs.host.push_back(job);
+    }
+    inv.upload(e->stream);
+    inv_key = key;
+  }
+
+  build_fwd(d_input);
+  e->stage_begin();
+  e->launch_fwd(fwd.dev.ptr, N);
+  e->stage_mark(1);
+  e->upload_weights(wtab_host.data(), wtab_host.size());
+  for (int k = 0; k < 3; ++k)
+  {
+    if (!kind_active[k]) continue;
+    e->launch_mac(static_mac, k * N, k * static_mac.npartials);
+    if (e->cur)
+    {
+      // 8B bytes * (H partitions + X partitions + accumulators)
+      const uint64_t hparts = active_parts[k] * uint64_t(m_local);
+      e->cur->mac_bytes += uint64_t(8) * B * (hparts + active_parts[k] + uint64_t(m_local));
+      e->cur->mac_terms += hparts;
+    }
+  }
+  e->stage_mark(2);
+  e->launch_inv(inv);
+  e->stage_mark(3);
+  e->stage_end();
+}
+
+// apf::math::wrap<float> (apf/apf/math.h:136-160)
+static float fwrap(float x, float full)
+{
+  x = std::fmod(x, full);
+  if (x < 0) x += full;
+  return x;
+}
+
+void Renderer::step_dynamic(const float* d_input, float* d_output)
+{
+  const int N = int(sources.size());
+  const int B = e->B;
+  const bool binaural = cfg.kind == SSR_RENDERER_BINAURAL;
+  wtab_host.assign(size_t(3) * std::max(N, 1), 0.0f);
+  MacPlan& plan = dyn_mac[0];
+  e->sync();  // staging tables of the previous block
+  plan.clear();
+  const float4* zero = reinterpret_cast<const float4*>(e->zero_part.ptr);
+
+  // terms of one (source, kind) with the pointer tables as they are NOW
+  struct Pending { int n; int kind; std::vector<const float2*> l, r; };
+  std::vector<Pending> pend;
+  auto snapshot = [&](int n, int kind)
+  {
+    Source& s = *sources[n];
+    pend.push_back({n, kind, s.chan[0].ptrs, s.chan[1].ptrs});
+  };
+
+  for (int n = 0; n < N; ++n)
+  {
+    Source& s = *sources[n];
+    base_weight(s);
+    bool filter_changed;
+    BlockParameter<float>* wp;
+    if (!binaural)
+    {
+      // src/brsrenderer.h:141-184
+      s.bw.assign(s.weighting_factor.get());
+      const float azi = ref_az;
+      s.index.assign(long(size_t(fwrap((azi - 90.0f) * float(s.angles) / 360.0f + 0.5f,
+                float(s.angles)))));
+      filter_changed = s.index.changed();
+      wp = &s.bw;
+    }
+    else
+    {
+      // src/binauralrenderer.h:261-314
+      float interp_factor = 0.0f, weight = 0.0f;
+      const float rx = ref_x + off_x, ry = ref_y + off_y;
+      const float ref_ori = ref_az + off_az;
+      const float dx = s.px - rx, dy = s.py - ry;
+      if (s.weighting_factor.get() != 0)
+      {
+        weight = 1;
+        if (s.plane) weight *= 0.5f / amplitude_reference_distance;
+        else
+        {
+          float dist = std::sqrt(dx * dx + dy * dy);
+          if (dist < 0.5f) interp_factor = 1.0f - 2 * dist;
+          dist = std::max(dist, 0.5f);
+          weight *= 0.5f / dist;
+        }
+        weight *= s.weighting_factor.get();
+      }
+      s.interp.assign(interp_factor);
+      s.bw.assign(weight);
+      const float fangles = float(angles);
+      // Position::orientation (src/position.cpp:76-79)
+      const float src_az = std::atan2(dy, dx) / (float(M_PI) / 180.0f);
+      const float rel = src_az - ref_ori;
+      s.index.assign(long(size_t(fwrap(rel * fangles / 360.0f + 0.5f, fangles))));
+      filter_changed = s.index.changed() || s.interp.changed();
+      wp = &s.bw;
+    }
+    const BlockParameter<float>& w = *wp;
+    const bool queues_empty = s.chan[0].queues_empty();
+    Mode mode;
+    if (w.both_eq(0.0f)) mode = NOTHING;
+    else if (queues_empty && !w.changed() && !filter_changed) mode = CONSTANT;
+    else if (binaural)
+    {
+      // fade_out is tested before fade_in (src/binauralrenderer.h:332-339)
+      if (w.get() == 0.0f) mode = FADE_OUT;
+      else if (w.old() == 0.0f) mode = FADE_IN;
+      else mode = CHANGE;
+    }
+    else
+    {
+      // fade_in before fade_out (src/brsrenderer.h:171-178)
+      if (w.old() == 0.0f) mode = FADE_IN;
+      else if (w.get() == 0.0f) mode = FADE_OUT;
+      else mode = CHANGE;
+    }
+    s.mode = mode;
+
+    // old state first (convolve_and_more(old weight)), then rotate / switch
+    if (mode != NOTHING && mode != FADE_IN && mode != CONSTANT) { snapshot(n, 1); wtab_host[N + n] = w.old(); }
+    for (int i = 0; i < 2; ++i)
+    {
+      FilterPtrTable& ch = s.chan[i];
+      if (!queues_empty) ch.rotate_queues();
+      if (filter_changed)
+      {
+        if (!binaural) ch.set_filter(*s.brtf, int(2 * s.index.get() + i));
+        else
+        {
+          const int hch = int(2 * s.index.get() + i);
+          if (s.interp.get() == 0.0f) ch.set_filter(*hrtfs, hch);
+          else
+          {
+            // Dirac interpolation into a temporary filter
+            // (src/binauralrenderer.h:365-379).  A temporary that is still
+            // referenced by an active or queued partition is not overwritten
+            // (the reference aliases them); a free one from
+            // the pool is used instead.
+            FilterSet* tmp = nullptr;
+            for (auto& t : s.temp[i])
+              if (!ch.references(t->data.ptr, t->data.ptr + t->data.count)) { tmp = t.get(); break; }
+            if (!tmp)
+            {
+              s.temp[i].emplace_back(new FilterSet(e, 1, partitions));
+              tmp = s.temp[i].back().get();
+            }
+            tmp->lerp_from(0, *hrtfs, hch, *neutral, 0, s.interp.get());
+            ch.set_filter(*tmp, 0);
+          }
+        }
+      }
+    }
+    if (mode == CONSTANT) { snapshot(n, 0); wtab_host[n] = w.get(); }
+    else if (mode == CHANGE || mode == FADE_IN) { snapshot(n, 2); wtab_host[2 * N + n] = w.get(); }
+  }
+
+  // one plan, up to three groups (const / old / new), rows = (left, right)
+  int group_of_kind[3] = {-1, -1, -1};
+  uint64_t hparts = 0, xparts = 0;
+  for (int k = 0; k < 3; ++k)
+  {
+    bool any = false;
+    for (auto& pd : pend) if (pd.kind == k) { any = true; break; }
+    if (!any) continue;
+    group_of_kind[k] = plan.begin_group();
+    for (auto& pd : pend)
+    {
+      if (pd.kind != k) continue;
+      Source& s = *sources[pd.n];
+      for (int p = 0; p < s.input->P; ++p)
+      {
+        const float2* l = pd.l[p];
+        const float2* r = pd.r[p];
+        if (!l && !r) continue;
+        const float4* h[2] = { l ? reinterpret_cast<const float4*>(l) : zero,
+                               r ? reinterpret_cast<const float4*>(r) : zero };
+        plan.add_term(s.input->id, p, k * N + pd.n, h);
+        hparts += (l ? 1 : 0) + (r ? 1 : 0);
+        xparts += 1;
+      }
+    }
+    plan.end_group();
+  }
+  plan.make_work(e->mac_slots());
+  plan.upload(e->stream);
+  e->ensure_partials(size_t(plan.npartials) * plan.MT);
+
+  inv.clear();
+  const float scale = 1.0f / float(2 * B);
+  int nrows = 0;
+  for (int ear = 0; ear < 2; ++ear)
+  {
+    InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(ear) * B};
+    for (int k = 0; k < 3; ++k)
+    {
+      if (group_of_kind[k] < 0) continue;
+      const auto& grp = plan.groups[group_of_kind[k]];
+      if (grp.term_end == grp.term_begin) continue;
+      inv.entries.host.push_back({grp.partial_first, grp.nsplit, 2, ear, k, scale});
+      job.n_entries++;
+      nrows++;
+    }
+    inv.jobs.host.push_back(job);
+  }
+  inv.upload(e->stream);
+
+  build_fwd(d_input);
+  e->stage_begin();
+  e->launch_fwd(fwd.dev.ptr, N);
+  e->stage_mark(1);
+  e->upload_weights(wtab_host.data(), wtab_host.size());
+  e->launch_mac(plan, 0, 0);
+  if (e->cur)
+  {
+    e->cur->mac_bytes += uint64_t(8) * B * (hparts + xparts + uint64_t(nrows));
+    e->cur->mac_terms += hparts;
+  }
+  e->stage_mark(2);
+  e->launch_inv(inv);
+  e->stage_mark(3);
+  e->stage_end();
+}
+
+void Renderer::step(const float* d_input, float* d_output)
+{
+  e->use_device();
+  if (cfg.kind == SSR_RENDERER_GENERIC) step_generic(d_input, d_output);
+  else step_dynamic(d_input, d_output);
+}
+
+void Renderer::process(int n, const float* const* in, float* const* out)
+{
+  if (outstanding) throw Error(SSR_ERR_STATE, "ssr_b200: process() while submitted blocks are pending");
+  submit(n, in);
+  wait(out);
+}
+
+void Renderer::submit(int n, const float* const* in)
+{
+  // assert(n == block_size()) (apf/apf/pointer_policy.h:114)
+  if (n != e->B) throw Error(SSR_ERR_INVALID, "ssr_b200: audio_callback: n != block size");
+  if (outstanding >= 2) throw Error(SSR_ERR_STATE, "ssr_b200: at most 2 blocks may be in flight");
+  e->use_device();
+  const int N = int(sources.size());
+  const int B = e->B;
+  const size_t in_floats = size_t(std::max(N, 1)) * B;
+  if (h_in.count < 2 * in_floats) { e->sync(); h_in.resize(2 * in_floats); d_in.resize(in_floats); fwd.host.clear(); }
+  static_assert(sizeof(float) == 4, "");
+  const int slot = int(submitted & 1);
+  float* hin = h_in.ptr + size_t(slot) * in_floats;
+  for (int i = 0; i < N; ++i) std::memcpy(hin + size_t(i) * B, in[i], B * sizeof(float));
+  if (N > 0)
+    SSR_CUDA(cudaMemcpyAsync(d_in.ptr, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  e->stats.h2d_bytes += uint64_t(N) * B * sizeof(float);
+  step(d_in.ptr, d_out.ptr);
+  float* hout = h_out.ptr + size_t(slot) * m_local * B;
+  SSR_CUDA(cudaMemcpyAsync(hout, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  e->stats.d2h_bytes += uint64_t(m_local) * B * sizeof(float);
+  if (!done[slot]) SSR_CUDA(cudaEventCreateWithFlags(&done[slot], cudaEventDisableTiming));
+  SSR_CUDA(cudaEventRecord(done[slot], e->stream));
+  submitted++;
+  outstanding++;
+}
+
+void Renderer::wait(float* const* out)
+{
+  if (!outstanding) throw Error(SSR_ERR_STATE, "ssr_b200: wait() without a submitted block");
+  e->use_device();
+  const int B = e->B;
+  const int slot = int((submitted - outstanding) & 1);
+  SSR_CUDA(cudaEventSynchronize(done[slot]));
+  const float* hout = h_out.ptr + size_t(slot) * m_local * B;
+  for (int m = 0; m < m_local; ++m) std::memcpy(out[m], hout + size_t(m) * B, B * sizeof(float));
+  outstanding--;
+}
+
+}  // namespace ssr_b200

@@ -1,0 +1,5 @@
+// Unity translation unit: the kernels in kernels.cuh are defined once and every
+// host file sees the same instantiations (one cubin, one set of symbols).
+#include "engine.cu"
+#include "renderer.cu"
+#include "capi.cu"

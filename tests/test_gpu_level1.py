@@ -1,0 +1,271 @@
+"""GPU parity, Level 1 (apf::conv class API) through the C ABI vs the oracle.
+
+The first tests restate the reference's own unit test
+(apf/unit_tests/test_convolver.cpp:37-238: block 8, 16-tap filter with 5,4,3 at
+taps 10..12, ramp signal) against the CUDA path.  Tolerance: the reference test
+uses Catch Approx = 1.19e-5 * (1 + |x|); BASELINE.json asks for 1e-5 of full
+scale, which is what every assert below uses (TOL)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+TEST_SIGNAL = np.array([0, 0, 0, 0, 0, .1, .2, .3, .4, .5, .6, .7, .8, .9, 0, 0, 0, 0], np.float32)
+FILTER_DATA = np.zeros(16, np.float32)
+FILTER_DATA[10:13] = [5, 4, 3]
+
+
+def close(a, b, tol=TOL):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape
+    err = np.abs(a - b).max() if a.size else 0.0
+    assert err <= tol, f"max abs err {err} > {tol}"
+
+
+def test_silence(capi, engine_factory):
+    # test_convolver.cpp:56-67: no filter set -> zeros
+    e = engine_factory(8)
+    inp = capi.Input(e, capi.min_partitions(8, 16))
+    out = capi.Output(inp)
+    for _ in range(2):
+        inp.add_block(TEST_SIGNAL[:8])
+        assert np.all(out.convolve() == 0.0)
+
+
+def test_impulse(capi, engine_factory):
+    # test_convolver.cpp:69-84
+    e = engine_factory(8)
+    inp = capi.Input(e, 2)
+    out = capi.Output(inp)
+    impulse = capi.FilterSet.from_time(e, np.array([[1.0]], np.float32))
+    inp.add_block(TEST_SIGNAL[:8])
+    out.set_filter(impulse)
+    close(out.convolve(), TEST_SIGNAL[:8])
+    inp.add_block(TEST_SIGNAL[8:16])
+    close(out.convolve(), TEST_SIGNAL[8:16])
+
+
+def test_and_more(capi, engine_factory):
+    # test_convolver.cpp:86-131: set_filter / queues_empty / rotate_queues protocol
+    e = engine_factory(8)
+    inp = capi.Input(e, 2)
+    out = capi.Output(inp)
+    filt = capi.FilterSet.from_time(e, FILTER_DATA[:, None])
+    out.set_filter(filt)
+    x = np.zeros(8, np.float32)
+    x[1] = 1
+    inp.add_block(x)
+    close(out.convolve(), np.zeros(8))
+    x[1] = 2
+    inp.add_block(x)
+    assert not out.queues_empty()
+    out.rotate_queues()
+    exp = np.zeros(8)
+    exp[3:6] = [5, 4, 3]
+    close(out.convolve(), exp)
+    x[1] = 0
+    inp.add_block(x)
+    assert out.queues_empty()
+    exp[3:6] = [10, 8, 6]
+    close(out.convolve(), exp)
+    inp.add_block(x)
+    assert out.queues_empty()
+    close(out.convolve(), np.zeros(8))
+    assert out.queues_empty()
+
+
+def test_static_output_impulse(capi, engine_factory):
+    # test_convolver.cpp:133-149
+    e = engine_factory(8)
+    inp = capi.Input(e, 1)
+    out = capi.StaticOutput(inp, taps=np.array([1.0], np.float32))
+    inp.add_block(TEST_SIGNAL[:8])
+    close(out.convolve(), TEST_SIGNAL[:8])
+    inp.add_block(TEST_SIGNAL[8:16])
+    close(out.convolve(), TEST_SIGNAL[8:16])
+
+
+def test_static_output_frequency_domain(capi, engine_factory):
+    # test_convolver.cpp:151-169: 3-partition filter, 7-partition input
+    e = engine_factory(8)
+    fd = capi.FilterSet(e, 1, 3)
+    fd.load_time(np.array([[1.0]], np.float32))
+    inp = capi.Input(e, 7)
+    out = capi.StaticOutput(inp, fs=fd)
+    assert inp.partitions == 7 and fd.partitions == 3
+    inp.add_block(TEST_SIGNAL[:8])
+    close(out.convolve(), TEST_SIGNAL[:8])
+
+
+def test_combinations(capi, engine_factory):
+    # test_convolver.cpp:171-238: StaticOutput, Convolver, StaticConvolver agree
+    e = engine_factory(8)
+    filt = capi.FilterSet.from_time(e, FILTER_DATA[:, None])
+    conv_input = capi.Input(e, 2)
+    so = capi.StaticOutput(conv_input, fs=filt)
+    conv_in = capi.Input(e, 2)
+    conv = capi.Output(conv_in)
+    conv.set_filter(filt)
+    conv.rotate_queues()
+    sconv_in = capi.Input(e, 2)
+    sconv = capi.StaticOutput(sconv_in, fs=filt)
+    x = np.zeros(8, np.float32)
+    seq = [(1.0, np.zeros(8)), (2.0, [0, 0, 0, 5, 4, 3, 0, 0]), (0.0, [0, 0, 0, 10, 8, 6, 0, 0]),
+           (0.0, np.zeros(8))]
+    for v, exp in seq:
+        x[1] = v
+        for i in (conv_input, conv_in, sconv_in):
+            i.add_block(x)
+        for o in (so, conv, sconv):
+            close(o.convolve(), exp)
+
+
+def test_block_size_errors(capi):
+    # "Convolver: block size must be a multiple of 8!" (convolver.h:163-166)
+    with pytest.raises(capi.SsrError) as ei:
+        capi.Engine(12)
+    assert ei.value.code == capi.SSR_ERR_BLOCK_SIZE
+    assert "multiple of 8" in ei.value.msg
+    with pytest.raises(capi.SsrError) as ei:
+        capi.Engine(24)  # multiple of 8 but not a power of two: documented deviation
+    assert ei.value.code == capi.SSR_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("B,L", [(8, 16), (16, 50), (64, 200), (256, 1000), (1024, 8192), (2048, 5000), (4096, 9000)])
+def test_filter_and_input_spectra_match_oracle(capi, co, engine_factory, B, L):
+    rng = np.random.default_rng(B + L)
+    e = engine_factory(B)
+    h = rng.uniform(-1, 1, L).astype(np.float32)
+    fs = capi.FilterSet.from_time(e, h[:, None])
+    fo = co.Filter(B, h)
+    assert fs.partitions == fo.partitions
+    scale = np.sqrt(B)
+    for p in range(fo.partitions):
+        got, zero = fs.download(0, p)
+        assert zero == fo.nodes[p].zero
+        close(got / scale, fo.nodes[p].data / scale, 2e-6)
+    # input FDL
+    P = fo.partitions
+    inp = capi.Input(e, P)
+    io = co.Input(B, P)
+    for t in range(P + 2):
+        x = rng.uniform(-1, 1, B).astype(np.float32)
+        inp.add_block(x)
+        io.add_block(x)
+    for p in range(P):
+        close(inp.download(p) / scale, io.spectra[p].data / scale, 2e-6)
+
+
+@pytest.mark.parametrize("B,P", [(8, 1), (8, 4), (64, 5), (1024, 8)])
+def test_random_switch_protocol_matches_oracle(capi, co, engine_factory, B, P):
+    rng = np.random.default_rng(100 + B + P)
+    e = engine_factory(B)
+    inp = capi.Input(e, P)
+    out = capi.Output(inp)
+    io = co.Input(B, P)
+    oo = co.Output(io)
+    taps = [rng.uniform(-1, 1, int(rng.integers(1, P * B + 1))).astype(np.float32) * (2.0 / np.sqrt(B))
+            for _ in range(5)]
+    fg = [capi.FilterSet.from_time(e, t[:, None], P) for t in taps]
+    fo = [co.Filter(B, t, P) for t in taps]
+    for t in range(30):
+        x = rng.uniform(-1, 1, B).astype(np.float32)
+        inp.add_block(x)
+        io.add_block(x)
+        assert out.queues_empty() == oo.queues_empty()
+        if not oo.queues_empty():
+            out.rotate_queues()
+            oo.rotate_queues()
+        if rng.random() < 0.35:
+            k = int(rng.integers(0, 5))
+            out.set_filter(fg[k])
+            oo.set_filter(fo[k])
+        w = float(rng.uniform(0.1, 1.0))
+        close(out.convolve(w), oo.convolve(w))
+
+
+def test_static_convolver_cfg1_vs_oracle_and_direct(capi, co, engine_factory):
+    # BASELINE config 1: 1 channel, 1024-sample block, 8192-tap IR
+    B, L, T = 1024, 8192, 24
+    rng = np.random.default_rng(1001)
+    e = engine_factory(B)
+    h = (rng.uniform(-1, 1, L) * np.exp(-6.9 * np.arange(L) / L)).astype(np.float32)
+    h *= np.float32(0.25 * np.sqrt(3) / np.sqrt((h.astype(np.float64) ** 2).sum()))
+    x = rng.uniform(-1, 1, T * B).astype(np.float32)
+    inp = capi.Input(e, capi.min_partitions(B, L))
+    out = capi.StaticOutput(inp, taps=h)
+    oc = co.StaticConvolver(B, taps=h)
+    y = np.empty_like(x)
+    for t in range(T):
+        blk = x[t * B:(t + 1) * B]
+        inp.add_block(blk)
+        oc.add_block(blk)
+        y[t * B:(t + 1) * B] = out.convolve()
+        close(y[t * B:(t + 1) * B], oc.convolve())
+    close(y, co.direct_convolution_f64(x, h))
+
+
+def test_zero_input_gives_exact_zeros(capi, engine_factory):
+    e = engine_factory(64)
+    inp = capi.Input(e, 3)
+    out = capi.StaticOutput(inp, taps=np.ones(150, np.float32))
+    for _ in range(4):
+        inp.add_block(np.zeros(64, np.float32))
+        assert np.all(out.convolve() == 0.0)
+
+
+def test_two_silent_blocks_mid_stream_is_correct(capi, co, engine_factory):
+    """The reference drops out of step after >= 2 all-zero input blocks
+    (convolver.h:561).  The engine computes the correct sum; the
+    oracle reproduces the reference's defect, so compare with direct convolution."""
+    B, L = 8, 32
+    rng = np.random.default_rng(3)
+    e = engine_factory(B)
+    h = rng.uniform(-1, 1, L).astype(np.float32)
+    x = rng.uniform(-1, 1, 10 * B).astype(np.float32)
+    x[3 * B:5 * B] = 0.0
+    inp = capi.Input(e, 4)
+    out = capi.StaticOutput(inp, taps=h)
+    y = np.concatenate([(inp.add_block(x[t * B:(t + 1) * B]), out.convolve())[1] for t in range(10)])
+    close(y, co.direct_convolution_f64(x, h))
+    oc = co.StaticConvolver(B, taps=h)
+    yo = np.concatenate([(oc.add_block(x[t * B:(t + 1) * B]), oc.convolve().copy())[1] for t in range(10)])
+    assert np.abs(yo - co.direct_convolution_f64(x, h)).max() > 1e-3  # documents the quirk
+
+
+def test_lerp_matches_transform_nested(capi, co, engine_factory):
+    # transform_nested with the lerp of binauralrenderer.h:372-377; unequal lengths
+    B = 64
+    rng = np.random.default_rng(9)
+    e = engine_factory(B)
+    a = rng.uniform(-1, 1, 150).astype(np.float32)
+    b = rng.uniform(-1, 1, 40).astype(np.float32)
+    fa, fb = capi.FilterSet.from_time(e, a[:, None], 3), capi.FilterSet.from_time(e, b[:, None])
+    dst = capi.FilterSet(e, 1, 4)
+    t = np.float32(0.3)
+    dst.lerp_from(0, fa, 0, fb, 0, float(t))
+    oa, ob, od = co.Filter(B, a, 3), co.Filter(B, b), co.Filter(B, None, 4)
+    co.transform_nested(oa, ob, od, lambda one, two: ((np.float32(1) - t) * one + t * two).astype(np.float32))
+    for p in range(4):
+        got, zero = dst.download(0, p)
+        assert zero == od.nodes[p].zero
+        if not zero:
+            close(got / 8, od.nodes[p].data / 8, 2e-6)
+
+
+def test_synthetic_ir_is_bit_identical_host_device(capi, engine_factory):
+    B, L = 256, 1000
+    e = engine_factory(B)
+    env = np.exp(-6.9 * np.arange(L) / L).astype(np.float32)
+    fs = capi.FilterSet(e, 3, capi.min_partitions(B, L))
+    fs.generate(L, seed=77, envelope=env, scale=0.125, channel_id_offset=10)
+    for c in range(3):
+        h = capi.synth_ir(77, 10 + c, L, env, 0.125)
+        ref = capi.FilterSet.from_time(e, h[:, None])
+        for p in range(fs.partitions):
+            a, _ = fs.download(c, p)
+            b, _ = ref.download(0, p)
+            assert np.array_equal(a, b)

@@ -1,0 +1,255 @@
+"""GPU parity, Level 2: the renderer block step through the C ABI vs the oracle
+restatement of src/{generic,brs,binaural}renderer.h on the same seeded inputs.
+Tolerance: 1e-5 of full scale (BASELINE.json); IRs are scaled so |y| ~<= 1."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def decaying(rng, frames, channels, gain):
+    env = np.exp(-6.9 * np.arange(frames) / frames)[:, None]
+    return (rng.uniform(-1, 1, (frames, channels)) * env * gain).astype(np.float32)
+
+
+def maxerr(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+
+
+@pytest.mark.parametrize("B,L,N,M", [(64, 200, 3, 4), (64, 64, 1, 1), (256, 1000, 5, 7), (1024, 3000, 4, 6)])
+def test_generic_with_control_changes(capi, co, engine_factory, B, L, N, M):
+    rng = np.random.default_rng(B + L + N + M)
+    e = engine_factory(B)
+    r = capi.Renderer(e, capi.GENERIC, outputs=M)
+    o = co.GenericRendererOracle(B, M)
+    gain = 0.5 / np.sqrt(N * L / 6.9)
+    ids = []
+    for n in range(N):
+        ir = decaying(rng, L, M, gain)
+        ids.append(r.add_source(ir))
+        o.add_source(ir)
+    worst = 0.0
+    for t in range(34):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        if t == 5:
+            r.set_gain(ids[-1], 0.5); o.sources[-1].gain = 0.5
+        if t == 9:
+            r.set_mute(ids[0], True); o.sources[0].mute = True
+        if t == 14:
+            r.set_mute(ids[0], False); o.sources[0].mute = False
+        if t == 18:
+            r.set_master_volume(0.7); o.master_volume = 0.7
+        if t == 22:
+            r.set_processing(False); o.processing = False
+        if t == 25:
+            r.set_processing(True); o.processing = True
+        y = r.process(x)
+        assert y.shape == (M, B)
+        worst = max(worst, maxerr(y, o.process(x)))
+    assert worst <= TOL, worst
+
+
+def test_generic_first_block_is_fade_in_and_matches_direct(capi, co, engine_factory):
+    B, L, N, M, T = 64, 150, 2, 3, 8
+    rng = np.random.default_rng(11)
+    e = engine_factory(B)
+    r = capi.Renderer(e, capi.GENERIC, outputs=M)
+    irs = [decaying(rng, L, M, 0.1) for _ in range(N)]
+    for ir in irs:
+        r.add_source(ir)
+    xs = rng.uniform(-1, 1, (T, N, B)).astype(np.float32)
+    y = np.stack([r.process(xs[t]) for t in range(T)])  # (T, M, B)
+    y = y.transpose(1, 0, 2).reshape(M, -1)
+    full = np.zeros((M, T * B))
+    for n in range(N):
+        sig = xs[:, n, :].reshape(-1)
+        for m in range(M):
+            full[m] += co.direct_convolution_f64(sig, irs[n][:, m])
+    _, fade_in = co.raised_cosine_fade(B)
+    assert maxerr(y[:, B:], full[:, B:]) <= TOL
+    assert maxerr(y[:, :B], full[:, :B] * fade_in) <= TOL
+
+
+def test_generic_output_shards_equal_slices_of_full(capi, engine_factory):
+    B, L, N, M = 128, 500, 3, 10
+    rng = np.random.default_rng(5)
+    e = engine_factory(B)
+    irs = [decaying(rng, L, M, 0.05) for _ in range(N)]
+    full = capi.Renderer(e, capi.GENERIC, outputs=M)
+    shards = [capi.Renderer(e, capi.GENERIC, outputs=M, output_first=f, output_count=c)
+              for f, c in ((0, 3), (3, 5), (8, 2))]
+    for ir in irs:
+        full.add_source(ir)
+        for s in shards:
+            s.add_source(ir)
+    for t in range(6):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        y = full.process(x)
+        ys = np.concatenate([s.process(x) for s in shards])
+        assert np.array_equal(y, ys)
+
+
+def test_generic_wrong_channel_count_is_rejected(capi, engine_factory):
+    # load_sndfile(name, sample_rate, outputs) (genericrenderer.h:94-98, sndfiletools.h:78-87)
+    e = engine_factory(64)
+    r = capi.Renderer(e, capi.GENERIC, outputs=4)
+    with pytest.raises(capi.SsrError) as ei:
+        r.add_source(np.zeros((10, 3), np.float32))
+    assert ei.value.code == capi.SSR_ERR_FILE
+    assert "channels instead of" in ei.value.msg
+
+
+@pytest.mark.parametrize("B,L,N,A", [(64, 300, 2, 8), (256, 2000, 3, 12), (1024, 4000, 2, 6)])
+def test_brs_head_rotation(capi, co, engine_factory, B, L, N, A):
+    rng = np.random.default_rng(B + L)
+    e = engine_factory(B)
+    r = capi.Renderer(e, capi.BRS)
+    o = co.BrsRendererOracle(B)
+    gain = 0.5 / np.sqrt(N * L / 6.9)
+    ids = []
+    for n in range(N):
+        brir = decaying(rng, L, 2 * A, gain)
+        ids.append(r.add_source(brir))
+        o.add_source(brir)
+    az = 0.0
+    worst = 0.0
+    for t in range(70):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        if 5 <= t < 20:
+            az += 17.0        # a switch every block: the sustained "rotating" case
+        if t == 30:
+            az = -123.0
+        if t == 44:
+            r.set_mute(ids[0], True); o.sources[0].mute = True
+        if t == 50:
+            r.set_mute(ids[0], False); o.sources[0].mute = False
+        if t == 55:
+            r.set_gain(ids[-1], 0.4); o.sources[-1].gain = 0.4
+        r.set_reference_orientation(az)
+        o.reference_orientation = az
+        y = r.process(x)
+        worst = max(worst, maxerr(y, o.process(x)))
+    assert worst <= TOL, worst
+
+
+def test_brs_odd_channel_count_is_rejected(capi, engine_factory):
+    e = engine_factory(64)
+    r = capi.Renderer(e, capi.BRS)
+    with pytest.raises(capi.SsrError) as ei:
+        r.add_source(np.zeros((10, 3), np.float32))
+    assert ei.value.code == capi.SSR_ERR_FILE
+    assert "multiple of 2" in ei.value.msg
+
+
+@pytest.mark.parametrize("B,L,A", [(64, 100, 16), (512, 512, 36)])
+def test_binaural_moving_sources_without_interpolation(capi, co, engine_factory, B, L, A):
+    rng = np.random.default_rng(B + A)
+    N = 3
+    e = engine_factory(B)
+    hrir = decaying(rng, L, 2 * A, 0.5 / np.sqrt(L / 6.9))
+    r = capi.Renderer(e, capi.BINAURAL)
+    r.load_hrirs(hrir)
+    o = co.BinauralRendererOracle(B, hrir)
+    ids = [r.add_source() for _ in range(N)]
+    for _ in range(N):
+        o.add_source()
+
+    def setpos(i, p):
+        r.set_position(ids[i], p[0], p[1])
+        o.sources[i].position = p
+
+    for i, p in enumerate([(0.0, 2.0), (1.5, -1.0), (-2.0, 0.3)]):
+        setpos(i, p)
+    worst = 0.0
+    for t in range(70):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        if 5 <= t < 25:
+            a = t * 0.3
+            setpos(0, (2 * np.cos(a), 2 * np.sin(a)))
+        if t == 45:
+            r.set_reference_orientation(77.0); o.reference_orientation = 77.0
+        if t == 50:
+            r.set_model(ids[2], True); o.sources[2].model_plane = True
+        if t == 52:
+            r.set_amplitude_reference_distance(2.0); o.amplitude_reference_distance = 2.0
+        if t == 55:
+            r.set_reference_position(0.5, -0.25); o.reference_position = (0.5, -0.25)
+        if t == 60:
+            r.set_gain(ids[0], 0.3); o.sources[0].gain = 0.3
+        if t == 63:
+            r.set_reference_offset_orientation(-20.0); o.reference_offset_orientation = -20.0
+        if t == 66:
+            r.set_reference_offset_position(0.1, 0.2); o.reference_offset_position = (0.1, 0.2)
+        y = r.process(x)
+        worst = max(worst, maxerr(y, o.process(x)))
+    assert worst <= TOL, worst
+
+
+def test_binaural_near_field_dirac_interpolation(capi, co, engine_factory):
+    """dist < 0.5 m: HRTF lerped with the neutral Dirac (binauralrenderer.h:291-294,
+    365-379).  P = 1 (HRIR shorter than the block, the normal case): the reference's
+    temporary_hrtf aliasing cannot occur."""
+    B, L, A, N = 256, 200, 12, 2
+    rng = np.random.default_rng(21)
+    e = engine_factory(B)
+    hrir = decaying(rng, L, 2 * A, 0.5 / np.sqrt(L / 6.9))
+    r = capi.Renderer(e, capi.BINAURAL)
+    r.load_hrirs(hrir)
+    o = co.BinauralRendererOracle(B, hrir)
+    ids = [r.add_source() for _ in range(N)]
+    for _ in range(N):
+        o.add_source()
+    r.set_position(ids[1], 0.0, 1.0); o.sources[1].position = (0.0, 1.0)
+    worst = 0.0
+    for t in range(30):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        p = (0.45 - 0.015 * t, 0.05)
+        r.set_position(ids[0], *p); o.sources[0].position = p
+        y = r.process(x)
+        worst = max(worst, maxerr(y, o.process(x)))
+    assert worst <= TOL, worst
+
+
+def test_binaural_odd_channel_count_is_rejected(capi, engine_factory):
+    e = engine_factory(64)
+    r = capi.Renderer(e, capi.BINAURAL)
+    with pytest.raises(capi.SsrError) as ei:
+        r.load_hrirs(np.zeros((10, 3), np.float32))
+    assert ei.value.code == capi.SSR_ERR_FILE
+    assert "HRIR file must be a multiple of 2" in ei.value.msg
+
+
+def test_pipelined_submit_wait_equals_process(capi, engine_factory):
+    B, L, N, M = 256, 900, 3, 5
+    rng = np.random.default_rng(8)
+    e = engine_factory(B)
+    irs = [decaying(rng, L, M, 0.05) for _ in range(N)]
+    a = capi.Renderer(e, capi.GENERIC, outputs=M)
+    b = capi.Renderer(e, capi.GENERIC, outputs=M)
+    for ir in irs:
+        a.add_source(ir); b.add_source(ir)
+    xs = rng.uniform(-1, 1, (7, N, B)).astype(np.float32)
+    ya = [a.process(x) for x in xs]
+    yb = []
+    b.submit(xs[0])
+    for t in range(1, len(xs)):
+        b.submit(xs[t])
+        yb.append(b.wait())
+    yb.append(b.wait())
+    for u, v in zip(ya, yb):
+        assert np.array_equal(u, v)
+
+
+def test_wrong_block_length_is_rejected(capi, engine_factory):
+    # assert(n == block_size()) (apf/apf/pointer_policy.h:114)
+    import ctypes as C
+    e = engine_factory(64)
+    r = capi.Renderer(e, capi.GENERIC, outputs=1)
+    r.add_source(np.ones((10, 1), np.float32))
+    x = np.zeros((1, 32), np.float32)
+    y = np.zeros((1, 64), np.float32)
+    ins, outs = r._ptr_arrays(x, y)
+    rc = capi.lib().ssr_renderer_process(r.h, 32, ins, outs)
+    assert rc == capi.SSR_ERR_INVALID
