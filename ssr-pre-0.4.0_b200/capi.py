@@ -169,6 +169,21 @@ class Engine:
         _check(lib().ssr_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h
         self.block_size = block_size
+        # Dependents (filter sets, inputs, outputs, renderers) hold raw pointers
+        # into the engine.  The garbage collector may finalise an engine before
+        # its dependents (and clears weakrefs first), so the engine keeps their
+        # raw handles and destroys whatever is still alive before itself.
+        self._handles = {}
+
+    def _adopt(self, child, destroy_name: str):
+        self._handles[id(child)] = (destroy_name, child.h)
+
+    def _release(self, child, destroy_name: str):
+        """Destroys child's handle unless the engine already did."""
+        if getattr(child, "h", None) and self.h:
+            self._handles.pop(id(child), None)
+            getattr(lib(), destroy_name)(child.h)
+        child.h = None
 
     def synchronize(self):
         _check(lib().ssr_engine_synchronize(self.h))
@@ -183,6 +198,9 @@ class Engine:
 
     def close(self):
         if getattr(self, "h", None):
+            for name, handle in reversed(list(self._handles.values())):
+                getattr(lib(), name)(handle)
+            self._handles = {}
             lib().ssr_engine_destroy(self.h)
             self.h = None
 
@@ -196,6 +214,7 @@ class FilterSet:
         h = C.c_void_p()
         _check(lib().ssr_filterset_create(engine.h, channels, partitions, C.byref(h)))
         self.h = h
+        engine._adopt(self, "ssr_filterset_destroy")
         self.channels, self.partitions = channels, partitions
 
     @classmethod
@@ -234,9 +253,7 @@ class FilterSet:
         return out, bool(z.value)
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().ssr_filterset_destroy(self.h)
-            self.h = None
+        self.engine._release(self, "ssr_filterset_destroy")
 
     def __del__(self):
         self.close()
@@ -250,6 +267,7 @@ class Input:
         h = C.c_void_p()
         _check(lib().ssr_input_create(engine.h, partitions, C.byref(h)))
         self.h = h
+        engine._adopt(self, "ssr_input_destroy")
         self.partitions = partitions
 
     def add_block(self, x):
@@ -263,9 +281,7 @@ class Input:
         return out
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().ssr_input_destroy(self.h)
-            self.h = None
+        self.engine._release(self, "ssr_input_destroy")
 
     def __del__(self):
         self.close()
@@ -278,9 +294,7 @@ class _OutBase:
         return np.ctypeslib.as_array(res, shape=(self.inp.engine.block_size,)).copy()
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().ssr_output_destroy(self.h)
-            self.h = None
+        self.inp.engine._release(self, "ssr_output_destroy")
 
     def __del__(self):
         self.close()
@@ -295,6 +309,7 @@ class Output(_OutBase):
         h = C.c_void_p()
         _check(lib().ssr_output_create(inp.h, OUTPUT_DYNAMIC, C.byref(h)))
         self.h = h
+        inp.engine._adopt(self, "ssr_output_destroy")
 
     def set_filter(self, fs: FilterSet, channel: int = 0):
         self._keep.append(fs)
@@ -319,6 +334,7 @@ class StaticOutput(_OutBase):
         h = C.c_void_p()
         _check(lib().ssr_output_create(inp.h, OUTPUT_STATIC, C.byref(h)))
         self.h = h
+        inp.engine._adopt(self, "ssr_output_destroy")
         _check(lib().ssr_output_bind_static(self.h, fs.h, channel))
 
 
@@ -333,6 +349,7 @@ class Renderer:
         h = C.c_void_p()
         _check(lib().ssr_renderer_create(engine.h, C.byref(cfg), C.byref(h)))
         self.h = h
+        engine._adopt(self, "ssr_renderer_destroy")
 
     @property
     def local_outputs(self) -> int:
@@ -413,9 +430,7 @@ class Renderer:
         _check(lib().ssr_renderer_process_device(self.h, d_in_ptr, d_out_ptr))
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().ssr_renderer_destroy(self.h)
-            self.h = None
+        self.engine._release(self, "ssr_renderer_destroy")
 
     def __del__(self):
         self.close()

@@ -159,15 +159,24 @@ def test_filter_and_input_spectra_match_oracle(capi, co, engine_factory, B, L):
         close(inp.download(p) / scale, io.spectra[p].data / scale, 2e-6)
 
 
-@pytest.mark.parametrize("B,P", [(8, 1), (8, 4), (64, 5), (1024, 8)])
-def test_random_switch_protocol_matches_oracle(capi, co, engine_factory, B, P):
+@pytest.mark.parametrize("B,P,short", [(8, 1, False), (8, 4, False), (64, 5, False), (1024, 8, False),
+                                       (64, 5, True), (256, 6, True)])
+def test_random_switch_protocol_matches_oracle(capi, co, engine_factory, B, P, short):
+    """short=False: every filter fills all P partitions, so the reference's
+    zero-skip defect (convolver.h:561: `continue` without `++input`) cannot
+    trigger and the oracle tracks the reference exactly.  short=True: filters
+    shorter than P partitions leave zero-flagged partitions BETWEEN live ones
+    during a staggered switch; there the reference goes out of step, so the
+    oracle is run with the defect switched off (correct pairing p <-> p)."""
     rng = np.random.default_rng(100 + B + P)
     e = engine_factory(B)
     inp = capi.Input(e, P)
     out = capi.Output(inp)
     io = co.Input(B, P)
     oo = co.Output(io)
-    taps = [rng.uniform(-1, 1, int(rng.integers(1, P * B + 1))).astype(np.float32) * (2.0 / np.sqrt(B))
+    oo.reference_zero_skip_quirk = not short
+    lo = 1 if short else (P - 1) * B + 1
+    taps = [rng.uniform(-1, 1, int(rng.integers(lo, P * B + 1))).astype(np.float32) * (2.0 / np.sqrt(B))
             for _ in range(5)]
     fg = [capi.FilterSet.from_time(e, t[:, None], P) for t in taps]
     fo = [co.Filter(B, t, P) for t in taps]
