@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- x-realtime of the partitioned-convolution hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (ours)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (reference CPU arm)
+
+Workload (config.workload): BASELINE.json config 5, the one its metric/target is
+quoted on -- GenericRenderer MIMO, 128 sources x 512 outputs, 48000-tap IRs
+(P = 47), B = 1024, 48 kHz.  Its 25.2 GB of partition spectra fit one B200, so
+N = 1 runs the full shape; N > 1 shards the outputs across ranks,
+total work fixed => "scaling": "strong".  A step = one audio block (1024 samples
+of all 128 sources) through forward FFT -> MAC -> inverse FFT + crossfade + sum
+[-> NCCL gather of the output blocks to rank 0].
+
+  value  device-resident: input blocks already in HBM, steps back to back.
+  e2e    the same through ssr_renderer_process / process_device with HOST
+         buffers: H2D of the block's inputs and D2H of its outputs inside the
+         timed region, one synchronous call per block (also gives p99 latency).
+  roofline  MAC kernel: algorithmic bytes (SURVEY 8d formula, counted by the
+         engine) / CUDA-event time of the MAC launches inside the timed region.
+  cpu_baseline  the reference's own GenericRenderer (oracle/_ref) on host cores,
+         on a bounded output shard of the same workload.
+
+The working set (>= 3.15 GB of spectra per GPU) is far larger than the 126 MB
+L2, so no explicit L2 flush is needed between steps (config.l2: "inputs>L2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "x-realtime @48kHz/1024-blk (src x out x taps)"
+UNIT = "x realtime"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5")
+    # reduced shapes for quick functional runs only (never the reported number)
+    ap.add_argument("--sources", type=int, default=0)
+    ap.add_argument("--outputs", type=int, default=0)
+    ap.add_argument("--taps", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--mac-variant", type=int, default=0)
+    return ap.parse_args()
+
+
+def get_workload(args):
+    entry.load_package()
+    import ssr_b200.workloads as wl
+    import copy
+    w = copy.copy(wl.WORKLOADS[args.workload])
+    reduced = False
+    if args.sources:
+        w.sources = args.sources; reduced = True
+    if args.outputs:
+        w.outputs = args.outputs; w.channels = args.outputs; reduced = True
+    if args.taps:
+        w.taps = args.taps; reduced = True
+    return w, reduced
+
+
+# ----------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smmax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smmax)) if smmax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- reference arm
+def run_reference_renderer(w, out_shard: int, blocks: int, warm: int, threads: int):
+    """The reference's own GenericRenderer (oracle/_ref/libssr_ref.so) on host
+    cores: `out_shard` of the workload's outputs, all sources, full taps.
+    Returns (seconds for `blocks` blocks, per-block ms)."""
+    from oracle import ref
+    import ssr_b200.workloads as wl
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    r = ref.Renderer("generic", w.block, w.fs, threads=threads)
+    r.add_outputs(out_shard)
+    for n in range(w.sources):
+        ir = wl.generic_ir(w, n, 0, out_shard, env, scale)
+        name = f"bench_ir_{n}"
+        ref.register_sndfile(name, ir, w.fs)
+        r.add_source(name)
+        ref.unregister_sndfile(name)
+    r.activate()
+    nin = 4
+    x = np.stack([wl.signal_block(w, t) for t in range(nin)])
+    if warm > 0:
+        r.run(x, warm, want_output=False)
+    _, secs, times = r.run(x, blocks, want_output=False, want_times=True)
+    return secs, times
+
+
+def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int):
+    """Pick the output shard so that (steps + warmup) blocks fit the budget.
+    Cost model from SURVEY 0.7: ~1.6 us per partition-MAC per core."""
+    per_out_block = w.sources * w.partitions * 1.6e-6 / max(1, min(threads, 64)) * 1.6
+    shard = w.outputs
+    while shard > 1 and per_out_block * shard * (steps + warmup) > budget_s:
+        shard //= 2
+    # host memory: spectra + time-domain IRs
+    while shard > 1 and w.sources * shard * (w.partitions * 8 * w.block + 4 * w.taps) > 24e9:
+        shard //= 2
+    return max(1, shard)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w, reduced = get_workload(args)
+    from oracle import ref
+    threads = os.cpu_count() or 1
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libssr_ref.so not built"}))
+        return 0
+    steps, warmup = args.steps, args.warmup
+    shard = reference_plan(w, steps, warmup, 150.0, threads)
+    threads_used = max(1, min(threads, shard))  # items are spread round-robin over outputs
+    secs, times = run_reference_renderer(w, shard, steps, warmup, threads_used)
+    ms = secs / steps * 1e3
+    # the shard does shard/outputs of the MAC + IFFT work of a block
+    full_ms = ms * (w.outputs / shard)
+    value = (w.block / w.fs) / (full_ms * 1e-3)
+    sample = (f"reference GenericRenderer {w.sources} src x {shard} of {w.outputs} outputs x {w.taps} taps, "
+              f"{steps} blocks after {warmup} warm-up; block time scaled x{w.outputs // shard} to the full "
+              f"output count (extrapolated); {ref.describe()}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": full_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.label() + (" [REDUCED]" if reduced else ""), "block": w.block,
+                   "sample_rate": w.fs, "partitions": w.partitions},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads_used, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "p99_block_ms": float(np.percentile(times, 99)) * (w.outputs / shard),
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------- our arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    entry.load_package()
+    import ssr_b200.capi as capi
+    import ssr_b200.workloads as wl
+
+    w, reduced = get_workload(args)
+    B = w.block
+    assert w.outputs % world == 0, "outputs must divide by the number of GPUs"
+    m_local = w.outputs // world
+    m_first = rank * m_local
+
+    # a dedicated (non-default) stream shared by torch, NCCL and the engine, so
+    # that torch.cuda.Event timing sees the engine's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    eng = capi.Engine(B, w.fs, device=local_rank, stream=stream.cuda_stream, mac_variant=args.mac_variant)
+    ren = capi.Renderer(eng, capi.GENERIC, outputs=w.outputs, output_first=m_first, output_count=m_local)
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    t0 = time.time()
+    for n in range(w.sources):
+        # filter-set loading (north_star item 1): generated and transformed on the
+        # device, resident in HBM; channel id = source * outputs + output
+        ren.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
+                                 envelope=env, scale=scale)
+    eng.synchronize()
+    load_s = time.time() - t0
+
+    # input blocks: host (pinned) ring for e2e, device ring for `value`
+    nring = 8
+    host_in = torch.empty((nring, w.sources, B), dtype=torch.float32).pin_memory()
+    for t in range(nring):
+        host_in[t] = torch.from_numpy(wl.signal_block(w, t))
+    dev_in = host_in.to(dev)
+    d_in_step = torch.empty((w.sources, B), dtype=torch.float32, device=dev)
+    d_out = torch.zeros((m_local, B), dtype=torch.float32, device=dev)
+    gathered = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    host_out = torch.empty((w.outputs, B), dtype=torch.float32).pin_memory()
+
+    def gather():
+        if world > 1:
+            # the path's only collective: output blocks -> host-facing rank, over NVLink
+            dist.gather(d_out, gathered, dst=0)
+
+    def step_device(t):
+        ren.process_device(dev_in[t % nring].data_ptr(), d_out.data_ptr())
+        gather()
+
+    def step_e2e(t):
+        d_in_step.copy_(host_in[t % nring], non_blocking=True)           # H2D (pinned)
+        ren.process_device(d_in_step.data_ptr(), d_out.data_ptr())
+        gather()
+        if rank == 0:
+            if world > 1:
+                for g in range(world):
+                    host_out[g * m_local:(g + 1) * m_local].copy_(gathered[g], non_blocking=True)
+            else:
+                host_out.copy_(d_out, non_blocking=True)                 # D2H
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- device-resident throughput (`value`)
+    for t in range(W):
+        step_device(t)
+    barrier()
+    eng.stats(reset=True)
+    eng.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for t in range(K):
+        step_device(W + t)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if rank == 0 else None
+    st = eng.stats(reset=True)
+    eng.set_timing(False)
+    ms_per_step = ms_total / K
+    value = (B / w.fs) / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer call (`e2e`), synchronous per block
+    for t in range(W):
+        step_e2e(t)
+    barrier()
+    lat = np.empty(K)
+    t_start = time.perf_counter()
+    for t in range(K):
+        tb = time.perf_counter()
+        step_e2e(W + t)
+        lat[t] = (time.perf_counter() - tb) * 1e3
+    barrier()
+    e2e_ms_total = max_over_ranks((time.perf_counter() - t_start) * 1e3)
+    e2e_value = (B / w.fs) / (e2e_ms_total / K * 1e-3)
+    p99 = max_over_ranks(float(np.percentile(lat, 99)))
+
+    # ---- roofline of the MAC kernel (this rank)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    mac_ms = st["ms_mac"]
+    achieved = (st["mac_bytes"] / 1e9) / (mac_ms * 1e-3) if mac_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{args.workload}_gpus{world}")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "ssrk::mac_kernel<4,2>", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "bytes_per_launch": st["mac_bytes"] / max(1, st["mac_launches"]),
+        "ms_per_launch": mac_ms / max(1, st["mac_launches"]),
+        "mac_share_of_step": mac_ms / max(1e-9, st["ms_total"]),
+        "fft_ms_per_step": st["ms_fft"] / max(1, st["blocks"]),
+        "ifft_ms_per_step": st["ms_ifft"] / max(1, st["blocks"]),
+        "fft_gflops": (w.sources * 56320 / 1e9) / max(1e-12, st["ms_fft"] / max(1, st["blocks"]) * 1e-3),
+        "ifft_gflops": (m_local * 56320 / 1e9) / max(1e-12, st["ms_ifft"] / max(1, st["blocks"]) * 1e-3),
+    }
+    launches = int(st["mac_launches"] + st["fft_launches"] + st["ifft_launches"])
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.label() + (" [REDUCED]" if reduced else ""), "block": B,
+                       "sample_rate": w.fs, "partitions": w.partitions,
+                       "parallelism": f"outputs sharded x{world}" if world > 1 else "single GPU",
+                       "outputs_per_gpu": m_local, "l2": "inputs>L2 (spectra per GPU >> 126 MB)",
+                       "filter_load_s": load_s,
+                       "spectra_gb_per_gpu": w.sources * m_local * w.partitions * 8 * B / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": w.sources * B * 4 * world,
+                    "d2h_bytes_per_step": w.outputs * B * 4,
+                    "ms_per_step": e2e_ms_total / K, "mode": "synchronous per block"},
+            "p99_block_ms": p99,
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "clocks": clocks,
+        }
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import ref
+            if ref.available():
+                threads = os.cpu_count() or 1
+                shard = reference_plan(w, 40, 5, args.cpu_seconds, threads)
+                used = max(1, min(threads, shard))
+                secs, _ = run_reference_renderer(w, shard, 40, 5, used)
+                full_ms = secs / 40 * 1e3 * (w.outputs / shard)
+                line["cpu_baseline"] = {
+                    "value": (B / w.fs) / (full_ms * 1e-3), "unit": UNIT, "cores": used, "kind": "reference",
+                    "sample": (f"reference GenericRenderer {w.sources} src x {shard} of {w.outputs} outputs, "
+                               f"40 blocks after 5 warm-up, block time scaled x{w.outputs // shard} "
+                               f"(extrapolated); {ref.describe()}")}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref/libssr_ref.so missing"}
+        except Exception as exc:  # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        print(json.dumps(line))
+    ren.close()
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

@@ -199,7 +199,7 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   p.term_meta = plan.meta.dev.ptr;
   p.term_h = plan.hptr.dev.ptr;
   p.work = plan.work.dev.ptr;
-  p.wtab = wtab.ptr;
+  p.wtab = wtab.dev.ptr;
   p.xring = d_xring.ptr;
   p.xparts = d_xparts.ptr;
   p.heads = d_heads.ptr;
@@ -228,10 +228,11 @@ void Engine::launch_inv(const InvPlan& plan)
 void Engine::upload_weights(const float* w, size_t n)
 {
   if (n == 0) return;
-  if (n > wtab.count) { sync(); wtab.resize(n + 64); }
-  // small and latency critical: a pageable-source async copy is staged by the
-  // driver at call time, so `w` may be reused immediately
-  SSR_CUDA(cudaMemcpyAsync(wtab.ptr, w, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+  // steady state (weights unchanged since the last upload): nothing to do
+  if (wtab.uploaded == n && wtab.host.size() == n
+      && std::memcmp(wtab.host.data(), w, n * sizeof(float)) == 0) return;
+  wtab.host.assign(w, w + n);
+  wtab.upload(stream);
 }
 
 void Engine::stage_begin()

@@ -88,15 +88,31 @@ struct Table
   PinnedArray<T> stage;
   DeviceArray<T> dev;
   size_t uploaded = 0;
+  cudaEvent_t staged = nullptr;   // recorded after the last staging -> device copy
+  Table() {}
+  Table(const Table&) = delete;
+  Table& operator=(const Table&) = delete;
+  ~Table() { if (staged) cudaEventDestroy(staged); }
+  // Asynchronous on `s`.  The staging buffer and the device copy are reused, so
+  // this first waits (on the host) until the previous upload has executed, and
+  // (growing the device buffer) until everything queued on `s` is done: kernels
+  // already queued may still read the old table.
   void upload(cudaStream_t s)
   {
     uploaded = host.size();
     if (host.empty()) return;
-    stage.ensure(host.size());
-    dev.ensure(host.size());
+    if (staged) SSR_CUDA(cudaEventSynchronize(staged));
+    else SSR_CUDA(cudaEventCreateWithFlags(&staged, cudaEventDisableTiming));
+    if (host.size() > dev.count || host.size() > stage.count)
+    {
+      SSR_CUDA(cudaStreamSynchronize(s));
+      stage.ensure(host.size());
+      dev.ensure(host.size());
+    }
     std::memcpy(stage.ptr, host.data(), host.size() * sizeof(T));
     SSR_CUDA(cudaMemcpyAsync(dev.ptr, stage.ptr, host.size() * sizeof(T),
           cudaMemcpyHostToDevice, s));
+    SSR_CUDA(cudaEventRecord(staged, s));
   }
 };
 
@@ -160,8 +176,7 @@ struct Engine
   int register_input(Input* in);
   void unregister_input(int id);
 
-  DeviceArray<float> wtab;         // weight slots
-  PinnedArray<float> wtab_stage;
+  Table<float> wtab;               // weight slots
   DeviceArray<float4> partials;
 
   // launches (all asynchronous on `stream`)
@@ -317,7 +332,10 @@ struct Renderer
   bool static_dirty = true;
   MacPlan dyn_mac[3];           // brs / binaural: const / old / new
   InvPlan inv;
-  Table<ssrk::FwdJob> fwd;
+  // forward-FFT job tables, one per distinct device input pointer (a caller
+  // cycling through a few input buffers never re-uploads in steady state)
+  std::vector<std::pair<const float*, std::unique_ptr<Table<ssrk::FwdJob>>>> fwd_cache;
+  Table<ssrk::FwdJob>* fwd = nullptr;
   std::vector<float> wtab_host;
   DeviceArray<float> d_in, d_out;
   PinnedArray<float> h_in, h_out;

@@ -95,7 +95,7 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
   }
   sources.push_back(std::move(s));
   static_dirty = true;
-  fwd.host.clear();
+  fwd_cache.clear();
   return sources.back()->id;
 }
 
@@ -108,7 +108,7 @@ void Renderer::rem_source(int id)
     {
       sources.erase(sources.begin() + i);
       static_dirty = true;
-      fwd.host.clear();
+      fwd_cache.clear();
       return;
     }
   throw Error(SSR_ERR_INVALID, "ssr_b200: no such source");
@@ -130,12 +130,14 @@ void Renderer::base_weight(Source& s)
 void Renderer::build_fwd(const float* d_input)
 {
   const int N = int(sources.size());
-  bool rebuild = int(fwd.host.size()) != N;
-  if (!rebuild && N > 0 && fwd.host[0].second.ptr != d_input) rebuild = true;
-  if (!rebuild) return;
-  fwd.host.resize(N);
-  for (int n = 0; n < N; ++n) fwd.host[n] = sources[n]->input->make_job(d_input + size_t(n) * e->B);
-  fwd.upload(e->stream);
+  for (auto& c : fwd_cache)
+    if (c.first == d_input) { fwd = c.second.get(); return; }
+  if (fwd_cache.size() >= 32) { e->sync(); fwd_cache.clear(); }
+  fwd_cache.emplace_back(d_input, std::unique_ptr<Table<FwdJob>>(new Table<FwdJob>()));
+  fwd = fwd_cache.back().second.get();
+  fwd->host.resize(N);
+  for (int n = 0; n < N; ++n) fwd->host[n] = sources[n]->input->make_job(d_input + size_t(n) * e->B);
+  fwd->upload(e->stream);
 }
 
 static Mode mode_from_weight(const BlockParameter<float>& f)
@@ -204,7 +206,6 @@ void Renderer::step_generic(const float* d_input, float* d_output)
   const int key = (kind_active[0] ? 1 : 0) | (kind_active[1] ? 2 : 0) | (kind_active[2] ? 4 : 0);
   if (key != inv_key || (inv.jobs.host.size() && inv.jobs.host[0].out != d_output))
   {
-    e->sync();
     inv.clear();
     const float scale = 1.0f / float(2 * B);
     for (int m = 0; m < m_local; ++m)
@@ -227,7 +228,7 @@ void Renderer::step_generic(const float* d_input, float* d_output)
 
   build_fwd(d_input);
   e->stage_begin();
-  e->launch_fwd(fwd.dev.ptr, N);
+  e->launch_fwd(fwd->dev.ptr, N);
   e->stage_mark(1);
   e->upload_weights(wtab_host.data(), wtab_host.size());
   for (int k = 0; k < 3; ++k)
@@ -263,7 +264,6 @@ void Renderer::step_dynamic(const float* d_input, float* d_output)
   const bool binaural = cfg.kind == SSR_RENDERER_BINAURAL;
   wtab_host.assign(size_t(3) * std::max(N, 1), 0.0f);
   MacPlan& plan = dyn_mac[0];
-  e->sync();  // staging tables of the previous block
   plan.clear();
   const float4* zero = reinterpret_cast<const float4*>(e->zero_part.ptr);
 
@@ -433,7 +433,7 @@ void Renderer::step_dynamic(const float* d_input, float* d_output)
 
   build_fwd(d_input);
   e->stage_begin();
-  e->launch_fwd(fwd.dev.ptr, N);
+  e->launch_fwd(fwd->dev.ptr, N);
   e->stage_mark(1);
   e->upload_weights(wtab_host.data(), wtab_host.size());
   e->launch_mac(plan, 0, 0);
@@ -471,7 +471,7 @@ void Renderer::submit(int n, const float* const* in)
   const int N = int(sources.size());
   const int B = e->B;
   const size_t in_floats = size_t(std::max(N, 1)) * B;
-  if (h_in.count < 2 * in_floats) { e->sync(); h_in.resize(2 * in_floats); d_in.resize(in_floats); fwd.host.clear(); }
+  if (h_in.count < 2 * in_floats) { e->sync(); h_in.resize(2 * in_floats); d_in.resize(in_floats); fwd_cache.clear(); }
   static_assert(sizeof(float) == 4, "");
   const int slot = int(submitted & 1);
   float* hin = h_in.ptr + size_t(slot) * in_floats;
