@@ -225,13 +225,12 @@ def main_ours(args):
 
     entry.load_package()
     import ssr_b200.capi as capi
+    import ssr_b200.multigpu as mg
     import ssr_b200.workloads as wl
 
     w, reduced = get_workload(args)
     B = w.block
-    assert w.outputs % world == 0, "outputs must divide by the number of GPUs"
-    m_local = w.outputs // world
-    m_first = rank * m_local
+    m_first, m_local = mg.shard_outputs(w.outputs, world, rank)
 
     # a dedicated (non-default) stream shared by torch, NCCL and the engine, so
     # that torch.cuda.Event timing sees the engine's kernels
@@ -246,7 +245,8 @@ def main_ours(args):
     for n in range(w.sources):
         # filter-set loading (north_star item 1): generated and transformed on the
         # device, resident in HBM; channel id = source * outputs + output
-        ren.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
+        ren.add_source_synthetic(w.taps, w.outputs, w.ir_seed,
+                                 channel_id_offset=mg.channel_id_offset(n, w.outputs),
                                  envelope=env, scale=scale)
     eng.synchronize()
     load_s = time.time() - t0

@@ -1,0 +1,164 @@
+"""Generates tests/golden/*.npz from the REFERENCE ITSELF (oracle/_ref/libssr_ref.so,
+the unmodified apf/apf/convolver.h + src/*renderer.h built by oracle/Makefile).
+
+Run here (where /root/reference exists):  python tests/golden/make_golden.py
+The fixtures travel to the GPU box, /root/reference does not.  Every fixture
+stores the exact inputs, the control script and the reference's outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def decaying(rng, frames, channels, gain):
+    env = np.exp(-6.9 * np.arange(frames) / frames)[:, None]
+    return (rng.uniform(-1, 1, (frames, channels)) * env * gain).astype(np.float32)
+
+
+def golden_level1():
+    """Dynamic Output protocol with random switches + StaticConvolver."""
+    rng = np.random.default_rng(4242)
+    B, P, T = 64, 4, 40
+    taps = [rng.uniform(-1, 1, int(n)).astype(np.float32) * 0.25
+            for n in rng.integers((P - 1) * B + 1, P * B + 1, size=4)]
+    filt = [ref.Filter(B, t, P) for t in taps]
+    inp = ref.Input(B, P)
+    out = ref.Output(inp)
+    x = rng.uniform(-1, 1, (T, B)).astype(np.float32)
+    switch = np.full(T, -1, np.int64)
+    weight = rng.uniform(0.1, 1.0, T).astype(np.float32)
+    y = np.zeros((T, B), np.float32)
+    qe = np.zeros(T, np.int64)
+    for t in range(T):
+        inp.add_block(x[t])
+        qe[t] = out.queues_empty()
+        if not qe[t]:
+            out.rotate_queues()
+        if rng.random() < 0.3:
+            switch[t] = int(rng.integers(0, 4))
+            out.set_filter(filt[switch[t]])
+        y[t] = out.convolve(float(weight[t]))
+    spectra = np.stack([np.stack([filt[k].get(p)[0] for p in range(P)]) for k in range(4)])
+    lens = np.array([t.size for t in taps])
+    tp = np.zeros((4, P * B), np.float32)
+    for k, t in enumerate(taps):
+        tp[k, :t.size] = t
+    # StaticConvolver, BASELINE config 1 shape, 6 blocks
+    B1, L1, T1 = 1024, 8192, 6
+    h1 = decaying(rng, L1, 1, 0.05)[:, 0]
+    x1 = rng.uniform(-1, 1, T1 * B1).astype(np.float32)
+    y1, _ = ref.static_convolver_run(B1, h1, x1)
+    np.savez_compressed(os.path.join(HERE, "level1.npz"), B=B, P=P, taps=tp, lens=lens, x=x, switch=switch,
+                        weight=weight, y=y, queues_empty=qe, spectra=spectra,
+                        cfg1_h=h1, cfg1_x=x1, cfg1_y=y1)
+
+
+def golden_generic():
+    rng = np.random.default_rng(777)
+    B, L, N, M, T = 64, 200, 3, 4, 30
+    irs = np.stack([decaying(rng, L, M, 0.1) for _ in range(N)])
+    r = ref.Renderer("generic", B, 48000, threads=2)
+    r.add_outputs(M)
+    ids = []
+    for n in range(N):
+        ref.register_sndfile(f"g{n}", irs[n], 48000)
+        ids.append(r.add_source(f"g{n}"))
+    r.activate()
+    x = rng.uniform(-1, 1, (T, N, B)).astype(np.float32)
+    # control script: (block, what, source index, value)
+    script = [(5, "gain", 1, 0.5), (9, "mute", 0, 1), (14, "mute", 0, 0), (18, "master_volume", -1, 0.7),
+              (22, "processing", -1, 0), (25, "processing", -1, 1)]
+    y = np.zeros((T, M, B), np.float32)
+    for t in range(T):
+        for (tb, what, n, v) in script:
+            if tb == t:
+                if n >= 0:
+                    r.set_source(ids[n], what, v)
+                else:
+                    r.set_state(what, v)
+        y[t] = r.process(x[t])
+    codes = {"gain": 0, "mute": 1, "master_volume": 2, "processing": 3}
+    np.savez_compressed(os.path.join(HERE, "generic.npz"), B=B, irs=irs, x=x, y=y,
+                        script_block=np.array([a for a, _, _, _ in script]),
+                        script_what=np.array([codes[b] for _, b, _, _ in script]),
+                        script_source=np.array([c for _, _, c, _ in script]),
+                        script_value=np.array([d for _, _, _, d in script], np.float32))
+
+
+def golden_brs():
+    rng = np.random.default_rng(888)
+    B, L, N, A, T = 64, 300, 2, 8, 50
+    brirs = np.stack([decaying(rng, L, 2 * A, 0.1) for _ in range(N)])
+    r = ref.Renderer("brs", B, 48000, threads=1)
+    r.load_reproduction_setup()
+    for n in range(N):
+        ref.register_sndfile(f"b{n}", brirs[n], 48000)
+        r.add_source(f"b{n}")
+    r.activate()
+    x = rng.uniform(-1, 1, (T, N, B)).astype(np.float32)
+    az = np.zeros(T, np.float32)
+    a = 0.0
+    for t in range(T):
+        if 5 <= t < 20:
+            a += 17.0
+        if t == 30:
+            a = -123.0
+        az[t] = a
+    y, _, _ = r.run(x, T, azimuth=az)
+    np.savez_compressed(os.path.join(HERE, "brs.npz"), B=B, brirs=brirs, x=x, az=az, y=y)
+
+
+def golden_binaural():
+    rng = np.random.default_rng(999)
+    B, L, N, A, T = 256, 200, 2, 12, 40
+    hrir = decaying(rng, L, 2 * A, 0.15)
+    ref.register_sndfile("h", hrir, 48000)
+    r = ref.Renderer("binaural", B, 48000, threads=2, hrir_file="h")
+    r.load_reproduction_setup()
+    ids = [r.add_source() for _ in range(N)]
+    r.activate()
+    x = rng.uniform(-1, 1, (T, N, B)).astype(np.float32)
+    pos = np.zeros((T, N, 2), np.float32)
+    y = np.zeros((T, 2, B), np.float32)
+    for t in range(T):
+        ang = 0.25 * t
+        pos[t, 0] = (2 * np.cos(ang), 2 * np.sin(ang))          # circling source
+        pos[t, 1] = (0.45 - 0.01 * t, 0.05) if t >= 10 else (0.0, 1.0)  # walks into the near field
+        for n in range(N):
+            r.set_source(ids[n], "position", float(pos[t, n, 0]), float(pos[t, n, 1]))
+        y[t] = r.process(x[t])
+    np.savez_compressed(os.path.join(HERE, "binaural.npz"), B=B, hrir=hrir, x=x, pos=pos, y=y)
+
+
+def golden_hrirs_fabian():
+    """Real-data fixture: the reference's shipped HRIR set
+    (data/impulse_responses/hrirs/hrirs_fabian.wav, 720 ch x 512 frames, 44.1 kHz,
+    int16) -- first two directions only, plus the reference's spectra for them."""
+    import wave
+    path = "/root/reference/data/impulse_responses/hrirs/hrirs_fabian.wav"
+    with wave.open(path, "rb") as wf:
+        ch, n, fs, sw = wf.getnchannels(), wf.getnframes(), wf.getframerate(), wf.getsampwidth()
+        raw = np.frombuffer(wf.readframes(n), dtype="<i2").reshape(n, ch)
+    data = (raw[:, :4].astype(np.float32) / 32768.0)
+    B = 512
+    spectra = np.stack([ref.Filter(B, data[:, c]).get(0)[0] for c in range(4)])
+    np.savez_compressed(os.path.join(HERE, "hrirs_fabian_4ch.npz"), B=B, fs=fs, channels=ch, frames=n,
+                        data=data, spectra=spectra)
+
+
+if __name__ == "__main__":
+    golden_level1()
+    golden_generic()
+    golden_brs()
+    golden_binaural()
+    golden_hrirs_fabian()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
