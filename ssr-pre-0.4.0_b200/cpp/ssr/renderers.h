@@ -1,0 +1,401 @@
+// ssr/renderers.h -- drop-in C++ adaptors for the block step of the reference's
+// convolution renderers, on top of the B200 engine's C ABI (Level 2 of
+// include/ssr_b200.h):
+//
+//   ssr::GenericRenderer   (src/genericrenderer.h)
+//   ssr::BinauralRenderer  (src/binauralrenderer.h)
+//   ssr::BrsRenderer       (src/brsrenderer.h)
+//
+// They keep the reference's names and per-block protocol as seen through
+// apf::pointer_policy<float*> (apf/apf/pointer_policy.h:58-122) and
+// RendererBase (src/rendererbase.h:84-103, 247-314, 419-423):
+//
+//   apf::parameter_map p; p.set("block_size", 1024); p.set("sample_rate", 48000);
+//   ssr::BinauralRenderer r(p);          // + "hrir_file", "hrir_size"
+//   r.load_reproduction_setup();
+//   int id = r.add_source(src_params);   // "properties_file" for Generic / BRS
+//   r.activate();
+//   r.state.reference_orientation = Orientation(az);
+//   r.get_source(id)->gain = 0.5f;
+//   r.audio_callback(1024, in, out);
+//
+// Whole blocks are batched into ONE engine step (forward FFT -> MAC -> inverse
+// FFT + crossfade + source sum); there is no per-pair convolve() call and no
+// worker-thread fan-out ("threads" is accepted and ignored).
+//
+// Out of scope and therefore different: GenericRenderer takes its loudspeaker
+// count from the parameter "outputs" (the reference parses the reproduction-setup
+// XML, src/loudspeakerrenderer.h:95-150); IR files are read by the small WAV
+// reader below instead of libsndfile (PCM 8/16/24/32 and IEEE float 32/64).
+#ifndef SSR_B200_SSR_RENDERERS_H
+#define SSR_B200_SSR_RENDERERS_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ssr_b200.h"
+
+#ifndef APF_PARAMETER_MAP_H
+namespace apf
+{
+/// Minimal stand-in for apf::parameter_map (apf/apf/parameter_map.h): a
+/// string -> string map with typed set/get.  If the reference header was
+/// included first, that one is used instead.
+class parameter_map
+{
+  public:
+    template<typename T>
+    const std::string& set(const std::string& k, const T& v)
+    {
+      std::ostringstream ss; ss << std::boolalpha << v;
+      return _map[k] = ss.str();
+    }
+    bool has_key(const std::string& k) const { return _map.count(k) != 0; }
+    const std::string& operator[](const std::string& k) const
+    {
+      auto it = _map.find(k);
+      if (it == _map.end()) throw std::out_of_range("Key \"" + k + "\" doesn't exist in map!");
+      return it->second;
+    }
+    template<typename T> T get(const std::string& k) const
+    {
+      std::istringstream ss((*this)[k]);
+      T v = T();
+      ss >> std::boolalpha >> v;
+      if (ss.fail()) throw std::invalid_argument("S2RV(): Couldn't convert \"" + (*this)[k] + "\"!");
+      return v;
+    }
+    template<typename T> T get(const std::string& k, const T& def) const
+    {
+      if (!has_key(k)) return def;
+      std::istringstream ss((*this)[k]);
+      T v = def;
+      ss >> std::boolalpha >> v;
+      return ss.fail() ? def : v;
+    }
+    std::string get(const std::string& k, const char* def) const
+    { return has_key(k) ? (*this)[k] : std::string(def); }
+  private:
+    std::map<std::string, std::string> _map;
+};
+}  // namespace apf
+#endif
+
+#ifndef SSR_POSITION_H
+struct Position { explicit Position(float x_ = 0, float y_ = 0) : x(x_), y(y_) {} float x, y; };
+#endif
+#ifndef SSR_ORIENTATION_H
+struct Orientation { explicit Orientation(float a = 0) : azimuth(a) {} float azimuth; };
+#endif
+
+namespace ssr
+{
+
+namespace b200
+{
+inline void check(int rc)
+{
+  if (rc == SSR_OK) return;
+  const std::string msg = ssr_last_error();
+  if (rc == SSR_ERR_CUDA || rc == SSR_ERR_NOMEM) throw std::runtime_error(msg);
+  throw std::logic_error(msg);  // the reference throws std::logic_error for bad IR sets
+}
+
+/// Interleaved float samples of a WAV file (frames x channels).
+struct SoundFile
+{
+  int channels = 0, samplerate = 0;
+  long frames = 0;
+  std::vector<float> data;
+};
+
+inline uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (uint32_t(p[3]) << 24); }
+inline uint16_t rd16(const unsigned char* p) { return uint16_t(p[0] | (p[1] << 8)); }
+
+/// Replaces apf::load_sndfile (apf/apf/sndfiletools.h:43-90), same checks and
+/// std::logic_error messages.
+inline SoundFile load_sndfile(const std::string& name, size_t sample_rate, size_t channels)
+{
+  if (name == "") throw std::logic_error("apf::load_sndfile(): Empty file name!");
+  SoundFile sf;
+  std::FILE* f = std::fopen(name.c_str(), "rb");
+  auto fail = [&] { if (f) std::fclose(f);
+    throw std::logic_error("apf::load_sndfile(): \"" + name + "\" couldn't be loaded!"); };
+  if (!f) fail();
+  unsigned char hdr[12];
+  if (std::fread(hdr, 1, 12, f) != 12 || std::memcmp(hdr, "RIFF", 4) || std::memcmp(hdr + 8, "WAVE", 4)) fail();
+  int format = 0, bits = 0;
+  bool have_fmt = false;
+  for (;;)
+  {
+    unsigned char ch[8];
+    if (std::fread(ch, 1, 8, f) != 8) fail();
+    const uint32_t size = rd32(ch + 4);
+    if (!std::memcmp(ch, "fmt ", 4))
+    {
+      std::vector<unsigned char> fmt(size);
+      if (size < 16 || std::fread(fmt.data(), 1, size, f) != size) fail();
+      format = rd16(fmt.data());
+      sf.channels = rd16(fmt.data() + 2);
+      sf.samplerate = int(rd32(fmt.data() + 4));
+      bits = rd16(fmt.data() + 14);
+      if (format == 0xFFFE && size >= 26) format = rd16(fmt.data() + 24);  // WAVE_FORMAT_EXTENSIBLE
+      have_fmt = true;
+      if (size & 1) std::fseek(f, 1, SEEK_CUR);
+    }
+    else if (!std::memcmp(ch, "data", 4))
+    {
+      if (!have_fmt || sf.channels <= 0 || bits % 8 != 0) fail();
+      const size_t bps = size_t(bits) / 8;
+      std::vector<unsigned char> raw(size);
+      const size_t got = std::fread(raw.data(), 1, size, f);
+      const size_t n = got / bps;
+      sf.frames = long(n / size_t(sf.channels));
+      sf.data.resize(size_t(sf.frames) * sf.channels);
+      for (size_t i = 0; i < sf.data.size(); ++i)
+      {
+        const unsigned char* p = raw.data() + i * bps;
+        float v = 0.0f;
+        if (format == 1)  // PCM, scaled like libsndfile's float conversion
+        {
+          if (bits == 8) v = (float(p[0]) - 128.0f) / 128.0f;
+          else if (bits == 16) v = float(int16_t(rd16(p))) / 32768.0f;
+          else if (bits == 24) v = float(int32_t((p[0] << 8) | (p[1] << 16) | (uint32_t(p[2]) << 24)) >> 8) / 8388608.0f;
+          else if (bits == 32) v = float(double(int32_t(rd32(p))) / 2147483648.0);
+          else fail();
+        }
+        else if (format == 3)
+        {
+          if (bits == 32) { uint32_t u = rd32(p); std::memcpy(&v, &u, 4); }
+          else if (bits == 64) { double d; std::memcpy(&d, p, 8); v = float(d); }
+          else fail();
+        }
+        else fail();
+        sf.data[i] = v;
+      }
+      break;
+    }
+    else std::fseek(f, long(size + (size & 1)), SEEK_CUR);
+  }
+  std::fclose(f);
+  f = nullptr;
+  if (!sf.channels) fail();
+  if (sample_rate && sample_rate != size_t(sf.samplerate))
+    throw std::logic_error("apf::load_sndfile(): \"" + name + "\" has sample rate "
+        + std::to_string(sf.samplerate) + " instead of " + std::to_string(sample_rate) + "!");
+  if (channels && channels != size_t(sf.channels))
+    throw std::logic_error("apf::load_sndfile(): \"" + name + "\" has "
+        + std::to_string(sf.channels) + " channels instead of " + std::to_string(channels) + "!");
+  return sf;
+}
+
+/// Assignable control value forwarding to a C setter (stands in for
+/// apf::SharedData<T>, apf/apf/shareddata.h:35-83: assignment takes effect at the
+/// start of the next audio_callback).
+template<typename T, typename F>
+class Shared
+{
+  public:
+    Shared(T init, F f) : _v(init), _f(f) {}
+    Shared& operator=(const T& v) { _v = v; _f(v); return *this; }
+    operator const T&() const { return _v; }
+    const T& get() const { return _v; }
+  private:
+    T _v; F _f;
+};
+
+enum model_t { point = 0, plane = 1 };
+
+class RendererCore
+{
+  public:
+    class Source
+    {
+      public:
+        Source(ssr_renderer* r, int id_)
+          : id(id_)
+          , position(Position(), [r, id_](const Position& p) { check(ssr_source_set_position(r, id_, p.x, p.y)); })
+          , orientation(Orientation(), [](const Orientation&) {})
+          , gain(1.0f, [r, id_](float g) { check(ssr_source_set_gain(r, id_, g)); })
+          , mute(false, [r, id_](bool m) { check(ssr_source_set_mute(r, id_, m)); })
+          , model(point, [r, id_](model_t m) { check(ssr_source_set_model(r, id_, m == plane)); })
+        {}
+        const int id;
+        Shared<Position, std::function<void(const Position&)>> position;
+        Shared<Orientation, std::function<void(const Orientation&)>> orientation;
+        Shared<float, std::function<void(float)>> gain;
+        Shared<bool, std::function<void(bool)>> mute;
+        Shared<model_t, std::function<void(model_t)>> model;
+    };
+
+    struct State
+    {
+      explicit State(ssr_renderer*& r)
+        : reference_position(Position(), [&r](const Position& p) { check(ssr_renderer_set_reference_position(r, p.x, p.y)); })
+        , reference_orientation(Orientation(), [&r](const Orientation& o) { check(ssr_renderer_set_reference_orientation(r, o.azimuth)); })
+        , reference_offset_position(Position(), [&r](const Position& p) { check(ssr_renderer_set_reference_offset_position(r, p.x, p.y)); })
+        , reference_offset_orientation(Orientation(), [&r](const Orientation& o) { check(ssr_renderer_set_reference_offset_orientation(r, o.azimuth)); })
+        , master_volume(1.0f, [&r](float v) { check(ssr_renderer_set_master_volume(r, v)); })
+        , processing(true, [&r](bool v) { check(ssr_renderer_set_processing(r, v)); })
+        , amplitude_reference_distance(3.0f, [&r](float v) { check(ssr_renderer_set_amplitude_reference_distance(r, v)); })
+      {}
+      Shared<Position, std::function<void(const Position&)>> reference_position;
+      Shared<Orientation, std::function<void(const Orientation&)>> reference_orientation;
+      Shared<Position, std::function<void(const Position&)>> reference_offset_position;
+      Shared<Orientation, std::function<void(const Orientation&)>> reference_offset_orientation;
+      Shared<float, std::function<void(float)>> master_volume;
+      Shared<bool, std::function<void(bool)>> processing;
+      Shared<float, std::function<void(float)>> amplitude_reference_distance;
+    };
+
+    int block_size() const { return _block_size; }
+    int sample_rate() const { return _sample_rate; }
+    int in_channels() const { return ssr_renderer_sources(_r); }
+    int out_channels() const { return ssr_renderer_local_outputs(_r); }
+
+    bool activate() { return true; }
+    bool deactivate() { return true; }
+
+    /// = pointer_policy::audio_callback (apf/apf/pointer_policy.h:112-122)
+    void audio_callback(int n, float* const* in, float* const* out)
+    {
+      check(ssr_renderer_process(_r, n, in, out));
+    }
+
+    Source* get_source(int id)
+    {
+      auto it = _sources.find(id);
+      return it == _sources.end() ? nullptr : it->second.get();
+    }
+
+    void rem_source(Source* s)
+    {
+      if (!s) return;
+      check(ssr_renderer_rem_source(_r, s->id));
+      _sources.erase(s->id);
+    }
+
+    void rem_all_sources() { while (!_sources.empty()) rem_source(_sources.begin()->second.get()); }
+
+    const apf::parameter_map params;
+    State state;
+
+    ssr_renderer* handle() const { return _r; }
+    ssr_engine* engine() const { return _e; }
+
+    RendererCore(const RendererCore&) = delete;
+    RendererCore& operator=(const RendererCore&) = delete;
+
+  protected:
+    RendererCore(const apf::parameter_map& p, ssr_renderer_kind kind)
+      : params(p), state(_r)
+      , _block_size(p.get<int>("block_size")), _sample_rate(p.get<int>("sample_rate"))
+      , _e(nullptr), _r(nullptr)
+    {
+      ssr_engine_config ec = ssr_engine_config();
+      ec.device = p.get("device", 0);
+      ec.block_size = _block_size;
+      ec.sample_rate = _sample_rate;
+      check(ssr_engine_create(&ec, &_e));
+      ssr_renderer_config rc = ssr_renderer_config();
+      rc.kind = kind;
+      rc.outputs = kind == SSR_RENDERER_GENERIC ? p.get("outputs", 0) : 2;
+      rc.output_first = p.get("output_first", 0);
+      rc.output_count = p.get("output_count", 0);
+      rc.master_volume_correction_db = float(p.get("master_volume_correction", 0.0));
+      const int rc_ = ssr_renderer_create(_e, &rc, &_r);
+      if (rc_ != SSR_OK) { const std::string m = ssr_last_error(); ssr_engine_destroy(_e); _e = nullptr;
+        throw std::logic_error(m); }
+    }
+
+    ~RendererCore()
+    {
+      _sources.clear();
+      if (_r) ssr_renderer_destroy(_r);
+      if (_e) ssr_engine_destroy(_e);
+    }
+
+    int register_source(int id)
+    {
+      _sources[id].reset(new Source(_r, id));
+      return id;
+    }
+
+    const int _block_size, _sample_rate;
+    ssr_engine* _e;
+    ssr_renderer* _r;
+    std::map<int, std::unique_ptr<Source>> _sources;
+};
+}  // namespace b200
+
+class GenericRenderer : public b200::RendererCore
+{
+  public:
+    static const char* name() { return "GenericRenderer"; }
+    explicit GenericRenderer(const apf::parameter_map& p) : RendererCore(p, SSR_RENDERER_GENERIC) {}
+    void load_reproduction_setup() {}  // loudspeaker count comes from "outputs"
+
+    /// = add_source with GenericRenderer::Source (src/genericrenderer.h:88-120):
+    /// "properties_file" must have exactly as many channels as there are outputs.
+    int add_source(const apf::parameter_map& p = apf::parameter_map())
+    {
+      auto ir = b200::load_sndfile(p.get("properties_file", ""), size_t(sample_rate())
+          , size_t(params.get("outputs", 0)));
+      int id = 0;
+      b200::check(ssr_renderer_add_source(_r, ir.data.data(), ir.frames, ir.channels, &id));
+      return register_source(id);
+    }
+};
+
+class BrsRenderer : public b200::RendererCore
+{
+  public:
+    static const char* name() { return "BrsRenderer"; }
+    explicit BrsRenderer(const apf::parameter_map& p) : RendererCore(p, SSR_RENDERER_BRS) {}
+    void load_reproduction_setup() {}  // two outputs (src/brsrenderer.h:278-301)
+
+    /// = add_source with BrsRenderer::Source (src/brsrenderer.h:90-139)
+    int add_source(const apf::parameter_map& p = apf::parameter_map())
+    {
+      auto ir = b200::load_sndfile(p.get("properties_file", ""), size_t(sample_rate()), 0);
+      int id = 0;
+      b200::check(ssr_renderer_add_source(_r, ir.data.data(), ir.frames, ir.channels, &id));
+      return register_source(id);
+    }
+};
+
+class BinauralRenderer : public b200::RendererCore
+{
+  public:
+    static const char* name() { return "BinauralRenderer"; }
+    explicit BinauralRenderer(const apf::parameter_map& p) : RendererCore(p, SSR_RENDERER_BINAURAL) {}
+
+    /// = BinauralRenderer::load_reproduction_setup -> _load_hrtfs
+    /// (src/binauralrenderer.h:117-169, 211-233)
+    void load_reproduction_setup()
+    {
+      auto hrirs = b200::load_sndfile(params["hrir_file"], size_t(sample_rate()), 0);
+      b200::check(ssr_renderer_load_hrirs(_r, hrirs.data.data(), hrirs.frames, hrirs.channels
+            , long(params.get("hrir_size", 0))));
+    }
+
+    int add_source(const apf::parameter_map& = apf::parameter_map())
+    {
+      int id = 0;
+      b200::check(ssr_renderer_add_source(_r, nullptr, 0, 0, &id));
+      return register_source(id);
+    }
+};
+
+}  // namespace ssr
+
+#endif
