@@ -207,6 +207,7 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   p.B = B;
   p.wtab_offset = wtab_offset;
   p.partial_offset = partial_offset;
+  p.l2_hints = (mac_variant == 3) ? 0 : 1;
   void* fn = mac_kernel_ptr(plan.MT, mac_nv(B));
   void* args[] = { &p };
   dim3 grid(nwork, mac_ktiles(B), 1);

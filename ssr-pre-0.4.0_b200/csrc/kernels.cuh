@@ -66,6 +66,38 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p)
   return r;
 }
 
+// L2 eviction-priority hints: the H stream (read once per block, 25 GB >> L2)
+// is marked evict-first, the frequency-domain delay line X (re-read by every
+// output group) evict-last, so H does not push X out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_normal()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ float4 ldg_stream_hint(const float4* p, uint64_t pol)
+{
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+
 // ---------------------------------------------------------------- FFT core
 // Complex FFT of size m (power of two) in shared memory, Stockham autosort,
 // radix-4 stages plus one radix-2 stage when log2(m) is odd.  `a` holds the
@@ -267,6 +299,7 @@ struct MacParams
   int B;
   int wtab_offset;                   // added to wslot (selects the weight "kind")
   int partial_offset;                // added to work.z
+  int l2_hints;                      // 1: evict-first for H, evict-last for X
 };
 
 constexpr int kMacTile = 64;
@@ -287,6 +320,8 @@ mac_kernel(const MacParams p)
   // B > 1024: blockIdx.y selects a 1024-bin tile of the spectrum
   const int tile_off = blockIdx.y * (NV * kThreads);
   const int tt = tile_off + t;
+  const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+  const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
 
   float4 acc[MT][NV];
   float nyq[MT];
@@ -348,12 +383,12 @@ mac_kernel(const MacParams p)
     { \
       const float4* xp = s_x[i]; \
       _Pragma("unroll") for (int v = 0; v < NV; ++v) \
-        if (valid[v]) xb[buf][v] = ldg_stream(xp + tt + v * kThreads); \
+        if (valid[v]) xb[buf][v] = ldg_stream_hint(xp + tt + v * kThreads, pol_x); \
       _Pragma("unroll") for (int j = 0; j < MT; ++j) \
       { \
         const float4* hp = s_h[i][j]; \
         _Pragma("unroll") for (int v = 0; v < NV; ++v) \
-          if (valid[v]) hb[buf][j][v] = ldg_stream(hp + tt + v * kThreads); \
+          if (valid[v]) hb[buf][j][v] = ldg_stream_hint(hp + tt + v * kThreads, pol_h); \
       } \
     }
 
@@ -459,15 +494,35 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
   {
     const InvEntry en = entries[job.first_entry + e];
     // A[k] = sum over split partials
-    for (int k = t; k < B; k += kThreads)
+    // (float4 = two bins per thread; the loop over partials is unrolled so that
+    // 8 independent loads are in flight per thread)
     {
-      float2 s = make_float2(0.f, 0.f);
-      for (int c = 0; c < en.part_count; ++c)
+      const float4* pbase = reinterpret_cast<const float4*>(partials)
+          + (size_t(en.part_first) * en.part_stride + en.part_row) * (B >> 1);
+      const size_t pstride = size_t(en.part_stride) * (B >> 1);
+      for (int k = t; k < (B >> 1); k += kThreads)
       {
-        const float2 v = partials[(size_t(en.part_first + c) * en.part_stride + en.part_row) * B + k];
-        s.x += v.x; s.y += v.y;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        int c = 0;
+        for (; c + 8 <= en.part_count; c += 8)
+        {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(pbase + size_t(c + u) * pstride + k);
+#pragma unroll
+          for (int u = 0; u < 8; u += 2)
+          {
+            s0.x += v[u].x; s0.y += v[u].y; s0.z += v[u].z; s0.w += v[u].w;
+            s1.x += v[u + 1].x; s1.y += v[u + 1].y; s1.z += v[u + 1].z; s1.w += v[u + 1].w;
+          }
+        }
+        for (; c < en.part_count; ++c)
+        {
+          const float4 v = __ldcs(pbase + size_t(c) * pstride + k);
+          s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+        }
+        reinterpret_cast<float4*>(a)[k] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
       }
-      a[k] = s;
     }
     __syncthreads();
     // Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k])
