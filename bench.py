@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--mac-variant", type=int, default=0)
+    ap.add_argument("--static-head", action="store_true", help="Binaural/BRS: no head rotation")
     return ap.parse_args()
 
 
@@ -141,8 +142,11 @@ def run_reference_renderer(w, out_shard: int, blocks: int, warm: int, threads: i
     scale = wl.ir_scale(w.sources, env)
     r = ref.Renderer("generic", w.block, w.fs, threads=threads)
     r.add_outputs(out_shard)
+    import ssr_b200.capi as capi
     for n in range(w.sources):
-        ir = wl.generic_ir(w, n, 0, out_shard, env, scale)
+        # same synthetic IRs as the GPU run (host twin of the device generator)
+        ir = np.stack([capi.synth_ir(w.ir_seed, n * w.outputs + m, w.taps, env, scale)
+                       for m in range(out_shard)], axis=1)
         name = f"bench_ir_{n}"
         ref.register_sndfile(name, ir, w.fs)
         r.add_source(name)
@@ -154,6 +158,74 @@ def run_reference_renderer(w, out_shard: int, blocks: int, warm: int, threads: i
         r.run(x, warm, want_output=False)
     _, secs, times = r.run(x, blocks, want_output=False, want_times=True)
     return secs, times
+
+
+def run_reference_dynamic(w, n_sources: int, blocks: int, warm: int, threads: int, rotate: bool):
+    """The reference's own BrsRenderer / BinauralRenderer on host cores with
+    `n_sources` of the workload's sources and the head rotating one filter step
+    per block (the same control script as the GPU run)."""
+    from oracle import ref
+    import ssr_b200.capi as capi
+    import ssr_b200.workloads as wl
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    angles = w.channels // 2
+
+    def ir_set(offset):
+        cols = [capi.synth_ir(w.ir_seed, offset + c, w.taps, env, scale) for c in range(w.channels)]
+        return np.stack(cols, axis=1)
+
+    if w.kind == "brs":
+        r = ref.Renderer("brs", w.block, w.fs, threads=threads)
+        r.load_reproduction_setup()
+        for n in range(n_sources):
+            ref.register_sndfile("bench_brir", ir_set(n * w.channels), w.fs)
+            r.add_source("bench_brir")
+            ref.unregister_sndfile("bench_brir")
+    else:
+        ref.register_sndfile("bench_hrir", ir_set(0), w.fs)
+        r = ref.Renderer("binaural", w.block, w.fs, threads=threads, hrir_file="bench_hrir")
+        r.load_reproduction_setup()
+        for i in range(n_sources):
+            sid = r.add_source()
+            a = 2 * np.pi * i / w.sources
+            r.set_source(sid, "position", float(2 * np.cos(a)), float(2 * np.sin(a)))
+    r.activate()
+    x = np.stack([wl.signal_block(w, t, n_sources) for t in range(4)])
+    az = lambda t0, n: np.array([((t0 + t) * 360.0 / angles) % 360.0 if rotate else 0.0 for t in range(n)],
+                                np.float32)
+    if warm > 0:
+        r.run(x, warm, azimuth=az(0, warm), want_output=False)
+    _, secs, times = r.run(x, blocks, azimuth=az(warm, blocks), want_output=False, want_times=True)
+    return secs, times
+
+
+def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, rotate: bool = True):
+    """Runs the reference CPU arm on a bounded sample of workload `w`.
+    Returns (full-workload ms per block, per-block ms scaled, cores used, sample text)."""
+    from oracle import ref
+    if w.kind == "generic":
+        shard = reference_plan(w, steps, warmup, budget_s, threads)
+        used = max(1, min(threads, shard))  # items are spread round-robin over outputs
+        secs, times = run_reference_renderer(w, shard, steps, warmup, used)
+        factor = w.outputs / shard
+        what = f"{w.sources} src x {shard} of {w.outputs} outputs x {w.taps} taps"
+    else:
+        # cost ~ sources * 2 ears * partitions * (1 or 2 evaluations)
+        per_src = 2 * w.partitions * (2 if rotate else 1) * 1.6e-6 * 1.6
+        nsrc = w.sources
+        while nsrc > 1 and (per_src * nsrc / max(1, min(threads, nsrc)) * (steps + warmup) > budget_s
+                            or nsrc * w.channels * (w.partitions * 8 * w.block + 4 * w.taps) > 24e9):
+            nsrc //= 2
+        used = max(1, min(threads, nsrc))
+        secs, times = run_reference_dynamic(w, nsrc, steps, warmup, used, rotate)
+        factor = w.sources / nsrc
+        what = (f"{nsrc} of {w.sources} src x 2 ears, {w.channels}-channel {w.taps}-tap set, "
+                f"head {'rotating one step per block' if rotate else 'static'}")
+    full_ms = secs / steps * 1e3 * factor
+    sample = (f"reference {w.name}: {what}; {steps} blocks after {warmup} warm-up; block time scaled "
+              f"x{factor:g} to the full workload{' (extrapolated)' if factor != 1 else ''}; {ref.describe()}")
+    return full_ms, times * factor, used, sample
 
 
 def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int):
@@ -180,16 +252,10 @@ def main_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libssr_ref.so not built"}))
         return 0
     steps, warmup = args.steps, args.warmup
-    shard = reference_plan(w, steps, warmup, 150.0, threads)
-    threads_used = max(1, min(threads, shard))  # items are spread round-robin over outputs
-    secs, times = run_reference_renderer(w, shard, steps, warmup, threads_used)
-    ms = secs / steps * 1e3
-    # the shard does shard/outputs of the MAC + IFFT work of a block
-    full_ms = ms * (w.outputs / shard)
+    entry.load_package()
+    full_ms, times, threads_used, sample = reference_sample(w, steps, warmup, 150.0, threads,
+                                                            rotate=not args.static_head)
     value = (w.block / w.fs) / (full_ms * 1e-3)
-    sample = (f"reference GenericRenderer {w.sources} src x {shard} of {w.outputs} outputs x {w.taps} taps, "
-              f"{steps} blocks after {warmup} warm-up; block time scaled x{w.outputs // shard} to the full "
-              f"output count (extrapolated); {ref.describe()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": full_ms, "higher_is_better": True,
@@ -199,7 +265,7 @@ def main_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads_used, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "p99_block_ms": float(np.percentile(times, 99)) * (w.outputs / shard),
+        "p99_block_ms": float(np.percentile(times, 99)),
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -230,7 +296,13 @@ def main_ours(args):
 
     w, reduced = get_workload(args)
     B = w.block
-    m_first, m_local = mg.shard_outputs(w.outputs, world, rank)
+    if w.kind == "generic":
+        m_first, m_local = mg.shard_outputs(w.outputs, world, rank)
+    else:
+        # Binaural / BRS have two outputs and do not shard (replicas only)
+        if world > 1:
+            raise SystemExit(f"{args.workload} does not shard over GPUs (replicas only); run with --gpus 1")
+        m_first, m_local = 0, 2
 
     # a dedicated (non-default) stream shared by torch, NCCL and the engine, so
     # that torch.cuda.Event timing sees the engine's kernels
@@ -238,18 +310,42 @@ def main_ours(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     eng = capi.Engine(B, w.fs, device=local_rank, stream=stream.cuda_stream, mac_variant=args.mac_variant)
-    ren = capi.Renderer(eng, capi.GENERIC, outputs=w.outputs, output_first=m_first, output_count=m_local)
     env = wl.envelope(w.taps)
     scale = wl.ir_scale(w.sources, env)
     t0 = time.time()
-    for n in range(w.sources):
-        # filter-set loading (north_star item 1): generated and transformed on the
-        # device, resident in HBM; channel id = source * outputs + output
-        ren.add_source_synthetic(w.taps, w.outputs, w.ir_seed,
-                                 channel_id_offset=mg.channel_id_offset(n, w.outputs),
-                                 envelope=env, scale=scale)
+    # filter-set loading (north_star item 1): generated and transformed on the
+    # device, resident in HBM
+    if w.kind == "generic":
+        ren = capi.Renderer(eng, capi.GENERIC, outputs=w.outputs, output_first=m_first, output_count=m_local)
+        for n in range(w.sources):
+            # channel id = source * outputs + output
+            ren.add_source_synthetic(w.taps, w.outputs, w.ir_seed,
+                                     channel_id_offset=mg.channel_id_offset(n, w.outputs),
+                                     envelope=env, scale=scale)
+    elif w.kind == "brs":
+        ren = capi.Renderer(eng, capi.BRS)
+        for n in range(w.sources):
+            ren.add_source_synthetic(w.taps, w.channels, w.ir_seed, channel_id_offset=n * w.channels,
+                                     envelope=env, scale=scale)
+    elif w.kind == "binaural":
+        ren = capi.Renderer(eng, capi.BINAURAL)
+        ren.generate_hrirs(w.channels, w.taps, w.ir_seed, envelope=env, scale=scale)
+        ids = [ren.add_source() for _ in range(w.sources)]
+        for i, sid in enumerate(ids):  # sources on a 2 m circle around the listener
+            a = 2 * np.pi * i / w.sources
+            ren.set_position(sid, float(2 * np.cos(a)), float(2 * np.sin(a)))
+    else:
+        raise SystemExit(f"workload kind {w.kind}: use ssr-pre-0.4.0_b200/lib/perf_static_convolver")
     eng.synchronize()
     load_s = time.time() - t0
+    angles = w.channels // 2 if w.kind != "generic" else 0
+    rotate = w.kind != "generic" and not args.static_head
+
+    def control(t):
+        # head rotation by one filter step per block: every (source, ear) switches
+        # filters each block -- the sustained crossfading case
+        if rotate:
+            ren.set_reference_orientation(float((t * 360.0 / angles) % 360.0))
 
     # input blocks: host (pinned) ring for e2e, device ring for `value`
     nring = 8
@@ -260,7 +356,8 @@ def main_ours(args):
     d_in_step = torch.empty((w.sources, B), dtype=torch.float32, device=dev)
     d_out = torch.zeros((m_local, B), dtype=torch.float32, device=dev)
     gathered = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
-    host_out = torch.empty((w.outputs, B), dtype=torch.float32).pin_memory()
+    n_out_total = w.outputs if w.kind == "generic" else 2
+    host_out = torch.empty((n_out_total, B), dtype=torch.float32).pin_memory()
 
     def gather():
         if world > 1:
@@ -268,10 +365,12 @@ def main_ours(args):
             dist.gather(d_out, gathered, dst=0)
 
     def step_device(t):
+        control(t)
         ren.process_device(dev_in[t % nring].data_ptr(), d_out.data_ptr())
         gather()
 
     def step_e2e(t):
+        control(t)
         d_in_step.copy_(host_in[t % nring], non_blocking=True)           # H2D (pinned)
         ren.process_device(d_in_step.data_ptr(), d_out.data_ptr())
         gather()
@@ -351,7 +450,7 @@ def main_ours(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "ssrk::mac_kernel<4,2>", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": "ssrk::mac_kernel<4,2>" if w.kind == "generic" else "ssrk::mac_kernel<2,2>", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "bytes_per_launch": st["mac_bytes"] / max(1, st["mac_launches"]),
         "ms_per_launch": mac_ms / max(1, st["mac_launches"]),
@@ -360,6 +459,7 @@ def main_ours(args):
         "ifft_ms_per_step": st["ms_ifft"] / max(1, st["blocks"]),
         "fft_gflops": (w.sources * 56320 / 1e9) / max(1e-12, st["ms_fft"] / max(1, st["blocks"]) * 1e-3),
         "ifft_gflops": (m_local * 56320 / 1e9) / max(1e-12, st["ms_ifft"] / max(1, st["blocks"]) * 1e-3),
+        "l2_resident": bool(st["mac_bytes"] / max(1, st["mac_launches"]) < 100e6),
     }
     launches = int(st["mac_launches"] + st["fft_launches"] + st["ifft_launches"])
 
@@ -372,12 +472,15 @@ def main_ours(args):
             "config": {"workload": w.label() + (" [REDUCED]" if reduced else ""), "block": B,
                        "sample_rate": w.fs, "partitions": w.partitions,
                        "parallelism": f"outputs sharded x{world}" if world > 1 else "single GPU",
+                       "head_rotation": ("one filter step per block" if rotate else "none") if w.kind != "generic" else "n/a",
                        "outputs_per_gpu": m_local, "l2": "inputs>L2 (spectra per GPU >> 126 MB)",
                        "filter_load_s": load_s,
-                       "spectra_gb_per_gpu": w.sources * m_local * w.partitions * 8 * B / 1e9},
+                       "spectra_gb_per_gpu": (w.sources * m_local if w.kind == "generic" else
+                                              (w.sources if w.kind == "brs" else 1) * w.channels)
+                       * w.partitions * 8 * B / 1e9},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": w.sources * B * 4 * world,
-                    "d2h_bytes_per_step": w.outputs * B * 4,
+                    "d2h_bytes_per_step": n_out_total * B * 4,
                     "ms_per_step": e2e_ms_total / K, "mode": "synchronous per block"},
             "p99_block_ms": p99,
             "gpu_launches": launches,
@@ -391,15 +494,10 @@ def main_ours(args):
             from oracle import ref
             if ref.available():
                 threads = os.cpu_count() or 1
-                shard = reference_plan(w, 40, 5, args.cpu_seconds, threads)
-                used = max(1, min(threads, shard))
-                secs, _ = run_reference_renderer(w, shard, 40, 5, used)
-                full_ms = secs / 40 * 1e3 * (w.outputs / shard)
+                full_ms, _, used, sample = reference_sample(w, 40, 5, args.cpu_seconds, threads, rotate=rotate)
                 line["cpu_baseline"] = {
                     "value": (B / w.fs) / (full_ms * 1e-3), "unit": UNIT, "cores": used, "kind": "reference",
-                    "sample": (f"reference GenericRenderer {w.sources} src x {shard} of {w.outputs} outputs, "
-                               f"40 blocks after 5 warm-up, block time scaled x{w.outputs // shard} "
-                               f"(extrapolated); {ref.describe()}")}
+                    "sample": sample}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref/libssr_ref.so missing"}

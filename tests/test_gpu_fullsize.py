@@ -1,0 +1,180 @@
+"""GPU parity at BASELINE.json's FULL sizes through size-independent properties
+(the oracle would need minutes to hours there): impulse-in -> impulse-response-out
+against host-regenerated synthetic IRs, linearity, and shard == slice.
+Tolerance 1e-5 of full scale (IRs are scaled so |y| ~<= 1 for full-scale input)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _wl():
+    import ssr_b200.workloads as wl
+    return wl
+
+
+def _impulse_blocks(w, hits, nblocks):
+    """hits: {source: (block, sample, amplitude)} -> (nblocks, sources, B) input."""
+    x = np.zeros((nblocks, w.sources, w.block), np.float32)
+    for n, (t, s, a) in hits.items():
+        x[t, n, s] = a
+    return x
+
+
+def _expected(w, capi, hits, out_channels, nblocks, ir_of):
+    """Sum of shifted, scaled IRs for the listed output channels: (len(out), nblocks * B)."""
+    T = nblocks * w.block
+    y = np.zeros((len(out_channels), T), np.float64)
+    for n, (t, s, a) in hits.items():
+        start = t * w.block + s
+        for i, m in enumerate(out_channels):
+            h = ir_of(n, m).astype(np.float64) * a
+            stop = min(T, start + h.size)
+            y[i, start:stop] += h[: stop - start]
+    return y
+
+
+def test_cfg4_generic_64x64_impulse_responses_and_linearity(capi, engine_factory):
+    wl = _wl()
+    w = wl.WORKLOADS["cfg4"]
+    e = engine_factory(w.block)
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+
+    def make():
+        r = capi.Renderer(e, capi.GENERIC, outputs=w.outputs)
+        for n in range(w.sources):
+            r.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
+                                   envelope=env, scale=scale)
+        return r
+
+    r = make()
+    nb = w.partitions + 4
+    hits = {3: (2, 17, 1.0), 40: (3, 1000, -0.5), 63: (2, 0, 0.25)}
+    x = _impulse_blocks(w, hits, nb)
+    y = np.stack([r.process(x[t]) for t in range(nb)])            # (nb, M, B)
+    y = y.transpose(1, 0, 2).reshape(w.outputs, -1)
+    outs = list(range(w.outputs))
+    exp = _expected(w, capi, hits, outs, nb, lambda n, m: capi.synth_ir(w.ir_seed, n * w.outputs + m, w.taps, env, scale))
+    assert np.abs(y - exp).max() <= TOL
+
+    # linearity on noise: R(a x1 + b x2) == a R(x1) + b R(x2)
+    ra, rb, rc = make(), make(), r
+    r.close()
+    rc = make()
+    a, b = np.float32(0.5), np.float32(-0.25)
+    worst = 0.0
+    for t in range(12):
+        x1 = wl.signal_block(w, t)
+        x2 = wl.signal_block(w, 100 + t)
+        lhs = rc.process(a * x1 + b * x2)
+        rhs = a * ra.process(x1) + b * rb.process(x2)
+        worst = max(worst, float(np.abs(lhs - rhs).max()))
+    assert worst <= TOL
+
+
+def test_cfg5_generic_128x512_x48000_impulse_responses(capi, engine_factory):
+    wl = _wl()
+    w = wl.WORKLOADS["cfg5"]                                        # 25.2 GB of spectra
+    e = engine_factory(w.block)
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    r = capi.Renderer(e, capi.GENERIC, outputs=w.outputs)
+    for n in range(w.sources):
+        r.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
+                               envelope=env, scale=scale)
+    nb = w.partitions + 3
+    hits = {0: (1, 5, 1.0), 77: (2, 513, 0.75), 127: (1, 1023, -1.0)}
+    x = _impulse_blocks(w, hits, nb)
+    y = np.stack([r.process(x[t]) for t in range(nb)]).transpose(1, 0, 2).reshape(w.outputs, -1)
+    outs = [0, 1, 2, 3, 63, 64, 200, 255, 256, 300, 447, 448, 510, 511]
+    exp = _expected(w, capi, hits, outs, nb, lambda n, m: capi.synth_ir(w.ir_seed, n * w.outputs + m, w.taps, env, scale))
+    assert np.abs(y[outs] - exp).max() <= TOL
+    # every other output is non-trivial too (no dead rows)
+    assert float(np.abs(y).max(axis=1).min()) > 1e-4
+
+    # an output shard renders exactly the corresponding slice (8-way sharding, rank 5)
+    s = capi.Renderer(e, capi.GENERIC, outputs=w.outputs, output_first=320, output_count=64)
+    for n in range(w.sources):
+        s.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
+                               envelope=env, scale=scale)
+    ys = np.stack([s.process(x[t]) for t in range(nb)]).transpose(1, 0, 2).reshape(64, -1)
+    assert np.array_equal(ys, y[320:384])
+
+
+def test_cfg3_brs_64_sources_360x2_brirs_head_turn(capi, engine_factory):
+    wl = _wl()
+    w = wl.WORKLOADS["cfg3"]                                        # 17.7 GB of spectra
+    e = engine_factory(w.block)
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    r = capi.Renderer(e, capi.BRS)
+    for n in range(w.sources):
+        r.add_source_synthetic(w.taps, w.channels, w.ir_seed, channel_id_offset=n * w.channels,
+                               envelope=env, scale=scale)
+    P = w.partitions
+    src = 5
+
+    def ir(angle_index, ear):
+        return capi.synth_ir(w.ir_seed, src * w.channels + 2 * angle_index + ear, w.taps, env, scale)
+
+    # 90 degrees is the middle of index 0 (src/brsrenderer.h:152-155); let the
+    # staggered switch settle (P - 1 rotations), then send an impulse
+    r.set_reference_orientation(90.0)
+    zero = np.zeros((w.sources, w.block), np.float32)
+    for _ in range(P + 1):
+        r.process(zero)
+    nb = P + 2
+    x = _impulse_blocks(w, {src: (0, 100, 1.0)}, nb)
+    y = np.stack([r.process(x[t]) for t in range(nb)]).transpose(1, 0, 2).reshape(2, -1)
+    for ear in range(2):
+        exp = np.zeros(nb * w.block)
+        h = ir(0, ear)
+        exp[100:100 + h.size] = h
+        assert np.abs(y[ear] - exp).max() <= TOL
+
+    # turn the head by 7 filter steps: index 7 = azimuth 97; every block keeps the
+    # filter that was current when it arrived, so after P blocks only BRIR pair 7 is heard
+    r.set_reference_orientation(97.0)
+    for _ in range(P + 1):
+        r.process(zero)
+    y = np.stack([r.process(x[t]) for t in range(nb)]).transpose(1, 0, 2).reshape(2, -1)
+    for ear in range(2):
+        exp = np.zeros(nb * w.block)
+        h = ir(7, ear)
+        exp[100:100 + h.size] = h
+        assert np.abs(y[ear] - exp).max() <= TOL
+
+
+def test_cfg2_binaural_32_sources_720_directions(capi, engine_factory):
+    wl = _wl()
+    w = wl.WORKLOADS["cfg2"]
+    e = engine_factory(w.block)
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    r = capi.Renderer(e, capi.BINAURAL)
+    r.generate_hrirs(w.channels, w.taps, w.ir_seed, envelope=env, scale=scale)
+    ids = [r.add_source() for _ in range(w.sources)]
+    angles = w.channels // 2
+    # source i at 2 m, azimuth i * 11.25 degrees -> weight 0.5 / 2, index = round(az * angles / 360)
+    az = [i * 360.0 / w.sources for i in range(w.sources)]
+    for i, sid in enumerate(ids):
+        a = np.deg2rad(az[i])
+        r.set_position(sid, float(2 * np.cos(a)), float(2 * np.sin(a)))
+    zero = np.zeros((w.sources, w.block), np.float32)
+    r.process(zero)
+    r.process(zero)
+    x = np.zeros((w.sources, w.block), np.float32)
+    for i in range(w.sources):
+        x[i, 3 * i] = 1.0                                            # staggered impulses
+    y = r.process(x)
+    exp = np.zeros((2, w.block))
+    for i in range(w.sources):
+        idx = int(np.float32(az[i]) * np.float32(angles) / np.float32(360.0) + np.float32(0.5)) % angles
+        for ear in range(2):
+            h = capi.synth_ir(w.ir_seed, 2 * idx + ear, w.taps, env, scale).astype(np.float64) * 0.25
+            n = min(w.block - 3 * i, h.size)
+            exp[ear, 3 * i:3 * i + n] += h[:n]
+    assert np.abs(y - exp).max() <= TOL
