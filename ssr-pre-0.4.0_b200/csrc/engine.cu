@@ -220,8 +220,25 @@ void Engine::launch_inv(const InvPlan& plan)
   const int njobs = int(plan.jobs.uploaded);
   if (njobs == 0) return;
   const size_t smem = size_t(2) * B * sizeof(float2);
+  // few output blocks with deep splits: reduce the partials in parallel first
+  const int nentries = int(plan.entries.uploaded);
+  int max_count = 0;
+  for (auto& en : plan.entries.host) max_count = std::max(max_count, en.part_count);
+  const bool pre_reduce = nentries > 0 && max_count >= 8 && njobs < 2 * sm_count;
+  const float2* red = nullptr;
+  if (pre_reduce)
+  {
+    const size_t need = size_t(nentries) * (B / 2);
+    if (need > reduced.count) { sync(); reduced.resize(need + need / 2); }
+    dim3 grid(nentries, (B / 2 + 31) / 32, 1);
+    reduce_partials_kernel<<<grid, kThreads, 0, stream>>>(plan.entries.dev.ptr, partials.ptr,
+        reduced.ptr, B / 2);
+    SSR_CUDA(cudaGetLastError());
+    if (cur) cur->ifft_launches++;
+    red = reinterpret_cast<const float2*>(reduced.ptr);
+  }
   inv_fft_kernel<<<njobs, kThreads, smem, stream>>>(plan.jobs.dev.ptr, plan.entries.dev.ptr,
-      reinterpret_cast<const float2*>(partials.ptr), B, tw.ptr, fade_out.ptr, fade_in.ptr);
+      reinterpret_cast<const float2*>(partials.ptr), red, B, tw.ptr, fade_out.ptr, fade_in.ptr);
   SSR_CUDA(cudaGetLastError());
   if (cur) cur->ifft_launches++;
 }

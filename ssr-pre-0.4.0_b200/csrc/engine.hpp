@@ -178,6 +178,7 @@ struct Engine
 
   Table<float> wtab;               // weight slots
   DeviceArray<float4> partials;
+  DeviceArray<float4> reduced;     // pre-reduced accumulators (see reduce_partials_kernel)
 
   // launches (all asynchronous on `stream`)
   void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs);

@@ -472,10 +472,48 @@ struct InvJob
 
 constexpr int kInvMaxRes = 8;  // B <= 4096: (B/2 float2) / 256 threads
 
+// Parallel pre-reduction of the split partial accumulators, used when there are
+// few output blocks but deep splits (Binaural / BRS: 2 outputs; sharded Generic):
+// grid (entries, (B/2)/32); warp w of a CTA sums partials w, w+8, ... for a
+// 64-bin tile, then the 8 warps are combined through shared memory.
+__global__ void __launch_bounds__(kThreads)
+reduce_partials_kernel(const InvEntry* __restrict__ entries, const float4* __restrict__ partials,
+                       float4* __restrict__ reduced, int nvec)
+{
+  __shared__ float4 s_part[kThreads / 32][32];
+  const InvEntry en = entries[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.y * 32 + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < nvec)
+  {
+    const float4* base = partials + (size_t(en.part_first) * en.part_stride + en.part_row) * nvec + idx;
+    const size_t pstride = size_t(en.part_stride) * nvec;
+#pragma unroll 4
+    for (int c = warp; c < en.part_count; c += kThreads / 32)
+    {
+      const float4 v = __ldcs(base + size_t(c) * pstride);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  s_part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && idx < nvec)
+  {
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w)
+    {
+      const float4 v = s_part[w][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reduced[size_t(blockIdx.x) * nvec + idx] = s;
+  }
+}
+
 // One CTA per output block.
 __global__ void __launch_bounds__(kThreads)
 inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
-               const float2* __restrict__ partials, int B,
+               const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
                const float2* __restrict__ tw,
                const float* __restrict__ fade_out, const float* __restrict__ fade_in)
 {
@@ -496,6 +534,12 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
     // A[k] = sum over split partials
     // (float4 = two bins per thread; the loop over partials is unrolled so that
     // 8 independent loads are in flight per thread)
+    if (reduced)
+    {
+      const float4* r = reinterpret_cast<const float4*>(reduced) + size_t(job.first_entry + e) * (B >> 1);
+      for (int k = t; k < (B >> 1); k += kThreads) reinterpret_cast<float4*>(a)[k] = __ldcs(r + k);
+    }
+    else
     {
       const float4* pbase = reinterpret_cast<const float4*>(partials)
           + (size_t(en.part_first) * en.part_stride + en.part_row) * (B >> 1);

@@ -101,7 +101,9 @@ def test_cfg5_generic_128x512_x48000_impulse_responses(capi, engine_factory):
         s.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
                                envelope=env, scale=scale)
     ys = np.stack([s.process(x[t]) for t in range(nb)]).transpose(1, 0, 2).reshape(64, -1)
-    assert np.array_equal(ys, y[320:384])
+    # (the split of the partition sum differs between the two plans, so equality
+    # holds to float32 summation order, not bit for bit)
+    assert np.abs(ys - y[320:384]).max() <= 2e-6
 
 
 def test_cfg3_brs_64_sources_360x2_brirs_head_turn(capi, engine_factory):

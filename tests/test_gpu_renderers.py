@@ -88,7 +88,7 @@ def test_generic_output_shards_equal_slices_of_full(capi, engine_factory):
         x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
         y = full.process(x)
         ys = np.concatenate([s.process(x) for s in shards])
-        assert np.array_equal(y, ys)
+        assert np.abs(y - ys).max() <= 2e-6  # same sum, possibly split differently
 
 
 def test_generic_wrong_channel_count_is_rejected(capi, engine_factory):
