@@ -8,7 +8,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libssr_b200.so")
+# SSR_B200_LIB: experiments only (A/B of two builds of the same library)
+LIB_PATH = os.environ.get("SSR_B200_LIB") or os.path.join(_HERE, "lib", "libssr_b200.so")
 
 SSR_OK = 0
 SSR_ERR_INVALID, SSR_ERR_BLOCK_SIZE, SSR_ERR_UNSUPPORTED = -1, -2, -3

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace ssr_b200
 {
@@ -53,15 +54,27 @@ void MacPlan::make_work(int slots)
 static int mac_nv(int B) { return B >= 1024 ? 2 : 1; }
 static int mac_ktiles(int B) { return B > 1024 ? B / 1024 : 1; }
 
-template<int MT, int NV> static void* mac_fn() { return (void*)mac_kernel<MT, NV>; }
+template<int MT, int NV, int ST = 2, int MINB = 1>
+static void* mac_fn() { return (void*)mac_kernel<MT, NV, ST, MINB>; }
 
-static void* mac_kernel_ptr(int MT, int NV)
+// variant (ssr_engine_config::mac_variant), experiments on the Generic kernel:
+//   0 default = 2-stage register pipeline, 2 CTAs / SM (128 registers): measured
+//     best, 6.7 TB/s on cfg5 even under the power cap (profiles/r1_mac_variants.md)
+//   1 = 3 stages, 4 = 4 stages (1 CTA / SM), 5 = 2 stages at 1 CTA / SM,
+//   3 = default without L2 eviction hints
+static void* mac_kernel_ptr(int MT, int NV, int variant)
 {
+  if (NV == 2 && MT == 4)
+  {
+    if (variant == 1) return mac_fn<4, 2, 3, 1>();
+    if (variant == 4) return mac_fn<4, 2, 4, 1>();
+    if (variant == 5) return mac_fn<4, 2, 2, 1>();
+    return mac_fn<4, 2, 2, 2>();
+  }
   if (NV == 2)
   {
     if (MT == 1) return mac_fn<1, 2>();
-    if (MT == 2) return mac_fn<2, 2>();
-    return mac_fn<4, 2>();
+    return mac_fn<2, 2>();
   }
   if (MT == 1) return mac_fn<1, 1>();
   if (MT == 2) return mac_fn<2, 1>();
@@ -72,6 +85,8 @@ Engine::Engine(const ssr_engine_config& cfg)
   : device(cfg.device), B(cfg.block_size), sample_rate(cfg.sample_rate)
   , mac_variant(cfg.mac_variant), stream(nullptr), own_stream(false)
 {
+  if (mac_variant == 0)
+    if (const char* v = std::getenv("SSR_B200_MAC_VARIANT")) mac_variant = std::atoi(v);  // experiments
   if (B <= 0 || B % 8 != 0)
     throw Error(SSR_ERR_BLOCK_SIZE, "Convolver: block size must be a multiple of 8!");
   if ((B & (B - 1)) != 0 || B > 4096)
@@ -167,7 +182,7 @@ int Engine::mac_slots() const
 {
   int occ = 0;
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, mac_kernel<4, 2>, kThreads, 0);
+      &occ, mac_kernel_ptr(4, 2, mac_variant), kThreads, 0);
   if (err != cudaSuccess || occ < 1) occ = 1;
   return sm_count * occ;
 }
@@ -208,7 +223,7 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   p.wtab_offset = wtab_offset;
   p.partial_offset = partial_offset;
   p.l2_hints = (mac_variant == 3) ? 0 : 1;
-  void* fn = mac_kernel_ptr(plan.MT, mac_nv(B));
+  void* fn = mac_kernel_ptr(plan.MT, mac_nv(B), mac_variant);
   void* args[] = { &p };
   dim3 grid(nwork, mac_ktiles(B), 1);
   SSR_CUDA(cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, stream));
