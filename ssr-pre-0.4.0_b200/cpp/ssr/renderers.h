@@ -115,6 +115,7 @@ struct SoundFile
 {
   int channels = 0, samplerate = 0;
   long frames = 0;
+  int format = 3, bits = 32;  // WAV format tag (1 PCM, 3 IEEE float) and sample width
   std::vector<float> data;
 };
 
@@ -188,6 +189,7 @@ inline SoundFile load_sndfile(const std::string& name, size_t sample_rate, size_
   }
   std::fclose(f);
   f = nullptr;
+  sf.format = format; sf.bits = bits;
   if (!sf.channels) fail();
   if (sample_rate && sample_rate != size_t(sf.samplerate))
     throw std::logic_error("apf::load_sndfile(): \"" + name + "\" has sample rate "
@@ -196,6 +198,40 @@ inline SoundFile load_sndfile(const std::string& name, size_t sample_rate, size_
     throw std::logic_error("apf::load_sndfile(): \"" + name + "\" has "
         + std::to_string(sf.channels) + " channels instead of " + std::to_string(channels) + "!");
   return sf;
+}
+
+/// Writes interleaved float samples as WAV (PCM 16/24/32 or IEEE float 32).
+inline void write_wav(const std::string& name, const float* data, long frames, int channels
+    , int samplerate, int format = 3, int bits = 32)
+{
+  if (!((format == 1 && (bits == 16 || bits == 24 || bits == 32)) || (format == 3 && bits == 32)))
+  { format = 3; bits = 32; }
+  std::FILE* f = std::fopen(name.c_str(), "wb");
+  if (!f) throw std::runtime_error("write_wav(): cannot open \"" + name + "\"");
+  const uint32_t bps = uint32_t(bits) / 8;
+  const uint32_t bytes = uint32_t(size_t(frames) * channels * bps);
+  auto put32 = [f](uint32_t v) { std::fwrite(&v, 4, 1, f); };
+  auto put16 = [f](uint16_t v) { std::fwrite(&v, 2, 1, f); };
+  std::fwrite("RIFF", 1, 4, f); put32(36 + bytes); std::fwrite("WAVE", 1, 4, f);
+  std::fwrite("fmt ", 1, 4, f); put32(16); put16(uint16_t(format)); put16(uint16_t(channels));
+  put32(uint32_t(samplerate)); put32(uint32_t(samplerate) * channels * bps);
+  put16(uint16_t(channels * bps)); put16(uint16_t(bits));
+  std::fwrite("data", 1, 4, f); put32(bytes);
+  const size_t n = size_t(frames) * channels;
+  if (format == 3) std::fwrite(data, 4, n, f);
+  else
+  {
+    const double full = bits == 16 ? 32768.0 : (bits == 24 ? 8388608.0 : 2147483648.0);
+    for (size_t i = 0; i < n; ++i)
+    {
+      double v = std::floor(double(data[i]) * full + 0.5);
+      if (v > full - 1) v = full - 1;
+      if (v < -full) v = -full;
+      const int32_t q = int32_t(v);
+      std::fwrite(&q, bps, 1, f);  // little endian host
+    }
+  }
+  std::fclose(f);
 }
 
 /// Assignable control value forwarding to a C setter (stands in for
