@@ -65,7 +65,8 @@ typedef struct ssr_engine_config
   int block_size;    /* B; reference parameter "block_size" (apf/apf/pointer_policy.h:75) */
   int sample_rate;   /* reference parameter "sample_rate" (pointer_policy.h:74) */
   void* stream;      /* cudaStream_t to run on, or NULL for an engine-owned stream */
-  int mac_variant;   /* 0 = default; see DESIGN.md (1 = register-prefetch, 2 = bulk-copy staged) */
+  int mac_variant;   /* 0 = default; other values select experimental MAC kernel builds
+                        (profiles/r1_mac_variants.md) */
   int reserved[7];
 } ssr_engine_config;
 
@@ -186,7 +187,11 @@ typedef enum ssr_renderer_kind
 {
   SSR_RENDERER_GENERIC = 0,   /* src/genericrenderer.h */
   SSR_RENDERER_BINAURAL = 1,  /* src/binauralrenderer.h */
-  SSR_RENDERER_BRS = 2        /* src/brsrenderer.h */
+  SSR_RENDERER_BRS = 2,       /* src/brsrenderer.h */
+  SSR_RENDERER_PREFILTER_BANK = 3  /* the per-input StaticConvolver stage of the WFS
+                                      renderer (src/wfsrenderer.h:72-88, 104-123): N
+                                      inputs -> N outputs, every input convolved with
+                                      the shared pre-filter; weight 1, no crossfade */
 } ssr_renderer_kind;
 
 typedef struct ssr_renderer_config
@@ -209,6 +214,11 @@ void ssr_renderer_destroy(ssr_renderer* r);
  * of 2!"); hrir_size = 0 means all frames. */
 int ssr_renderer_load_hrirs(ssr_renderer* r, const float* data, long frames, int channels,
                             long hrir_size);
+/* Prefilter bank: = WfsRenderer ctor (src/wfsrenderer.h:75-87): single-channel
+ * pre-filter, `frames` taps; must be loaded before inputs are added.  Inputs are
+ * added with ssr_renderer_add_source(r, NULL, 0, 0, &id); output i belongs to
+ * input i (ssr_renderer_local_outputs() == number of inputs). */
+int ssr_renderer_load_prefilter(ssr_renderer* r, const float* taps, long frames);
 /* synthetic HRIR set generated on the device (bench workloads) */
 int ssr_renderer_generate_hrirs(ssr_renderer* r, int channels, long taps, uint64_t seed,
                                 const float* envelope, float scale);

@@ -15,7 +15,7 @@ SSR_OK = 0
 SSR_ERR_INVALID, SSR_ERR_BLOCK_SIZE, SSR_ERR_UNSUPPORTED = -1, -2, -3
 SSR_ERR_CUDA, SSR_ERR_NOMEM, SSR_ERR_STATE, SSR_ERR_FILE = -4, -5, -6, -7
 OUTPUT_DYNAMIC, OUTPUT_STATIC = 0, 1
-GENERIC, BINAURAL, BRS = 0, 1, 2
+GENERIC, BINAURAL, BRS, PREFILTER_BANK = 0, 1, 2, 3
 
 _f32p = C.POINTER(C.c_float)
 _pp = C.POINTER(_f32p)
@@ -89,6 +89,7 @@ SIGNATURES = {
     "ssr_renderer_create": (C.c_int, [C.c_void_p, C.POINTER(RendererConfig), C.POINTER(C.c_void_p)]),
     "ssr_renderer_destroy": (None, [C.c_void_p]),
     "ssr_renderer_load_hrirs": (C.c_int, [C.c_void_p, _f32p, C.c_long, C.c_int, C.c_long]),
+    "ssr_renderer_load_prefilter": (C.c_int, [C.c_void_p, _f32p, C.c_long]),
     "ssr_renderer_generate_hrirs": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_uint64, _f32p, C.c_float]),
     "ssr_renderer_add_source": (C.c_int, [C.c_void_p, _f32p, C.c_long, C.c_int, C.POINTER(C.c_int)]),
     "ssr_renderer_add_source_synthetic": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_uint64, C.c_uint64, _f32p, C.c_float, C.POINTER(C.c_int)]),
@@ -363,6 +364,10 @@ class Renderer:
     def load_hrirs(self, frames_by_channels, hrir_size: int = 0):
         a = _f32(frames_by_channels)
         _check(lib().ssr_renderer_load_hrirs(self.h, _ptr(a), a.shape[0], a.shape[1], hrir_size))
+
+    def load_prefilter(self, taps):
+        t = _f32(taps)
+        _check(lib().ssr_renderer_load_prefilter(self.h, _ptr(t), t.size))
 
     def generate_hrirs(self, channels: int, taps: int, seed: int, envelope=None, scale: float = 1.0):
         env = None if envelope is None else _f32(envelope)

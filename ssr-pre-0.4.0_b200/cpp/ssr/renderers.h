@@ -432,6 +432,31 @@ class BinauralRenderer : public b200::RendererCore
     }
 };
 
+/// The pre-filter stage of the WFS renderer (src/wfsrenderer.h:60-123): the
+/// renderer loads "prefilter_file" (single channel) and every Input owns a
+/// StaticConvolver on it whose output feeds the (out-of-scope) delay line.
+/// Here all inputs are convolved in one batched step per block.
+class WfsPrefilterBank : public b200::RendererCore
+{
+  public:
+    static const char* name() { return "WfsPrefilterBank"; }
+    explicit WfsPrefilterBank(const apf::parameter_map& p)
+      : RendererCore(p, SSR_RENDERER_PREFILTER_BANK)
+    {
+      // load_sndfile(prefilter_file, sample_rate, 1) (src/wfsrenderer.h:75-76)
+      auto pf = b200::load_sndfile(params.get("prefilter_file", ""), size_t(sample_rate()), 1);
+      b200::check(ssr_renderer_load_prefilter(_r, pf.data.data(), pf.frames));
+    }
+
+    /// adds one input; its pre-filtered signal is output number in_channels() - 1
+    int add_input()
+    {
+      int id = 0;
+      b200::check(ssr_renderer_add_source(_r, nullptr, 0, 0, &id));
+      return id;
+    }
+};
+
 }  // namespace ssr
 
 #endif

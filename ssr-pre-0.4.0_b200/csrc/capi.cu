@@ -302,6 +302,20 @@ int ssr_renderer_load_hrirs(ssr_renderer* r, const float* data, long frames, int
   });
 }
 
+int ssr_renderer_load_prefilter(ssr_renderer* r, const float* taps, long frames)
+{
+  return guarded([&] {
+    require(r && taps, "renderer_load_prefilter: null argument");
+    Renderer& R = r->impl;
+    require(R.cfg.kind == SSR_RENDERER_PREFILTER_BANK, "load_prefilter: not a prefilter bank");
+    require(R.sources.empty(), "load_prefilter: inputs already exist");
+    require(frames > 0, "load_prefilter: empty pre-filter");
+    R.partitions = int(min_partitions(R.e->B, frames));
+    R.hrtfs.reset(new FilterSet(R.e, 1, R.partitions));
+    R.hrtfs->load_time(0, 1, taps, frames, 1, 1);
+  });
+}
+
 int ssr_renderer_generate_hrirs(ssr_renderer* r, int channels, long taps, uint64_t seed,
                                 const float* envelope, float scale)
 {
@@ -355,9 +369,9 @@ int ssr_renderer_add_source(ssr_renderer* r, const float* ir, long frames, int c
     require(r, "null renderer");
     Renderer& R = r->impl;
     int sid;
-    if (R.cfg.kind == SSR_RENDERER_BINAURAL)
+    if (R.cfg.kind == SSR_RENDERER_BINAURAL || R.cfg.kind == SSR_RENDERER_PREFILTER_BANK)
     {
-      require(ir == nullptr, "add_source: BinauralRenderer sources take no IR set");
+      require(ir == nullptr, "add_source: this renderer's sources take no IR set");
       sid = R.add_source(nullptr, 0);
     }
     else

@@ -349,6 +349,7 @@ struct Renderer
   void step(const float* d_input, float* d_output);   // async on e->stream
   void step_generic(const float* d_input, float* d_output);
   void step_dynamic(const float* d_input, float* d_output);
+  void step_bank(const float* d_input, float* d_output);
   void build_fwd(const float* d_input);
   void process(int n, const float* const* in, float* const* out);
   // pipelined

@@ -36,6 +36,10 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
     if (m_first < 0 || m_local <= 0 || m_first + m_local > M_total)
       throw Error(SSR_ERR_INVALID, "ssr_b200: bad output shard");
   }
+  else if (cfg.kind == SSR_RENDERER_PREFILTER_BANK)
+  {
+    M_total = 0; m_first = 0; m_local = 0;  // one output per input, grows with add_source
+  }
   else
   {
     if (cfg.outputs != 0 && cfg.outputs != 2)
@@ -46,8 +50,8 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   static_mac.MT = kGenericMT;
   for (auto& p : dyn_mac) p.MT = 2;
-  d_out.resize(size_t(m_local) * e->B);
-  h_out.resize(size_t(2) * m_local * e->B);
+  d_out.resize(size_t(std::max(m_local, 1)) * e->B);
+  h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
 }
 
 Renderer::~Renderer()
@@ -85,6 +89,16 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
     s->input.reset(new Input(e, s->brtf->partitions));
     for (int i = 0; i < 2; ++i) s->chan.emplace_back(s->brtf->partitions);
   }
+  else if (cfg.kind == SSR_RENDERER_PREFILTER_BANK)
+  {
+    if (!hrtfs) throw Error(SSR_ERR_STATE, "ssr_b200: prefilter bank: load the pre-filter before adding inputs");
+    // StaticConvolver(*_pre_filter) per input (src/wfsrenderer.h:111-113)
+    s->input.reset(new Input(e, partitions));
+    M_total = m_local = int(sources.size()) + 1;
+    d_out.resize(size_t(m_local) * e->B);
+    h_out.resize(size_t(2) * m_local * e->B);
+    inv_key = -1;
+  }
   else
   {
     if (!hrtfs) throw Error(SSR_ERR_STATE, "ssr_b200: BinauralRenderer: load HRIRs before adding sources");
@@ -107,6 +121,7 @@ void Renderer::rem_source(int id)
     if (sources[i]->id == id)
     {
       sources.erase(sources.begin() + i);
+      if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) { M_total = m_local = int(sources.size()); inv_key = -1; }
       static_dirty = true;
       fwd_cache.clear();
       return;
@@ -448,10 +463,76 @@ void Renderer::step_dynamic(const float* d_input, float* d_output)
   e->stage_end();
 }
 
+// Prefilter bank: out[i] = in[i] * prefilter, every block
+// (WfsRenderer::Input::Process, src/wfsrenderer.h:116-120: add_block; convolve()).
+void Renderer::step_bank(const float* d_input, float* d_output)
+{
+  const int N = int(sources.size());
+  const int B = e->B;
+  if (static_dirty)
+  {
+    static_mac.clear();
+    static_mac.MT = 1;
+    for (int n = 0; n < N; ++n)
+    {
+      static_mac.begin_group();
+      for (int p = 0; p < partitions; ++p)
+      {
+        const float2* ptr = hrtfs->part_or_null(0, p);
+        if (!ptr) continue;
+        const float4* h = reinterpret_cast<const float4*>(ptr);
+        static_mac.add_term(sources[n]->input->id, p, 0, &h);
+      }
+      static_mac.end_group();
+    }
+    static_mac.make_work(e->mac_slots());
+    static_mac.upload(e->stream);
+    e->ensure_partials(size_t(static_mac.npartials) * static_mac.MT);
+    static_dirty = false;
+    inv_key = -1;
+  }
+  if (inv_key != 1 || (inv.jobs.host.size() && inv.jobs.host[0].out != d_output))
+  {
+    inv.clear();
+    const float scale = 1.0f / float(2 * B);
+    for (int n = 0; n < N; ++n)
+    {
+      const auto& grp = static_mac.groups[n];
+      InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(n) * B};
+      if (grp.term_end > grp.term_begin)
+      {
+        inv.entries.host.push_back({grp.partial_first, grp.nsplit, 1, 0, 0, scale});
+        job.n_entries = 1;
+      }
+      inv.jobs.host.push_back(job);
+    }
+    inv.upload(e->stream);
+    inv_key = 1;
+  }
+  const float one = 1.0f;
+  build_fwd(d_input);
+  e->stage_begin();
+  e->launch_fwd(fwd->dev.ptr, N);
+  e->stage_mark(1);
+  e->upload_weights(&one, 1);
+  e->launch_mac(static_mac, 0, 0);
+  if (e->cur)
+  {
+    const uint64_t parts = uint64_t(N) * uint64_t(hrtfs->valid[0]);
+    e->cur->mac_bytes += uint64_t(8) * B * (2 * parts + uint64_t(N));
+    e->cur->mac_terms += parts;
+  }
+  e->stage_mark(2);
+  e->launch_inv(inv);
+  e->stage_mark(3);
+  e->stage_end();
+}
+
 void Renderer::step(const float* d_input, float* d_output)
 {
   e->use_device();
   if (cfg.kind == SSR_RENDERER_GENERIC) step_generic(d_input, d_output);
+  else if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) step_bank(d_input, d_output);
   else step_dynamic(d_input, d_output);
 }
 

@@ -253,3 +253,39 @@ def test_wrong_block_length_is_rejected(capi, engine_factory):
     ins, outs = r._ptr_arrays(x, y)
     rc = capi.lib().ssr_renderer_process(r.h, 32, ins, outs)
     assert rc == capi.SSR_ERR_INVALID
+
+
+@pytest.mark.parametrize("B,L,N", [(64, 128, 5), (1024, 128, 16), (256, 700, 3)])
+def test_wfs_prefilter_bank(capi, co, engine_factory, B, L, N):
+    """The per-input StaticConvolver stage of the WFS renderer
+    (src/wfsrenderer.h:75-87, 111-120): every input convolved with the shared
+    pre-filter, batched into one step.  Oracle: one StaticConvolver per input."""
+    rng = np.random.default_rng(B + L + N)
+    e = engine_factory(B)
+    h = decaying(rng, L, 1, 0.3)[:, 0]
+    r = capi.Renderer(e, capi.PREFILTER_BANK)
+    r.load_prefilter(h)
+    for _ in range(N):
+        r.add_source()
+    assert r.local_outputs == N
+    filt = co.Filter(B, h)
+    oc = [co.StaticConvolver(B, filt=filt) for _ in range(N)]
+    worst = 0.0
+    for t in range(8):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        y = r.process(x)
+        assert y.shape == (N, B)
+        for n in range(N):
+            oc[n].add_block(x[n])
+            worst = max(worst, maxerr(y[n], oc[n].convolve()))
+    assert worst <= TOL, worst
+    # inputs may be added later (a new WFS source): the new one starts from silence
+    r.add_source()
+    oc.append(co.StaticConvolver(B, filt=filt))
+    for t in range(3):
+        x = rng.uniform(-1, 1, (N + 1, B)).astype(np.float32)
+        y = r.process(x)
+        for n in range(N + 1):
+            oc[n].add_block(x[n])
+            worst = max(worst, maxerr(y[n], oc[n].convolve()))
+    assert worst <= TOL, worst
