@@ -253,6 +253,16 @@ int ssr_renderer_set_master_volume(ssr_renderer* r, float v);
 int ssr_renderer_set_processing(ssr_renderer* r, int on);
 int ssr_renderer_set_amplitude_reference_distance(ssr_renderer* r, float d);
 
+/* Level meters = the reference's apf::enable_queries policy
+ * (src/rendererbase.h:431-437, 468-474; shown by the GUI, src/controller.h:406-528):
+ * per source the maximum |input sample| of the last block (pre-fader) and that
+ * value times the source's weighting factor, per local output the maximum
+ * |output sample|.  Computed inside the forward / inverse kernels when enabled;
+ * off by default like the reference's disable_queries.  Arrays may be NULL. */
+int ssr_renderer_set_level_metering(ssr_renderer* r, int on);
+int ssr_renderer_get_levels(ssr_renderer* r, float* source_pre_fader, float* source_levels,
+                            float* output_levels);
+
 /* One audio block = apf::pointer_policy<float*>::audio_callback(n, in, out)
  * (apf/apf/pointer_policy.h:58,112-122): `in` has one pointer per source (in
  * add order), `out` one per LOCAL output; each points at B host floats.

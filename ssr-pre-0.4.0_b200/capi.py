@@ -106,6 +106,8 @@ SIGNATURES = {
     "ssr_renderer_set_master_volume": (C.c_int, [C.c_void_p, C.c_float]),
     "ssr_renderer_set_processing": (C.c_int, [C.c_void_p, C.c_int]),
     "ssr_renderer_set_amplitude_reference_distance": (C.c_int, [C.c_void_p, C.c_float]),
+    "ssr_renderer_set_level_metering": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssr_renderer_get_levels": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "ssr_renderer_process": (C.c_int, [C.c_void_p, C.c_int, _pp, _pp]),
     "ssr_renderer_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_renderer_submit": (C.c_int, [C.c_void_p, C.c_int, _pp]),
@@ -404,6 +406,17 @@ class Renderer:
     def set_master_volume(self, v): _check(lib().ssr_renderer_set_master_volume(self.h, v))
     def set_processing(self, on): _check(lib().ssr_renderer_set_processing(self.h, int(on)))
     def set_amplitude_reference_distance(self, d): _check(lib().ssr_renderer_set_amplitude_reference_distance(self.h, d))
+
+    def set_level_metering(self, on: bool):
+        _check(lib().ssr_renderer_set_level_metering(self.h, int(on)))
+
+    def get_levels(self):
+        """(source pre-fader levels, source levels, output levels) of the last block."""
+        pre = np.zeros(max(1, self.n_sources), np.float32)
+        lev = np.zeros(max(1, self.n_sources), np.float32)
+        out = np.zeros(max(1, self.local_outputs), np.float32)
+        _check(lib().ssr_renderer_get_levels(self.h, _ptr(pre), _ptr(lev), _ptr(out)))
+        return pre[:self.n_sources], lev[:self.n_sources], out[:self.local_outputs]
 
     def _ptr_arrays(self, x: np.ndarray, y: np.ndarray):
         ins = (_f32p * max(1, x.shape[0]))(*[x[i].ctypes.data_as(_f32p) for i in range(x.shape[0])])

@@ -429,6 +429,19 @@ int ssr_renderer_set_master_volume(ssr_renderer* r, float v) { SSR_STATE_SETTER(
 int ssr_renderer_set_processing(ssr_renderer* r, int on) { SSR_STATE_SETTER(R.processing = on != 0); }
 int ssr_renderer_set_amplitude_reference_distance(ssr_renderer* r, float d) { SSR_STATE_SETTER(R.amplitude_reference_distance = d); }
 
+int ssr_renderer_set_level_metering(ssr_renderer* r, int on)
+{
+  return guarded([&] { require(r, "null renderer"); r->impl.set_metering(on != 0); });
+}
+
+int ssr_renderer_get_levels(ssr_renderer* r, float* source_pre_fader, float* source_levels, float* output_levels)
+{
+  return guarded([&] {
+    require(r, "null renderer");
+    r->impl.get_levels(source_pre_fader, source_levels, output_levels);
+  });
+}
+
 int ssr_renderer_process(ssr_renderer* r, int n, const float* const* in, float* const* out)
 {
   return guarded([&] {

@@ -574,6 +574,7 @@ FwdJob Input::make_job(const float* d_cur)
   j.head = e->d_heads.ptr + id;
   j.parts = P;
   j.save_second = prev.ptr;
+  j.level = nullptr;
   return j;
 }
 
@@ -629,7 +630,7 @@ const float* Output::convolve(float weight)
   {
     // nothing contributed: the reference returns its zero-filled buffer
     // without an IFFT (convolver.h:448-452)
-    inv.jobs.host.push_back({0, 0, d_res.ptr});
+    inv.jobs.host.push_back({0, 0, d_res.ptr, nullptr});
   }
   else
   {
@@ -640,7 +641,7 @@ const float* Output::convolve(float weight)
     e->upload_weights(&weight, 1);
     e->launch_mac(mac, 0, 0);
     inv.entries.host.push_back({0, mac.groups[0].nsplit, 1, 0, 0, 1.0f / float(2 * B)});
-    inv.jobs.host.push_back({0, 1, d_res.ptr});
+    inv.jobs.host.push_back({0, 1, d_res.ptr, nullptr});
   }
   inv.upload(e->stream);
   e->launch_inv(inv);

@@ -350,6 +350,12 @@ struct Renderer
   void step_generic(const float* d_input, float* d_output);
   void step_dynamic(const float* d_input, float* d_output);
   void step_bank(const float* d_input, float* d_output);
+  // level meters
+  bool metering = false;
+  DeviceArray<float> d_levels;   // [sources | local outputs]
+  float* level_ptr(int index);
+  void set_metering(bool on);
+  void get_levels(float* pre_fader, float* levels, float* outputs);
   void build_fwd(const float* d_input);
   void process(int n, const float* const* in, float* const* out);
   // pipelined

@@ -98,6 +98,23 @@ __device__ __forceinline__ float4 ldg_stream_hint(const float4* p, uint64_t pol)
   return r;
 }
 
+// max over the CTA (all threads must call); result valid in thread 0
+__device__ __forceinline__ float block_max(float v)
+{
+  __shared__ float s_max[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32)
+  {
+    v = threadIdx.x < kThreads / 32 ? s_max[threadIdx.x] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  }
+  return v;
+}
+
 // ---------------------------------------------------------------- FFT core
 // Complex FFT of size m (power of two) in shared memory, Stockham autosort,
 // radix-4 stages plus one radix-2 stage when log2(m) is odd.  `a` holds the
@@ -196,6 +213,8 @@ struct FwdJob
   int* head;          // ring head (device); advanced by this kernel
   int parts;          // ring length
   float* save_second; // if non-null: B floats <- second half (becomes "prev")
+  float* level;       // if non-null: max |second half| (level meter,
+                      //  src/rendererbase.h:431-435 math::max_amplitude)
 };
 
 __device__ __forceinline__ float fwd_sample(const FwdHalf& h, int i)
@@ -246,6 +265,14 @@ fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict_
       const float2 v = a[j];
       reinterpret_cast<float2*>(job.save_second)[j - half] = v;
     }
+  }
+
+  if (job.level)
+  {
+    float m = 0.0f;
+    for (int j = t + half; j < B; j += kThreads) { const float2 v = a[j]; m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))); }
+    m = block_max(m);
+    if (t == 0) *job.level = m;
   }
 
   const float2* z = fft_smem<false>(a, b, B, tw);
@@ -496,6 +523,7 @@ struct InvJob
   int first_entry;
   int n_entries;    // 0 -> output block is zeros (combine_channels.h:126-129)
   float* out;       // B floats (device)
+  float* level;     // if non-null: max |out| (src/rendererbase.h:468-472)
 };
 
 constexpr int kInvMaxRes = 8;  // B <= 4096: (B/2 float2) / 256 threads
@@ -638,11 +666,21 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
     __syncthreads();  // z (smem) is rewritten by the next entry
   }
 
+  float m = 0.0f;
 #pragma unroll
   for (int q = 0; q < kInvMaxRes; ++q)
   {
     const int jj = t + q * kThreads;
-    if (jj < half) reinterpret_cast<float2*>(job.out)[jj] = res[q];
+    if (jj < half)
+    {
+      reinterpret_cast<float2*>(job.out)[jj] = res[q];
+      m = fmaxf(m, fmaxf(fabsf(res[q].x), fabsf(res[q].y)));
+    }
+  }
+  if (job.level)
+  {
+    m = block_max(m);
+    if (t == 0) *job.level = m;
   }
 }
 

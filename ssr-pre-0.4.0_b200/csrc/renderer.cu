@@ -108,6 +108,8 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
     s->bw = BlockParameter<float>(0.0f);  // _weight(0.0f) (src/binauralrenderer.h:245)
   }
   sources.push_back(std::move(s));
+  if (metering) { d_levels.release(); (void)level_ptr(0); }
+  inv_key = -1;
   static_dirty = true;
   fwd_cache.clear();
   return sources.back()->id;
@@ -127,6 +129,49 @@ void Renderer::rem_source(int id)
       return;
     }
   throw Error(SSR_ERR_INVALID, "ssr_b200: no such source");
+}
+
+// level meters (apf::enable_queries, src/rendererbase.h:431-437, 468-474)
+float* Renderer::level_ptr(int index)
+{
+  if (!metering) return nullptr;
+  const size_t need = sources.size() + size_t(std::max(m_local, 1)) + 8;
+  if (d_levels.count < need)
+  {
+    e->sync();
+    d_levels.resize(need + 64);
+    SSR_CUDA(cudaMemsetAsync(d_levels.ptr, 0, d_levels.count * sizeof(float), e->stream));
+  }
+  return d_levels.ptr + index;
+}
+
+void Renderer::set_metering(bool on)
+{
+  if (on == metering) return;
+  e->sync();
+  metering = on;
+  if (on) (void)level_ptr(0);
+  fwd_cache.clear();
+  inv_key = -1;
+  inv.clear();
+}
+
+void Renderer::get_levels(float* pre_fader, float* levels, float* outputs)
+{
+  if (!metering) throw Error(SSR_ERR_STATE, "ssr_b200: level metering is off");
+  e->use_device();
+  e->sync();
+  const int N = int(sources.size());
+  std::vector<float> tmp(size_t(N) + m_local);
+  if (!tmp.empty())
+    SSR_CUDA(cudaMemcpy(tmp.data(), level_ptr(0), tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int n = 0; n < N; ++n)
+  {
+    if (pre_fader) pre_fader[n] = tmp[n];
+    // _level = _pre_fader_level * weighting_factor (src/rendererbase.h:434)
+    if (levels) levels[n] = tmp[n] * sources[n]->weighting_factor.get();
+  }
+  for (int m = 0; m < m_local; ++m) if (outputs) outputs[m] = tmp[N + m];
 }
 
 // RendererBase::Source::Process (src/rendererbase.h:386-407)
@@ -151,7 +196,11 @@ void Renderer::build_fwd(const float* d_input)
   fwd_cache.emplace_back(d_input, std::unique_ptr<Table<FwdJob>>(new Table<FwdJob>()));
   fwd = fwd_cache.back().second.get();
   fwd->host.resize(N);
-  for (int n = 0; n < N; ++n) fwd->host[n] = sources[n]->input->make_job(d_input + size_t(n) * e->B);
+  for (int n = 0; n < N; ++n)
+  {
+    fwd->host[n] = sources[n]->input->make_job(d_input + size_t(n) * e->B);
+    fwd->host[n].level = level_ptr(n);
+  }
   fwd->upload(e->stream);
 }
 
@@ -227,7 +276,7 @@ void Renderer::step_generic(const float* d_input, float* d_output)
     {
       const int g = m / kGenericMT, row = m % kGenericMT;
       const auto& grp = static_mac.groups[g];
-      InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(m) * B};
+      InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(m) * B, level_ptr(int(sources.size()) + m)};
       for (int k = 0; k < 3; ++k)
       {
         if (!kind_active[k]) continue;
@@ -432,7 +481,7 @@ void Renderer::step_dynamic(const float* d_input, float* d_output)
   int nrows = 0;
   for (int ear = 0; ear < 2; ++ear)
   {
-    InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(ear) * B};
+    InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(ear) * B, level_ptr(N + ear)};
     for (int k = 0; k < 3; ++k)
     {
       if (group_of_kind[k] < 0) continue;
@@ -498,7 +547,7 @@ void Renderer::step_bank(const float* d_input, float* d_output)
     for (int n = 0; n < N; ++n)
     {
       const auto& grp = static_mac.groups[n];
-      InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(n) * B};
+      InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(n) * B, level_ptr(N + n)};
       if (grp.term_end > grp.term_begin)
       {
         inv.entries.host.push_back({grp.partial_first, grp.nsplit, 1, 0, 0, scale});

@@ -289,3 +289,36 @@ def test_wfs_prefilter_bank(capi, co, engine_factory, B, L, N):
             oc[n].add_block(x[n])
             worst = max(worst, maxerr(y[n], oc[n].convolve()))
     assert worst <= TOL, worst
+
+
+@pytest.mark.parametrize("kind", ["generic", "brs"])
+def test_level_meters(capi, engine_factory, kind):
+    """apf::enable_queries level meters (src/rendererbase.h:431-437, 468-474):
+    pre-fader = max |input|, level = pre-fader * weighting_factor, output = max |out|."""
+    B, L, N = 256, 600, 3
+    rng = np.random.default_rng(17)
+    e = engine_factory(B)
+    if kind == "generic":
+        M = 5
+        r = capi.Renderer(e, capi.GENERIC, outputs=M)
+        ids = [r.add_source(decaying(rng, L, M, 0.1)) for _ in range(N)]
+    else:
+        M = 2
+        r = capi.Renderer(e, capi.BRS)
+        ids = [r.add_source(decaying(rng, L, 8, 0.1)) for _ in range(N)]
+    with pytest.raises(capi.SsrError):
+        r.get_levels()                      # metering is off by default (disable_queries)
+    r.set_level_metering(True)
+    r.set_gain(ids[1], 0.5)
+    r.set_master_volume(0.8)
+    for t in range(4):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32) * np.float32(0.1 * (t + 1))
+        y = r.process(x)
+        pre, lev, out = r.get_levels()
+        assert np.allclose(pre, np.abs(x).max(axis=1), rtol=0, atol=0)
+        w = np.array([0.8, 0.4, 0.8], np.float32)
+        assert np.allclose(lev, pre * w, rtol=1e-6)
+        assert np.allclose(out, np.abs(y).max(axis=1), rtol=0, atol=0)
+    r.set_level_metering(False)
+    y2 = r.process(x)
+    assert y2.shape == (M, B)
