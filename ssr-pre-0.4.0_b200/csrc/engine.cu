@@ -501,21 +501,35 @@ FilterPtrTable::FilterPtrTable(int partitions)
   qstart.assign(queues.size(), 0);
 }
 
-void FilterPtrTable::set_static(const FilterSet& fs, int ch)
+static std::vector<const float2*> partition_list(const FilterSet& fs, int ch)
 {
-  for (int p = 0; p < P; ++p) ptrs[p] = fs.part_or_null(ch, p);  // missing -> empty
+  std::vector<const float2*> parts(size_t(fs.partitions));
+  for (int p = 0; p < fs.partitions; ++p) parts[p] = fs.part_or_null(ch, p);
+  return parts;
 }
 
-void FilterPtrTable::set_filter(const FilterSet& fs, int ch)
+void FilterPtrTable::set_static(const FilterSet& fs, int ch) { set_static_ptrs(partition_list(fs, ch)); }
+void FilterPtrTable::set_filter(const FilterSet& fs, int ch) { set_filter_ptrs(partition_list(fs, ch)); }
+
+void FilterPtrTable::set_static_ptrs(const std::vector<const float2*>& parts)
+{
+  // fewer partitions given -> the rest is empty; more -> ignored (convolver.h:733-738)
+  for (int p = 0; p < P; ++p) ptrs[p] = p < int(parts.size()) ? parts[p] : nullptr;
+  ++version;
+}
+
+void FilterPtrTable::set_filter_ptrs(const std::vector<const float2*>& parts)
 {
   // first partition immediately; partition i+1 at the tail of queue i
-  if (fs.partitions > 0) ptrs[0] = fs.part_or_null(ch, 0);
+  if (!parts.empty()) ptrs[0] = parts[0];
   for (size_t i = 0; i < queues.size(); ++i)
   {
     auto& q = queues[i];
     const size_t last = (size_t(qstart[i]) + i) % q.size();
-    q[last] = Slot{fs.part_or_null(ch, int(i) + 1), true};  // beyond the filter -> empty
+    // beyond the filter -> the (non-null in the reference) empty partition
+    q[last] = Slot{i + 1 < parts.size() ? parts[i + 1] : nullptr, true};
   }
+  ++version;
 }
 
 bool FilterPtrTable::queues_empty() const
@@ -535,6 +549,7 @@ void FilterPtrTable::rotate_queues()
     front = Slot{nullptr, false};  // becomes the new back
     qstart[i] = int((size_t(qstart[i]) + 1) % q.size());
   }
+  ++version;
 }
 
 bool FilterPtrTable::references(const float2* lo, const float2* hi) const
@@ -614,36 +629,48 @@ const float* Output::convolve(float weight)
 {
   e->use_device();
   const int B = e->B;
-  mac.clear();
-  mac.begin_group();
-  for (int p = 0; p < table.P; ++p)
+  // The MAC / inverse tables only depend on the pointer table: rebuild them when
+  // set_filter / rotate_queues / bind changed it, otherwise relaunch as they are.
+  const bool zero = (weight == 0.0f);
+  if (planned_version != table.version || planned_zero != zero)
   {
-    // zero-flagged partitions are skipped (convolver.h:561)
-    if (!table.ptrs[p]) continue;
-    const float4* h = reinterpret_cast<const float4*>(table.ptrs[p]);
-    mac.add_term(in->id, p, 0, &h);
+    mac.clear();
+    mac.begin_group();
+    for (int p = 0; p < table.P; ++p)
+    {
+      // zero-flagged partitions are skipped (convolver.h:561)
+      if (!table.ptrs[p]) continue;
+      const float4* h = reinterpret_cast<const float4*>(table.ptrs[p]);
+      mac.add_term(in->id, p, 0, &h);
+    }
+    mac.end_group();
+    planned_terms = int(mac.meta.host.size());
+    inv.clear();
+    if (planned_terms == 0 || zero)
+    {
+      // nothing contributed: the reference returns its zero-filled buffer
+      // without an IFFT (convolver.h:448-452)
+      inv.jobs.host.push_back({0, 0, d_res.ptr, nullptr});
+    }
+    else
+    {
+      mac.make_work(e->mac_slots());
+      mac.upload(e->stream);
+      e->ensure_partials(size_t(mac.npartials) * mac.MT);
+      inv.entries.host.push_back({0, mac.groups[0].nsplit, 1, 0, 0, 1.0f / float(2 * B)});
+      inv.jobs.host.push_back({0, 1, d_res.ptr, nullptr});
+    }
+    inv.upload(e->stream);
+    planned_version = table.version;
+    planned_zero = zero;
   }
-  mac.end_group();
-  const int nterms = int(mac.meta.host.size());
-  inv.clear();
-  if (nterms == 0 || weight == 0.0f)
+  if (planned_terms > 0 && !zero)
   {
-    // nothing contributed: the reference returns its zero-filled buffer
-    // without an IFFT (convolver.h:448-452)
-    inv.jobs.host.push_back({0, 0, d_res.ptr, nullptr});
-  }
-  else
-  {
-    mac.make_work(e->mac_slots());
-    e->sync();  // staging tables of the previous call
-    mac.upload(e->stream);
+    // other objects of this engine may have grown the shared partial buffer
     e->ensure_partials(size_t(mac.npartials) * mac.MT);
     e->upload_weights(&weight, 1);
     e->launch_mac(mac, 0, 0);
-    inv.entries.host.push_back({0, mac.groups[0].nsplit, 1, 0, 0, 1.0f / float(2 * B)});
-    inv.jobs.host.push_back({0, 1, d_res.ptr, nullptr});
   }
-  inv.upload(e->stream);
   e->launch_inv(inv);
   SSR_CUDA(cudaMemcpyAsync(h_res.ptr, d_res.ptr, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   e->stats.d2h_bytes += B * sizeof(float);

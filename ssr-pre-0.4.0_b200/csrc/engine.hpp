@@ -238,6 +238,11 @@ struct FilterPtrTable
   std::vector<int> qstart;
   void set_static(const FilterSet& fs, int ch);    // StaticOutput::_set_filter :729-739
   void set_filter(const FilterSet& fs, int ch);    // :642-658
+  // the same on a plain list of partition pointers (null = zero-flagged,
+  // entries beyond the list = empty partition); pure host logic
+  void set_static_ptrs(const std::vector<const float2*>& parts);
+  void set_filter_ptrs(const std::vector<const float2*>& parts);
+  uint64_t version = 0;                            // bumped whenever `ptrs` may have changed
   bool queues_empty() const;                       // :666-677
   void rotate_queues();                            // :683-699
   bool references(const float2* lo, const float2* hi) const;
@@ -268,6 +273,9 @@ struct Output
   FilterPtrTable table;
   MacPlan mac;
   InvPlan inv;
+  uint64_t planned_version = ~uint64_t(0);   // table.version the cached plan was built from
+  int planned_terms = 0;
+  bool planned_zero = false;
   DeviceArray<float> d_res;
   PinnedArray<float> h_res;
   const float* convolve(float weight);

@@ -1,0 +1,172 @@
+// CPU-only test (no GPU, no CUDA call) of the engine's pure host logic:
+//  * FilterPtrTable = Output::set_filter / queues_empty / rotate_queues
+//    (apf/apf/convolver.h:618-699), checked against a literal restatement of the
+//    reference's shifting queues and against the sequence the reference's unit
+//    test expects (apf/unit_tests/test_convolver.cpp:86-131);
+//  * MacPlan::make_work: every term of every group is covered exactly once by
+//    contiguous chunks, partial indices are unique, chunks are balanced.
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <vector>
+
+#include "../../ssr-pre-0.4.0_b200/csrc/engine.hpp"
+
+using namespace ssr_b200;
+
+static int failures = 0, checks = 0;
+#define CHECK(cond) do { ++checks; if (!(cond)) { ++failures; \
+  std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); } } while (0)
+
+// literal restatement of the reference's data structure: _queues[i] has i+1
+// slots and is shifted by one on every rotate (convolver.h:623-624, 642-699).
+// The reference's "_empty_partition" is a valid non-null pointer; here it is a
+// distinguished address.
+struct LiteralQueues
+{
+  explicit LiteralQueues(int P_, const float2* empty_) : P(P_), empty(empty_), ptrs(P_, empty_)
+  { for (int i = 0; i + 1 < P; ++i) queues.emplace_back(size_t(i + 1), nullptr); }
+  void set_filter(const std::vector<const float2*>& f)
+  {
+    size_t k = 0;
+    if (k < f.size()) ptrs[0] = f[k++];
+    for (size_t i = 0; i < queues.size(); ++i) queues[i][i] = (k >= f.size()) ? empty : f[k++];
+  }
+  bool queues_empty() const
+  {
+    if (queues.empty()) return true;
+    for (auto p : queues.back()) if (p) return false;
+    return true;
+  }
+  void rotate_queues()
+  {
+    for (size_t i = 0; i < queues.size(); ++i)
+    {
+      auto& q = queues[i];
+      if (q.front()) ptrs[i + 1] = q.front();
+      for (size_t j = 0; j + 1 < q.size(); ++j) q[j] = q[j + 1];
+      q.back() = nullptr;
+    }
+  }
+  int P; const float2* empty;
+  std::vector<const float2*> ptrs;
+  std::vector<std::vector<const float2*>> queues;
+};
+
+static unsigned rng_state = 4711u;
+static unsigned rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
+
+static void test_ptr_table()
+{
+  static float2 storage[64][64];  // fake partition addresses: filter f, partition p
+  static float2 empty_marker;
+  for (int P : {1, 2, 3, 5, 8, 47})
+  {
+    FilterPtrTable t(P);
+    LiteralQueues lit(P, &empty_marker);
+    CHECK(t.queues_empty());
+    for (int step = 0; step < 400; ++step)
+    {
+      const unsigned op = rnd() % 10;
+      if (op < 3)
+      {
+        const int f = int(rnd() % 64);
+        const int len = 1 + int(rnd() % (P + 2));  // shorter, equal or longer than P
+        std::vector<const float2*> parts;
+        for (int p = 0; p < len && p < 64; ++p) parts.push_back(&storage[f][p]);
+        t.set_filter_ptrs(parts);
+        lit.set_filter(parts);
+      }
+      else if (op < 8)
+      {
+        // the renderers rotate only while the queues are not empty
+        if (!lit.queues_empty()) { t.rotate_queues(); lit.rotate_queues(); }
+      }
+      else { t.rotate_queues(); lit.rotate_queues(); }  // rotating empty queues is harmless
+      CHECK(t.queues_empty() == lit.queues_empty());
+      bool same = true;
+      for (int p = 0; p < P; ++p)
+      {
+        const float2* want = lit.ptrs[p] == &empty_marker ? nullptr : lit.ptrs[p];
+        same = same && (t.ptrs[p] == want);
+      }
+      CHECK(same);
+    }
+  }
+
+  // the sequence of test_convolver.cpp:86-131 (P = 2)
+  FilterPtrTable t(2);
+  std::vector<const float2*> f = { &storage[1][0], &storage[1][1] };
+  t.set_filter_ptrs(f);
+  CHECK(t.ptrs[0] == &storage[1][0] && t.ptrs[1] == nullptr);
+  CHECK(!t.queues_empty());
+  t.rotate_queues();
+  CHECK(t.ptrs[1] == &storage[1][1]);
+  CHECK(t.queues_empty());
+
+  // StaticOutput::_set_filter: fewer partitions -> rest empty, more -> ignored
+  FilterPtrTable s(3);
+  s.set_static_ptrs({ &storage[2][0] });
+  CHECK(s.ptrs[0] == &storage[2][0] && s.ptrs[1] == nullptr && s.ptrs[2] == nullptr);
+  s.set_static_ptrs({ &storage[3][0], &storage[3][1], &storage[3][2], &storage[3][3] });
+  CHECK(s.ptrs[2] == &storage[3][2]);
+  const uint64_t v = s.version;
+  s.rotate_queues();
+  CHECK(s.version != v);
+}
+
+static void test_make_work()
+{
+  for (int trial = 0; trial < 300; ++trial)
+  {
+    MacPlan plan;
+    plan.MT = 1 << (rnd() % 3);
+    const int G = 1 + int(rnd() % 140);
+    const bool uniform = rnd() % 2;
+    const int base = 1 + int(rnd() % 7000);
+    long total = 0;
+    const float4* h[4] = { nullptr, nullptr, nullptr, nullptr };
+    for (int g = 0; g < G; ++g)
+    {
+      plan.begin_group();
+      const int n = uniform ? base : int(rnd() % (base + 1));  // empty groups allowed
+      for (int i = 0; i < n && total < 200000; ++i, ++total) plan.add_term(g, i, 0, h);
+      plan.end_group();
+    }
+    const int slots = 148 * (1 + int(rnd() % 2));
+    plan.make_work(slots);
+    CHECK(int(plan.work.host.size()) == plan.npartials);
+    std::set<int> partial_ids;
+    size_t w = 0;
+    bool ok = true;
+    int max_chunk = 0, min_chunk = 1 << 30;
+    for (auto& g : plan.groups)
+    {
+      ok = ok && g.nsplit >= 1 && g.partial_first == int(w);
+      int pos = g.term_begin;
+      for (int s = 0; s < g.nsplit; ++s, ++w)
+      {
+        const int4 item = plan.work.host[w];
+        ok = ok && item.x == pos && item.y >= item.x && item.z == g.partial_first + s;
+        partial_ids.insert(item.z);
+        pos = item.y;
+        if (g.term_end > g.term_begin) { max_chunk = std::max(max_chunk, item.y - item.x); min_chunk = std::min(min_chunk, item.y - item.x); }
+      }
+      ok = ok && pos == g.term_end;
+    }
+    CHECK(ok);
+    CHECK(w == plan.work.host.size());
+    CHECK(int(partial_ids.size()) == plan.npartials);
+    if (uniform && total < 200000) CHECK(max_chunk - min_chunk <= 1);  // balanced
+    // no pathological over-splitting: at most one CTA per term (plus empty groups)
+    CHECK(plan.npartials <= total + G);
+  }
+}
+
+int main()
+{
+  test_ptr_table();
+  test_make_work();
+  std::printf("%s (%d assertions, %d failed)\n", failures ? "FAILED" : "All tests passed", checks, failures);
+  return failures ? 1 : 0;
+}
