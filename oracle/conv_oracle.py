@@ -584,6 +584,13 @@ class GenericRendererOracle(_RendererBase):
         self.sources.append(s)
         return len(self.sources) - 1
 
+    def rem_source(self, index: int):
+        """RendererBase::rem_source (rendererbase.h:289-314): the source's channels
+        are taken out of every output's list (undistribute_list); no fade-out."""
+        s = self.sources.pop(index)
+        for m, ch in enumerate(s.channels):
+            self.out_lists[m].remove(ch)
+
     def process(self, x: np.ndarray) -> np.ndarray:
         x = np.asarray(x, F32)
         for n, s in enumerate(self.sources):  # source phase (genericrenderer.h:122-129)

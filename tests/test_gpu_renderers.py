@@ -322,3 +322,56 @@ def test_level_meters(capi, engine_factory, kind):
     r.set_level_metering(False)
     y2 = r.process(x)
     assert y2.shape == (M, B)
+
+
+def test_generic_sources_added_and_removed_mid_stream_and_unequal_ir_lengths(capi, co, engine_factory):
+    """add_source / rem_source while running (src/rendererbase.h:247-314) and sources
+    whose IR files have different lengths (different partition counts per source)."""
+    B, M = 128, 3
+    rng = np.random.default_rng(33)
+    e = engine_factory(B)
+    r = capi.Renderer(e, capi.GENERIC, outputs=M)
+    o = co.GenericRendererOracle(B, M)
+    lengths = [100, 1000, 257, 2048]
+    ids = []
+
+    def add(L):
+        ir = decaying(rng, L, M, 0.1)
+        ids.append(r.add_source(ir))
+        o.add_source(ir)
+
+    # no sources at all: silence
+    assert np.all(r.process(np.zeros((0, B), np.float32)) == 0.0)
+    add(lengths[0]); add(lengths[1])
+    worst = 0.0
+    for t in range(30):
+        if t == 6:
+            add(lengths[2])                      # a new source fades in from weight 0
+        if t == 12:
+            r.rem_source(ids.pop(0)); o.rem_source(0)
+        if t == 20:
+            add(lengths[3])
+        n = len(ids)
+        x = rng.uniform(-1, 1, (n, B)).astype(np.float32)
+        y = r.process(x)
+        worst = max(worst, maxerr(y, o.process(x)))
+    assert worst <= TOL, worst
+    assert r.n_sources == 3
+
+
+def test_small_block_sizes_through_the_renderers(capi, co, engine_factory):
+    # block size 8 (the reference's unit-test size) and 16 through Level 2
+    for B in (8, 16):
+        rng = np.random.default_rng(B)
+        e = engine_factory(B)
+        r = capi.Renderer(e, capi.BRS)
+        o = co.BrsRendererOracle(B)
+        brir = decaying(rng, 5 * B - 3, 6, 0.2)
+        r.add_source(brir); o.add_source(brir)
+        worst = 0.0
+        for t in range(25):
+            az = 30.0 * t
+            r.set_reference_orientation(az); o.reference_orientation = az
+            x = rng.uniform(-1, 1, (1, B)).astype(np.float32)
+            worst = max(worst, maxerr(r.process(x), o.process(x)))
+        assert worst <= TOL, worst
