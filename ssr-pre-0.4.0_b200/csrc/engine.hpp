@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <deque>
@@ -34,6 +35,11 @@ struct Error : std::runtime_error
     throw ::ssr_b200::Error(SSR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
+// Bumped whenever a device buffer moves or a device table changes its length:
+// anything a captured CUDA graph has baked in (pointers, grid sizes).  Table
+// CONTENT may change without invalidating a graph.
+inline std::atomic<uint64_t> g_layout_epoch{1};
+
 // ------------------------------------------------------------ memory helpers
 template<typename T>
 struct DeviceArray
@@ -45,11 +51,12 @@ struct DeviceArray
   DeviceArray(const DeviceArray&) = delete;
   DeviceArray& operator=(const DeviceArray&) = delete;
   ~DeviceArray() { release(); }
-  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; count = 0; }
+  void release() { if (ptr) { cudaFree(ptr); ++g_layout_epoch; } ptr = nullptr; count = 0; }
   void resize(size_t n)
   {
     release();
     if (n == 0) return;
+    ++g_layout_epoch;
     cudaError_t err = cudaMalloc(&ptr, n * sizeof(T));
     if (err != cudaSuccess)
       throw Error(err == cudaErrorMemoryAllocation ? SSR_ERR_NOMEM : SSR_ERR_CUDA,
@@ -99,6 +106,7 @@ struct Table
   // already queued may still read the old table.
   void upload(cudaStream_t s)
   {
+    if (uploaded != host.size()) ++g_layout_epoch;
     uploaded = host.size();
     if (host.empty()) return;
     if (staged) SSR_CUDA(cudaEventSynchronize(staged));
@@ -354,10 +362,29 @@ struct Renderer
   int add_source(std::unique_ptr<FilterSet> irs, int channels);
   void rem_source(int id);
   void base_weight(Source& s);
+  // One block = prepare (host logic, table / weight uploads) + launch (kernel
+  // launches only, capturable into a CUDA graph).
+  struct StepDesc
+  {
+    const float* d_input = nullptr; float* d_output = nullptr;
+    int N = 0;
+    int kind_mask = 0;                 // generic: accumulator kinds active (const / old / new)
+    uint64_t hparts[3] = {0, 0, 0}, xparts[3] = {0, 0, 0};
+    int nrows = 0;
+    bool graphable = false;
+  };
+  StepDesc prepare(const float* d_input, float* d_output);
+  void launch(const StepDesc& d);
   void step(const float* d_input, float* d_output);   // async on e->stream
-  void step_generic(const float* d_input, float* d_output);
-  void step_dynamic(const float* d_input, float* d_output);
-  void step_bank(const float* d_input, float* d_output);
+  StepDesc prepare_generic(const float* d_input, float* d_output);
+  StepDesc prepare_dynamic(const float* d_input, float* d_output);
+  StepDesc prepare_bank(const float* d_input, float* d_output);
+  // CUDA graphs of the steady-state host-buffer step {H2D, kernels, D2H}
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; int seen = 0; };
+  GraphEntry graphs[2][8];             // [pinned slot][kind mask]
+  bool use_graphs = true;
+  uint64_t graph_launches = 0;
+  void drop_graphs();
   // level meters
   bool metering = false;
   DeviceArray<float> d_levels;   // [sources | local outputs]

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace ssr_b200
 {
@@ -48,6 +49,7 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   }
   // apf::math::dB2linear (src/rendererbase.h:234-235)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
+  if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
   static_mac.MT = kGenericMT;
   for (auto& p : dyn_mac) p.MT = 2;
   d_out.resize(size_t(std::max(m_local, 1)) * e->B);
@@ -59,6 +61,7 @@ Renderer::~Renderer()
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (auto ev : done) if (ev) cudaEventDestroy(ev);
+  drop_graphs();
 }
 
 Renderer::Source* Renderer::find(int id)
@@ -214,8 +217,10 @@ static Mode mode_from_weight(const BlockParameter<float>& f)
   return CHANGE;
 }
 
-void Renderer::step_generic(const float* d_input, float* d_output)
+Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_output)
 {
+  StepDesc d;
+  d.d_input = d_input; d.d_output = d_output;
   const int N = int(sources.size());
   const int B = e->B;
   wtab_host.assign(size_t(3) * std::max(N, 1), 0.0f);
@@ -291,26 +296,18 @@ void Renderer::step_generic(const float* d_input, float* d_output)
   }
 
   build_fwd(d_input);
-  e->stage_begin();
-  e->launch_fwd(fwd->dev.ptr, N);
-  e->stage_mark(1);
   e->upload_weights(wtab_host.data(), wtab_host.size());
+  d.N = N;
+  d.kind_mask = key;
   for (int k = 0; k < 3; ++k)
   {
-    if (!kind_active[k]) continue;
-    e->launch_mac(static_mac, k * N, k * static_mac.npartials);
-    if (e->cur)
-    {
-      // 8B bytes * (H partitions + X partitions + accumulators)
-      const uint64_t hparts = active_parts[k] * uint64_t(m_local);
-      e->cur->mac_bytes += uint64_t(8) * B * (hparts + active_parts[k] + uint64_t(m_local));
-      e->cur->mac_terms += hparts;
-    }
+    // H partitions, X partitions; + m_local accumulators per pass
+    d.hparts[k] = active_parts[k] * uint64_t(m_local);
+    d.xparts[k] = active_parts[k];
   }
-  e->stage_mark(2);
-  e->launch_inv(inv);
-  e->stage_mark(3);
-  e->stage_end();
+  d.nrows = m_local;
+  d.graphable = true;
+  return d;
 }
 
 // apf::math::wrap<float> (apf/apf/math.h:136-160)
@@ -321,8 +318,10 @@ static float fwrap(float x, float full)
   return x;
 }
 
-void Renderer::step_dynamic(const float* d_input, float* d_output)
+Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_output)
 {
+  StepDesc d;
+  d.d_input = d_input; d.d_output = d_output;
   const int N = int(sources.size());
   const int B = e->B;
   const bool binaural = cfg.kind == SSR_RENDERER_BINAURAL;
@@ -496,26 +495,21 @@ void Renderer::step_dynamic(const float* d_input, float* d_output)
   inv.upload(e->stream);
 
   build_fwd(d_input);
-  e->stage_begin();
-  e->launch_fwd(fwd->dev.ptr, N);
-  e->stage_mark(1);
   e->upload_weights(wtab_host.data(), wtab_host.size());
-  e->launch_mac(plan, 0, 0);
-  if (e->cur)
-  {
-    e->cur->mac_bytes += uint64_t(8) * B * (hparts + xparts + uint64_t(nrows));
-    e->cur->mac_terms += hparts;
-  }
-  e->stage_mark(2);
-  e->launch_inv(inv);
-  e->stage_mark(3);
-  e->stage_end();
+  d.N = N;
+  d.kind_mask = 1;
+  d.hparts[0] = hparts; d.xparts[0] = xparts; d.nrows = nrows;
+  d.graphable = false;  // tables (and grid sizes) change from block to block
+  (void)B;
+  return d;
 }
 
 // Prefilter bank: out[i] = in[i] * prefilter, every block
 // (WfsRenderer::Input::Process, src/wfsrenderer.h:116-120: add_block; convolve()).
-void Renderer::step_bank(const float* d_input, float* d_output)
+Renderer::StepDesc Renderer::prepare_bank(const float* d_input, float* d_output)
 {
+  StepDesc d;
+  d.d_input = d_input; d.d_output = d_output;
   const int N = int(sources.size());
   const int B = e->B;
   if (static_dirty)
@@ -560,16 +554,52 @@ void Renderer::step_bank(const float* d_input, float* d_output)
   }
   const float one = 1.0f;
   build_fwd(d_input);
-  e->stage_begin();
-  e->launch_fwd(fwd->dev.ptr, N);
-  e->stage_mark(1);
   e->upload_weights(&one, 1);
-  e->launch_mac(static_mac, 0, 0);
-  if (e->cur)
+  const uint64_t parts = uint64_t(N) * uint64_t(hrtfs->valid[0]);
+  d.N = N;
+  d.kind_mask = 1;
+  d.hparts[0] = parts; d.xparts[0] = parts; d.nrows = N;
+  d.graphable = true;
+  (void)B;
+  return d;
+}
+
+Renderer::StepDesc Renderer::prepare(const float* d_input, float* d_output)
+{
+  e->use_device();
+  if (cfg.kind == SSR_RENDERER_GENERIC) return prepare_generic(d_input, d_output);
+  if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) return prepare_bank(d_input, d_output);
+  return prepare_dynamic(d_input, d_output);
+}
+
+// Kernel launches of one block; nothing else (capturable into a CUDA graph).
+void Renderer::launch(const StepDesc& d)
+{
+  const int B = e->B;
+  e->stage_begin();
+  e->launch_fwd(fwd->dev.ptr, d.N);
+  e->stage_mark(1);
+  if (cfg.kind == SSR_RENDERER_GENERIC)
   {
-    const uint64_t parts = uint64_t(N) * uint64_t(hrtfs->valid[0]);
-    e->cur->mac_bytes += uint64_t(8) * B * (2 * parts + uint64_t(N));
-    e->cur->mac_terms += parts;
+    for (int k = 0; k < 3; ++k)
+    {
+      if (!(d.kind_mask & (1 << k))) continue;
+      e->launch_mac(static_mac, k * d.N, k * static_mac.npartials);
+      if (e->cur)
+      {
+        e->cur->mac_bytes += uint64_t(8) * B * (d.hparts[k] + d.xparts[k] + uint64_t(d.nrows));
+        e->cur->mac_terms += d.hparts[k];
+      }
+    }
+  }
+  else
+  {
+    e->launch_mac(cfg.kind == SSR_RENDERER_PREFILTER_BANK ? static_mac : dyn_mac[0], 0, 0);
+    if (e->cur)
+    {
+      e->cur->mac_bytes += uint64_t(8) * B * (d.hparts[0] + d.xparts[0] + uint64_t(d.nrows));
+      e->cur->mac_terms += d.hparts[0];
+    }
   }
   e->stage_mark(2);
   e->launch_inv(inv);
@@ -579,10 +609,18 @@ void Renderer::step_bank(const float* d_input, float* d_output)
 
 void Renderer::step(const float* d_input, float* d_output)
 {
-  e->use_device();
-  if (cfg.kind == SSR_RENDERER_GENERIC) step_generic(d_input, d_output);
-  else if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) step_bank(d_input, d_output);
-  else step_dynamic(d_input, d_output);
+  const StepDesc d = prepare(d_input, d_output);
+  launch(d);
+}
+
+void Renderer::drop_graphs()
+{
+  for (auto& slot : graphs)
+    for (auto& g : slot)
+    {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      g = GraphEntry();
+    }
 }
 
 void Renderer::process(int n, const float* const* in, float* const* out)
@@ -606,13 +644,53 @@ void Renderer::submit(int n, const float* const* in)
   const int slot = int(submitted & 1);
   float* hin = h_in.ptr + size_t(slot) * in_floats;
   for (int i = 0; i < N; ++i) std::memcpy(hin + size_t(i) * B, in[i], B * sizeof(float));
-  if (N > 0)
-    SSR_CUDA(cudaMemcpyAsync(d_in.ptr, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  e->stats.h2d_bytes += uint64_t(N) * B * sizeof(float);
-  step(d_in.ptr, d_out.ptr);
   float* hout = h_out.ptr + size_t(slot) * m_local * B;
-  SSR_CUDA(cudaMemcpyAsync(hout, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  e->stats.h2d_bytes += uint64_t(N) * B * sizeof(float);
   e->stats.d2h_bytes += uint64_t(m_local) * B * sizeof(float);
+
+  const StepDesc d = prepare(d_in.ptr, d_out.ptr);
+  auto body = [&]
+  {
+    if (N > 0)
+      SSR_CUDA(cudaMemcpyAsync(d_in.ptr, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    launch(d);
+    SSR_CUDA(cudaMemcpyAsync(hout, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  };
+  // Steady state (no table moved or resized since the last blocks): replay
+  // {H2D, forward FFT, MAC, inverse FFT, D2H} as one CUDA graph per pinned slot
+  // and accumulator-kind mask.  Per-stage event timing needs separate launches.
+  bool done_by_graph = false;
+  if (use_graphs && d.graphable && !e->timing && d.kind_mask > 0 && d.kind_mask < 8)
+  {
+    GraphEntry& g = graphs[slot][d.kind_mask];
+    const uint64_t epoch = g_layout_epoch.load();
+    if (g.exec && g.epoch == epoch)
+    {
+      SSR_CUDA(cudaGraphLaunch(g.exec, e->stream));
+      ++graph_launches;
+      done_by_graph = true;
+    }
+    else if (g.epoch == epoch && ++g.seen >= 2)
+    {
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      SSR_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      try { body(); }
+      catch (...) { cudaStreamEndCapture(e->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+      SSR_CUDA(cudaStreamEndCapture(e->stream, &graph));
+      cudaError_t err = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (err == cudaSuccess)
+      {
+        SSR_CUDA(cudaGraphLaunch(g.exec, e->stream));
+        ++graph_launches;
+        done_by_graph = true;
+      }
+      else { g.exec = nullptr; use_graphs = false; }  // fall back to plain launches for good
+    }
+    else if (g.epoch != epoch) { g.epoch = epoch; g.seen = 0; if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } }
+  }
+  if (!done_by_graph) body();
   if (!done[slot]) SSR_CUDA(cudaEventCreateWithFlags(&done[slot], cudaEventDisableTiming));
   SSR_CUDA(cudaEventRecord(done[slot], e->stream));
   submitted++;
