@@ -206,15 +206,15 @@ void Engine::ensure_partials(size_t nspectra)
   }
 }
 
-void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset)
+void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights)
 {
   const int nwork = int(plan.work.uploaded);
   if (nwork == 0) return;
   MacParams p;
-  p.term_meta = plan.meta.dev.ptr;
-  p.term_h = plan.hptr.dev.ptr;
-  p.work = plan.work.dev.ptr;
-  p.wtab = wtab.dev.ptr;
+  p.term_meta = plan.meta.device();
+  p.term_h = plan.hptr.device();
+  p.work = plan.work.device();
+  p.wtab = weights ? weights : wtab.device();
   p.xring = d_xring.ptr;
   p.xparts = d_xparts.ptr;
   p.heads = d_heads.ptr;
@@ -246,13 +246,13 @@ void Engine::launch_inv(const InvPlan& plan)
     const size_t need = size_t(nentries) * (B / 2);
     if (need > reduced.count) { sync(); reduced.resize(need + need / 2); }
     dim3 grid(nentries, (B / 2 + 31) / 32, 1);
-    reduce_partials_kernel<<<grid, kThreads, 0, stream>>>(plan.entries.dev.ptr, partials.ptr,
+    reduce_partials_kernel<<<grid, kThreads, 0, stream>>>(plan.entries.device(), partials.ptr,
         reduced.ptr, B / 2);
     SSR_CUDA(cudaGetLastError());
     if (cur) cur->ifft_launches++;
     red = reinterpret_cast<const float2*>(reduced.ptr);
   }
-  inv_fft_kernel<<<njobs, kThreads, smem, stream>>>(plan.jobs.dev.ptr, plan.entries.dev.ptr,
+  inv_fft_kernel<<<njobs, kThreads, smem, stream>>>(plan.jobs.device(), plan.entries.device(),
       reinterpret_cast<const float2*>(partials.ptr), red, B, tw.ptr, fade_out.ptr, fade_in.ptr);
   SSR_CUDA(cudaGetLastError());
   if (cur) cur->ifft_launches++;
@@ -495,67 +495,90 @@ void FilterSet::download(int ch, int p, float* sorted_out, int* zero)
 
 // ------------------------------------------------------------------ FilterPtrTable
 FilterPtrTable::FilterPtrTable(int partitions)
-  : P(partitions), ptrs(partitions, nullptr)
-{
-  for (int i = 0; i + 1 < P; ++i) queues.emplace_back(size_t(i + 1), Slot{nullptr, false});
-  qstart.assign(queues.size(), 0);
-}
+  : P(partitions), base_ptrs(partitions, nullptr)
+{}
 
-static std::vector<const float2*> partition_list(const FilterSet& fs, int ch)
+void FilterPtrTable::set_static(const FilterSet& fs, int ch)
 {
   std::vector<const float2*> parts(size_t(fs.partitions));
   for (int p = 0; p < fs.partitions; ++p) parts[p] = fs.part_or_null(ch, p);
-  return parts;
+  set_static_ptrs(parts);
 }
-
-void FilterPtrTable::set_static(const FilterSet& fs, int ch) { set_static_ptrs(partition_list(fs, ch)); }
-void FilterPtrTable::set_filter(const FilterSet& fs, int ch) { set_filter_ptrs(partition_list(fs, ch)); }
 
 void FilterPtrTable::set_static_ptrs(const std::vector<const float2*>& parts)
 {
   // fewer partitions given -> the rest is empty; more -> ignored (convolver.h:733-738)
-  for (int p = 0; p < P; ++p) ptrs[p] = p < int(parts.size()) ? parts[p] : nullptr;
+  for (int p = 0; p < P; ++p) base_ptrs[p] = p < int(parts.size()) ? parts[p] : nullptr;
+  events.clear();
   ++version;
+}
+
+void FilterPtrTable::push_event(Event ev)
+{
+  // a second set_filter() before the next rotate overwrites the same queue slots
+  if (!events.empty() && events.back().t_set == ev.t_set) events.back() = std::move(ev);
+  else events.push_back(std::move(ev));
+  ++version;
+}
+
+void FilterPtrTable::set_filter(const FilterSet& fs, int ch)
+{
+  Event ev{T, fs.part(ch, 0), size_t(fs.e->B), fs.flags.data() + size_t(ch) * fs.partitions,
+           fs.partitions, nullptr};
+  push_event(std::move(ev));
 }
 
 void FilterPtrTable::set_filter_ptrs(const std::vector<const float2*>& parts)
 {
-  // first partition immediately; partition i+1 at the tail of queue i
-  if (!parts.empty()) ptrs[0] = parts[0];
-  for (size_t i = 0; i < queues.size(); ++i)
-  {
-    auto& q = queues[i];
-    const size_t last = (size_t(qstart[i]) + i) % q.size();
-    // beyond the filter -> the (non-null in the reference) empty partition
-    q[last] = Slot{i + 1 < parts.size() ? parts[i + 1] : nullptr, true};
-  }
-  ++version;
+  Event ev{T, nullptr, 0, nullptr, 0, std::make_shared<std::vector<const float2*>>(parts)};
+  push_event(std::move(ev));
 }
 
 bool FilterPtrTable::queues_empty() const
 {
-  if (queues.empty()) return true;
-  for (auto& s : queues.back()) if (s.set) return false;
-  return true;
+  // "some non-null pointer in the last queue" (convolver.h:669-676): an event
+  // whose partition P-1 is not active yet
+  if (P < 2) return true;
+  return events.empty() || events.back().t_set + uint64_t(P - 1) <= T;
 }
 
 void FilterPtrTable::rotate_queues()
 {
-  for (size_t i = 0; i < queues.size(); ++i)
+  ++T;
+  // an event all of whose partitions are active supersedes everything older:
+  // fold the newest such event into the base table
+  int fold = -1;
+  for (int i = int(events.size()) - 1; i >= 0; --i)
+    if (events[i].t_set + uint64_t(P - 1) <= T) { fold = i; break; }
+  if (fold >= 0)
   {
-    auto& q = queues[i];
-    Slot& front = q[qstart[i]];
-    if (front.set) ptrs[i + 1] = front.ptr;
-    front = Slot{nullptr, false};  // becomes the new back
-    qstart[i] = int((size_t(qstart[i]) + 1) % q.size());
+    // partitions for which a newer event already qualifies are taken from it in current()
+    for (int p = 0; p < P; ++p) base_ptrs[p] = events[fold].part(p);
+    events.erase(events.begin(), events.begin() + fold + 1);
   }
   ++version;
 }
 
+const std::vector<const float2*>& FilterPtrTable::current()
+{
+  if (_ptrs_version == version) return _ptrs;
+  _ptrs.resize(size_t(P));
+  int idx = int(events.size()) - 1;
+  for (int p = 0; p < P; ++p)
+  {
+    // t_set + p grows with p, so the newest qualifying event only moves backwards
+    while (idx >= 0 && events[idx].t_set + uint64_t(p) > T) --idx;
+    _ptrs[p] = idx >= 0 ? events[idx].part(p) : base_ptrs[p];
+  }
+  _ptrs_version = version;
+  return _ptrs;
+}
+
 bool FilterPtrTable::references(const float2* lo, const float2* hi) const
 {
-  for (auto p : ptrs) if (p >= lo && p < hi) return true;
-  for (auto& q : queues) for (auto& s : q) if (s.set && s.ptr >= lo && s.ptr < hi) return true;
+  for (auto p : base_ptrs) if (p >= lo && p < hi) return true;
+  for (auto& ev : events)
+    for (int p = 0; p < P; ++p) { const float2* q = ev.part(p); if (q >= lo && q < hi) return true; }
   return false;
 }
 
@@ -600,7 +623,7 @@ void Input::add_block(const float* x)
   std::memcpy(stage.ptr, x, e->B * sizeof(float));
   SSR_CUDA(cudaMemcpyAsync(cur.ptr, stage.ptr, e->B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->stats.h2d_bytes += e->B * sizeof(float);
-  e->launch_fwd(job.dev.ptr, 1);
+  e->launch_fwd(job.device(), 1);
 }
 
 void Input::download(int p, float* sorted_out)
@@ -636,11 +659,12 @@ const float* Output::convolve(float weight)
   {
     mac.clear();
     mac.begin_group();
+    const auto& ptrs = table.current();
     for (int p = 0; p < table.P; ++p)
     {
       // zero-flagged partitions are skipped (convolver.h:561)
-      if (!table.ptrs[p]) continue;
-      const float4* h = reinterpret_cast<const float4*>(table.ptrs[p]);
+      if (!ptrs[p]) continue;
+      const float4* h = reinterpret_cast<const float4*>(ptrs[p]);
       mac.add_term(in->id, p, 0, &h);
     }
     mac.end_group();

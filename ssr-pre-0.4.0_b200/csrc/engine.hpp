@@ -95,6 +95,8 @@ struct Table
   PinnedArray<T> stage;
   DeviceArray<T> dev;
   size_t uploaded = 0;
+  T* ext = nullptr;               // device copy inside a BlockArena (not owned), or null
+  T* device() const { return ext ? ext : dev.ptr; }
   cudaEvent_t staged = nullptr;   // recorded after the last staging -> device copy
   Table() {}
   Table(const Table&) = delete;
@@ -106,6 +108,7 @@ struct Table
   // already queued may still read the old table.
   void upload(cudaStream_t s)
   {
+    ext = nullptr;
     if (uploaded != host.size()) ++g_layout_epoch;
     uploaded = host.size();
     if (host.empty()) return;
@@ -121,6 +124,50 @@ struct Table
     SSR_CUDA(cudaMemcpyAsync(dev.ptr, stage.ptr, host.size() * sizeof(T),
           cudaMemcpyHostToDevice, s));
     SSR_CUDA(cudaEventRecord(staged, s));
+  }
+};
+
+// All per-block tables of a renderer in ONE pinned staging buffer and ONE
+// host-to-device copy (Binaural / BRS rebuild their tables every block).  Two
+// buffers alternate, so building block t+1 only waits for block t-1's copy.
+struct BlockArena
+{
+  PinnedArray<unsigned char> stage[2];
+  DeviceArray<unsigned char> dev[2];
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  int cur = 0;
+  size_t off = 0;
+  BlockArena() {}
+  BlockArena(const BlockArena&) = delete;
+  BlockArena& operator=(const BlockArena&) = delete;
+  ~BlockArena() { for (auto ev : copied) if (ev) cudaEventDestroy(ev); }
+  static size_t align(size_t n) { return (n + 255) & ~size_t(255); }
+  void begin(size_t total_bytes, cudaStream_t s)
+  {
+    cur ^= 1;
+    if (copied[cur]) SSR_CUDA(cudaEventSynchronize(copied[cur]));
+    else SSR_CUDA(cudaEventCreateWithFlags(&copied[cur], cudaEventDisableTiming));
+    if (total_bytes > stage[cur].count)
+    {
+      SSR_CUDA(cudaStreamSynchronize(s));  // kernels still reading the old device buffer
+      stage[cur].resize(total_bytes + total_bytes / 2 + 4096);
+      dev[cur].resize(stage[cur].count);
+    }
+    off = 0;
+  }
+  template<typename T> void put(Table<T>& t)
+  {
+    const size_t bytes = t.host.size() * sizeof(T);
+    if (bytes) std::memcpy(stage[cur].ptr + off, t.host.data(), bytes);
+    t.ext = reinterpret_cast<T*>(dev[cur].ptr + off);
+    t.uploaded = t.host.size();
+    off += align(bytes);
+  }
+  template<typename T> static size_t bytes_of(const Table<T>& t) { return align(t.host.size() * sizeof(T)); }
+  void commit(cudaStream_t s)
+  {
+    if (off) SSR_CUDA(cudaMemcpyAsync(dev[cur].ptr, stage[cur].ptr, off, cudaMemcpyHostToDevice, s));
+    SSR_CUDA(cudaEventRecord(copied[cur], s));
   }
 };
 
@@ -190,7 +237,7 @@ struct Engine
 
   // launches (all asynchronous on `stream`)
   void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs);
-  void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset);
+  void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr);
   void launch_inv(const InvPlan& plan);
   void upload_weights(const float* w, size_t n);
   void ensure_partials(size_t npartial_spectra);
@@ -239,21 +286,47 @@ struct FilterPtrTable
 {
   explicit FilterPtrTable(int partitions);
   int P;
-  std::vector<const float2*> ptrs;             // _filter_ptrs
-  // _queues[i] (i = 0..P-2) has i+1 slots; kept as rings so rotate is O(P)
-  struct Slot { const float2* ptr; bool set; };
-  std::vector<std::vector<Slot>> queues;
-  std::vector<int> qstart;
+
+  // The reference keeps P-1 shifting queues of lengths 1..P-1 (O(P^2) slots and
+  // pointer moves per rotate, convolver.h:623-624,690-698).  All queues are fed
+  // together by set_filter(), so the same behaviour follows from a short list of
+  // switch EVENTS: partition p of a filter installed after T_set rotations is
+  // used once T >= T_set + p, i.e.
+  //     ptr[p](T) = part p of the newest event with T_set + p <= T   (else base[p]).
+  // rotate_queues() is then O(1) and the table is materialised on demand in
+  // O(P + events).
+  struct Event
+  {
+    uint64_t t_set;
+    const float2* base; size_t stride; const uint8_t* flags; int nparts;   // a FilterSet channel ...
+    std::shared_ptr<std::vector<const float2*>> list;                       // ... or an explicit list
+    const float2* part(int p) const
+    {
+      if (list) return p < int(list->size()) ? (*list)[p] : nullptr;
+      return (p < nparts && flags[p]) ? base + size_t(p) * stride : nullptr;  // beyond -> empty
+    }
+  };
+  uint64_t T = 0;                                  // rotate_queues() calls so far
+  std::vector<const float2*> base_ptrs;            // table before / below all pending events
+  std::vector<Event> events;                       // ascending t_set, at most one per T
+
   void set_static(const FilterSet& fs, int ch);    // StaticOutput::_set_filter :729-739
   void set_filter(const FilterSet& fs, int ch);    // :642-658
   // the same on a plain list of partition pointers (null = zero-flagged,
   // entries beyond the list = empty partition); pure host logic
   void set_static_ptrs(const std::vector<const float2*>& parts);
   void set_filter_ptrs(const std::vector<const float2*>& parts);
-  uint64_t version = 0;                            // bumped whenever `ptrs` may have changed
+  uint64_t version = 0;                            // bumped whenever the table may have changed
   bool queues_empty() const;                       // :666-677
   void rotate_queues();                            // :683-699
+  // _filter_ptrs as of now (null = empty / zero-flagged partition)
+  const std::vector<const float2*>& current();
   bool references(const float2* lo, const float2* hi) const;
+
+  private:
+    std::vector<const float2*> _ptrs;
+    uint64_t _ptrs_version = ~uint64_t(0);
+    void push_event(Event ev);
 };
 
 // ------------------------------------------------------------ Level 1 objects
@@ -354,6 +427,11 @@ struct Renderer
   std::vector<std::pair<const float*, std::unique_ptr<Table<ssrk::FwdJob>>>> fwd_cache;
   Table<ssrk::FwdJob>* fwd = nullptr;
   std::vector<float> wtab_host;
+  int mac_slots_cached = 0;
+  BlockArena arena;                      // per-block tables of the dynamic renderers
+  Table<float> dyn_wtab;                 // their weights travel in the arena too
+  std::vector<ssrk::MacTermMeta> kind_meta[3];
+  std::vector<const float4*> kind_h[3];  // [terms][2 ears], per accumulator kind
   DeviceArray<float> d_in, d_out;
   PinnedArray<float> h_in, h_out;
   int inv_key = -1;

@@ -14,7 +14,9 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 namespace ssr_b200
@@ -23,6 +25,31 @@ namespace ssr_b200
 using namespace ssrk;
 
 static constexpr int kGenericMT = 4;
+
+// SSR_B200_PROFILE_HOST=1: wall time of the host-side sections of a block,
+// printed when the renderer is destroyed (development aid)
+struct HostProfile
+{
+  bool on = std::getenv("SSR_B200_PROFILE_HOST") != nullptr;
+  double acc[8] = {0}; uint64_t n = 0;
+  std::chrono::steady_clock::time_point t;
+  void start() { if (on) t = std::chrono::steady_clock::now(); }
+  void lap(int i)
+  {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  void report(const char* what)
+  {
+    if (!on || !n) return;
+    std::printf("[ssr_b200 host profile] %s: %llu blocks; us/block:", what, (unsigned long long)n);
+    for (int i = 0; i < 8; ++i) if (acc[i] > 0) std::printf(" s%d=%.1f", i, acc[i] / n);
+    std::printf("\n");
+  }
+};
+static HostProfile g_prof;
 
 Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   : e(e_), cfg(c)
@@ -62,6 +89,7 @@ Renderer::~Renderer()
   cudaStreamSynchronize(e->stream);
   for (auto ev : done) if (ev) cudaEventDestroy(ev);
   drop_graphs();
+  g_prof.report("s0 source logic, s1 plan, s2 inv+arena, s3 fwd table, s4 launches");
 }
 
 Renderer::Source* Renderer::find(int id)
@@ -330,13 +358,28 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   plan.clear();
   const float4* zero = reinterpret_cast<const float4*>(e->zero_part.ptr);
 
-  // terms of one (source, kind) with the pointer tables as they are NOW
-  struct Pending { int n; int kind; std::vector<const float2*> l, r; };
-  std::vector<Pending> pend;
+  // terms of one (source, kind) with the pointer tables as they are NOW, appended
+  // to the kind's term list (vectors are members: no allocation in steady state)
+  for (int k = 0; k < 3; ++k) { kind_meta[k].clear(); kind_h[k].clear(); }
+  uint64_t hparts = 0, xparts = 0;
+  g_prof.start();
   auto snapshot = [&](int n, int kind)
   {
     Source& s = *sources[n];
-    pend.push_back({n, kind, s.chan[0].ptrs, s.chan[1].ptrs});
+    const auto& lp = s.chan[0].current();
+    const auto& rp = s.chan[1].current();
+    const int id = s.input->id, P = s.input->P;
+    for (int p = 0; p < P; ++p)
+    {
+      const float2* l = lp[p];
+      const float2* r = rp[p];
+      if (!l && !r) continue;
+      kind_meta[kind].push_back({id, p, kind * N + n, 0});
+      kind_h[kind].push_back(l ? reinterpret_cast<const float4*>(l) : zero);
+      kind_h[kind].push_back(r ? reinterpret_cast<const float4*>(r) : zero);
+      hparts += (l ? 1 : 0) + (r ? 1 : 0);
+      xparts += 1;
+    }
   };
 
   for (int n = 0; n < N; ++n)
@@ -444,36 +487,21 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     else if (mode == CHANGE || mode == FADE_IN) { snapshot(n, 2); wtab_host[2 * N + n] = w.get(); }
   }
 
+  g_prof.lap(0);
   // one plan, up to three groups (const / old / new), rows = (left, right)
   int group_of_kind[3] = {-1, -1, -1};
-  uint64_t hparts = 0, xparts = 0;
   for (int k = 0; k < 3; ++k)
   {
-    bool any = false;
-    for (auto& pd : pend) if (pd.kind == k) { any = true; break; }
-    if (!any) continue;
+    if (kind_meta[k].empty()) continue;
     group_of_kind[k] = plan.begin_group();
-    for (auto& pd : pend)
-    {
-      if (pd.kind != k) continue;
-      Source& s = *sources[pd.n];
-      for (int p = 0; p < s.input->P; ++p)
-      {
-        const float2* l = pd.l[p];
-        const float2* r = pd.r[p];
-        if (!l && !r) continue;
-        const float4* h[2] = { l ? reinterpret_cast<const float4*>(l) : zero,
-                               r ? reinterpret_cast<const float4*>(r) : zero };
-        plan.add_term(s.input->id, p, k * N + pd.n, h);
-        hparts += (l ? 1 : 0) + (r ? 1 : 0);
-        xparts += 1;
-      }
-    }
+    plan.meta.host.insert(plan.meta.host.end(), kind_meta[k].begin(), kind_meta[k].end());
+    plan.hptr.host.insert(plan.hptr.host.end(), kind_h[k].begin(), kind_h[k].end());
     plan.end_group();
   }
-  plan.make_work(e->mac_slots());
-  plan.upload(e->stream);
+  if (mac_slots_cached == 0) mac_slots_cached = e->mac_slots();
+  plan.make_work(mac_slots_cached);
   e->ensure_partials(size_t(plan.npartials) * plan.MT);
+  g_prof.lap(1);
 
   inv.clear();
   const float scale = 1.0f / float(2 * B);
@@ -492,10 +520,18 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     }
     inv.jobs.host.push_back(job);
   }
-  inv.upload(e->stream);
+
+  // one staging buffer, one copy for every table of this block
+  dyn_wtab.host = wtab_host;
+  arena.begin(BlockArena::bytes_of(plan.meta) + BlockArena::bytes_of(plan.hptr) + BlockArena::bytes_of(plan.work)
+      + BlockArena::bytes_of(inv.jobs) + BlockArena::bytes_of(inv.entries) + BlockArena::bytes_of(dyn_wtab), e->stream);
+  arena.put(plan.meta); arena.put(plan.hptr); arena.put(plan.work);
+  arena.put(inv.jobs); arena.put(inv.entries); arena.put(dyn_wtab);
+  arena.commit(e->stream);
+  g_prof.lap(2);
 
   build_fwd(d_input);
-  e->upload_weights(wtab_host.data(), wtab_host.size());
+  g_prof.lap(3);
   d.N = N;
   d.kind_mask = 1;
   d.hparts[0] = hparts; d.xparts[0] = xparts; d.nrows = nrows;
@@ -577,7 +613,7 @@ void Renderer::launch(const StepDesc& d)
 {
   const int B = e->B;
   e->stage_begin();
-  e->launch_fwd(fwd->dev.ptr, d.N);
+  e->launch_fwd(fwd->device(), d.N);
   e->stage_mark(1);
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
@@ -594,7 +630,8 @@ void Renderer::launch(const StepDesc& d)
   }
   else
   {
-    e->launch_mac(cfg.kind == SSR_RENDERER_PREFILTER_BANK ? static_mac : dyn_mac[0], 0, 0);
+    if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) e->launch_mac(static_mac, 0, 0);
+    else e->launch_mac(dyn_mac[0], 0, 0, dyn_wtab.device());
     if (e->cur)
     {
       e->cur->mac_bytes += uint64_t(8) * B * (d.hparts[0] + d.xparts[0] + uint64_t(d.nrows));
@@ -610,7 +647,10 @@ void Renderer::launch(const StepDesc& d)
 void Renderer::step(const float* d_input, float* d_output)
 {
   const StepDesc d = prepare(d_input, d_output);
+  g_prof.start();
   launch(d);
+  g_prof.lap(4);
+  g_prof.n++;
 }
 
 void Renderer::drop_graphs()

@@ -88,7 +88,7 @@ static void test_ptr_table()
       for (int p = 0; p < P; ++p)
       {
         const float2* want = lit.ptrs[p] == &empty_marker ? nullptr : lit.ptrs[p];
-        same = same && (t.ptrs[p] == want);
+        same = same && (t.current()[p] == want);
       }
       CHECK(same);
     }
@@ -98,18 +98,18 @@ static void test_ptr_table()
   FilterPtrTable t(2);
   std::vector<const float2*> f = { &storage[1][0], &storage[1][1] };
   t.set_filter_ptrs(f);
-  CHECK(t.ptrs[0] == &storage[1][0] && t.ptrs[1] == nullptr);
+  CHECK(t.current()[0] == &storage[1][0] && t.current()[1] == nullptr);
   CHECK(!t.queues_empty());
   t.rotate_queues();
-  CHECK(t.ptrs[1] == &storage[1][1]);
+  CHECK(t.current()[1] == &storage[1][1]);
   CHECK(t.queues_empty());
 
   // StaticOutput::_set_filter: fewer partitions -> rest empty, more -> ignored
   FilterPtrTable s(3);
   s.set_static_ptrs({ &storage[2][0] });
-  CHECK(s.ptrs[0] == &storage[2][0] && s.ptrs[1] == nullptr && s.ptrs[2] == nullptr);
+  CHECK(s.current()[0] == &storage[2][0] && s.current()[1] == nullptr && s.current()[2] == nullptr);
   s.set_static_ptrs({ &storage[3][0], &storage[3][1], &storage[3][2], &storage[3][3] });
-  CHECK(s.ptrs[2] == &storage[3][2]);
+  CHECK(s.current()[2] == &storage[3][2]);
   const uint64_t v = s.version;
   s.rotate_queues();
   CHECK(s.version != v);
