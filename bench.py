@@ -211,10 +211,54 @@ def run_reference_dynamic(w, n_sources: int, blocks: int, warm: int, threads: in
     return secs, times
 
 
+def port_sample(w, steps: int, warmup: int):
+    """Fallback when oracle/_ref is not built: the numpy restatement
+    (oracle/conv_oracle.py, kind "port", one core) on ONE output of a Generic
+    workload / one source of a Binaural/BRS workload, scaled to the full shape."""
+    from oracle import conv_oracle as co
+    import ssr_b200.capi as capi
+    import ssr_b200.workloads as wl
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    steps, warmup = min(steps, 10), min(warmup, 2)
+    if w.kind == "generic":
+        nsrc = min(w.sources, 8)
+        o = co.GenericRendererOracle(w.block, 1)
+        for n in range(nsrc):
+            o.add_source(capi.synth_ir(w.ir_seed, n * w.outputs, w.taps, env, scale)[:, None])
+        factor = (w.sources / nsrc) * w.outputs
+        what = f"{nsrc} of {w.sources} src x 1 of {w.outputs} outputs"
+    else:
+        nsrc = 1
+        cols = np.stack([capi.synth_ir(w.ir_seed, c, w.taps, env, scale) for c in range(w.channels)], axis=1)
+        if w.kind == "brs":
+            o = co.BrsRendererOracle(w.block)
+            o.add_source(cols)
+        else:
+            o = co.BinauralRendererOracle(w.block, cols)
+            o.add_source()
+            o.sources[0].position = (2.0, 0.0)
+        factor = w.sources
+        what = f"1 of {w.sources} src x 2 ears"
+    x = np.stack([wl.signal_block(w, t, nsrc) for t in range(4)])
+    times = []
+    for t in range(warmup + steps):
+        t0 = time.perf_counter()
+        o.process(x[t % 4])
+        if t >= warmup:
+            times.append((time.perf_counter() - t0) * 1e3)
+    times = np.array(times) * factor
+    sample = (f"numpy PORT of the reference (oracle/conv_oracle.py; oracle/_ref not built): {w.name}, {what}; "
+              f"{steps} blocks; block time scaled x{factor:g} (extrapolated)")
+    return float(times.mean()), times, 1, sample, "port"
+
+
 def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, rotate: bool = True):
     """Runs the reference CPU arm on a bounded sample of workload `w`.
-    Returns (full-workload ms per block, per-block ms scaled, cores used, sample text)."""
+    Returns (full-workload ms per block, per-block ms scaled, cores used, sample text, kind)."""
     from oracle import ref
+    if not ref.available():
+        return port_sample(w, steps, warmup)
     if w.kind == "generic":
         shard = reference_plan(w, steps, warmup, budget_s, threads)
         used = max(1, min(threads, shard))  # items are spread round-robin over outputs
@@ -236,7 +280,7 @@ def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, 
     full_ms = secs / steps * 1e3 * factor
     sample = (f"reference {w.name}: {what}; {steps} blocks after {warmup} warm-up; block time scaled "
               f"x{factor:g} to the full workload{' (extrapolated)' if factor != 1 else ''}; {ref.describe()}")
-    return full_ms, times * factor, used, sample
+    return full_ms, times * factor, used, sample, "reference"
 
 
 def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int):
@@ -259,13 +303,10 @@ def main_reference(args):
     w, reduced = get_workload(args)
     from oracle import ref
     threads = os.cpu_count() or 1
-    if not ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libssr_ref.so not built"}))
-        return 0
     steps, warmup = args.steps, args.warmup
     entry.load_package()
-    full_ms, times, threads_used, sample = reference_sample(w, steps, warmup, 150.0, threads,
-                                                            rotate=not args.static_head)
+    full_ms, times, threads_used, sample, kind = reference_sample(w, steps, warmup, 150.0, threads,
+                                                                  rotate=not args.static_head)
     value = (w.block / w.fs) / (full_ms * 1e-3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -273,7 +314,7 @@ def main_reference(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w.label() + (" [REDUCED]" if reduced else ""), "block": w.block,
                    "sample_rate": w.fs, "partitions": w.partitions},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads_used, "kind": "reference",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads_used, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "p99_block_ms": float(np.percentile(times, 99)),
@@ -300,6 +341,11 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if not os.path.exists(os.path.join(entry.PKG_DIR, "lib", "libssr_b200.so")):
+        if rank == 0:
+            entry.build()  # fresh checkout: the built library is git-ignored
+        if world > 1:
+            dist.barrier()
     entry.load_package()
     import ssr_b200.capi as capi
     import ssr_b200.multigpu as mg
@@ -527,16 +573,11 @@ def main_ours(args):
     # ---- CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            from oracle import ref
-            if ref.available():
-                threads = os.cpu_count() or 1
-                full_ms, _, used, sample = reference_sample(w, 40, 5, args.cpu_seconds, threads, rotate=rotate)
-                line["cpu_baseline"] = {
-                    "value": (B / w.fs) / (full_ms * 1e-3), "unit": UNIT, "cores": used, "kind": "reference",
-                    "sample": sample}
-            else:
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                                        "sample": "oracle/_ref/libssr_ref.so missing"}
+            threads = os.cpu_count() or 1
+            full_ms, _, used, sample, kind = reference_sample(w, 40, 5, args.cpu_seconds, threads, rotate=rotate)
+            line["cpu_baseline"] = {
+                "value": (B / w.fs) / (full_ms * 1e-3), "unit": UNIT, "cores": used, "kind": kind,
+                "sample": sample}
         except Exception as exc:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                     "sample": f"failed: {exc}"}
