@@ -140,6 +140,7 @@ Engine::Engine(const ssr_engine_config& cfg)
   {
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
   }
   SSR_CUDA(cudaDeviceSynchronize());
 }
@@ -194,6 +195,39 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs)
   fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr);
   SSR_CUDA(cudaGetLastError());
   if (cur) cur->fft_launches++;
+}
+
+void Engine::launch_fwd_batch(const FwdBatch& batch, int nparts, int nchannels)
+{
+  if (nparts <= 0 || nchannels <= 0) return;
+  const size_t smem = size_t(2) * B * sizeof(float2);
+  // grid (partition, channel lo, channel hi): gridDim.y is limited to 65535
+  const int gy = std::min(nchannels, 32768);
+  for (int c0 = 0; c0 < nchannels; c0 += gy * 65535)
+  {
+    FwdBatch b = batch;
+    const int n = std::min(nchannels - c0, gy * 65535);
+    b.first_channel += c0;
+    b.id_offset += uint64_t(c0);
+    if (!b.synth) b.time += long(c0) * b.channel_stride;
+    // full rows of gy channels, then the remainder
+    const int gz = n / gy;
+    if (gz > 0)
+    {
+      fwd_fft_batch_kernel<<<dim3(nparts, gy, gz), kThreads, smem, stream>>>(b, B, tw.ptr);
+      SSR_CUDA(cudaGetLastError());
+    }
+    const int rem = n - gz * gy;
+    if (rem > 0)
+    {
+      FwdBatch r = b;
+      r.first_channel += gz * gy;
+      r.id_offset += uint64_t(gz) * gy;
+      if (!r.synth) r.time += long(gz) * gy * r.channel_stride;
+      fwd_fft_batch_kernel<<<dim3(nparts, rem, 1), kThreads, smem, stream>>>(r, B, tw.ptr);
+      SSR_CUDA(cudaGetLastError());
+    }
+  }
 }
 
 void Engine::ensure_partials(size_t nspectra)
@@ -350,26 +384,20 @@ void FilterSet::load_time(int first_channel, int nch, const float* host, long fr
     SSR_CUDA(cudaMemcpyAsync(d_time.ptr, host, size_t(extent) * sizeof(float),
           cudaMemcpyHostToDevice, e->stream));
   const int nvalid = int(std::min<long>(partitions, (frames + B - 1) / B));
-  std::vector<FwdJob> jobs;
-  jobs.reserve(size_t(nch) * nvalid);
   for (int c = 0; c < nch; ++c)
   {
     const int ch = first_channel + c;
     valid[ch] = nvalid;
     for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
-    for (int p = 0; p < nvalid; ++p)
-    {
-      FwdJob j{};
-      j.first.ptr = d_time.ptr + c * channel_stride + long(p) * B * frame_stride;
-      j.first.stride = frame_stride;
-      j.first.count = int(std::min<long>(B, frames - long(p) * B));
-      j.second.ptr = nullptr; j.second.count = 0; j.second.stride = 1;
-      j.dst = part(ch, p);
-      jobs.push_back(j);
-    }
   }
-  run_fwd_jobs(e, jobs);
-  e->sync();
+  FwdBatch batch{};
+  batch.time = d_time.ptr;
+  batch.frame_stride = frame_stride; batch.channel_stride = channel_stride;
+  batch.frames = frames;
+  batch.set = data.ptr; batch.partitions = partitions; batch.first_channel = first_channel;
+  batch.synth = 0;
+  e->launch_fwd_batch(batch, nvalid, nch);
+  e->sync();  // d_time goes out of scope
 }
 
 void FilterSet::set_partition_time(int ch, int p, const float* taps, int n)
@@ -410,36 +438,20 @@ void FilterSet::generate(int first_channel, int nch, long taps, uint64_t seed, u
           cudaMemcpyHostToDevice, e->stream));
   }
   const int nvalid = int(std::min<long>(partitions, (taps + B - 1) / B));
-  std::vector<FwdJob> jobs;
-  const size_t batch_channels = std::max<size_t>(1, (size_t(1) << 16) / size_t(nvalid));
-  for (int c0 = 0; c0 < nch; c0 += int(batch_channels))
+  for (int c = 0; c < nch; ++c)
   {
-    const int c1 = int(std::min<size_t>(nch, c0 + batch_channels));
-    jobs.clear();
-    for (int c = c0; c < c1; ++c)
-    {
-      const int ch = first_channel + c;
-      valid[ch] = nvalid;
-      for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
-      const uint64_t key = synth_key(seed, id_offset + uint64_t(c));
-      for (int p = 0; p < nvalid; ++p)
-      {
-        FwdJob j{};
-        j.first.ptr = d_env.ptr;
-        j.first.stride = 1;
-        j.first.count = int(std::min<long>(B, taps - long(p) * B));
-        j.first.synth = 1;
-        j.first.key = key;
-        j.first.first_index = uint64_t(p) * B;
-        j.first.scale = scale;
-        j.second.stride = 1;
-        j.dst = part(ch, p);
-        jobs.push_back(j);
-      }
-    }
-    run_fwd_jobs(e, jobs);
+    const int ch = first_channel + c;
+    valid[ch] = nvalid;
+    for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
   }
-  e->sync();
+  FwdBatch batch{};
+  batch.time = d_env.ptr;
+  batch.frame_stride = 1; batch.channel_stride = 0;
+  batch.frames = taps;
+  batch.set = data.ptr; batch.partitions = partitions; batch.first_channel = first_channel;
+  batch.synth = 1; batch.scale = scale; batch.seed = seed; batch.id_offset = id_offset;
+  e->launch_fwd_batch(batch, nvalid, nch);
+  e->sync();  // d_env goes out of scope
 }
 
 void FilterSet::lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t)

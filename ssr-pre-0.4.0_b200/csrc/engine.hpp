@@ -237,6 +237,7 @@ struct Engine
 
   // launches (all asynchronous on `stream`)
   void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs);
+  void launch_fwd_batch(const ssrk::FwdBatch& batch, int nparts, int nchannels);
   void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr);
   void launch_inv(const InvPlan& plan);
   void upload_weights(const float* w, size_t n);

@@ -230,13 +230,11 @@ __device__ __forceinline__ float fwd_sample(const FwdHalf& h, int i)
 }
 
 // One CTA per transform.  B = block size = complex FFT size; smem = 2 * B float2.
-__global__ void __launch_bounds__(kThreads)
-fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw)
+__device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const float2* __restrict__ tw)
 {
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B;
-  const FwdJob job = jobs[blockIdx.x];
   const int t = threadIdx.x;
   const int half = B >> 1;
 
@@ -305,6 +303,62 @@ fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict_
   // thread 0 may publish the new one now.  No other CTA of this launch touches
   // this ring; the next kernel in stream order (MAC) sees the new value.
   if (!job.dst && t == 0) *job.head = new_head;
+}
+
+__global__ void __launch_bounds__(kThreads)
+fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw)
+{
+  const FwdJob job = jobs[blockIdx.x];
+  fwd_fft_body(job, B, tw);
+}
+
+// Filter-set loading: one launch transforms `channels x nvalid` partitions described
+// by ONE descriptor (no per-transform job table): CTA (p, c) transforms taps
+// [p*B, p*B + B) of channel c into set[(first_channel + c) * partitions + p].
+struct FwdBatch
+{
+  const float* time;       // time-domain taps (memory mode) or the envelope table (synth mode)
+  long frame_stride, channel_stride;
+  long frames;             // taps per channel
+  float2* set;             // filter set base
+  int partitions;          // partitions per channel in the set
+  int first_channel;       // channel offset in the set
+  int synth;               // 1: generate u(seed, id_offset + c, tap) * envelope[tap] * scale
+  float scale;
+  uint64_t seed, id_offset;
+};
+
+__global__ void __launch_bounds__(kThreads)
+fwd_fft_batch_kernel(const FwdBatch batch, int B, const float2* __restrict__ tw)
+{
+  const int p = blockIdx.x;
+  const long c = blockIdx.y + long(blockIdx.z) * gridDim.y;
+  FwdJob job;
+  const long first_tap = long(p) * B;
+  const long left = batch.frames - first_tap;
+  job.first.count = int(left < B ? left : B);
+  job.first.synth = batch.synth;
+  job.first.scale = batch.scale;
+  job.first.pad = 0;
+  if (batch.synth)
+  {
+    job.first.ptr = batch.time;   // envelope (indexed by first_index + i) or null
+    job.first.stride = 1;
+    job.first.key = synth_key(batch.seed, batch.id_offset + uint64_t(c));
+    job.first.first_index = uint64_t(first_tap);
+  }
+  else
+  {
+    job.first.ptr = batch.time + c * batch.channel_stride + first_tap * batch.frame_stride;
+    job.first.stride = batch.frame_stride;
+    job.first.key = 0; job.first.first_index = 0;
+  }
+  job.second.ptr = nullptr; job.second.stride = 1; job.second.count = 0; job.second.synth = 0;
+  job.second.key = 0; job.second.first_index = 0; job.second.scale = 0.f; job.second.pad = 0;
+  job.dst = batch.set + (size_t(batch.first_channel + c) * batch.partitions + p) * B;
+  job.ring = nullptr; job.head = nullptr; job.parts = 0;
+  job.save_second = nullptr; job.level = nullptr;
+  fwd_fft_body(job, B, tw);
 }
 
 // ---------------------------------------------------------------- MAC
