@@ -1,5 +1,6 @@
 // engine.cu -- engine core: device resources, launches, filter sets, Level-1 objects.
 #include "engine.hpp"
+#include "fft1024.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -87,6 +88,11 @@ Engine::Engine(const ssr_engine_config& cfg)
 {
   if (mac_variant == 0)
     if (const char* v = std::getenv("SSR_B200_MAC_VARIANT")) mac_variant = std::atoi(v);  // experiments
+  // B = 1024: one-warp-per-transform register FFT (fft1024.cuh); SSR_B200_FFT=generic
+  // selects the shared-memory Stockham kernels instead (A/B experiments)
+  const char* fft_env = std::getenv("SSR_B200_FFT");
+  fft1024 = (B == 1024) && !(fft_env && std::string(fft_env) == "generic");
+  fft1024_always = fft_env && std::string(fft_env) == "fft1024";  // also for small launches (tests, A/B)
   if (B <= 0 || B % 8 != 0)
     throw Error(SSR_ERR_BLOCK_SIZE, "Convolver: block size must be a multiple of 8!");
   if ((B & (B - 1)) != 0 || B > 4096)
@@ -191,8 +197,19 @@ int Engine::mac_slots() const
 void Engine::launch_fwd(const FwdJob* d_jobs, int njobs)
 {
   if (njobs <= 0) return;
-  const size_t smem = size_t(2) * B * sizeof(float2);
-  fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr);
+  // One warp per transform wins on throughput (2.2x at filter load), one CTA per
+  // transform on latency; the block loop rarely has enough transforms to fill
+  // the machine (profiles/r1_fft_kernels.md)
+  if (fft1024 && (njobs >= kFft1024MinJobs || fft1024_always))
+  {
+    const int ctas = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
+    fwd_fft1024_kernel<<<ctas, kWarpsPerCta * 32, 0, stream>>>(d_jobs, njobs, tw.ptr);
+  }
+  else
+  {
+    const size_t smem = size_t(2) * B * sizeof(float2);
+    fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr);
+  }
   SSR_CUDA(cudaGetLastError());
   if (cur) cur->fft_launches++;
 }
@@ -200,6 +217,14 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs)
 void Engine::launch_fwd_batch(const FwdBatch& batch, int nparts, int nchannels)
 {
   if (nparts <= 0 || nchannels <= 0) return;
+  if (fft1024)
+  {
+    const long total = long(nparts) * nchannels;
+    const long ctas = (total + kWarpsPerCta - 1) / kWarpsPerCta;
+    fwd_fft1024_batch_kernel<<<unsigned(ctas), kWarpsPerCta * 32, 0, stream>>>(batch, nparts, total, tw.ptr);
+    SSR_CUDA(cudaGetLastError());
+    return;
+  }
   const size_t smem = size_t(2) * B * sizeof(float2);
   // grid (partition, channel lo, channel hi): gridDim.y is limited to 65535
   const int gy = std::min(nchannels, 32768);
@@ -286,8 +311,15 @@ void Engine::launch_inv(const InvPlan& plan)
     if (cur) cur->ifft_launches++;
     red = reinterpret_cast<const float2*>(reduced.ptr);
   }
-  inv_fft_kernel<<<njobs, kThreads, smem, stream>>>(plan.jobs.device(), plan.entries.device(),
-      reinterpret_cast<const float2*>(partials.ptr), red, B, tw.ptr, fade_out.ptr, fade_in.ptr);
+  if (fft1024 && (njobs >= kFft1024MinJobs || fft1024_always))
+  {
+    const int ctas = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
+    inv_fft1024_kernel<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.jobs.device(), njobs, plan.entries.device(),
+        reinterpret_cast<const float2*>(partials.ptr), red, tw.ptr, fade_out.ptr, fade_in.ptr);
+  }
+  else
+    inv_fft_kernel<<<njobs, kThreads, smem, stream>>>(plan.jobs.device(), plan.entries.device(),
+        reinterpret_cast<const float2*>(partials.ptr), red, B, tw.ptr, fade_out.ptr, fade_in.ptr);
   SSR_CUDA(cudaGetLastError());
   if (cur) cur->ifft_launches++;
 }

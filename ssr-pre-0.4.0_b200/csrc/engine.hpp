@@ -216,6 +216,9 @@ struct Engine
   ~Engine();
 
   int device, B, sample_rate, sm_count, mac_variant;
+  bool fft1024 = false;            // B == 1024: register/shuffle FFT kernels (fft1024.cuh)
+  bool fft1024_always = false;
+  static constexpr int kFft1024MinJobs = 1024;
   cudaStream_t stream;
   bool own_stream;
 
