@@ -424,7 +424,7 @@ struct Renderer
   // per-block plans
   MacPlan static_mac;           // generic: built when the source list changes
   bool static_dirty = true;
-  MacPlan dyn_mac[3];           // brs / binaural: const / old / new
+  MacPlan dyn_mac;              // brs / binaural: one plan, groups = const / old / new
   InvPlan inv;
   // forward-FFT job tables, one per distinct device input pointer (a caller
   // cycling through a few input buffers never re-uploads in steady state)

@@ -78,7 +78,7 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
   static_mac.MT = kGenericMT;
-  for (auto& p : dyn_mac) p.MT = 2;
+  dyn_mac.MT = 2;
   d_out.resize(size_t(std::max(m_local, 1)) * e->B);
   h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
 }
@@ -354,7 +354,7 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   const int B = e->B;
   const bool binaural = cfg.kind == SSR_RENDERER_BINAURAL;
   wtab_host.assign(size_t(3) * std::max(N, 1), 0.0f);
-  MacPlan& plan = dyn_mac[0];
+  MacPlan& plan = dyn_mac;
   plan.clear();
   const float4* zero = reinterpret_cast<const float4*>(e->zero_part.ptr);
 
@@ -631,7 +631,7 @@ void Renderer::launch(const StepDesc& d)
   else
   {
     if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) e->launch_mac(static_mac, 0, 0);
-    else e->launch_mac(dyn_mac[0], 0, 0, dyn_wtab.device());
+    else e->launch_mac(dyn_mac, 0, 0, dyn_wtab.device());
     if (e->cur)
     {
       e->cur->mac_bytes += uint64_t(8) * B * (d.hparts[0] + d.xparts[0] + uint64_t(d.nrows));
