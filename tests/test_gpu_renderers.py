@@ -375,3 +375,49 @@ def test_small_block_sizes_through_the_renderers(capi, co, engine_factory):
             x = rng.uniform(-1, 1, (1, B)).astype(np.float32)
             worst = max(worst, maxerr(r.process(x), o.process(x)))
         assert worst <= TOL, worst
+
+
+@pytest.mark.parametrize("B", [2048, 4096])
+def test_large_block_sizes_use_spectrum_tiles(capi, co, engine_factory, B):
+    """B > 1024: the MAC kernel walks the spectrum in 1024-bin tiles (grid.y) and the
+    FFT kernels need > 48 KiB of dynamic shared memory at B = 4096."""
+    rng = np.random.default_rng(B)
+    N, M, L = 3, 5, 3 * B + 17
+    e = engine_factory(B)
+    r = capi.Renderer(e, capi.GENERIC, outputs=M)
+    o = co.GenericRendererOracle(B, M)
+    gain = 0.5 / np.sqrt(N * L / 6.9)
+    for n in range(N):
+        ir = decaying(rng, L, M, gain)
+        r.add_source(ir); o.add_source(ir)
+    b = capi.Renderer(e, capi.BRS)
+    ob = co.BrsRendererOracle(B)
+    brir = decaying(rng, 2 * B + 5, 8, 0.5 / np.sqrt(2 * B / 6.9))
+    b.add_source(brir); ob.add_source(brir)
+    worst = 0.0
+    for t in range(10):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        if t == 4:
+            r.set_gain(1, 0.25); o.sources[0].gain = 0.25
+        worst = max(worst, maxerr(r.process(x), o.process(x)))
+        az = 45.0 * t
+        b.set_reference_orientation(az); ob.reference_orientation = az
+        worst = max(worst, maxerr(b.process(x[:1]), ob.process(x[:1])))
+    assert worst <= TOL, worst
+
+
+def test_many_sources_one_output_and_many_outputs_one_source(capi, co, engine_factory):
+    B = 64
+    rng = np.random.default_rng(99)
+    e = engine_factory(B)
+    for N, M in ((150, 1), (1, 37)):
+        r = capi.Renderer(e, capi.GENERIC, outputs=M)
+        o = co.GenericRendererOracle(B, M)
+        for n in range(N):
+            ir = decaying(rng, 130, M, 0.3 / np.sqrt(N))
+            r.add_source(ir); o.add_source(ir)
+        worst = 0.0
+        for t in range(6):
+            x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+            worst = max(worst, maxerr(r.process(x), o.process(x)))
+        assert worst <= TOL, (N, M, worst)
