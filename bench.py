@@ -412,7 +412,10 @@ def main_ours(args):
     dev_in = host_in.to(dev)
     d_in_step = torch.empty((w.sources, B), dtype=torch.float32, device=dev)
     d_out = torch.zeros((m_local, B), dtype=torch.float32, device=dev)
-    gathered = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # gather target: one contiguous (world, M/G, B) tensor whose slices receive the ranks' blocks,
+    # so the host-facing rank needs a single D2H copy per block
+    gathered_all = torch.empty((world, m_local, B), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    gathered = list(gathered_all.unbind(0)) if gathered_all is not None else None
     n_out_total = w.outputs if w.kind == "generic" else 2
     host_out = torch.empty((n_out_total, B), dtype=torch.float32).pin_memory()
 
@@ -452,8 +455,7 @@ def main_ours(args):
         gather()
         if rank == 0:
             if world > 1:
-                for g in range(world):
-                    host_out[g * m_local:(g + 1) * m_local].copy_(gathered[g], non_blocking=True)
+                host_out.copy_(gathered_all.view(world * m_local, B), non_blocking=True)   # D2H
             else:
                 host_out.copy_(d_out, non_blocking=True)                 # D2H
         torch.cuda.synchronize()
