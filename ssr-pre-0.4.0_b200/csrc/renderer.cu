@@ -107,11 +107,9 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
     s->irs = std::move(irs);
-    int P = 0;
-    for (int v : s->irs->valid) P = std::max(P, v);
     // Input(block, min_partitions(block, frames)) (src/genericrenderer.h:109-110)
     s->input.reset(new Input(e, s->irs->partitions));
-    (void)P; (void)channels;
+    (void)channels;
   }
   else if (cfg.kind == SSR_RENDERER_BRS)
   {
