@@ -421,3 +421,58 @@ def test_many_sources_one_output_and_many_outputs_one_source(capi, co, engine_fa
             x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
             worst = max(worst, maxerr(r.process(x), o.process(x)))
         assert worst <= TOL, (N, M, worst)
+
+
+def test_cuda_graph_replay_survives_control_and_topology_changes(capi, co, engine_factory):
+    """The static renderers replay {H2D, kernels, D2H} as a CUDA graph in steady state
+    (DESIGN.md 3.5).  Gain / mute changes (different accumulator-kind masks), level
+    metering toggles, added and removed sources and two-deep pipelining must all keep
+    the output equal to the oracle's."""
+    B, M = 256, 6
+    rng = np.random.default_rng(2024)
+    e = engine_factory(B)
+    r = capi.Renderer(e, capi.GENERIC, outputs=M)
+    o = co.GenericRendererOracle(B, M)
+    ids = []
+
+    def add(L):
+        ir = decaying(rng, L, M, 0.08)
+        ids.append(r.add_source(ir)); o.add_source(ir)
+
+    for L in (700, 300, 1000):
+        add(L)
+    T = 90
+    events = {12: ("gain", 0, 0.5), 13: ("gain", 0, 0.7), 30: ("mute", 1, True), 41: ("mute", 1, False),
+              50: ("meter", None, True), 58: ("meter", None, False), 64: ("add", None, 450),
+              75: ("rem", 1, None), 82: ("gain", 0, 0.2)}
+    xs, exp = [], []
+    pending_x = None
+    worst = 0.0
+    got = []
+    for t in range(T):
+        if t in events:
+            what, i, v = events[t]
+            # topology / metering changes need an empty pipeline (they synchronise anyway)
+            if what in ("add", "rem", "meter") and pending_x is not None:
+                got.append(r.wait()); pending_x = None
+            if what == "gain":
+                r.set_gain(ids[i], v); o.sources[i].gain = v
+            elif what == "mute":
+                r.set_mute(ids[i], v); o.sources[i].mute = v
+            elif what == "meter":
+                r.set_level_metering(v)
+            elif what == "add":
+                add(v)
+            elif what == "rem":
+                r.rem_source(ids.pop(i)); o.rem_source(i)
+        x = rng.uniform(-1, 1, (len(ids), B)).astype(np.float32)
+        exp.append(o.process(x))
+        r.submit(x)
+        if pending_x is not None:
+            got.append(r.wait())
+        pending_x = x
+    got.append(r.wait())
+    assert len(got) == T
+    for a, b in zip(got, exp):
+        worst = max(worst, maxerr(a, b))
+    assert worst <= TOL, worst
