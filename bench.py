@@ -61,6 +61,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--mac-variant", type=int, default=0)
     ap.add_argument("--static-head", action="store_true", help="Binaural/BRS: no head rotation")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: output blocks reach rank 0 by peer-memory stores fused into the "
+                         "inverse kernel (default) or by an NCCL gather (A/B baseline)")
     return ap.parse_args()
 
 
@@ -419,9 +422,25 @@ def main_ours(args):
     n_out_total = w.outputs if w.kind == "generic" else 2
     host_out = torch.empty((n_out_total, B), dtype=torch.float32).pin_memory()
 
+    # N > 1: the path's only exchange step, output blocks -> host-facing rank over
+    # NVLink.  Default: fused into the inverse kernel (peer-memory stores + arrival
+    # counters, no collective per block); --gather nccl or a failed peer mapping:
+    # NCCL gather after the inverse kernel.
+    peer = None
+    if world > 1 and args.gather == "peer":
+        peer = mg.connect_peer_gather(capi, eng, ren, w.outputs, world, rank, dev)
+    gather_mode = "single GPU" if world == 1 else (
+        "peer-memory stores fused into the inverse kernel (CUDA IPC over NVLink)" if peer is not None
+        else "NCCL gather")
+
     def gather():
-        if world > 1:
-            # the path's only collective: output blocks -> host-facing rank, over NVLink
+        if world == 1:
+            return
+        if peer is not None:
+            if rank == 0:
+                peer.wait()      # one-warp kernel: every rank's blocks of this block have arrived
+                peer.release()   # device-resident run: nothing reads the slot
+        else:
             dist.gather(d_out, gathered, dst=0)
 
     def step_device(t):
@@ -443,7 +462,9 @@ def main_ours(args):
     lib = capi.lib()
 
     def step_e2e(t):
-        if world == 1:
+        if world == 1 or peer is not None:
+            # the reference-facing call on every rank; with the gather bound, rank 0's
+            # `out` receives ALL outputs and the other ranks deliver none
             control(t)
             rc = lib.ssr_renderer_process(ren.h, B, in_ptr_sets[t % nring], out_ptrs)
             if rc != 0:
@@ -553,7 +574,7 @@ def main_ours(args):
                        "sample_rate": w.fs, "partitions": w.partitions,
                        "parallelism": f"outputs sharded x{world}" if world > 1 else "single GPU",
                        "head_rotation": ("one filter step per block" if rotate else "none") if w.kind != "generic" else "n/a",
-                       "outputs_per_gpu": m_local, "l2": "inputs>L2 (spectra per GPU >> 126 MB)",
+                       "outputs_per_gpu": m_local, "gather": gather_mode, "l2": "inputs>L2 (spectra per GPU >> 126 MB)",
                        "filter_load_s": load_s,
                        "spectra_gb_per_gpu": (w.sources * m_local if w.kind == "generic" else
                                               (w.sources if w.kind == "brs" else 1) * w.channels)
@@ -564,8 +585,11 @@ def main_ours(args):
                     "ms_per_step": e2e_ms_total / K,
                     "mode": ("ssr_renderer_process (C ABI, host channel pointers), synchronous per block"
                              if world == 1 else
-                             "per rank: pinned H2D -> ssr_renderer_process_device -> NCCL gather -> D2H on "
-                             "rank 0, synchronous per block")},
+                             ("per rank: ssr_renderer_process (C ABI, host channel pointers) with the output "
+                              "gather bound; rank 0 receives all outputs; synchronous per block"
+                              if peer is not None else
+                              "per rank: pinned H2D -> ssr_renderer_process_device -> NCCL gather -> D2H on "
+                              "rank 0, synchronous per block"))},
             "p99_block_ms": p99,
             "gpu_launches": launches,
             "roofline": roofline,
@@ -584,9 +608,15 @@ def main_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                     "sample": f"failed: {exc}"}
 
+    if peer is not None:
+        peer.check()   # a timed-out wait would have produced garbage: fail loudly
     if rank == 0:
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()  # the root's gather buffer outlives every peer's last store
     ren.close()
+    if peer is not None:
+        peer.close()
     eng.close()
     if world > 1:
         dist.barrier()

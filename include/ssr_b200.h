@@ -53,6 +53,7 @@ typedef struct ssr_filterset ssr_filterset;
 typedef struct ssr_input ssr_input;
 typedef struct ssr_output ssr_output;
 typedef struct ssr_renderer ssr_renderer;
+typedef struct ssr_gather ssr_gather;
 
 const char* ssr_last_error(void);
 int ssr_abi_version(void);
@@ -282,6 +283,47 @@ int ssr_renderer_submit(ssr_renderer* r, int n, const float* const* in);
 int ssr_renderer_wait(ssr_renderer* r, float* const* out);
 
 int ssr_renderer_local_outputs(const ssr_renderer* r);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU output gather over NVLink peer memory.
+ *
+ * The Generic renderer shards by output channel: rank g renders outputs
+ * [first_g, first_g + count_g) -- in the reference these are the Output items
+ * apf::MimoProcessor spreads round-robin over its worker threads
+ * (apf/apf/mimoprocessor.h:452-483, src/genericrenderer.h:122-180).  The one
+ * exchange step is bringing the output blocks to the host-facing rank ("root").
+ * With a gather bound, the inverse-FFT kernel of every rank stores its blocks
+ * straight into the root's gather buffer (peer ranks: through NVLink peer
+ * memory) and counts its CTAs in on a system-scope counter; the root runs a
+ * one-warp wait kernel instead of a collective.  Two slots alternate by block
+ * parity; a peer may run at most two blocks ahead of the root's release.
+ *
+ * One engine (= one GPU) per rank; ranks may be processes (CUDA IPC handle,
+ * 64 bytes, carried by whatever the host uses: torch.distributed, MPI, a pipe)
+ * or engines of one process (ssr_gather_connect_local).
+ *   root:  ssr_gather_create -> ssr_gather_export -> (send handle)
+ *   peer:  ssr_gather_create -> ssr_gather_import(handle)
+ *   all:   ssr_renderer_bind_gather(renderer, gather)
+ * Then ssr_renderer_process(r, n, in, out) is the same audio_callback on every
+ * rank; on the root `out` has one pointer per output of the WHOLE renderer
+ * (ssr_gather_total_outputs), on the other ranks `out` is ignored (may be NULL).
+ * With ssr_renderer_process_device() (d_out ignored) the root calls
+ * ssr_gather_wait() -> device pointer to total_outputs x B floats of this
+ * block, valid until ssr_gather_release(), both stream-ordered; the root must
+ * release every block (peers wait for it, with a 20 s time-out that sets a
+ * sticky error reported by ssr_gather_status()). */
+#define SSR_GATHER_HANDLE_BYTES 64
+int ssr_gather_create(ssr_engine* e, int world, int rank, int root, const int* outputs_per_rank,
+                      ssr_gather** out);
+void ssr_gather_destroy(ssr_gather* g);
+int ssr_gather_export(ssr_gather* g, void* handle /* SSR_GATHER_HANDLE_BYTES */);
+int ssr_gather_import(ssr_gather* g, const void* handle);
+int ssr_gather_connect_local(ssr_gather* g, ssr_gather* root);
+int ssr_renderer_bind_gather(ssr_renderer* r, ssr_gather* g /* NULL: unbind */);
+int ssr_gather_wait(ssr_gather* g, const float** d_block);
+int ssr_gather_release(ssr_gather* g);
+int ssr_gather_status(ssr_gather* g);  /* SSR_OK, or SSR_ERR_STATE after a time-out (synchronises) */
+int ssr_gather_total_outputs(const ssr_gather* g);
 
 #ifdef __cplusplus
 }

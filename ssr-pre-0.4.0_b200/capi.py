@@ -113,7 +113,18 @@ SIGNATURES = {
     "ssr_renderer_submit": (C.c_int, [C.c_void_p, C.c_int, _pp]),
     "ssr_renderer_wait": (C.c_int, [C.c_void_p, _pp]),
     "ssr_renderer_local_outputs": (C.c_int, [C.c_void_p]),
+    "ssr_gather_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "ssr_gather_destroy": (None, [C.c_void_p]),
+    "ssr_gather_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_gather_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_gather_connect_local": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_renderer_bind_gather": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_gather_wait": (C.c_int, [C.c_void_p, C.POINTER(_f32p)]),
+    "ssr_gather_release": (C.c_int, [C.c_void_p]),
+    "ssr_gather_status": (C.c_int, [C.c_void_p]),
+    "ssr_gather_total_outputs": (C.c_int, [C.c_void_p]),
 }
+GATHER_HANDLE_BYTES = 64
 
 
 def lib():
@@ -342,6 +353,62 @@ class StaticOutput(_OutBase):
         _check(lib().ssr_output_bind_static(self.h, fs.h, channel))
 
 
+class Gather:
+    """Output gather over NVLink peer memory (include/ssr_b200.h, "Multi-GPU output
+    gather"): the root owns the buffer, peers map it (CUDA IPC handle from another
+    process, or connect_local() for engines of one process)."""
+
+    def __init__(self, engine: Engine, world: int, rank: int, outputs_per_rank: Sequence[int], root: int = 0):
+        self.engine = engine
+        self.world, self.rank, self.root = world, rank, root
+        counts = (C.c_int * world)(*[int(c) for c in outputs_per_rank])
+        h = C.c_void_p()
+        _check(lib().ssr_gather_create(engine.h, world, rank, root, counts, C.byref(h)))
+        self.h = h
+        engine._adopt(self, "ssr_gather_destroy")
+
+    @property
+    def is_root(self) -> bool:
+        return self.rank == self.root
+
+    @property
+    def total_outputs(self) -> int:
+        return lib().ssr_gather_total_outputs(self.h)
+
+    def export_handle(self) -> bytes:
+        buf = C.create_string_buffer(GATHER_HANDLE_BYTES)
+        _check(lib().ssr_gather_export(self.h, buf))
+        return buf.raw
+
+    def import_handle(self, handle: bytes):
+        if len(handle) != GATHER_HANDLE_BYTES:
+            raise ValueError("gather handle must be 64 bytes")
+        buf = C.create_string_buffer(bytes(handle), GATHER_HANDLE_BYTES)
+        _check(lib().ssr_gather_import(self.h, buf))
+
+    def connect_local(self, root: "Gather"):
+        _check(lib().ssr_gather_connect_local(self.h, root.h))
+
+    def wait(self) -> int:
+        """Root: stream-ordered wait for the block just rendered; device address of
+        the (total_outputs, B) float32 block."""
+        p = _f32p()
+        _check(lib().ssr_gather_wait(self.h, C.byref(p)))
+        return C.cast(p, C.c_void_p).value
+
+    def release(self):
+        _check(lib().ssr_gather_release(self.h))
+
+    def check(self):
+        _check(lib().ssr_gather_status(self.h))
+
+    def close(self):
+        self.engine._release(self, "ssr_gather_destroy")
+
+    def __del__(self):
+        self.close()
+
+
 class Renderer:
     def __init__(self, engine: Engine, kind: int, outputs: int = 2, output_first: int = 0,
                  output_count: int = 0, master_volume_correction_db: float = 0.0):
@@ -353,11 +420,25 @@ class Renderer:
         h = C.c_void_p()
         _check(lib().ssr_renderer_create(engine.h, C.byref(cfg), C.byref(h)))
         self.h = h
+        self.gather = None
         engine._adopt(self, "ssr_renderer_destroy")
 
     @property
     def local_outputs(self) -> int:
         return lib().ssr_renderer_local_outputs(self.h)
+
+    def bind_gather(self, gather: Optional[Gather]):
+        """Multi-GPU: output blocks go to the gather's root; process() then returns
+        ALL outputs on the root and an empty array on the other ranks."""
+        _check(lib().ssr_renderer_bind_gather(self.h, gather.h if gather is not None else None))
+        self.gather = gather
+
+    @property
+    def host_outputs(self) -> int:
+        """Output blocks process()/wait() deliver on this rank."""
+        if self.gather is None:
+            return self.local_outputs
+        return self.gather.total_outputs if self.gather.is_root else 0
 
     @property
     def n_sources(self) -> int:
@@ -420,14 +501,17 @@ class Renderer:
 
     def _ptr_arrays(self, x: np.ndarray, y: np.ndarray):
         ins = (_f32p * max(1, x.shape[0]))(*[x[i].ctypes.data_as(_f32p) for i in range(x.shape[0])])
-        outs = (_f32p * y.shape[0])(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
+        outs = (_f32p * max(1, y.shape[0]))(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
         return ins, outs
 
-    def process(self, x) -> np.ndarray:
-        """x: (sources, B) host floats -> (local_outputs, B); = audio_callback."""
+    def process(self, x, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """x: (sources, B) host floats -> (local_outputs, B); = audio_callback.
+        Page-locked contiguous x / out are used in place by the copy engines."""
         B = self.engine.block_size
         x = _f32(x).reshape(-1, B)
-        y = np.empty((self.local_outputs, B), np.float32)
+        y = np.empty((self.host_outputs, B), np.float32) if out is None else out
+        if y.dtype != np.float32 or y.shape != (self.host_outputs, B) or not y.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 (host_outputs, B) array")
         ins, outs = self._ptr_arrays(x, y)
         _check(lib().ssr_renderer_process(self.h, B, ins, outs))
         return y
@@ -440,8 +524,8 @@ class Renderer:
 
     def wait(self) -> np.ndarray:
         B = self.engine.block_size
-        y = np.empty((self.local_outputs, B), np.float32)
-        outs = (_f32p * y.shape[0])(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
+        y = np.empty((self.host_outputs, B), np.float32)
+        outs = (_f32p * max(1, y.shape[0]))(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
         _check(lib().ssr_renderer_wait(self.h, outs))
         return y
 

@@ -12,6 +12,7 @@ struct ssr_engine { Engine impl; explicit ssr_engine(const ssr_engine_config& c)
 struct ssr_filterset { FilterSet impl; ssr_filterset(Engine* e, int c, int p) : impl(e, c, p) {} };
 struct ssr_input { Input impl; ssr_input(Engine* e, int p) : impl(e, p) {} };
 struct ssr_output { Output impl; ssr_output(Input* i, ssr_output_kind k) : impl(i, k) {} };
+struct ssr_gather { Gather impl; ssr_gather(Engine* e, int w, int r, int root, const int* c) : impl(e, w, r, root, c) {} };
 struct ssr_renderer { Renderer impl; ssr_renderer(Engine* e, const ssr_renderer_config& c) : impl(e, c) {} };
 
 namespace
@@ -445,7 +446,9 @@ int ssr_renderer_get_levels(ssr_renderer* r, float* source_pre_fader, float* sou
 int ssr_renderer_process(ssr_renderer* r, int n, const float* const* in, float* const* out)
 {
   return guarded([&] {
-    require(r && out, "renderer_process: null argument");
+    require(r != nullptr, "renderer_process: null argument");
+    // a non-root rank of a gather delivers no output blocks: out may be null there
+    require(out || (r->impl.gather && !r->impl.gather->is_root()), "renderer_process: null output array");
     require(in || r->impl.sources.empty(), "renderer_process: null input array");
     r->impl.process(n, in, out);
   });
@@ -454,7 +457,7 @@ int ssr_renderer_process(ssr_renderer* r, int n, const float* const* in, float* 
 int ssr_renderer_process_device(ssr_renderer* r, const float* d_in, float* d_out)
 {
   return guarded([&] {
-    require(r && d_out, "renderer_process_device: null argument");
+    require(r && (d_out || r->impl.gather), "renderer_process_device: null argument");
     r->impl.step(d_in, d_out);
   });
 }
@@ -466,7 +469,75 @@ int ssr_renderer_submit(ssr_renderer* r, int n, const float* const* in)
 
 int ssr_renderer_wait(ssr_renderer* r, float* const* out)
 {
-  return guarded([&] { require(r && out, "renderer_wait: null argument"); r->impl.wait(out); });
+  return guarded([&] {
+    require(r != nullptr, "renderer_wait: null argument");
+    require(out || (r->impl.gather && !r->impl.gather->is_root()), "renderer_wait: null output array");
+    r->impl.wait(out);
+  });
 }
+
+/* ------------------------------------------------------------------ gather */
+
+int ssr_gather_create(ssr_engine* e, int world, int rank, int root, const int* outputs_per_rank,
+                      ssr_gather** out)
+{
+  return guarded([&] {
+    require(e && out, "gather_create: null argument");
+    *out = nullptr;
+    *out = new ssr_gather(&e->impl, world, rank, root, outputs_per_rank);
+  });
+}
+
+void ssr_gather_destroy(ssr_gather* g) { delete g; }
+
+int ssr_gather_export(ssr_gather* g, void* handle)
+{
+  return guarded([&] { require(g && handle, "gather_export: null argument"); g->impl.export_handle(handle); });
+}
+
+int ssr_gather_import(ssr_gather* g, const void* handle)
+{
+  return guarded([&] { require(g && handle, "gather_import: null argument"); g->impl.import_handle(handle); });
+}
+
+int ssr_gather_connect_local(ssr_gather* g, ssr_gather* root)
+{
+  return guarded([&] {
+    require(g && root, "gather_connect_local: null argument");
+    require(root->impl.is_root() && root->impl.base, "gather_connect_local: second argument is not a root gather");
+    require(root->impl.M_total == g->impl.M_total && root->impl.world == g->impl.world
+        && root->impl.e->B == g->impl.e->B, "gather_connect_local: layouts differ");
+    g->impl.import_pointer(root->impl.base, root->impl.e->device);
+  });
+}
+
+int ssr_renderer_bind_gather(ssr_renderer* r, ssr_gather* g)
+{
+  return guarded([&] { require(r, "null renderer"); r->impl.bind_gather(g ? &g->impl : nullptr); });
+}
+
+int ssr_gather_wait(ssr_gather* g, const float** d_block)
+{
+  return guarded([&] {
+    require(g && d_block, "gather_wait: null argument");
+    *d_block = g->impl.wait();
+  });
+}
+
+int ssr_gather_release(ssr_gather* g)
+{
+  return guarded([&] { require(g, "null gather"); g->impl.release(); });
+}
+
+int ssr_gather_status(ssr_gather* g)
+{
+  int flag = -1;
+  int rc = guarded([&] { require(g, "null gather"); flag = g->impl.status(); });
+  if (rc != SSR_OK) return rc;
+  if (flag) { g_error = "ssr_b200: gather: a wait on a peer rank timed out"; return SSR_ERR_STATE; }
+  return SSR_OK;
+}
+
+int ssr_gather_total_outputs(const ssr_gather* g) { return g ? g->impl.M_total : 0; }
 
 }  // extern "C"

@@ -242,7 +242,7 @@ struct Engine
   void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs);
   void launch_fwd_batch(const ssrk::FwdBatch& batch, int nparts, int nchannels);
   void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr);
-  void launch_inv(const InvPlan& plan);
+  void launch_inv(const InvPlan& plan, const ssrk::GatherArgs& ga = ssrk::GatherArgs{});
   void upload_weights(const float* w, size_t n);
   void ensure_partials(size_t npartial_spectra);
   int mac_slots() const;           // CTAs resident at once for the MAC kernel
@@ -259,6 +259,13 @@ struct Engine
   void fold_stats();
   void sync() { SSR_CUDA(cudaStreamSynchronize(stream)); }
   void use_device() { SSR_CUDA(cudaSetDevice(device)); }
+
+  // Is [p, p + bytes) page-locked host memory (cudaMallocHost / cudaHostRegister)?
+  // Answers are cached by address: a stale "pinned" answer only costs speed, since
+  // cudaMemcpyAsync stays correct on pageable memory.
+  struct PinnedRange { const void* p; size_t bytes; bool pinned; };
+  std::vector<PinnedRange> pinned_cache;
+  bool is_pinned(const void* p, size_t bytes);
 };
 
 // ------------------------------------------------------------ filter sets
@@ -366,6 +373,56 @@ struct Output
   const float* convolve(float weight);
 };
 
+// ------------------------------------------------------------ multi-GPU output gather
+// The path's only exchange step: every rank's M/G x B output blocks go
+// to the host-facing rank.  Instead of a collective after the inverse kernel, the
+// inverse kernel of a peer rank stores its blocks straight into the root's gather
+// buffer through NVLink peer memory and counts its CTAs in on a system-scope
+// counter (ssrk::GatherArgs); the root only runs a one-warp wait kernel.
+//
+// One device allocation on the root (exported with cudaIpcGetMemHandle, or shared
+// by pointer between engines of one process):
+//   [control block 4 KiB: consumed | arrived[rank] (one 128-byte line each)]
+//   [slot 0: M_total x B floats][slot 1: M_total x B floats]
+struct Gather
+{
+  Gather(Engine* e, int world, int rank, int root, const int* outputs_per_rank);
+  ~Gather();
+  Engine* e;
+  int world, rank, root;
+  std::vector<int> counts, firsts;   // outputs per rank, first output of each rank
+  int M_total = 0;
+  bool is_root() const { return rank == root; }
+
+  static constexpr size_t kControlBytes = 4096;
+  static constexpr int kMaxWorld = 24;
+  unsigned char* base = nullptr;     // root: own allocation; peer: mapped pointer
+  bool owns = false, ipc_mapped = false;
+  DeviceArray<int> d_error;          // local sticky timeout flag
+  DeviceArray<int> d_ctas;           // root: CTAs per rank (0 for the root)
+  uint64_t epoch = 0;                // blocks rendered into the buffer so far
+  uint64_t waited = 0, released = 0; // root bookkeeping
+
+  size_t slot_floats() const { return size_t(M_total) * e->B; }
+  size_t total_bytes() const { return kControlBytes + 2 * slot_floats() * sizeof(float); }
+  unsigned long long* consumed_ptr() const { return reinterpret_cast<unsigned long long*>(base); }
+  unsigned long long* arrived_ptr(int g) const
+  { return reinterpret_cast<unsigned long long*>(base) + size_t(1 + g) * ssrk::kGatherCounterStride; }
+  float* slot_ptr(int slot) const
+  { return reinterpret_cast<float*>(base + kControlBytes) + size_t(slot) * slot_floats(); }
+
+  void export_handle(void* handle64) const;            // root
+  void import_handle(const void* handle64);            // peer, other process (CUDA IPC)
+  void import_pointer(void* root_base, int root_device);  // peer, same process
+  bool ready() const { return base != nullptr; }
+  // kernel arguments for the block about to be rendered (epoch), then ++epoch
+  ssrk::GatherArgs next_block();
+  // root: stream-ordered wait for block (epoch - 1) of every rank; returns its slot
+  const float* wait();
+  void release();                                      // root: after the reads of that slot were queued
+  int status();                                        // 0 ok, 1 a wait timed out (synchronises)
+};
+
 // ------------------------------------------------------------ Level 2
 template<typename T>
 struct BlockParameter  // apf::BlockParameter (apf/apf/misc.h:94-195)
@@ -461,9 +518,9 @@ struct Renderer
   StepDesc prepare_generic(const float* d_input, float* d_output);
   StepDesc prepare_dynamic(const float* d_input, float* d_output);
   StepDesc prepare_bank(const float* d_input, float* d_output);
-  // CUDA graphs of the steady-state host-buffer step {H2D, kernels, D2H}
+  // CUDA graphs of the steady-state kernel sequence of a host-buffer step
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; int seen = 0; };
-  GraphEntry graphs[2][8];             // [pinned slot][kind mask]
+  GraphEntry graphs[8];                // [kind mask]
   bool use_graphs = true;
   uint64_t graph_launches = 0;
   void drop_graphs();
@@ -475,11 +532,16 @@ struct Renderer
   void get_levels(float* pre_fader, float* levels, float* outputs);
   void build_fwd(const float* d_input);
   void process(int n, const float* const* in, float* const* out);
+  // multi-GPU: output blocks go to a Gather (not owned) instead of d_output
+  Gather* gather = nullptr;
+  void bind_gather(Gather* g);
   // pipelined
   int outstanding = 0;
   uint64_t submitted = 0;
   cudaEvent_t done[2] = {nullptr, nullptr};
+  bool slot_direct[2] = {false, false};  // the slot's D2H went straight into the caller's buffer
   void submit(int n, const float* const* in);
+  void submit_block(int n, const float* const* in, float* const* direct_out);
   void wait(float* const* out);
 };
 

@@ -582,6 +582,82 @@ struct InvJob
 
 constexpr int kInvMaxRes = 8;  // B <= 4096: (B/2 float2) / 256 threads
 
+// Multi-GPU output gather fused into the inverse kernel: the output
+// blocks of a rank are stored straight into the host-facing rank's gather buffer
+// over NVLink peer memory (InvJob::out + out_offset points into it), and every
+// CTA then bumps a system-scope arrival counter in that buffer's control block.
+// Two slots alternate by block parity; before storing block t a CTA checks that
+// the root has released block t-2 (`consumed >= need_consumed`).  All pointers
+// null / zero: plain local stores.
+struct GatherArgs
+{
+  long long out_offset;                    // floats added to every InvJob::out (slot * slot stride)
+  const unsigned long long* consumed;      // root's "blocks released" counter (peer memory), or null
+  unsigned long long need_consumed;
+  unsigned long long* arrived;             // this rank's arrival counter on the root (peer memory), or null
+  int* error;                              // local sticky flag: a wait timed out
+};
+
+constexpr unsigned long long kGatherTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// spins until *p >= target; gives up (sticky error flag) after kGatherTimeoutNs so
+// that a dead peer can never hang the GPU
+__device__ __noinline__ void gather_wait_ge(const unsigned long long* p, unsigned long long target, int* error)
+{
+  if (ld_acquire_sys(p) >= target) return;
+  if (error && *reinterpret_cast<volatile int*>(error)) return;
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(p) < target)
+  {
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > kGatherTimeoutNs)
+    {
+      if (error) *reinterpret_cast<volatile int*>(error) = 1;
+      return;
+    }
+  }
+}
+
+// root: wait until every peer rank has delivered its output blocks of block
+// `epoch` (0-based): arrived[g] >= (epoch + 1) * ctas[g].  One thread per rank.
+struct GatherWaitArgs
+{
+  const unsigned long long* arrived;   // [world], 16 counters apart (128 bytes)
+  const int* ctas;                     // [world] CTAs (= output blocks) per rank; 0 for the root itself
+  int world;
+  unsigned long long epoch;
+  int* error;
+};
+constexpr int kGatherCounterStride = 16;  // unsigned long longs between counters (one 128-byte line each)
+
+__global__ void gather_wait_kernel(GatherWaitArgs a)
+{
+  const int g = threadIdx.x;
+  if (g < a.world && a.ctas[g] > 0)
+    gather_wait_ge(a.arrived + size_t(g) * kGatherCounterStride,
+        (a.epoch + 1) * (unsigned long long)a.ctas[g], a.error);
+}
+
+// root: block `epoch` has been read out of its slot -> peers may overwrite it
+__global__ void gather_release_kernel(unsigned long long* consumed, unsigned long long value)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(consumed), "l"(value) : "memory");
+}
+
 // Parallel pre-reduction of the split partial accumulators, used when there are
 // few output blocks but deep splits (Binaural / BRS: 2 outputs; sharded Generic):
 // grid (entries, (B/2)/32); warp w of a CTA sums partials w, w+8, ... for a
@@ -625,7 +701,8 @@ __global__ void __launch_bounds__(kThreads)
 inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
                const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
                const float2* __restrict__ tw,
-               const float* __restrict__ fade_out, const float* __restrict__ fade_in)
+               const float* __restrict__ fade_out, const float* __restrict__ fade_in,
+               const GatherArgs ga)
 {
   extern __shared__ float2 smem[];
   float2* a = smem;
@@ -633,6 +710,9 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
   const InvJob job = jobs[blockIdx.x];
   const int t = threadIdx.x;
   const int half = B >> 1;
+  // flow control of the fused gather: the slot this block goes to must have been
+  // read out by the root (checked by one thread while the others start loading)
+  if (ga.consumed && t == 0) gather_wait_ge(ga.consumed, ga.need_consumed, ga.error);
 
   float2 res[kInvMaxRes];
 #pragma unroll
@@ -720,14 +800,16 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
     __syncthreads();  // z (smem) is rewritten by the next entry
   }
 
+  if (ga.consumed) __syncthreads();  // thread 0's slot check precedes every store
   float m = 0.0f;
+  float2* out = reinterpret_cast<float2*>(job.out + ga.out_offset);
 #pragma unroll
   for (int q = 0; q < kInvMaxRes; ++q)
   {
     const int jj = t + q * kThreads;
     if (jj < half)
     {
-      reinterpret_cast<float2*>(job.out)[jj] = res[q];
+      out[jj] = res[q];
       m = fmaxf(m, fmaxf(fabsf(res[q].x), fabsf(res[q].y)));
     }
   }
@@ -735,6 +817,16 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
   {
     m = block_max(m);
     if (t == 0) *job.level = m;
+  }
+  if (ga.arrived)
+  {
+    // all stores of this CTA (peer memory, over NVLink) -> fence -> arrival count
+    __syncthreads();
+    if (t == 0)
+    {
+      __threadfence_system();
+      atomicAdd_system(ga.arrived, 1ull);
+    }
   }
 }
 

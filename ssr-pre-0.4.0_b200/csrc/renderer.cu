@@ -332,7 +332,7 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
     d.xparts[k] = active_parts[k];
   }
   d.nrows = m_local;
-  d.graphable = true;
+  d.graphable = gather == nullptr;  // the gather's kernel arguments change every block
   return d;
 }
 
@@ -598,9 +598,35 @@ Renderer::StepDesc Renderer::prepare_bank(const float* d_input, float* d_output)
   return d;
 }
 
+// Multi-GPU: from now on the inverse kernel stores this rank's output blocks into
+// the gather buffer (the root's own HBM, or the root's buffer through NVLink peer
+// memory) and signals their arrival; d_output of step() is ignored.
+void Renderer::bind_gather(Gather* g)
+{
+  if (outstanding) throw Error(SSR_ERR_STATE, "ssr_b200: bind_gather() while submitted blocks are pending");
+  e->use_device();
+  e->sync();
+  if (g)
+  {
+    if (cfg.kind != SSR_RENDERER_GENERIC)
+      throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: only the Generic renderer shards its outputs (Binaural/BRS: replicas only)");
+    if (g->e != e) throw Error(SSR_ERR_INVALID, "ssr_b200: gather belongs to another engine");
+    if (g->M_total != M_total || g->counts[g->rank] != m_local || g->firsts[g->rank] != m_first)
+      throw Error(SSR_ERR_INVALID, "ssr_b200: gather layout does not match the renderer's output shard");
+    if (!g->ready()) throw Error(SSR_ERR_STATE, "ssr_b200: gather: buffer not connected (import the root's handle first)");
+  }
+  gather = g;
+  inv_key = -1;
+  drop_graphs();
+  if (g && g->is_root()) h_out.resize(size_t(2) * M_total * e->B);
+  else h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
+}
+
 Renderer::StepDesc Renderer::prepare(const float* d_input, float* d_output)
 {
   e->use_device();
+  // slot 0 of the gather buffer; the kernel adds the slot offset of the block
+  if (gather) d_output = gather->slot_ptr(0) + size_t(m_first) * e->B;
   if (cfg.kind == SSR_RENDERER_GENERIC) return prepare_generic(d_input, d_output);
   if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) return prepare_bank(d_input, d_output);
   return prepare_dynamic(d_input, d_output);
@@ -637,7 +663,8 @@ void Renderer::launch(const StepDesc& d)
     }
   }
   e->stage_mark(2);
-  e->launch_inv(inv);
+  if (gather) e->launch_inv(inv, gather->next_block());
+  else e->launch_inv(inv);
   e->stage_mark(3);
   e->stage_end();
 }
@@ -653,22 +680,35 @@ void Renderer::step(const float* d_input, float* d_output)
 
 void Renderer::drop_graphs()
 {
-  for (auto& slot : graphs)
-    for (auto& g : slot)
-    {
-      if (g.exec) cudaGraphExecDestroy(g.exec);
-      g = GraphEntry();
-    }
+  for (auto& g : graphs)
+  {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = GraphEntry();
+  }
+}
+
+// true if the B-float channel blocks behind `ptrs` form one contiguous array in
+// page-locked host memory (then the DMA engine can use them in place)
+static bool contiguous_pinned(Engine* e, const float* const* ptrs, int count, int B)
+{
+  if (count <= 0 || !ptrs || !ptrs[0]) return false;
+  for (int i = 1; i < count; ++i)
+    if (ptrs[i] != ptrs[0] + size_t(i) * B) return false;
+  return e->is_pinned(ptrs[0], size_t(count) * B * sizeof(float));
 }
 
 void Renderer::process(int n, const float* const* in, float* const* out)
 {
   if (outstanding) throw Error(SSR_ERR_STATE, "ssr_b200: process() while submitted blocks are pending");
-  submit(n, in);
+  // synchronous call: the caller's buffers stay valid until we return, so pinned
+  // contiguous channel arrays are used in place (no staging copies)
+  submit_block(n, in, out);
   wait(out);
 }
 
-void Renderer::submit(int n, const float* const* in)
+void Renderer::submit(int n, const float* const* in) { submit_block(n, in, nullptr); }
+
+void Renderer::submit_block(int n, const float* const* in, float* const* direct_out)
 {
   // assert(n == block_size()) (apf/apf/pointer_policy.h:114)
   if (n != e->B) throw Error(SSR_ERR_INVALID, "ssr_b200: audio_callback: n != block size");
@@ -680,27 +720,38 @@ void Renderer::submit(int n, const float* const* in)
   if (h_in.count < 2 * in_floats) { e->sync(); h_in.resize(2 * in_floats); d_in.resize(in_floats); fwd_cache.clear(); }
   static_assert(sizeof(float) == 4, "");
   const int slot = int(submitted & 1);
-  float* hin = h_in.ptr + size_t(slot) * in_floats;
-  for (int i = 0; i < N; ++i) std::memcpy(hin + size_t(i) * B, in[i], B * sizeof(float));
-  float* hout = h_out.ptr + size_t(slot) * m_local * B;
+  // with a gather bound the root delivers ALL outputs, the other ranks none
+  const int n_host_out = gather ? (gather->is_root() ? M_total : 0) : m_local;
+  const float* hin = nullptr;
+  if (direct_out && N > 0 && contiguous_pinned(e, in, N, B)) hin = in[0];
+  else
+  {
+    float* stage = h_in.ptr + size_t(slot) * in_floats;
+    for (int i = 0; i < N; ++i) std::memcpy(stage + size_t(i) * B, in[i], B * sizeof(float));
+    hin = stage;
+  }
+  float* hout = h_out.ptr + size_t(slot) * n_host_out * B;
+  slot_direct[slot] = false;
+  if (direct_out && n_host_out > 0 && contiguous_pinned(e, direct_out, n_host_out, B))
+  {
+    hout = direct_out[0];
+    slot_direct[slot] = true;
+  }
   e->stats.h2d_bytes += uint64_t(N) * B * sizeof(float);
-  e->stats.d2h_bytes += uint64_t(m_local) * B * sizeof(float);
+  e->stats.d2h_bytes += uint64_t(n_host_out) * B * sizeof(float);
 
   const StepDesc d = prepare(d_in.ptr, d_out.ptr);
-  auto body = [&]
-  {
-    if (N > 0)
-      SSR_CUDA(cudaMemcpyAsync(d_in.ptr, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    launch(d);
-    SSR_CUDA(cudaMemcpyAsync(hout, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-  };
-  // Steady state (no table moved or resized since the last blocks): replay
-  // {H2D, forward FFT, MAC, inverse FFT, D2H} as one CUDA graph per pinned slot
-  // and accumulator-kind mask.  Per-stage event timing needs separate launches.
+  if (N > 0)
+    SSR_CUDA(cudaMemcpyAsync(d_in.ptr, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  // Steady state (no table moved or resized since the last blocks): the kernel
+  // sequence {forward FFT, MAC passes, [partial reduce], inverse FFT} is replayed
+  // as one CUDA graph per accumulator-kind mask; the two copies stay outside so
+  // that they can use the caller's buffers.  Per-stage event timing needs
+  // separate launches.
   bool done_by_graph = false;
   if (use_graphs && d.graphable && !e->timing && d.kind_mask > 0 && d.kind_mask < 8)
   {
-    GraphEntry& g = graphs[slot][d.kind_mask];
+    GraphEntry& g = graphs[d.kind_mask];
     const uint64_t epoch = g_layout_epoch.load();
     if (g.exec && g.epoch == epoch)
     {
@@ -713,7 +764,7 @@ void Renderer::submit(int n, const float* const* in)
       if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
       cudaGraph_t graph = nullptr;
       SSR_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-      try { body(); }
+      try { launch(d); }
       catch (...) { cudaStreamEndCapture(e->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
       SSR_CUDA(cudaStreamEndCapture(e->stream, &graph));
       cudaError_t err = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -728,7 +779,18 @@ void Renderer::submit(int n, const float* const* in)
     }
     else if (g.epoch != epoch) { g.epoch = epoch; g.seen = 0; if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } }
   }
-  if (!done_by_graph) body();
+  if (!done_by_graph) launch(d);
+  if (gather)
+  {
+    if (gather->is_root())
+    {
+      const float* all = gather->wait();  // every rank's blocks of this block have arrived
+      SSR_CUDA(cudaMemcpyAsync(hout, all, size_t(M_total) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+      gather->release();
+    }
+  }
+  else
+    SSR_CUDA(cudaMemcpyAsync(hout, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   if (!done[slot]) SSR_CUDA(cudaEventCreateWithFlags(&done[slot], cudaEventDisableTiming));
   SSR_CUDA(cudaEventRecord(done[slot], e->stream));
   submitted++;
@@ -742,8 +804,12 @@ void Renderer::wait(float* const* out)
   const int B = e->B;
   const int slot = int((submitted - outstanding) & 1);
   SSR_CUDA(cudaEventSynchronize(done[slot]));
-  const float* hout = h_out.ptr + size_t(slot) * m_local * B;
-  for (int m = 0; m < m_local; ++m) std::memcpy(out[m], hout + size_t(m) * B, B * sizeof(float));
+  const int n_host_out = gather ? (gather->is_root() ? M_total : 0) : m_local;
+  if (!slot_direct[slot])
+  {
+    const float* hout = h_out.ptr + size_t(slot) * n_host_out * B;
+    for (int m = 0; m < n_host_out; ++m) std::memcpy(out[m], hout + size_t(m) * B, B * sizeof(float));
+  }
   outstanding--;
 }
 

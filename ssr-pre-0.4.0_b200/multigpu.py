@@ -3,10 +3,19 @@
 out[m] = sum_n sum_p X[n,p] * H[n,m,p] has no coupling between different m, so
 rank g owns outputs [g*M/G, (g+1)*M/G) -- the slab H[:, m_shard] -- and a
 replicated frequency-domain delay line (every rank receives the same N x B input
-block and forward-transforms it itself).  The only collective is a gather of the
-M/G x B output blocks to the host-facing rank, issued with torch.distributed
-(NCCL over NVLink on GPUs; gloo in the CPU tests).  No reduction, no exchange of
+block and forward-transforms it itself).  The only exchange step is bringing the
+M/G x B output blocks to the host-facing rank.  No reduction, no exchange of
 spectra.  One process per GPU.
+
+Two implementations of that step:
+  * connect_peer_gather(): the product path.  The root's gather buffer is mapped
+    into every rank (CUDA IPC handle broadcast with torch.distributed); each
+    rank's inverse-FFT kernel stores its output blocks straight into it over
+    NVLink peer memory and signals arrival (csrc/kernels.cuh GatherArgs), so no
+    collective runs per block.
+  * gather_outputs(): a plain torch.distributed gather (NCCL on GPUs, gloo in the
+    CPU tests) -- the fallback when peer mapping is unavailable, and the A/B
+    baseline for the fused path.
 """
 from __future__ import annotations
 
@@ -45,3 +54,39 @@ def assemble(blocks: List):
     """Rank-ordered shard blocks -> the full (M, B) output block."""
     import torch
     return torch.cat(list(blocks), dim=0)
+
+
+def connect_peer_gather(capi, engine, renderer, outputs: int, world: int, rank: int, device):
+    """Creates the rank's ssr_gather, distributes the root's CUDA IPC handle and
+    binds the renderer to it.  Collective: every rank must call it.  Returns the
+    capi.Gather, or None on ALL ranks if any rank could not map the root's buffer
+    (the caller then uses gather_outputs())."""
+    import torch
+    import torch.distributed as dist
+    _, count = shard_outputs(outputs, world, rank)
+    gather, ok = None, 1
+    handle = torch.zeros(capi.GATHER_HANDLE_BYTES, dtype=torch.uint8, device=device)
+    try:
+        gather = capi.Gather(engine, world, rank, [count] * world)
+        if rank == 0:
+            handle.copy_(torch.frombuffer(bytearray(gather.export_handle()), dtype=torch.uint8))
+    except capi.SsrError:
+        ok = 0
+    if world > 1:
+        dist.broadcast(handle, src=0)
+    if ok and rank != 0:
+        try:
+            gather.import_handle(bytes(handle.cpu().numpy().tobytes()))
+        except capi.SsrError:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if gather is not None:
+            gather.close()
+        return None
+    renderer.bind_gather(gather)
+    if world > 1:
+        dist.barrier()  # nobody renders into the buffer before every rank is bound
+    return gather
