@@ -135,6 +135,8 @@ Engine::Engine(const ssr_engine_config& cfg)
 
   zero_part.resize(B);
   SSR_CUDA(cudaMemset(zero_part.ptr, 0, B * sizeof(float2)));
+  d_dyn_stats.resize(2);
+  SSR_CUDA(cudaMemset(d_dyn_stats.ptr, 0, 2 * sizeof(unsigned long long)));
 
   d_xring.resize(kMaxInputs); d_xparts.resize(kMaxInputs); d_heads.resize(kMaxInputs);
   SSR_CUDA(cudaMemset(d_xring.ptr, 0, kMaxInputs * sizeof(void*)));
@@ -142,12 +144,19 @@ Engine::Engine(const ssr_engine_config& cfg)
   SSR_CUDA(cudaMemset(d_heads.ptr, 0, kMaxInputs * sizeof(int)));
 
   const size_t fft_smem = size_t(2) * B * sizeof(float2);
-  if (fft_smem > 48 * 1024)
+  if (2 * fft_smem > 48 * 1024)
   {
-    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
-    SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
   }
+  // the inverse kernel runs up to kInvMaxGroups transforms side by side (3 x 16 KiB
+  // at B = 1024, which with its static shared memory already exceeds 48 KiB)
+  // (+ one staged twiddle table per CTA)
+  SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem * 2)));
+  if (inv_groups(2) == 2)
+    SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem * 3)));
+  if (inv_groups(3) == 3)
+    SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem * 4)));
   SSR_CUDA(cudaDeviceSynchronize());
 }
 
@@ -194,9 +203,10 @@ int Engine::mac_slots() const
   return sm_count * occ;
 }
 
-void Engine::launch_fwd(const FwdJob* d_jobs, int njobs)
+void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ring_update)
 {
   if (njobs <= 0) return;
+  FwdRingUpdate ru{nullptr, nullptr, nullptr, 0};
   // One warp per transform wins on throughput (2.2x at filter load), one CTA per
   // transform on latency; the block loop rarely has enough transforms to fill
   // the machine (profiles/r1_fft_kernels.md)
@@ -207,11 +217,14 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs)
   }
   else
   {
-    const size_t smem = size_t(2) * B * sizeof(float2);
-    fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr);
+    const size_t smem = size_t(4) * B * sizeof(float2);  // data + staged twiddles
+    if (ring_update) { ru = *ring_update; ring_update = nullptr; }  // folded into this launch
+    fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr, ru);
   }
   SSR_CUDA(cudaGetLastError());
   if (cur) cur->fft_launches++;
+  if (ring_update)  // the warp-per-transform kernel ran: update the filter ring separately
+    launch_dyn_ring_update(ring_update->ctl, ring_update->upd, ring_update->ring, 2 * njobs, ring_update->R);
 }
 
 void Engine::launch_fwd_batch(const FwdBatch& batch, int nparts, int nchannels)
@@ -269,7 +282,7 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
 {
   const int nwork = int(plan.work.uploaded);
   if (nwork == 0) return;
-  MacParams p;
+  MacParams p{};
   p.term_meta = plan.meta.device();
   p.term_h = plan.hptr.device();
   p.work = plan.work.device();
@@ -287,6 +300,84 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   dim3 grid(nwork, mac_ktiles(B), 1);
   SSR_CUDA(cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, stream));
   if (cur) cur->mac_launches++;
+}
+
+int Engine::dyn_mac_slots() const
+{
+  int occ = 0;
+  void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 1, true> : (void*)mac_kernel<2, 1, 2, 1, true>;
+  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0);
+  if (err != cudaSuccess || occ < 1) occ = 1;
+  return sm_count * occ;
+}
+
+// thread groups (= accumulator entries transformed side by side) of an inverse
+// launch: as many as the jobs have entries, within the shared-memory budget
+int Engine::inv_groups(int max_entries) const
+{
+  const size_t per_group = size_t(2) * B * sizeof(float2);  // the twiddle table takes as much again
+  int g = std::max(1, std::min(max_entries, kInvMaxGroups));
+  while (g > 1 && per_group * (g + 1) > size_t(200) * 1024) --g;
+  return g;
+}
+
+void Engine::launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const float2* red,
+                               const GatherArgs& ga, const int* kind_counts)
+{
+  const size_t smem = size_t(2) * B * sizeof(float2) * (groups + 1);
+  const float2* part = reinterpret_cast<const float2*>(partials.ptr);
+  if (groups == 3)
+    inv_fft_kernel<3><<<njobs, kThreads * 3, smem, stream>>>(plan.jobs.device(), plan.entries.device(), part, red, B,
+        tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+  else if (groups == 2)
+    inv_fft_kernel<2><<<njobs, kThreads * 2, smem, stream>>>(plan.jobs.device(), plan.entries.device(), part, red, B,
+        tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+  else
+    inv_fft_kernel<1><<<njobs, kThreads, smem, stream>>>(plan.jobs.device(), plan.entries.device(), part, red, B,
+        tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+}
+
+void Engine::launch_dyn_ring_update(const DynCtl* ctl, const DynRingEntry* upd, DynRingEntry* ring, int rows, int R)
+{
+  if (rows <= 0) return;
+  dyn_ring_update_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(ctl, upd, ring, rows, R);
+  SSR_CUDA(cudaGetLastError());
+}
+
+void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights)
+{
+  MacParams p{};
+  p.wtab = weights;
+  p.xring = d_xring.ptr;
+  p.xparts = d_xparts.ptr;
+  p.heads = d_heads.ptr;
+  p.partials = partials.ptr;
+  p.B = B;
+  p.l2_hints = (mac_variant == 3) ? 0 : 1;
+  p.zero = reinterpret_cast<const float4*>(zero_part.ptr);
+  p.dyn = dyn;
+  p.dyn.stats = cur ? d_dyn_stats.ptr : nullptr;
+  void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 1, true> : (void*)mac_kernel<2, 1, 2, 1, true>;
+  void* args[] = { &p };
+  dim3 grid(G, mac_ktiles(B), 1);
+  SSR_CUDA(cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, stream));
+  if (cur) cur->mac_launches++;
+}
+
+// reduce the generated-terms partials per (ear, kind), then one inverse CTA per ear
+void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, int G)
+{
+  const int njobs = int(plan.jobs.uploaded);
+  if (njobs == 0) return;
+  const size_t need = size_t(6) * (B / 2);
+  if (need > reduced.count) { sync(); reduced.resize(need); }
+  dim3 grid(6, (B / 2 + 31) / 32, 1);
+  dyn_reduce_kernel<<<grid, kThreads, 0, stream>>>(ctl, Pmax, G, partials.ptr, reduced.ptr, B / 2);
+  SSR_CUDA(cudaGetLastError());
+  if (cur) cur->ifft_launches++;
+  launch_inv_kernel(inv_groups(3), njobs, plan, reinterpret_cast<const float2*>(reduced.ptr), GatherArgs{}, ctl->n);
+  SSR_CUDA(cudaGetLastError());
+  if (cur) cur->ifft_launches++;
 }
 
 void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
@@ -319,8 +410,11 @@ void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
         reinterpret_cast<const float2*>(partials.ptr), red, tw.ptr, fade_out.ptr, fade_in.ptr);
   }
   else
-    inv_fft_kernel<<<njobs, kThreads, smem, stream>>>(plan.jobs.device(), plan.entries.device(),
-        reinterpret_cast<const float2*>(partials.ptr), red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga);
+  {
+    int max_entries = 1;
+    for (auto& j : plan.jobs.host) max_entries = std::max(max_entries, j.n_entries);
+    launch_inv_kernel(inv_groups(max_entries), njobs, plan, red, ga, nullptr);
+  }
   SSR_CUDA(cudaGetLastError());
   if (cur) cur->ifft_launches++;
 }
@@ -527,6 +621,12 @@ void Engine::fold_stats()
     free_events.push_back(p);
   }
   pending.clear();
+  // partitions read by generated-terms MAC launches (counted on the device)
+  unsigned long long hx[2] = {0, 0};
+  SSR_CUDA(cudaMemcpy(hx, d_dyn_stats.ptr, sizeof(hx), cudaMemcpyDeviceToHost));
+  stats.mac_bytes += uint64_t(8) * B * ((hx[0] - dyn_h_seen) + (hx[1] - dyn_x_seen));
+  stats.mac_terms += hx[0] - dyn_h_seen;
+  dyn_h_seen = hx[0]; dyn_x_seen = hx[1];
 }
 
 // ------------------------------------------------------------------ FilterSet
@@ -538,6 +638,30 @@ FilterSet::FilterSet(Engine* e_, int channels_, int partitions_)
   data.resize(size_t(channels) * partitions * e->B);
   valid.assign(channels, 0);
   flags.assign(size_t(channels) * partitions, 0);
+}
+
+const unsigned char* FilterSet::device_flags()
+{
+  if (flags_dirty || !d_flags.ptr)
+  {
+    e->use_device();
+    if (d_flags.count < flags.size()) { e->sync(); d_flags.resize(flags.size()); }
+    // pageable source: the driver stages it before returning; ordered on the stream
+    // behind the kernels that still read the previous flags
+    SSR_CUDA(cudaMemcpyAsync(d_flags.ptr, flags.data(), flags.size(), cudaMemcpyHostToDevice, e->stream));
+    all_set.assign(size_t(channels), 1);
+    for (int ch = 0; ch < channels; ++ch)
+      for (int p = 0; p < partitions; ++p)
+        if (!flags[size_t(ch) * partitions + p]) { all_set[ch] = 0; break; }
+    flags_dirty = false;
+  }
+  return d_flags.ptr;
+}
+
+const unsigned char* FilterSet::device_flags_row(int ch)
+{
+  const unsigned char* base = device_flags();
+  return all_set[ch] ? nullptr : base + size_t(ch) * partitions;
 }
 
 static void run_fwd_jobs(Engine* e, std::vector<FwdJob>& jobs)
@@ -575,6 +699,7 @@ void FilterSet::load_time(int first_channel, int nch, const float* host, long fr
     const int ch = first_channel + c;
     valid[ch] = nvalid;
     for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
+    flags_dirty = true;
   }
   FwdBatch batch{};
   batch.time = d_time.ptr;
@@ -595,6 +720,7 @@ void FilterSet::set_partition_time(int ch, int p, const float* taps, int n)
   {
     // chunk == 0 -> zero flag, no FFT (convolver.h:218-221)
     flags[size_t(ch) * partitions + p] = 0;
+    flags_dirty = true;
     return;
   }
   DeviceArray<float> d{size_t(n)};
@@ -606,6 +732,7 @@ void FilterSet::set_partition_time(int ch, int p, const float* taps, int n)
   jobs[0].dst = part(ch, p);
   run_fwd_jobs(e, jobs);
   flags[size_t(ch) * partitions + p] = 1;
+  flags_dirty = true;
   valid[ch] = std::max(valid[ch], p + 1);
 }
 
@@ -629,6 +756,7 @@ void FilterSet::generate(int first_channel, int nch, long taps, uint64_t seed, u
     const int ch = first_channel + c;
     valid[ch] = nvalid;
     for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
+    flags_dirty = true;
   }
   FwdBatch batch{};
   batch.time = d_env.ptr;
@@ -650,6 +778,7 @@ void FilterSet::lerp_from(int dch, const FilterSet& a, int ach, const FilterSet&
   {
     const float2* pa = a.part_or_null(ach, p);
     const float2* pb = b.part_or_null(bch, p);
+    flags_dirty = true;
     if (!pa && !pb) { flags[size_t(dch) * partitions + p] = 0; continue; }
     flags[size_t(dch) * partitions + p] = 1;
     jobs.push_back({reinterpret_cast<const float4*>(pa), reinterpret_cast<const float4*>(pb),

@@ -239,10 +239,21 @@ struct Engine
   DeviceArray<float4> reduced;     // pre-reduced accumulators (see reduce_partials_kernel)
 
   // launches (all asynchronous on `stream`)
-  void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs);
+  void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs, const ssrk::FwdRingUpdate* ring_update = nullptr);
   void launch_fwd_batch(const ssrk::FwdBatch& batch, int nparts, int nchannels);
   void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr);
   void launch_inv(const InvPlan& plan, const ssrk::GatherArgs& ga = ssrk::GatherArgs{});
+  // dynamic renderers: terms generated on the device (ssrk::DynTables), static launch shapes
+  void launch_mac_dyn(const ssrk::DynTables& dyn, int G, const float* weights);
+  void launch_inv_dyn(const InvPlan& plan, const ssrk::DynCtl* ctl, int Pmax, int G);
+  void launch_dyn_ring_update(const ssrk::DynCtl* ctl, const ssrk::DynRingEntry* upd,
+                              ssrk::DynRingEntry* ring, int rows, int R);
+  int dyn_mac_slots() const;
+  int inv_groups(int max_entries) const;
+  void launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const float2* red,
+                         const ssrk::GatherArgs& ga, const int* kind_counts);       // CTAs resident at once for the generated-terms MAC kernel
+  DeviceArray<unsigned long long> d_dyn_stats;  // [2] H / X partitions read by generated-terms launches
+  uint64_t dyn_h_seen = 0, dyn_x_seen = 0;
   void upload_weights(const float* w, size_t n);
   void ensure_partials(size_t npartial_spectra);
   int mac_slots() const;           // CTAs resident at once for the MAC kernel
@@ -277,6 +288,12 @@ struct FilterSet
   DeviceArray<float2> data;          // [channels][partitions][B]
   std::vector<int> valid;            // per channel: partitions [0, valid) carry data
   std::vector<uint8_t> flags;        // per (channel, partition): 1 = non-zero-flagged
+  DeviceArray<unsigned char> d_flags;  // device mirror of `flags` (generated MAC terms read it)
+  bool flags_dirty = true;
+  const unsigned char* device_flags(); // uploads when stale (stream-ordered)
+  std::vector<uint8_t> all_set;        // per channel: no zero-flagged partition
+  // device flags of one channel, or null when every partition carries data
+  const unsigned char* device_flags_row(int ch);
   const float2* part(int ch, int p) const { return data.ptr + (size_t(ch) * partitions + p) * e->B; }
   float2* part(int ch, int p) { return data.ptr + (size_t(ch) * partitions + p) * e->B; }
   // null for zero-flagged partitions (fft_node::zero, convolver.h:91-96)
@@ -458,7 +475,13 @@ struct Renderer
     BlockParameter<float> bw{-1.0f};
     BlockParameter<long> index{-1};
     BlockParameter<float> interp{-1.0f};
-    std::vector<FilterPtrTable> chan;                 // 2 ears
+    // Staggered filter switch of the two ears' Outputs (convolver.h:618-699) as
+    // "current filter by block index": latest = the filter set_filter() installed
+    // last, hist[ear][b mod (P + 1)] = latest as of block b (mirror of the device ring)
+    ssrk::DynRingEntry latest[2] = {{nullptr, nullptr, 0, 0}, {nullptr, nullptr, 0, 0}};
+    std::vector<ssrk::DynRingEntry> hist[2];
+    bool has_switched = false;
+    long long last_switch = 0;                        // block index of the last set_filter()
     std::vector<std::vector<std::unique_ptr<FilterSet>>> temp;  // per ear: pool of temporary_hrtf
     Mode mode = NOTHING;
   };
@@ -481,18 +504,24 @@ struct Renderer
   // per-block plans
   MacPlan static_mac;           // generic: built when the source list changes
   bool static_dirty = true;
-  MacPlan dyn_mac;              // brs / binaural: one plan, groups = const / old / new
   InvPlan inv;
+  // brs / binaural: terms are generated on the device (ssrk::DynTables)
+  long long dyn_b = 0;                   // block counter
+  int dyn_Pmax = 1, dyn_R = 2, dyn_G = 0;
+  DeviceArray<ssrk::DynRingEntry> dyn_ring;   // [sources][2 ears][R]
+  DeviceArray<unsigned char> dyn_dev;    // this block's control data (one small upload)
+  PinnedArray<unsigned char> dyn_stage[2];
+  cudaEvent_t dyn_copied[2] = {nullptr, nullptr};
+  int dyn_slot = 0;
+  ssrk::DynTables dyn_tables{};
+  const float* dyn_wtab_dev = nullptr;
+  const ssrk::DynRingEntry* dyn_upd_dev = nullptr;
   // forward-FFT job tables, one per distinct device input pointer (a caller
   // cycling through a few input buffers never re-uploads in steady state)
   std::vector<std::pair<const float*, std::unique_ptr<Table<ssrk::FwdJob>>>> fwd_cache;
   Table<ssrk::FwdJob>* fwd = nullptr;
   std::vector<float> wtab_host;
   int mac_slots_cached = 0;
-  BlockArena arena;                      // per-block tables of the dynamic renderers
-  Table<float> dyn_wtab;                 // their weights travel in the arena too
-  std::vector<ssrk::MacTermMeta> kind_meta[3];
-  std::vector<const float4*> kind_h[3];  // [terms][2 ears], per accumulator kind
   DeviceArray<float> d_in, d_out;
   PinnedArray<float> h_in, h_out;
   int inv_key = -1;

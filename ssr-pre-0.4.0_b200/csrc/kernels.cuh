@@ -120,11 +120,21 @@ __device__ __forceinline__ float block_max(float v)
 // radix-4 stages plus one radix-2 stage when log2(m) is odd.  `a` holds the
 // input; the result ends up in the returned buffer (a or b).  tw[i] =
 // exp(-2 pi i * i / (2m)), i in [0, 2m); INVERSE conjugates the twiddles.
-template<bool INVERSE>
-__device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
-                                            const float2* __restrict__ tw)
+// barrier `bar` over kThreads threads (0 = the whole CTA of a kThreads-thread kernel;
+// the inverse kernel runs one kThreads-thread group per accumulator entry, each on
+// its own named barrier)
+__device__ __forceinline__ void group_sync(int bar)
 {
-  const int t = threadIdx.x;
+  asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(kThreads) : "memory");
+}
+
+// TWS: `tw` is a shared-memory copy of the twiddle table (the latency-bound
+// block-loop kernels stage it once instead of going to L1/L2 in every stage)
+template<bool INVERSE, bool TWS = false>
+__device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
+                                            const float2* __restrict__ tw,
+                                            const int t = threadIdx.x, const int bar = 0)
+{
   float2* src = a;
   float2* dst = b;
   int Ns = 1;
@@ -145,9 +155,9 @@ __device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
         float2 v3 = src[j + 3 * q];
         if (Ns > 1)
         {
-          float2 w1 = __ldg(&tw[k * tstep]);
-          float2 w2 = __ldg(&tw[2 * k * tstep]);
-          float2 w3 = __ldg(&tw[3 * k * tstep]);
+          float2 w1 = TWS ? tw[k * tstep] : __ldg(&tw[k * tstep]);
+          float2 w2 = TWS ? tw[2 * k * tstep] : __ldg(&tw[2 * k * tstep]);
+          float2 w3 = TWS ? tw[3 * k * tstep] : __ldg(&tw[3 * k * tstep]);
           if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
           v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
         }
@@ -176,7 +186,7 @@ __device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
         float2 v1 = src[j + q];
         if (Ns > 1)
         {
-          float2 w1 = __ldg(&tw[k * tstep]);
+          float2 w1 = TWS ? tw[k * tstep] : __ldg(&tw[k * tstep]);
           if (INVERSE) w1.y = -w1.y;
           v1 = cmul(v1, w1);
         }
@@ -186,10 +196,20 @@ __device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
       }
       Ns <<= 1; rem >>= 1;
     }
-    __syncthreads();
+    group_sync(bar);
     float2* tmp = src; src = dst; dst = tmp;
   }
   return src;
+}
+
+// copies the 2B-entry twiddle table into shared memory (all `nthreads` threads of
+// the CTA take part; the caller's next CTA-wide barrier publishes it)
+__device__ __forceinline__ void stage_twiddles(float2* stw, const float2* __restrict__ tw, int B,
+                                               int tid, int nthreads)
+{
+  const float4* src = reinterpret_cast<const float4*>(tw);
+  float4* dst = reinterpret_cast<float4*>(stw);
+  for (int i = tid; i < B; i += nthreads) dst[i] = __ldg(src + i);
 }
 
 // ---------------------------------------------------------------- forward
@@ -229,14 +249,22 @@ __device__ __forceinline__ float fwd_sample(const FwdHalf& h, int i)
   return h.ptr ? h.ptr[long(i) * h.stride] : 0.0f;
 }
 
-// One CTA per transform.  B = block size = complex FFT size; smem = 2 * B float2.
-__device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const float2* __restrict__ tw)
+// One CTA per transform.  B = block size = complex FFT size; smem = 2 * B float2
+// (TWS: + 2 * B float2 for the staged twiddle table).
+template<bool TWS = false>
+__device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const float2* __restrict__ tw_global)
 {
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B;
   const int t = threadIdx.x;
   const int half = B >> 1;
+  const float2* tw = tw_global;
+  if (TWS)
+  {
+    stage_twiddles(smem + 2 * B, tw_global, B, t, kThreads);  // published by the barrier after the input load
+    tw = smem + 2 * B;
+  }
 
   int new_head = 0;
   if (!job.dst)
@@ -273,7 +301,7 @@ __device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const flo
     if (t == 0) *job.level = m;
   }
 
-  const float2* z = fft_smem<false>(a, b, B, tw);
+  const float2* z = fft_smem<false, TWS>(a, b, B, tw);
 
   float2* dst = job.dst;
   if (!dst) dst = job.ring + size_t(new_head) * B;
@@ -292,7 +320,7 @@ __device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const flo
       const float2 zk = z[k], zk2 = z[k2];
       const float er = 0.5f * (zk.x + zk2.x), ei = 0.5f * (zk.y - zk2.y);
       const float orr = 0.5f * (zk.y + zk2.y), oi = -0.5f * (zk.x - zk2.x);
-      const float2 w = __ldg(&tw[k]);
+      const float2 w = TWS ? tw[k] : __ldg(&tw[k]);
       const float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;
       dst[k] = make_float2(er + tr, ei + ti);
       if (k2 != k) dst[k2] = make_float2(er - tr, -(ei - ti));
@@ -305,11 +333,25 @@ __device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const flo
   if (!job.dst && t == 0) *job.head = new_head;
 }
 
+// Dynamic renderers: CTA n (= source slot n) also records the two ears' current
+// filters of this block in the filter ring (see DynTables; declared below).
+struct DynRingEntry;
+struct DynCtl;
+struct FwdRingUpdate
+{
+  const DynCtl* ctl;            // null: nothing to do
+  const DynRingEntry* upd;      // [sources][2]
+  DynRingEntry* ring;           // [sources][2][R]
+  int R;
+};
+__device__ __forceinline__ void fwd_ring_update(const FwdRingUpdate& u, int source, int ear);
+
 __global__ void __launch_bounds__(kThreads)
-fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw)
+fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru)
 {
   const FwdJob job = jobs[blockIdx.x];
-  fwd_fft_body(job, B, tw);
+  if (ru.ctl && threadIdx.x < 2) fwd_ring_update(ru, blockIdx.x, threadIdx.x);
+  fwd_fft_body<true>(job, B, tw);
 }
 
 // Filter-set loading: one launch transforms `channels x nvalid` partitions described
@@ -366,6 +408,62 @@ fwd_fft_batch_kernel(const FwdBatch batch, int B, const float2* __restrict__ tw)
 //   acc[row j] += w * X[input, partition p blocks ago] * H_j
 struct MacTermMeta { int input; int p; int wslot; int pad; };
 
+// Dynamic renderers (Binaural / BRS): the term list is not uploaded, it is GENERATED
+// by the MAC kernel from a few hundred bytes of per-block control data.
+//
+// Staggered filter switch (apf/apf/convolver.h:618-699): partition p of a filter
+// installed in block b_set becomes active in block b_set + p.  Equivalently, in
+// block b partition p uses "the filter that was current in block b - p".  So the
+// device keeps, per (source, ear), a ring of the current filter by block index;
+// the state after this block's switch reads ring[b - p], the state before it
+// ("old", crossfaded out) reads ring[b - 1 - p].
+struct DynRingEntry
+{
+  const float4* base;            // partition 0 of the filter channel (null: empty, convolver.h:415)
+  const unsigned char* flags;    // per partition: 1 = carries data (0: fft_node::zero); null = all of them
+  int nparts;                    // partitions of that filter; beyond -> empty (convolver.h:650-656)
+  int pad;
+};
+
+struct DynCtl                    // uploaded once per block
+{
+  long long b;                   // block index of the state AFTER this block's switch
+  int n[3];                      // sources in the constant / old / new accumulator group
+  int pad;
+};
+
+struct DynTables
+{
+  const DynCtl* ctl;
+  const int* lists;              // [3][nsrc] source slots per group
+  const DynRingEntry* ring;      // [nsrc][2 ears][R]
+  const int* src_input;          // [nsrc] input id (X ring) of a source slot
+  const int* src_parts;          // [nsrc] partitions of its delay line
+  unsigned long long* stats;     // [2]: H partitions read, X partitions read (or null)
+  int nsrc, R, Pmax;
+};
+
+// CTAs [first, first + count) of a G-CTA launch work on group k; proportional to
+// the group sizes, at least one CTA per non-empty group.  Every CTA (and the
+// reduction that follows) evaluates this identically from the control block.
+constexpr int kDynMinTermsPerCta = 4;  // small problems use fewer CTAs (fewer partials to sum)
+
+__device__ __forceinline__ void dyn_split(const int* n, int Pmax, int G, int k, int& first, int& count)
+{
+  const int tot = n[0] + n[1] + n[2];
+  const int A = (n[0] > 0) + (n[1] > 0) + (n[2] > 0);
+  first = 0; count = 0;
+  int off = 0;
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+  {
+    int g = n[q] > 0 ? 1 + int((long long)(G - A) * n[q] / tot) : 0;
+    g = min(g, (n[q] * Pmax + kDynMinTermsPerCta - 1) / kDynMinTermsPerCta);
+    if (q == k) { first = off; count = g; }
+    off += g;
+  }
+}
+
 struct MacParams
 {
   const MacTermMeta* term_meta;      // [nterms]
@@ -381,13 +479,16 @@ struct MacParams
   int wtab_offset;                   // added to wslot (selects the weight "kind")
   int partial_offset;                // added to work.z
   int l2_hints;                      // 1: evict-first for H, evict-last for X
+  const float4* zero;                // an all-zero partition
+  DynTables dyn;                     // mac_kernel<..., DYN = true>: generated terms
 };
 
 constexpr int kMacTile = 64;
 
 // STAGES = depth of the register software pipeline (loads of term i + STAGES - 1
 // are issued before term i is consumed); MINB = CTAs per SM asked of ptxas.
-template<int MT, int NV, int STAGES = 2, int MINB = 1>
+// DYN: terms generated from MacParams::dyn (dynamic renderers, MT == 2 = the ears)
+template<int MT, int NV, int STAGES = 2, int MINB = 1, bool DYN = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 mac_kernel(const MacParams p)
 {
@@ -398,8 +499,32 @@ mac_kernel(const MacParams p)
 
   const int t = threadIdx.x;
   const int lane = t & 31;
-  const int4 wk = p.work[blockIdx.x];
   const int nvec = p.B >> 1;  // float4 per partition
+  static_assert(!DYN || MT == 2, "generated terms: rows are the two ears");
+  int4 wk;
+  int kind = 0;
+  if constexpr (DYN)
+  {
+    // generated work: which group this CTA serves and its slice of the group's
+    // (source, partition) terms
+    const int n0 = p.dyn.ctl->n[0], n1 = p.dyn.ctl->n[1], n2 = p.dyn.ctl->n[2];
+    const int nn[3] = {n0, n1, n2};
+    int first = 0, count = 0;
+    kind = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+      int f, c;
+      dyn_split(nn, p.dyn.Pmax, gridDim.x, k, f, c);
+      if (int(blockIdx.x) >= f && int(blockIdx.x) < f + c) { kind = k; first = f; count = c; }
+    }
+    if (kind < 0) return;
+    const int terms = nn[kind] * p.dyn.Pmax;
+    const int chunk = (terms + count - 1) / count;
+    const int s = int(blockIdx.x) - first;
+    wk = make_int4(min(terms, s * chunk), min(terms, (s + 1) * chunk), int(blockIdx.x), 0);
+  }
+  else wk = p.work[blockIdx.x];
   // B > 1024: blockIdx.y selects a 1024-bin tile of the spectrum
   const int tile_off = blockIdx.y * (NV * kThreads);
   const int tt = tile_off + t;
@@ -433,11 +558,37 @@ mac_kernel(const MacParams p)
         const int i = base + lane;
         bool ok = false;
         MacTermMeta m; float w = 0.f;
+        const float4* hgen[2] = {nullptr, nullptr};
         if (i < tile_n)
         {
-          m = p.term_meta[tb + i];
-          w = p.wtab[m.wslot + p.wtab_offset];
-          ok = (w != 0.0f);
+          if constexpr (DYN)
+          {
+            {
+              const int src = p.dyn.lists[kind * p.dyn.nsrc + (tb + i) / p.dyn.Pmax];
+              m.input = p.dyn.src_input[src];
+              m.p = (tb + i) % p.dyn.Pmax;
+              w = p.wtab[kind * p.dyn.nsrc + src];
+              if (m.p < p.dyn.src_parts[src] && w != 0.0f)
+              {
+                long long time = p.dyn.ctl->b - (kind == 1 ? 1 : 0) - m.p;
+                int slot = int(time % p.dyn.R);
+                if (slot < 0) slot += p.dyn.R;
+#pragma unroll
+                for (int ear = 0; ear < 2; ++ear)
+                {
+                  const DynRingEntry en = p.dyn.ring[(size_t(src) * 2 + ear) * p.dyn.R + slot];
+                  if (en.base && m.p < en.nparts && (!en.flags || en.flags[m.p])) hgen[ear] = en.base + size_t(m.p) * nvec;
+                }
+                ok = hgen[0] || hgen[1];
+              }
+            }
+          }
+          else
+          {
+            m = p.term_meta[tb + i];
+            w = p.wtab[m.wslot + p.wtab_offset];
+            ok = (w != 0.0f);
+          }
         }
         const unsigned mask = __ballot_sync(0xffffffffu, ok);
         if (ok)
@@ -448,10 +599,30 @@ mac_kernel(const MacParams p)
           if (slot < 0) slot += parts;
           s_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
           s_w[pos] = w;
+          if constexpr (DYN)
+          {
+            s_h[pos][0] = hgen[0] ? hgen[0] : p.zero;
+            s_h[pos][1] = hgen[1] ? hgen[1] : p.zero;
+          }
+          else
+          {
 #pragma unroll
-          for (int j = 0; j < MT; ++j) s_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+            for (int j = 0; j < MT; ++j) s_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+          }
         }
         count += __popc(mask);
+        if (DYN && p.dyn.stats && blockIdx.y == 0)
+        {
+          // traffic accounting: H and X partitions this CTA reads
+          const int nh = __popc(__ballot_sync(0xffffffffu, hgen[0] != nullptr))
+              + __popc(__ballot_sync(0xffffffffu, hgen[1] != nullptr));
+          if (lane == 0 && nh)
+          {
+            atomicAdd(p.dyn.stats, (unsigned long long)nh);
+            // X[n, p] counts once: the old-state group re-reads it from L2
+            if (kind != 1) atomicAdd(p.dyn.stats + 1, (unsigned long long)__popc(mask));
+          }
+        }
       }
       if (lane == 0) s_count = count;
     }
@@ -696,31 +867,108 @@ reduce_partials_kernel(const InvEntry* __restrict__ entries, const float4* __res
   }
 }
 
-// One CTA per output block.
+// Dynamic renderers: the same pre-reduction with the split derived from the
+// control block (see dyn_split); grid (2 ears x 3 kinds, (B/2)/32).  Entry
+// ear * 3 + kind of `reduced` receives the sum; inactive kinds are skipped (the
+// inverse kernel skips them too).
 __global__ void __launch_bounds__(kThreads)
+dyn_reduce_kernel(const DynCtl* __restrict__ ctl, int Pmax, int G, const float4* __restrict__ partials,
+                  float4* __restrict__ reduced, int nvec)
+{
+  __shared__ float4 s_part[kThreads / 32][32];
+  const int ear = blockIdx.x / 3, kind = blockIdx.x % 3;
+  const int nn[3] = {ctl->n[0], ctl->n[1], ctl->n[2]};
+  if (nn[kind] == 0) return;
+  int first, count;
+  dyn_split(nn, Pmax, G, kind, first, count);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.y * 32 + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < nvec)
+  {
+    const float4* base = partials + (size_t(first) * 2 + ear) * nvec + idx;
+    const size_t pstride = size_t(2) * nvec;
+#pragma unroll 4
+    for (int c = warp; c < count; c += kThreads / 32)
+    {
+      const float4 v = __ldcs(base + size_t(c) * pstride);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  s_part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && idx < nvec)
+  {
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w)
+    {
+      const float4 v = s_part[w][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reduced[size_t(blockIdx.x) * nvec + idx] = s;
+  }
+}
+
+__device__ __forceinline__ void fwd_ring_update(const FwdRingUpdate& u, int source, int ear)
+{
+  int slot = int(u.ctl->b % u.R);
+  if (slot < 0) slot += u.R;
+  const int row = source * 2 + ear;
+  u.ring[size_t(row) * u.R + slot] = u.upd[row];
+}
+
+// ring[(source, ear)][b mod R] = the filter that is current in block b
+__global__ void dyn_ring_update_kernel(const DynCtl* __restrict__ ctl, const DynRingEntry* __restrict__ upd,
+                                       DynRingEntry* __restrict__ ring, int rows, int R)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  int slot = int(ctl->b % R);
+  if (slot < 0) slot += R;
+  ring[size_t(i) * R + slot] = upd[i];
+}
+
+// One CTA per output block, one kThreads-thread GROUP per accumulator entry of the
+// block (constant / fade-out / fade-in, <= kInvMaxGroups): the up to three inverse
+// transforms of a crossfading output run side by side instead of one after the
+// other; group 0 adds the faded results and stores the block.
+constexpr int kInvMaxGroups = 3;
+
+template<int GROUPS>
+__global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 4 : 1)
 inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
                const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
                const float2* __restrict__ tw,
                const float* __restrict__ fade_out, const float* __restrict__ fade_in,
-               const GatherArgs ga)
+               const GatherArgs ga, const int* __restrict__ kind_counts)
 {
   extern __shared__ float2 smem[];
-  float2* a = smem;
-  float2* b = smem + B;
+  __shared__ float s_max[kThreads / 32];
+  const int g = GROUPS == 1 ? 0 : threadIdx.x / kThreads;  // entry group
+  const int t = threadIdx.x - g * kThreads;                // thread within the group
+  constexpr int ngroups = GROUPS;
+  float2* a = smem + size_t(g) * 2 * B;
+  float2* b = a + B;
   const InvJob job = jobs[blockIdx.x];
-  const int t = threadIdx.x;
   const int half = B >> 1;
+  // twiddle table -> shared memory, once for all groups
+  float2* stw = smem + size_t(GROUPS) * 2 * B;
+  stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);
+  __syncthreads();
   // flow control of the fused gather: the slot this block goes to must have been
   // read out by the root (checked by one thread while the others start loading)
-  if (ga.consumed && t == 0) gather_wait_ge(ga.consumed, ga.need_consumed, ga.error);
+  if (ga.consumed && threadIdx.x == 0) gather_wait_ge(ga.consumed, ga.need_consumed, ga.error);
 
   float2 res[kInvMaxRes];
 #pragma unroll
   for (int q = 0; q < kInvMaxRes; ++q) res[q] = make_float2(0.f, 0.f);
 
-  for (int e = 0; e < job.n_entries; ++e)
+  // entries beyond the launched groups are handled by the last group in turn
+  for (int e = g; e < job.n_entries; e += ngroups)
   {
     const InvEntry en = entries[job.first_entry + e];
+    // dynamic renderers: accumulator kinds without sources this block are skipped
+    if (kind_counts && kind_counts[en.fade] == 0) continue;
     // A[k] = sum over split partials
     // (float4 = two bins per thread; the loop over partials is unrolled so that
     // 8 independent loads are in flight per thread)
@@ -758,7 +1006,7 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
         reinterpret_cast<float4*>(a)[k] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
       }
     }
-    __syncthreads();
+    group_sync(g + 1);
     // Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k])
     for (int k = t; k <= half; k += kThreads)
     {
@@ -773,15 +1021,15 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
         const float2 xk = a[k], xk2 = a[k2];
         const float er = xk.x + xk2.x, ei = xk.y - xk2.y;
         const float dr = xk.x - xk2.x, di = xk.y + xk2.y;
-        float2 w = __ldg(&tw[k]);
+        float2 w = stw[k];
         w.y = -w.y;  // w^{-k}
         const float tr = -(dr * w.y + di * w.x), ti = dr * w.x - di * w.y;
         b[k] = make_float2(er + tr, ei + ti);
         if (k2 != k) b[k2] = make_float2(er - tr, -(ei - ti));
       }
     }
-    __syncthreads();
-    const float2* z = fft_smem<true>(b, a, B, tw);
+    group_sync(g + 1);
+    const float2* z = fft_smem<true, true>(b, a, B, stw, t, g + 1);
     // keep the second half: time index i = 2j, 2j+1 with j >= B/2
 #pragma unroll
     for (int q = 0; q < kInvMaxRes; ++q)
@@ -797,32 +1045,70 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
         res[q].y = fmaf(v.y, f1, res[q].y);
       }
     }
-    __syncthreads();  // z (smem) is rewritten by the next entry
+    group_sync(g + 1);  // z (smem) is rewritten by the group's next entry / the hand-over below
+  }
+
+  // groups 1.. hand their faded blocks to group 0 through their own smem region
+  if (ngroups > 1)
+  {
+    if (g > 0)
+    {
+#pragma unroll
+      for (int q = 0; q < kInvMaxRes; ++q)
+      {
+        const int jj = t + q * kThreads;
+        if (jj < half) a[jj] = res[q];
+      }
+    }
+    __syncthreads();
+    if (g == 0)
+      for (int gg = 1; gg < ngroups; ++gg)
+      {
+        const float2* other = smem + size_t(gg) * 2 * B;
+#pragma unroll
+        for (int q = 0; q < kInvMaxRes; ++q)
+        {
+          const int jj = t + q * kThreads;
+          if (jj < half) { const float2 v = other[jj]; res[q].x += v.x; res[q].y += v.y; }
+        }
+      }
   }
 
   if (ga.consumed) __syncthreads();  // thread 0's slot check precedes every store
-  float m = 0.0f;
-  float2* out = reinterpret_cast<float2*>(job.out + ga.out_offset);
+  if (g == 0)
+  {
+    float m = 0.0f;
+    float2* out = reinterpret_cast<float2*>(job.out + ga.out_offset);
 #pragma unroll
-  for (int q = 0; q < kInvMaxRes; ++q)
-  {
-    const int jj = t + q * kThreads;
-    if (jj < half)
+    for (int q = 0; q < kInvMaxRes; ++q)
     {
-      out[jj] = res[q];
-      m = fmaxf(m, fmaxf(fabsf(res[q].x), fabsf(res[q].y)));
+      const int jj = t + q * kThreads;
+      if (jj < half)
+      {
+        out[jj] = res[q];
+        m = fmaxf(m, fmaxf(fabsf(res[q].x), fabsf(res[q].y)));
+      }
     }
-  }
-  if (job.level)
-  {
-    m = block_max(m);
-    if (t == 0) *job.level = m;
+    if (job.level)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((t & 31) == 0) s_max[t >> 5] = m;
+      group_sync(1);
+      if (t < 32)
+      {
+        m = t < kThreads / 32 ? s_max[t] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (t == 0) *job.level = m;
+      }
+    }
   }
   if (ga.arrived)
   {
     // all stores of this CTA (peer memory, over NVLink) -> fence -> arrival count
     __syncthreads();
-    if (t == 0)
+    if (threadIdx.x == 0)
     {
       __threadfence_system();
       atomicAdd_system(ga.arrived, 1ull);

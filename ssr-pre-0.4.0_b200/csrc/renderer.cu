@@ -78,7 +78,6 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
   static_mac.MT = kGenericMT;
-  dyn_mac.MT = 2;
   d_out.resize(size_t(std::max(m_local, 1)) * e->B);
   h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
 }
@@ -88,6 +87,7 @@ Renderer::~Renderer()
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (auto ev : done) if (ev) cudaEventDestroy(ev);
+  for (auto ev : dyn_copied) if (ev) cudaEventDestroy(ev);
   drop_graphs();
   g_prof.report("s0 source logic, s1 plan, s2 inv+arena, s3 fwd table, s4 launches");
 }
@@ -116,7 +116,7 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
     s->brtf = std::move(irs);
     s->angles = channels / 2;
     s->input.reset(new Input(e, s->brtf->partitions));
-    for (int i = 0; i < 2; ++i) s->chan.emplace_back(s->brtf->partitions);
+    for (int i = 0; i < 2; ++i) s->hist[i].assign(size_t(s->brtf->partitions) + 1, DynRingEntry{nullptr, nullptr, 0, 0});
   }
   else if (cfg.kind == SSR_RENDERER_PREFILTER_BANK)
   {
@@ -132,7 +132,7 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
   {
     if (!hrtfs) throw Error(SSR_ERR_STATE, "ssr_b200: BinauralRenderer: load HRIRs before adding sources");
     s->input.reset(new Input(e, partitions));
-    for (int i = 0; i < 2; ++i) s->chan.emplace_back(partitions);
+    for (int i = 0; i < 2; ++i) s->hist[i].assign(size_t(partitions) + 1, DynRingEntry{nullptr, nullptr, 0, 0});
     s->temp.resize(2);
     s->bw = BlockParameter<float>(0.0f);  // _weight(0.0f) (src/binauralrenderer.h:245)
   }
@@ -344,6 +344,12 @@ static float fwrap(float x, float full)
   return x;
 }
 
+// Binaural / BRS.  The host keeps the reference's per-source decisions (weights,
+// filter index, crossfade mode, queues_empty) and uploads ~80 bytes per source;
+// the (source, partition) term list of the staggered filter switch is generated
+// inside the MAC kernel from a per-(source, ear) ring of "current filter by block"
+// (ssrk::DynTables).  Every launch has a fixed shape, so the block replays as a
+// CUDA graph like the static renderers.
 Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_output)
 {
   StepDesc d;
@@ -351,41 +357,71 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   const int N = int(sources.size());
   const int B = e->B;
   const bool binaural = cfg.kind == SSR_RENDERER_BINAURAL;
-  wtab_host.assign(size_t(3) * std::max(N, 1), 0.0f);
-  MacPlan& plan = dyn_mac;
-  plan.clear();
-  const float4* zero = reinterpret_cast<const float4*>(e->zero_part.ptr);
-
-  // terms of one (source, kind) with the pointer tables as they are NOW, appended
-  // to the kind's term list (vectors are members: no allocation in steady state)
-  for (int k = 0; k < 3; ++k) { kind_meta[k].clear(); kind_h[k].clear(); }
-  uint64_t hparts = 0, xparts = 0;
   g_prof.start();
-  auto snapshot = [&](int n, int kind)
+
+  if (static_dirty)
   {
-    Source& s = *sources[n];
-    const auto& lp = s.chan[0].current();
-    const auto& rp = s.chan[1].current();
-    const int id = s.input->id, P = s.input->P;
-    for (int p = 0; p < P; ++p)
+    // source list changed: re-lay the device ring from the hosts' histories
+    e->sync();
+    dyn_Pmax = 1;
+    for (auto& s : sources) dyn_Pmax = std::max(dyn_Pmax, s->input->P);
+    dyn_R = dyn_Pmax + 1;
+    std::vector<DynRingEntry> ring(size_t(std::max(N, 1)) * 2 * dyn_R, DynRingEntry{nullptr, nullptr, 0, 0});
+    for (int n = 0; n < N; ++n)
     {
-      const float2* l = lp[p];
-      const float2* r = rp[p];
-      if (!l && !r) continue;
-      kind_meta[kind].push_back({id, p, kind * N + n, 0});
-      kind_h[kind].push_back(l ? reinterpret_cast<const float4*>(l) : zero);
-      kind_h[kind].push_back(r ? reinterpret_cast<const float4*>(r) : zero);
-      hparts += (l ? 1 : 0) + (r ? 1 : 0);
-      xparts += 1;
+      Source& s = *sources[n];
+      const long long Hn = s.input->P + 1;
+      for (int ear = 0; ear < 2; ++ear)
+        for (long long tau = dyn_b - (Hn - 1); tau <= dyn_b; ++tau)
+        {
+          if (tau < 0) continue;
+          ring[(size_t(n) * 2 + ear) * dyn_R + size_t(tau % dyn_R)] = s.hist[ear][size_t(tau % Hn)];
+        }
     }
+    dyn_ring.resize(ring.size());
+    SSR_CUDA(cudaMemcpy(dyn_ring.ptr, ring.data(), ring.size() * sizeof(DynRingEntry), cudaMemcpyHostToDevice));
+    dyn_G = e->dyn_mac_slots();
+    e->ensure_partials(size_t(dyn_G) * 2);
+    static_dirty = false;
+    inv_key = -1;
+  }
+
+  // layout of the per-block control upload
+  const size_t off_lists = sizeof(DynCtl);
+  const size_t off_input = off_lists + size_t(3) * N * sizeof(int);
+  const size_t off_parts = off_input + size_t(N) * sizeof(int);
+  const size_t off_w = off_parts + size_t(N) * sizeof(int);
+  size_t off_upd = off_w + size_t(3) * N * sizeof(float);
+  off_upd = (off_upd + 15) & ~size_t(15);
+  const size_t total = off_upd + size_t(2) * N * sizeof(DynRingEntry);
+  dyn_slot ^= 1;
+  if (dyn_copied[dyn_slot]) SSR_CUDA(cudaEventSynchronize(dyn_copied[dyn_slot]));
+  else SSR_CUDA(cudaEventCreateWithFlags(&dyn_copied[dyn_slot], cudaEventDisableTiming));
+  if (dyn_stage[dyn_slot].count < total) dyn_stage[dyn_slot].resize(total + total / 2 + 256);
+  if (dyn_dev.count < total) { e->sync(); dyn_dev.resize(total + total / 2 + 256); }
+  unsigned char* st = dyn_stage[dyn_slot].ptr;
+  DynCtl* ctl = reinterpret_cast<DynCtl*>(st);
+  int* lists = reinterpret_cast<int*>(st + off_lists);
+  int* src_input = reinterpret_cast<int*>(st + off_input);
+  int* src_parts = reinterpret_cast<int*>(st + off_parts);
+  float* wtab = reinterpret_cast<float*>(st + off_w);
+  DynRingEntry* upd = reinterpret_cast<DynRingEntry*>(st + off_upd);
+  std::memset(wtab, 0, size_t(3) * N * sizeof(float));
+
+  const long long b = ++dyn_b;   // block index of the state after this block's switch
+  int nk[3] = {0, 0, 0};
+  auto select = [&](int n, int kind, float w)
+  {
+    lists[kind * N + nk[kind]++] = n;
+    wtab[kind * N + n] = w;
   };
 
   for (int n = 0; n < N; ++n)
   {
     Source& s = *sources[n];
+    const int P = s.input->P;
     base_weight(s);
     bool filter_changed;
-    BlockParameter<float>* wp;
     if (!binaural)
     {
       // src/brsrenderer.h:141-184
@@ -394,7 +430,6 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
       s.index.assign(long(size_t(fwrap((azi - 90.0f) * float(s.angles) / 360.0f + 0.5f,
                 float(s.angles)))));
       filter_changed = s.index.changed();
-      wp = &s.bw;
     }
     else
     {
@@ -424,10 +459,12 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
       const float rel = src_az - ref_ori;
       s.index.assign(long(size_t(fwrap(rel * fangles / 360.0f + 0.5f, fangles))));
       filter_changed = s.index.changed() || s.interp.changed();
-      wp = &s.bw;
     }
-    const BlockParameter<float>& w = *wp;
-    const bool queues_empty = s.chan[0].queues_empty();
+    const BlockParameter<float>& w = s.bw;
+    // Output::queues_empty() (convolver.h:666-677) before this block's rotate: the
+    // last partition of a filter installed in block b0 becomes active in block
+    // b0 + P - 1, so the queues are empty from block b0 + P on
+    const bool queues_empty = P < 2 || !s.has_switched || b >= s.last_switch + P;
     Mode mode;
     if (w.both_eq(0.0f)) mode = NOTHING;
     else if (queues_empty && !w.changed() && !filter_changed) mode = CONSTANT;
@@ -447,19 +484,25 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     }
     s.mode = mode;
 
-    // old state first (convolve_and_more(old weight)), then rotate / switch
-    if (mode != NOTHING && mode != FADE_IN && mode != CONSTANT) { snapshot(n, 1); wtab_host[N + n] = w.old(); }
-    for (int i = 0; i < 2; ++i)
+    // old state (convolve_and_more(old weight)) = the tables of block b - 1;
+    // rotate_queues() is implicit in the block index; then the switch
+    if (mode != NOTHING && mode != FADE_IN && mode != CONSTANT) select(n, 1, w.old());
+    if (filter_changed)
     {
-      FilterPtrTable& ch = s.chan[i];
-      if (!queues_empty) ch.rotate_queues();
-      if (filter_changed)
+      for (int i = 0; i < 2; ++i)
       {
-        if (!binaural) ch.set_filter(*s.brtf, int(2 * s.index.get() + i));
+        if (!binaural)
+        {
+          const int hch = int(2 * s.index.get() + i);
+          s.latest[i] = DynRingEntry{reinterpret_cast<const float4*>(s.brtf->part(hch, 0)),
+              s.brtf->device_flags_row(hch), s.brtf->partitions, 0};
+        }
         else
         {
           const int hch = int(2 * s.index.get() + i);
-          if (s.interp.get() == 0.0f) ch.set_filter(*hrtfs, hch);
+          if (s.interp.get() == 0.0f)
+            s.latest[i] = DynRingEntry{reinterpret_cast<const float4*>(hrtfs->part(hch, 0)),
+                hrtfs->device_flags_row(hch), hrtfs->partitions, 0};
           else
           {
             // Dirac interpolation into a temporary filter
@@ -469,72 +512,77 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
             // the pool is used instead.
             FilterSet* tmp = nullptr;
             for (auto& t : s.temp[i])
-              if (!ch.references(t->data.ptr, t->data.ptr + t->data.count)) { tmp = t.get(); break; }
+            {
+              const float4* lo = reinterpret_cast<const float4*>(t->data.ptr);
+              const float4* hi = reinterpret_cast<const float4*>(t->data.ptr + t->data.count);
+              bool used = false;
+              for (auto& h : s.hist[i]) used |= (h.base >= lo && h.base < hi);
+              if (!used) { tmp = t.get(); break; }
+            }
             if (!tmp)
             {
               s.temp[i].emplace_back(new FilterSet(e, 1, partitions));
               tmp = s.temp[i].back().get();
             }
             tmp->lerp_from(0, *hrtfs, hch, *neutral, 0, s.interp.get());
-            ch.set_filter(*tmp, 0);
+            s.latest[i] = DynRingEntry{reinterpret_cast<const float4*>(tmp->part(0, 0)),
+                tmp->device_flags_row(0), tmp->partitions, 0};
           }
         }
       }
+      s.has_switched = true;
+      s.last_switch = b;
     }
-    if (mode == CONSTANT) { snapshot(n, 0); wtab_host[n] = w.get(); }
-    else if (mode == CHANGE || mode == FADE_IN) { snapshot(n, 2); wtab_host[2 * N + n] = w.get(); }
+    for (int i = 0; i < 2; ++i)
+    {
+      s.hist[i][size_t(b % (P + 1))] = s.latest[i];
+      upd[n * 2 + i] = s.latest[i];
+    }
+    src_input[n] = s.input->id;
+    src_parts[n] = P;
+    if (mode == CONSTANT) select(n, 0, w.get());
+    else if (mode == CHANGE || mode == FADE_IN) select(n, 2, w.get());
   }
-
+  ctl->b = b;
+  ctl->n[0] = nk[0]; ctl->n[1] = nk[1]; ctl->n[2] = nk[2]; ctl->pad = 0;
   g_prof.lap(0);
-  // one plan, up to three groups (const / old / new), rows = (left, right)
-  int group_of_kind[3] = {-1, -1, -1};
-  for (int k = 0; k < 3; ++k)
-  {
-    if (kind_meta[k].empty()) continue;
-    group_of_kind[k] = plan.begin_group();
-    plan.meta.host.insert(plan.meta.host.end(), kind_meta[k].begin(), kind_meta[k].end());
-    plan.hptr.host.insert(plan.hptr.host.end(), kind_h[k].begin(), kind_h[k].end());
-    plan.end_group();
-  }
-  if (mac_slots_cached == 0) mac_slots_cached = e->mac_slots();
-  plan.make_work(mac_slots_cached);
-  e->ensure_partials(size_t(plan.npartials) * plan.MT);
+
+  SSR_CUDA(cudaMemcpyAsync(dyn_dev.ptr, st, total, cudaMemcpyHostToDevice, e->stream));
+  SSR_CUDA(cudaEventRecord(dyn_copied[dyn_slot], e->stream));
+  dyn_tables.ctl = reinterpret_cast<const DynCtl*>(dyn_dev.ptr);
+  dyn_tables.lists = reinterpret_cast<const int*>(dyn_dev.ptr + off_lists);
+  dyn_tables.src_input = reinterpret_cast<const int*>(dyn_dev.ptr + off_input);
+  dyn_tables.src_parts = reinterpret_cast<const int*>(dyn_dev.ptr + off_parts);
+  dyn_tables.ring = dyn_ring.ptr;
+  dyn_tables.stats = nullptr;
+  dyn_tables.nsrc = N; dyn_tables.R = dyn_R; dyn_tables.Pmax = dyn_Pmax;
+  dyn_wtab_dev = reinterpret_cast<const float*>(dyn_dev.ptr + off_w);
+  dyn_upd_dev = reinterpret_cast<const DynRingEntry*>(dyn_dev.ptr + off_upd);
   g_prof.lap(1);
 
-  inv.clear();
-  const float scale = 1.0f / float(2 * B);
-  int nrows = 0;
-  for (int ear = 0; ear < 2; ++ear)
+  // the inverse tables are static: one job per ear, one entry per accumulator kind
+  if (inv_key != 1 || (inv.jobs.host.size() && inv.jobs.host[0].out != d_output))
   {
-    InvJob job{int(inv.entries.host.size()), 0, d_output + size_t(ear) * B, level_ptr(N + ear)};
-    for (int k = 0; k < 3; ++k)
+    inv.clear();
+    const float scale = 1.0f / float(2 * B);
+    for (int ear = 0; ear < 2; ++ear)
     {
-      if (group_of_kind[k] < 0) continue;
-      const auto& grp = plan.groups[group_of_kind[k]];
-      if (grp.term_end == grp.term_begin) continue;
-      inv.entries.host.push_back({grp.partial_first, grp.nsplit, 2, ear, k, scale});
-      job.n_entries++;
-      nrows++;
+      inv.jobs.host.push_back(InvJob{ear * 3, 3, d_output + size_t(ear) * B, level_ptr(N + ear)});
+      for (int k = 0; k < 3; ++k) inv.entries.host.push_back({0, 0, 2, ear, k, scale});
     }
-    inv.jobs.host.push_back(job);
+    inv.upload(e->stream);
+    inv_key = 1;
   }
-
-  // one staging buffer, one copy for every table of this block
-  dyn_wtab.host = wtab_host;
-  arena.begin(BlockArena::bytes_of(plan.meta) + BlockArena::bytes_of(plan.hptr) + BlockArena::bytes_of(plan.work)
-      + BlockArena::bytes_of(inv.jobs) + BlockArena::bytes_of(inv.entries) + BlockArena::bytes_of(dyn_wtab), e->stream);
-  arena.put(plan.meta); arena.put(plan.hptr); arena.put(plan.work);
-  arena.put(inv.jobs); arena.put(inv.entries); arena.put(dyn_wtab);
-  arena.commit(e->stream);
   g_prof.lap(2);
 
   build_fwd(d_input);
   g_prof.lap(3);
   d.N = N;
   d.kind_mask = 1;
-  d.hparts[0] = hparts; d.xparts[0] = xparts; d.nrows = nrows;
-  d.graphable = false;  // tables (and grid sizes) change from block to block
-  (void)B;
+  // partitions read are counted by the kernel (Engine::d_dyn_stats); the
+  // accumulators written per output are known here
+  d.nrows = 2 * ((nk[0] > 0) + (nk[1] > 0) + (nk[2] > 0));
+  d.graphable = true;
   return d;
 }
 
@@ -637,7 +685,14 @@ void Renderer::launch(const StepDesc& d)
 {
   const int B = e->B;
   e->stage_begin();
-  e->launch_fwd(fwd->device(), d.N);
+  const bool dynamic = cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS;
+  if (dynamic && d.N > 0)
+  {
+    // the forward kernel's CTA n also records source n's current filters in the ring
+    const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
+    e->launch_fwd(fwd->device(), d.N, &ru);
+  }
+  else e->launch_fwd(fwd->device(), d.N);
   e->stage_mark(1);
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
@@ -655,7 +710,10 @@ void Renderer::launch(const StepDesc& d)
   else
   {
     if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) e->launch_mac(static_mac, 0, 0);
-    else e->launch_mac(dyn_mac, 0, 0, dyn_wtab.device());
+    else
+    {
+      e->launch_mac_dyn(dyn_tables, dyn_G, dyn_wtab_dev);
+    }
     if (e->cur)
     {
       e->cur->mac_bytes += uint64_t(8) * B * (d.hparts[0] + d.xparts[0] + uint64_t(d.nrows));
@@ -663,7 +721,9 @@ void Renderer::launch(const StepDesc& d)
     }
   }
   e->stage_mark(2);
-  if (gather) e->launch_inv(inv, gather->next_block());
+  if (cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS)
+    e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G);
+  else if (gather) e->launch_inv(inv, gather->next_block());
   else e->launch_inv(inv);
   e->stage_mark(3);
   e->stage_end();

@@ -135,11 +135,11 @@ def test_gather_device_path_wait_release(capi, co):
     err = 0.0
     for t in range(7):
         x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
-        d_in = []
+        d_in = [torch.from_numpy(x).to(f"cuda:{_device_for(g)}") for g in range(2)]
+        for g in range(2):
+            torch.cuda.synchronize(_device_for(g))  # torch's stream is not the engines' stream
         for g in (1, 0):
-            d = torch.from_numpy(x).to(f"cuda:{_device_for(g)}")
-            d_in.append(d)
-            rens[g].process_device(d.data_ptr(), 0)
+            rens[g].process_device(d_in[g].data_ptr(), 0)
         ptr = gathers[0].wait()
         y = np.empty((M, B), np.float32)
         engines[0].synchronize()
