@@ -144,8 +144,11 @@ Engine::Engine(const ssr_engine_config& cfg)
   SSR_CUDA(cudaMemset(d_heads.ptr, 0, kMaxInputs * sizeof(int)));
 
   const size_t fft_smem = size_t(2) * B * sizeof(float2);
+  if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
   if (2 * fft_smem > 48 * 1024)
   {
+    SSR_CUDA(cudaFuncSetAttribute(level1_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(level1_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
   }
@@ -335,6 +338,17 @@ void Engine::launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const
   else
     inv_fft_kernel<1><<<njobs, kThreads, smem, stream>>>(plan.jobs.device(), plan.entries.device(), part, red, B,
         tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+}
+
+void Engine::launch_level1_fused(const FusedParams& p)
+{
+  const size_t smem = size_t(4) * B * sizeof(float2);
+  const int nv = std::max(1, (B / 2) / kThreads);
+  if (nv >= 8) level1_fused_kernel<8><<<1, kThreads, smem, stream>>>(p, tw.ptr);
+  else if (nv == 4) level1_fused_kernel<4><<<1, kThreads, smem, stream>>>(p, tw.ptr);
+  else if (nv == 2) level1_fused_kernel<2><<<1, kThreads, smem, stream>>>(p, tw.ptr);
+  else level1_fused_kernel<1><<<1, kThreads, smem, stream>>>(p, tw.ptr);
+  SSR_CUDA(cudaGetLastError());
 }
 
 void Engine::launch_dyn_ring_update(const DynCtl* ctl, const DynRingEntry* upd, DynRingEntry* ring, int rows, int R)
@@ -946,17 +960,32 @@ FwdJob Input::make_job(const float* d_cur)
 void Input::add_block(const float* x)
 {
   e->use_device();
-  e->sync();  // the single staging buffer may still be in flight
+  // a block nobody convolved yet is transformed now (the delay line advances once
+  // per add_block); then wait until the staging buffer is free
+  if (fwd_pending) flush();
+  // (a fused launch has been waited for by convolve(): the buffer is free then)
+  if (stage_busy) { e->sync(); stage_busy = false; }
   std::memcpy(stage.ptr, x, e->B * sizeof(float));
-  SSR_CUDA(cudaMemcpyAsync(cur.ptr, stage.ptr, e->B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->stats.h2d_bytes += e->B * sizeof(float);
+  fwd_pending = true;
+  if (!e->level1_fused) flush();
+}
+
+void Input::flush()
+{
+  if (!fwd_pending) return;
+  e->use_device();
+  SSR_CUDA(cudaMemcpyAsync(cur.ptr, stage.ptr, e->B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->launch_fwd(job.device(), 1);
+  fwd_pending = false;
+  stage_busy = true;   // the copy out of the staging buffer is asynchronous
 }
 
 void Input::download(int p, float* sorted_out)
 {
   if (p < 0 || p >= P) throw Error(SSR_ERR_INVALID, "ssr_b200: input_download: bad partition");
   e->use_device();
+  flush();
   e->sync();
   int head = 0;
   SSR_CUDA(cudaMemcpy(&head, e->d_heads.ptr + id, sizeof(int), cudaMemcpyDeviceToHost));
@@ -972,6 +1001,8 @@ Output::Output(Input* in_, ssr_output_kind kind_)
 {
   e->use_device();
   d_res.resize(e->B); h_res.resize(e->B);
+  h_flag.resize(16);
+  h_flag.ptr[0] = 0;
   mac.MT = 1;
 }
 
@@ -1015,6 +1046,9 @@ const float* Output::convolve(float weight)
     planned_version = table.version;
     planned_zero = zero;
   }
+  if (e->level1_fused && !zero && planned_terms > 0 && planned_terms <= kFusedMaxTerms)
+    return convolve_fused(weight);
+  in->flush();
   if (planned_terms > 0 && !zero)
   {
     // other objects of this engine may have grown the shared partial buffer
@@ -1026,6 +1060,43 @@ const float* Output::convolve(float weight)
   SSR_CUDA(cudaMemcpyAsync(h_res.ptr, d_res.ptr, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   e->stats.d2h_bytes += B * sizeof(float);
   e->sync();
+  return h_res.ptr;
+}
+
+// One launch, no copy engine, no stream synchronisation (see level1_fused_kernel).
+const float* Output::convolve_fused(float weight)
+{
+  const int B = e->B;
+  FusedParams p{};
+  p.fwd = in->make_job(in->stage.ptr);   // the kernel reads the block from mapped host memory
+  p.do_fwd = in->fwd_pending ? 1 : 0;
+  p.term_meta = mac.meta.device();
+  p.term_h = mac.hptr.device();
+  p.nterms = planned_terms;
+  p.xring = e->d_xring.ptr;
+  p.xparts = e->d_xparts.ptr;
+  p.heads = e->d_heads.ptr;
+  p.scale = weight / float(2 * B);       // weight / n (convolver.h:458)
+  p.out = h_res.ptr;
+  p.flag = h_flag.ptr;
+  p.seq = ++fused_seq;
+  p.B = B;
+  e->launch_level1_fused(p);
+  in->fwd_pending = false;
+  e->stats.d2h_bytes += B * sizeof(float);
+  // spin on the completion flag; a failed launch / faulted context ends the wait
+  volatile int* flag = h_flag.ptr;
+  for (unsigned spins = 0; *flag != p.seq; ++spins)
+  {
+    if ((spins & 0xfffu) == 0xfffu)
+    {
+      const cudaError_t q = cudaStreamQuery(e->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady)
+        throw Error(SSR_ERR_CUDA, std::string("level1_fused_kernel: ") + cudaGetErrorString(q));
+      if (q == cudaSuccess && *flag != p.seq)
+        throw Error(SSR_ERR_CUDA, "level1_fused_kernel finished without delivering its block");
+    }
+  }
   return h_res.ptr;
 }
 

@@ -218,6 +218,8 @@ struct Engine
   int device, B, sample_rate, sm_count, mac_variant;
   bool fft1024 = false;            // B == 1024: register/shuffle FFT kernels (fft1024.cuh)
   bool fft1024_always = false;
+  bool level1_fused = true;        // Level 1: one launch per convolve() for short term lists
+  void launch_level1_fused(const ssrk::FusedParams& p);
   static constexpr int kFft1024MinJobs = 1024;
   cudaStream_t stream;
   bool own_stream;
@@ -368,6 +370,11 @@ struct Input
   DeviceArray<float> prev, cur;      // B floats each
   PinnedArray<float> stage;
   Table<ssrk::FwdJob> job;
+  // add_block() only stages the block; the forward transform runs inside the first
+  // Output::convolve() of the block (fused launch) or when flush() is called
+  bool fwd_pending = false;
+  bool stage_busy = false;           // an asynchronous copy may still read the staging buffer
+  void flush();                      // run a pending forward transform now (asynchronous)
   ssrk::FwdJob make_job(const float* d_cur);
   void add_block(const float* x);
   void download(int p, float* sorted_out);
@@ -387,7 +394,10 @@ struct Output
   bool planned_zero = false;
   DeviceArray<float> d_res;
   PinnedArray<float> h_res;
+  PinnedArray<int> h_flag;           // completion flag of the fused launch (mapped host memory)
+  int fused_seq = 0;
   const float* convolve(float weight);
+  const float* convolve_fused(float weight);
 };
 
 // ------------------------------------------------------------ multi-GPU output gather
