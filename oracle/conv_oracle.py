@@ -650,6 +650,13 @@ class BrsRendererOracle(_RendererBase):
         self.sources.append(s)
         return len(self.sources) - 1
 
+    def rem_source(self, index: int):
+        """RendererBase::rem_source (rendererbase.h:289-314): the source's two
+        channels leave the ears' lists (undistribute_list); no fade-out."""
+        s = self.sources.pop(index)
+        for e in range(2):
+            self.out_lists[e].remove(s.channels[e])
+
     def process(self, x: np.ndarray) -> np.ndarray:
         x = np.asarray(x, F32)
         for n, s in enumerate(self.sources):  # brsrenderer.h:141-210
@@ -729,6 +736,12 @@ class BinauralRendererOracle(_RendererBase):
             self.out_lists[e].append(s.channels[e])
         self.sources.append(s)
         return len(self.sources) - 1
+
+    def rem_source(self, index: int):
+        """RendererBase::rem_source (rendererbase.h:289-314), as for BRS."""
+        s = self.sources.pop(index)
+        for e in range(2):
+            self.out_lists[e].remove(s.channels[e])
 
     def process(self, x: np.ndarray) -> np.ndarray:
         x = np.asarray(x, F32)

@@ -8,6 +8,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 CFG5="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 CFG3="python bench.py --workload cfg3 --steps 6 --warmup 50 --no-cpu-baseline"
+CFG1="ssr-pre-0.4.0_b200/lib/perf_static_convolver 50"
+FULL="--set full --clock-control none --import-source on"
 
 $CFG5 > $OUT/plain_cfg5.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
@@ -15,30 +17,27 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
 echo "launch list rc=$?"
 
 $CFG5 > $OUT/plain_cfg5.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:mac_kernel -s 2 -c 2 \
-    -o $OUT/mac_${TAG} $CFG5 > $OUT/ncu_mac.log 2>&1
+ncu $FULL -k regex:mac_kernel -s 2 -c 2 -o $OUT/mac_${TAG} $CFG5 > $OUT/ncu_mac.log 2>&1
 echo "mac full rc=$?"
 
-# block-loop FFT kernels: skip the 128 filter-load launches of fwd_fft_kernel
+# block-loop FFT kernels (filter loading uses the batch kernels, not these)
 $CFG5 > $OUT/plain_cfg5.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fwd_fft_kernel -s 130 -c 2 \
-    -o $OUT/fwd_${TAG} $CFG5 > $OUT/ncu_fwd.log 2>&1
+ncu $FULL -k regex:fwd_fft_kernel -s 2 -c 2 -o $OUT/fwd_${TAG} $CFG5 > $OUT/ncu_fwd.log 2>&1
 echo "fwd full rc=$?"
 
 $CFG5 > $OUT/plain_cfg5.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:inv_fft_kernel -s 2 -c 2 \
-    -o $OUT/inv_${TAG} $CFG5 > $OUT/ncu_inv.log 2>&1
+ncu $FULL -k regex:inv_fft_kernel -s 2 -c 2 -o $OUT/inv_${TAG} $CFG5 > $OUT/ncu_inv.log 2>&1
 echo "inv full rc=$?"
 
-# filter-load FFT (24064 transforms per launch)
-$CFG5 > $OUT/plain_cfg5.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fwd_fft_kernel -s 10 -c 1 \
-    -o $OUT/fwdload_${TAG} $CFG5 > $OUT/ncu_fwdload.log 2>&1
-echo "fwd load full rc=$?"
-
-# BRS, head rotating every block (MT = 2 kernel, old + new filter tables)
+# BRS, head rotating every block: generated-terms MAC (old + new filter state), the
+# partial reduction and the three-group inverse kernel
 $CFG3 > $OUT/plain_cfg3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:mac_kernel -s 52 -c 2 \
-    -o $OUT/mac_cfg3_${TAG} $CFG3 > $OUT/ncu_mac_cfg3.log 2>&1
-echo "mac cfg3 full rc=$?"
+ncu $FULL -k regex:"mac_kernel|dyn_reduce_kernel|inv_fft_kernel" -s 150 -c 3 \
+    -o $OUT/cfg3_${TAG} $CFG3 > $OUT/ncu_cfg3.log 2>&1
+echo "cfg3 full rc=$?"
+
+# Level 1 fused kernel (cfg1: StaticConvolver, 8 partitions)
+$CFG1 > $OUT/plain_cfg1.log 2>&1 && \
+ncu $FULL -k regex:level1_fused_kernel -s 20 -c 2 -o $OUT/level1_${TAG} $CFG1 > $OUT/ncu_level1.log 2>&1
+echo "level1 full rc=$?"
 ls -la $OUT | tail -20

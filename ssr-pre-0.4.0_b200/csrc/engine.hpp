@@ -95,8 +95,7 @@ struct Table
   PinnedArray<T> stage;
   DeviceArray<T> dev;
   size_t uploaded = 0;
-  T* ext = nullptr;               // device copy inside a BlockArena (not owned), or null
-  T* device() const { return ext ? ext : dev.ptr; }
+  T* device() const { return dev.ptr; }
   cudaEvent_t staged = nullptr;   // recorded after the last staging -> device copy
   Table() {}
   Table(const Table&) = delete;
@@ -108,7 +107,6 @@ struct Table
   // already queued may still read the old table.
   void upload(cudaStream_t s)
   {
-    ext = nullptr;
     if (uploaded != host.size()) ++g_layout_epoch;
     uploaded = host.size();
     if (host.empty()) return;
@@ -124,50 +122,6 @@ struct Table
     SSR_CUDA(cudaMemcpyAsync(dev.ptr, stage.ptr, host.size() * sizeof(T),
           cudaMemcpyHostToDevice, s));
     SSR_CUDA(cudaEventRecord(staged, s));
-  }
-};
-
-// All per-block tables of a renderer in ONE pinned staging buffer and ONE
-// host-to-device copy (Binaural / BRS rebuild their tables every block).  Two
-// buffers alternate, so building block t+1 only waits for block t-1's copy.
-struct BlockArena
-{
-  PinnedArray<unsigned char> stage[2];
-  DeviceArray<unsigned char> dev[2];
-  cudaEvent_t copied[2] = {nullptr, nullptr};
-  int cur = 0;
-  size_t off = 0;
-  BlockArena() {}
-  BlockArena(const BlockArena&) = delete;
-  BlockArena& operator=(const BlockArena&) = delete;
-  ~BlockArena() { for (auto ev : copied) if (ev) cudaEventDestroy(ev); }
-  static size_t align(size_t n) { return (n + 255) & ~size_t(255); }
-  void begin(size_t total_bytes, cudaStream_t s)
-  {
-    cur ^= 1;
-    if (copied[cur]) SSR_CUDA(cudaEventSynchronize(copied[cur]));
-    else SSR_CUDA(cudaEventCreateWithFlags(&copied[cur], cudaEventDisableTiming));
-    if (total_bytes > stage[cur].count)
-    {
-      SSR_CUDA(cudaStreamSynchronize(s));  // kernels still reading the old device buffer
-      stage[cur].resize(total_bytes + total_bytes / 2 + 4096);
-      dev[cur].resize(stage[cur].count);
-    }
-    off = 0;
-  }
-  template<typename T> void put(Table<T>& t)
-  {
-    const size_t bytes = t.host.size() * sizeof(T);
-    if (bytes) std::memcpy(stage[cur].ptr + off, t.host.data(), bytes);
-    t.ext = reinterpret_cast<T*>(dev[cur].ptr + off);
-    t.uploaded = t.host.size();
-    off += align(bytes);
-  }
-  template<typename T> static size_t bytes_of(const Table<T>& t) { return align(t.host.size() * sizeof(T)); }
-  void commit(cudaStream_t s)
-  {
-    if (off) SSR_CUDA(cudaMemcpyAsync(dev[cur].ptr, stage[cur].ptr, off, cudaMemcpyHostToDevice, s));
-    SSR_CUDA(cudaEventRecord(copied[cur], s));
   }
 };
 

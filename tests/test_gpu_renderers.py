@@ -512,3 +512,85 @@ def test_process_uses_pinned_channel_arrays_in_place(capi, co, engine_factory):
         staged = rens[1].process(x.copy())                       # pageable: staged
         assert np.array_equal(got, staged)
         assert float(np.abs(got - ora.process(x)).max()) <= TOL
+
+
+def test_brs_unequal_ir_lengths_sources_added_and_removed_while_the_head_turns(capi, co, engine_factory):
+    """The device-side filter ring (ssrk::DynTables) with sources of different
+    partition counts (P = 1, 3, 5), a source added mid-stream (its staggered
+    switch starts from an empty table), one removed while its queues are still
+    rotating (the ring is re-laid from the hosts' histories), and the head turning
+    in every block throughout -- against the reference's queue semantics
+    (apf/apf/convolver.h:618-699, src/brsrenderer.h:141-210)."""
+    B, A = 64, 10
+    rng = np.random.default_rng(99)
+    e = engine_factory(B)
+    r = capi.Renderer(e, capi.BRS)
+    o = co.BrsRendererOracle(B)
+    lengths = [40, 190, 300]
+    ids = []
+    for L in lengths[:2]:
+        brir = decaying(rng, L, 2 * A, 0.05)
+        ids.append(r.add_source(brir)); o.add_source(brir)
+    az, worst = 0.0, 0.0
+    for t in range(60):
+        if t == 12:
+            brir = decaying(rng, lengths[2], 2 * A, 0.05)
+            ids.append(r.add_source(brir)); o.add_source(brir)
+        if t == 31:
+            r.rem_source(ids.pop(1)); o.rem_source(1)
+        if t == 45:
+            r.set_processing(False); o.processing = False
+        if t == 50:
+            r.set_processing(True); o.processing = True
+        n = len(ids)
+        x = rng.uniform(-1, 1, (n, B)).astype(np.float32)
+        if t < 40 or t % 3 == 0:
+            az += 360.0 / A + 3.0   # a new BRIR pair in (almost) every block
+        r.set_reference_orientation(az); o.reference_orientation = az
+        y = r.process(x)
+        worst = max(worst, maxerr(y, o.process(x)))
+    assert worst <= TOL, worst
+
+
+def test_binaural_multi_partition_hrirs_staggered_switch(capi, co, engine_factory):
+    """HRIRs longer than the block (P = 4): every move of a source starts a
+    staggered switch that takes P blocks; moves arrive faster than that, stop
+    (queues run empty -> constant mode), a source is muted across a switch and one
+    is removed."""
+    B, L, A, N = 64, 250, 16, 3
+    rng = np.random.default_rng(5)
+    e = engine_factory(B)
+    hrir = decaying(rng, L, 2 * A, 0.5 / np.sqrt(L / 6.9))
+    r = capi.Renderer(e, capi.BINAURAL)
+    r.load_hrirs(hrir)
+    o = co.BinauralRendererOracle(B, hrir)
+    ids = [r.add_source() for _ in range(N)]
+    for _ in range(N):
+        o.add_source()
+
+    def setpos(i, p):
+        r.set_position(ids[i], p[0], p[1])
+        o.sources[i].position = p
+
+    for i, p in enumerate([(0.0, 2.0), (1.5, -1.0), (-2.0, 0.3)]):
+        setpos(i, p)
+    worst = 0.0
+    for t in range(64):
+        if t == 40:
+            r.rem_source(ids.pop(0)); o.rem_source(0)
+        n = len(ids)
+        x = rng.uniform(-1, 1, (n, B)).astype(np.float32)
+        if 3 <= t < 18 or t in (25, 27, 44):
+            a = t * 0.45
+            setpos(n - 1, (2 * np.cos(a), 2 * np.sin(a)))
+        if t == 8:
+            r.set_mute(ids[1], True); o.sources[1].mute = True
+        if t == 10:
+            setpos(1, (0.3, 2.5))   # switches while muted: no audio, queues still advance
+        if t == 13:
+            r.set_mute(ids[1], False); o.sources[1].mute = False
+        if t == 50:
+            r.set_reference_orientation(200.0); o.reference_orientation = 200.0
+        y = r.process(x)
+        worst = max(worst, maxerr(y, o.process(x)))
+    assert worst <= TOL, worst
