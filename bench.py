@@ -563,7 +563,8 @@ def main_ours(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "ssrk::mac_kernel<4,2>" if w.kind == "generic" else "ssrk::mac_kernel<2,2>", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": ("ssrk::mac_kernel<4,2,2,2,false>" if w.kind == "generic"
+                                   else "ssrk::mac_kernel<2,2,2,1,true> (terms generated on the device)"), "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "bytes_per_launch": st["mac_bytes"] / max(1, st["mac_launches"]),
         "ms_per_launch": mac_ms / max(1, st["mac_launches"]),

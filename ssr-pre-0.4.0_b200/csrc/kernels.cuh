@@ -448,7 +448,7 @@ struct DynTables
 // reduction that follows) evaluates this identically from the control block.
 constexpr int kDynMinTermsPerCta = 4;  // small problems use fewer CTAs (fewer partials to sum)
 
-__device__ __forceinline__ void dyn_split(const int* n, int Pmax, int G, int k, int& first, int& count)
+__host__ __device__ __forceinline__ void dyn_split(const int* n, int Pmax, int G, int k, int& first, int& count)
 {
   const int tot = n[0] + n[1] + n[2];
   const int A = (n[0] > 0) + (n[1] > 0) + (n[2] > 0);
@@ -458,7 +458,8 @@ __device__ __forceinline__ void dyn_split(const int* n, int Pmax, int G, int k, 
   for (int q = 0; q < 3; ++q)
   {
     int g = n[q] > 0 ? 1 + int((long long)(G - A) * n[q] / tot) : 0;
-    g = min(g, (n[q] * Pmax + kDynMinTermsPerCta - 1) / kDynMinTermsPerCta);
+    const int cap = (n[q] * Pmax + kDynMinTermsPerCta - 1) / kDynMinTermsPerCta;
+    if (g > cap) g = cap;
     if (q == k) { first = off; count = g; }
     off += g;
   }

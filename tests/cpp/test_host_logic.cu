@@ -4,7 +4,13 @@
 //    reference's shifting queues and against the sequence the reference's unit
 //    test expects (apf/unit_tests/test_convolver.cpp:86-131);
 //  * MacPlan::make_work: every term of every group is covered exactly once by
-//    contiguous chunks, partial indices are unique, chunks are balanced.
+//    contiguous chunks, partial indices are unique, chunks are balanced;
+//  * the rule the dynamic renderers' device-side term generation rests on
+//    (kernels.cuh, DynTables): with the renderers' protocol (old state, rotate
+//    while the queues are not empty, set_filter), in block b partition p uses the
+//    filter that was current in block b - p, the state before the switch is the
+//    previous block's state, and queues_empty() <=> b >= b_set + P;
+//  * ssrk::dyn_split: the CTA ranges of the three accumulator groups.
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -163,10 +169,101 @@ static void test_make_work()
   }
 }
 
+// One Output driven like BrsRenderer / BinauralRenderer drive it
+// (src/brsrenderer.h:186-205): per block  [old state] -> rotate_queues() if the
+// queues were not empty -> set_filter() if the filter changed -> [new state].
+static void test_filter_ring_rule()
+{
+  static float2 storage[64][64];
+  static float2 empty_marker;
+  for (int P : {1, 2, 3, 4, 7, 47})
+  {
+    LiteralQueues lit(P, &empty_marker);
+    // ring[b] = index of the filter current in block b (-1: none yet) and its length
+    std::vector<int> cur_filter(1, -1), cur_len(1, 0);   // block 0 = before the first block
+    long long last_set = 0; bool has_set = false;
+    std::vector<const float2*> prev_state(P, &empty_marker);
+    for (long long b = 1; b <= 500; ++b)
+    {
+      // queues_empty before this block's rotate, by the block-index rule
+      const bool rule_empty = P < 2 || !has_set || b >= last_set + P;
+      CHECK(rule_empty == lit.queues_empty());
+      // old state = the table as the previous block left it
+      bool same_old = true;
+      for (int p = 0; p < P; ++p) same_old = same_old && lit.ptrs[p] == prev_state[p];
+      CHECK(same_old);
+      if (!lit.queues_empty()) lit.rotate_queues();
+      int f = cur_filter.back(), len = cur_len.back();
+      const unsigned op = rnd() % 10;
+      // bursts of switches in consecutive blocks, pauses longer than P blocks
+      const bool change = (b % 97 < 40) ? op < 8 : (b % 97 < 40 + P + 3 ? false : op < 2);
+      if (change)
+      {
+        f = int(rnd() % 64);
+        len = 1 + int(rnd() % (P + 2));
+        if (len > 64) len = 64;
+        std::vector<const float2*> parts;
+        for (int p = 0; p < len; ++p) parts.push_back(&storage[f][p]);
+        lit.set_filter(parts);
+        last_set = b; has_set = true;
+      }
+      cur_filter.push_back(f); cur_len.push_back(len);
+      // new state: partition p = part p of the filter current in block b - p
+      bool same_new = true;
+      for (int p = 0; p < P; ++p)
+      {
+        const long long tau = b - p;
+        const float2* want = &empty_marker;
+        if (tau >= 1 && cur_filter[size_t(tau)] >= 0 && p < cur_len[size_t(tau)])
+          want = &storage[cur_filter[size_t(tau)]][p];
+        same_new = same_new && lit.ptrs[p] == want;
+      }
+      CHECK(same_new);
+      prev_state = lit.ptrs;
+    }
+  }
+}
+
+static void test_dyn_split()
+{
+  for (int trial = 0; trial < 2000; ++trial)
+  {
+    int n[3];
+    for (int& v : n) v = (rnd() % 3 == 0) ? 0 : int(rnd() % 200);
+    const int Pmax = 1 + int(rnd() % 60);
+    const int G = 3 + int(rnd() % 600);
+    int next = 0;
+    bool ok = true;
+    for (int k = 0; k < 3; ++k)
+    {
+      int first = -1, count = -1;
+      ssrk::dyn_split(n, Pmax, G, k, first, count);
+      ok = ok && first == next;                       // contiguous, in group order
+      ok = ok && ((n[k] == 0) == (count == 0));       // exactly the non-empty groups get CTAs
+      const int terms = n[k] * Pmax;
+      ok = ok && count <= std::max(1, (terms + ssrk::kDynMinTermsPerCta - 1) / ssrk::kDynMinTermsPerCta);
+      if (count > 0)
+      {
+        // the kernel's chunking covers every term exactly once
+        const int chunk = (terms + count - 1) / count;
+        long covered = 0;
+        for (int s = 0; s < count; ++s)
+          covered += std::min(terms, (s + 1) * chunk) - std::min(terms, s * chunk);
+        ok = ok && covered == terms;
+      }
+      next = first + count;
+    }
+    ok = ok && next <= G;
+    CHECK(ok);
+  }
+}
+
 int main()
 {
   test_ptr_table();
   test_make_work();
+  test_filter_ring_rule();
+  test_dyn_split();
   std::printf("%s (%d assertions, %d failed)\n", failures ? "FAILED" : "All tests passed", checks, failures);
   return failures ? 1 : 0;
 }
