@@ -97,10 +97,16 @@ typedef struct ssr_engine_stats
   uint64_t mac_terms;     /* partition-MACs (8*B flops each at 8 flops / complex MAC) */
   uint64_t h2d_bytes, d2h_bytes;
   int timing_enabled;
-  int reserved[7];
+  int timing_every;          /* every timing_every-th block step carries the stage events */
+  uint64_t launches_total;   /* every kernel the engine launched (timed or not, graph replays included) */
+  int reserved[4];
 } ssr_engine_stats;
 
-int ssr_engine_set_timing(ssr_engine* e, int enabled);  /* per-stage CUDA events */
+/* Per-stage CUDA events.  enabled = 0: off; 1: every block step; k > 1: every k-th
+ * block step (the four event records cost ~10 us of stream time per block, which
+ * matters for the 50 us blocks of the small workloads; ms_*, blocks, mac_bytes and
+ * the per-kind launch counts then describe the sampled steps only). */
+int ssr_engine_set_timing(ssr_engine* e, int enabled);
 int ssr_engine_get_stats(ssr_engine* e, ssr_engine_stats* out, int reset);
 
 /* ------------------------------------------------------------- filter sets */

@@ -32,7 +32,8 @@ class EngineStats(C.Structure):
                 ("fft_launches", C.c_uint64), ("ifft_launches", C.c_uint64),
                 ("mac_bytes", C.c_uint64), ("mac_terms", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("timing_enabled", C.c_int), ("reserved", C.c_int * 7)]
+                ("timing_enabled", C.c_int), ("timing_every", C.c_int),
+                ("launches_total", C.c_uint64), ("reserved", C.c_int * 4)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -203,8 +204,9 @@ class Engine:
     def synchronize(self):
         _check(lib().ssr_engine_synchronize(self.h))
 
-    def set_timing(self, on: bool):
-        _check(lib().ssr_engine_set_timing(self.h, int(on)))
+    def set_timing(self, on, every: int = 1):
+        """Per-stage CUDA events on every `every`-th block step (0 / False: off)."""
+        _check(lib().ssr_engine_set_timing(self.h, (max(1, int(every)) if on else 0)))
 
     def stats(self, reset: bool = False) -> dict:
         st = EngineStats()

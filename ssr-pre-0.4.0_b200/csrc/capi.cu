@@ -69,6 +69,8 @@ int ssr_engine_set_timing(ssr_engine* e, int enabled)
     e->impl.use_device();
     e->impl.fold_stats();
     e->impl.timing = enabled != 0;
+    e->impl.timing_every = enabled > 1 ? enabled : 1;
+    e->impl.timing_counter = 0;
   });
 }
 
@@ -80,6 +82,7 @@ int ssr_engine_get_stats(ssr_engine* e, ssr_engine_stats* out, int reset)
     e->impl.fold_stats();
     *out = e->impl.stats;
     out->timing_enabled = e->impl.timing ? 1 : 0;
+    out->timing_every = e->impl.timing_every;
     if (reset) e->impl.stats = ssr_engine_stats{};
   });
 }

@@ -51,6 +51,24 @@ void MacPlan::make_work(int slots)
   }
 }
 
+// ------------------------------------------------------------------ launches
+// pdl: programmatic dependent launch -- the kernel may be scheduled while the
+// previous kernel of the stream drains (it starts with grid_dependency_wait()),
+// which hides most of the launch latency between the 3-4 small kernels of a block.
+template<typename... KArgs, typename... Args>
+static void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          bool pdl, Args&&... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SSR_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 // ------------------------------------------------------------------ Engine
 static int mac_nv(int B) { return B >= 1024 ? 2 : 1; }
 static int mac_ktiles(int B) { return B > 1024 ? B / 1024 : 1; }
@@ -144,6 +162,7 @@ Engine::Engine(const ssr_engine_config& cfg)
   SSR_CUDA(cudaMemset(d_heads.ptr, 0, kMaxInputs * sizeof(int)));
 
   const size_t fft_smem = size_t(2) * B * sizeof(float2);
+  if (const char* v = std::getenv("SSR_B200_PDL")) pdl = std::atoi(v) != 0;  // A/B experiments
   if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
   if (2 * fft_smem > 48 * 1024)
   {
@@ -225,6 +244,7 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
     fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr, ru);
   }
   SSR_CUDA(cudaGetLastError());
+  count_launch();
   if (cur) cur->fft_launches++;
   if (ring_update)  // the warp-per-transform kernel ran: update the filter ring separately
     launch_dyn_ring_update(ring_update->ctl, ring_update->upd, ring_update->ring, 2 * njobs, ring_update->R);
@@ -281,6 +301,18 @@ void Engine::ensure_partials(size_t nspectra)
   }
 }
 
+void Engine::launch_mac_fn(void* fn, dim3 grid, void** args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SSR_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+}
+
 void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights)
 {
   const int nwork = int(plan.work.uploaded);
@@ -301,7 +333,8 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   void* fn = mac_kernel_ptr(plan.MT, mac_nv(B), mac_variant);
   void* args[] = { &p };
   dim3 grid(nwork, mac_ktiles(B), 1);
-  SSR_CUDA(cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, stream));
+  launch_mac_fn(fn, grid, args);
+  count_launch();
   if (cur) cur->mac_launches++;
 }
 
@@ -330,14 +363,14 @@ void Engine::launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const
   const size_t smem = size_t(2) * B * sizeof(float2) * (groups + 1);
   const float2* part = reinterpret_cast<const float2*>(partials.ptr);
   if (groups == 3)
-    inv_fft_kernel<3><<<njobs, kThreads * 3, smem, stream>>>(plan.jobs.device(), plan.entries.device(), part, red, B,
-        tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+    launch_kernel(inv_fft_kernel<3>, dim3(njobs), dim3(kThreads * 3), smem, stream, pdl, plan.jobs.device(),
+        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
   else if (groups == 2)
-    inv_fft_kernel<2><<<njobs, kThreads * 2, smem, stream>>>(plan.jobs.device(), plan.entries.device(), part, red, B,
-        tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+    launch_kernel(inv_fft_kernel<2>, dim3(njobs), dim3(kThreads * 2), smem, stream, pdl, plan.jobs.device(),
+        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
   else
-    inv_fft_kernel<1><<<njobs, kThreads, smem, stream>>>(plan.jobs.device(), plan.entries.device(), part, red, B,
-        tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+    launch_kernel(inv_fft_kernel<1>, dim3(njobs), dim3(kThreads), smem, stream, pdl, plan.jobs.device(),
+        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
 }
 
 void Engine::launch_level1_fused(const FusedParams& p)
@@ -374,7 +407,8 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights)
   void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 1, true> : (void*)mac_kernel<2, 1, 2, 1, true>;
   void* args[] = { &p };
   dim3 grid(G, mac_ktiles(B), 1);
-  SSR_CUDA(cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, stream));
+  launch_mac_fn(fn, grid, args);
+  count_launch();
   if (cur) cur->mac_launches++;
 }
 
@@ -386,11 +420,14 @@ void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, in
   const size_t need = size_t(6) * (B / 2);
   if (need > reduced.count) { sync(); reduced.resize(need); }
   dim3 grid(6, (B / 2 + 31) / 32, 1);
-  dyn_reduce_kernel<<<grid, kThreads, 0, stream>>>(ctl, Pmax, G, partials.ptr, reduced.ptr, B / 2);
+  launch_kernel(dyn_reduce_kernel, grid, dim3(kThreads), 0, stream, pdl, ctl, Pmax, G,
+      static_cast<const float4*>(partials.ptr), reduced.ptr, B / 2);
   SSR_CUDA(cudaGetLastError());
+  count_launch();
   if (cur) cur->ifft_launches++;
   launch_inv_kernel(inv_groups(3), njobs, plan, reinterpret_cast<const float2*>(reduced.ptr), GatherArgs{}, ctl->n);
   SSR_CUDA(cudaGetLastError());
+  count_launch();
   if (cur) cur->ifft_launches++;
 }
 
@@ -410,10 +447,12 @@ void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
     const size_t need = size_t(nentries) * (B / 2);
     if (need > reduced.count) { sync(); reduced.resize(need + need / 2); }
     dim3 grid(nentries, (B / 2 + 31) / 32, 1);
-    reduce_partials_kernel<<<grid, kThreads, 0, stream>>>(plan.entries.device(), partials.ptr,
+    launch_kernel(reduce_partials_kernel, grid, dim3(kThreads), 0, stream, pdl,
+        static_cast<const InvEntry*>(plan.entries.device()), static_cast<const float4*>(partials.ptr),
         reduced.ptr, B / 2);
     SSR_CUDA(cudaGetLastError());
-    if (cur) cur->ifft_launches++;
+    count_launch();
+  if (cur) cur->ifft_launches++;
     red = reinterpret_cast<const float2*>(reduced.ptr);
   }
   const bool gathering = ga.out_offset != 0 || ga.consumed || ga.arrived;
@@ -430,6 +469,7 @@ void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
     launch_inv_kernel(inv_groups(max_entries), njobs, plan, red, ga, nullptr);
   }
   SSR_CUDA(cudaGetLastError());
+  count_launch();
   if (cur) cur->ifft_launches++;
 }
 
@@ -598,7 +638,7 @@ void Engine::upload_weights(const float* w, size_t n)
 
 void Engine::stage_begin()
 {
-  if (!timing) { cur = nullptr; return; }
+  if (!timing || (timing_counter++ % uint64_t(timing_every)) != 0) { cur = nullptr; return; }
   StageEvents se{};
   if (!free_events.empty()) { se = free_events.back(); free_events.pop_back(); }
   else for (auto& ev : se.ev) SSR_CUDA(cudaEventCreate(&ev));

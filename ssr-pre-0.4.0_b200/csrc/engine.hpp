@@ -172,6 +172,8 @@ struct Engine
   int device, B, sample_rate, sm_count, mac_variant;
   bool fft1024 = false;            // B == 1024: register/shuffle FFT kernels (fft1024.cuh)
   bool fft1024_always = false;
+  bool pdl = true;                 // programmatic dependent launch of the MAC / reduce / inverse kernels
+  void launch_mac_fn(void* fn, dim3 grid, void** args);
   bool level1_fused = true;        // Level 1: one launch per convolve() for short term lists
   void launch_level1_fused(const ssrk::FusedParams& p);
   static constexpr int kFft1024MinJobs = 1024;
@@ -216,6 +218,9 @@ struct Engine
 
   // stats
   bool timing = false;
+  int timing_every = 1;            // stage events on every timing_every-th block step
+  uint64_t timing_counter = 0;
+  void count_launch(int n = 1) { stats.launches_total += uint64_t(n); }
   ssr_engine_stats stats{};
   std::vector<StageEvents> pending;
   std::vector<StageEvents> free_events;
@@ -512,7 +517,7 @@ struct Renderer
   StepDesc prepare_dynamic(const float* d_input, float* d_output);
   StepDesc prepare_bank(const float* d_input, float* d_output);
   // CUDA graphs of the steady-state kernel sequence of a host-buffer step
-  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; int seen = 0; };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; int seen = 0; int kernels = 0; };
   GraphEntry graphs[8];                // [kind mask]
   bool use_graphs = true;
   uint64_t graph_launches = 0;

@@ -53,6 +53,15 @@ __host__ __device__ inline float synth_uniform(uint64_t key, uint64_t index)
 }
 
 // ---------------------------------------------------------------- small helpers
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-
+// serialization attribute may be scheduled while its predecessor in the stream is
+// still draining; it must not touch the predecessor's results before this wait
+// (which also makes them visible).  Without the attribute this is a no-op.
+__device__ __forceinline__ void grid_dependency_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -498,6 +507,7 @@ mac_kernel(const MacParams p)
   __shared__ float s_w[kMacTile];
   __shared__ int s_count;
 
+  grid_dependency_wait();
   const int t = threadIdx.x;
   const int lane = t & 31;
   const int nvec = p.B >> 1;  // float4 per partition
@@ -839,6 +849,7 @@ reduce_partials_kernel(const InvEntry* __restrict__ entries, const float4* __res
                        float4* __restrict__ reduced, int nvec)
 {
   __shared__ float4 s_part[kThreads / 32][32];
+  grid_dependency_wait();
   const InvEntry en = entries[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.y * 32 + lane;
@@ -877,6 +888,7 @@ dyn_reduce_kernel(const DynCtl* __restrict__ ctl, int Pmax, int G, const float4*
                   float4* __restrict__ reduced, int nvec)
 {
   __shared__ float4 s_part[kThreads / 32][32];
+  grid_dependency_wait();
   const int ear = blockIdx.x / 3, kind = blockIdx.x % 3;
   const int nn[3] = {ctl->n[0], ctl->n[1], ctl->n[2]};
   if (nn[kind] == 0) return;
@@ -954,7 +966,8 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
   const int half = B >> 1;
   // twiddle table -> shared memory, once for all groups
   float2* stw = smem + size_t(GROUPS) * 2 * B;
-  stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);
+  stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);  // constants: may overlap the predecessor's tail
+  grid_dependency_wait();
   __syncthreads();
   // flow control of the fused gather: the slot this block goes to must have been
   // read out by the root (checked by one thread while the others start loading)

@@ -817,16 +817,19 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
     {
       SSR_CUDA(cudaGraphLaunch(g.exec, e->stream));
       ++graph_launches;
+      e->count_launch(g.kernels);
       done_by_graph = true;
     }
     else if (g.epoch == epoch && ++g.seen >= 2)
     {
       if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
       cudaGraph_t graph = nullptr;
+      const uint64_t before = e->stats.launches_total;
       SSR_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
       try { launch(d); }
       catch (...) { cudaStreamEndCapture(e->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
       SSR_CUDA(cudaStreamEndCapture(e->stream, &graph));
+      g.kernels = int(e->stats.launches_total - before);  // counted once here, once per replay below
       cudaError_t err = cudaGraphInstantiate(&g.exec, graph, 0);
       cudaGraphDestroy(graph);
       if (err == cudaSuccess)
