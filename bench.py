@@ -566,7 +566,9 @@ def main_ours(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": ("ssrk::mac_kernel<4,2,2,2,false>" if w.kind == "generic"
+        "bound": "hbm", "kernel": (("ssrk::mac_tma_kernel<4,5> (cp.async.bulk staged)" if args.mac_variant in (0, 7) and B >= 1024
+                                    else f"MAC variant {args.mac_variant} (profiles/r1_mac_variants.md)")
+                                   if w.kind == "generic"
                                    else "ssrk::mac_kernel<2,2,2,1,true> (terms generated on the device)"), "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "bytes_per_launch": st["mac_bytes"] / max(1, st["mac_launches"]),

@@ -66,8 +66,9 @@ typedef struct ssr_engine_config
   int block_size;    /* B; reference parameter "block_size" (apf/apf/pointer_policy.h:75) */
   int sample_rate;   /* reference parameter "sample_rate" (pointer_policy.h:74) */
   void* stream;      /* cudaStream_t to run on, or NULL for an engine-owned stream */
-  int mac_variant;   /* 0 = default; other values select experimental MAC kernel builds
-                        (profiles/r1_mac_variants.md) */
+  int mac_variant;   /* 0 = default (bulk-copy staged MAC for the four-row plans at
+                        B >= 1024); other values select the other MAC kernel builds
+                        (2 = register-staged; profiles/r1_mac_variants.md) */
   int reserved[7];
 } ssr_engine_config;
 

@@ -17,7 +17,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
 echo "launch list rc=$?"
 
 $CFG5 > $OUT/plain_cfg5.log 2>&1 && \
-ncu $FULL -k regex:mac_kernel -s 2 -c 2 -o $OUT/mac_${TAG} $CFG5 > $OUT/ncu_mac.log 2>&1
+ncu $FULL -k regex:"mac_(tma_)?kernel" -s 2 -c 2 -o $OUT/mac_${TAG} $CFG5 > $OUT/ncu_mac.log 2>&1
 echo "mac full rc=$?"
 
 # block-loop FFT kernels (filter loading uses the batch kernels, not these)

@@ -76,11 +76,16 @@ static int mac_ktiles(int B) { return B > 1024 ? B / 1024 : 1; }
 template<int MT, int NV, int ST = 2, int MINB = 1>
 static void* mac_fn() { return (void*)mac_kernel<MT, NV, ST, MINB>; }
 
-// variant (ssr_engine_config::mac_variant), experiments on the Generic kernel:
-//   0 default = 2-stage register pipeline, 2 CTAs / SM (128 registers): measured
-//     best, 6.7 TB/s on cfg5 even under the power cap (profiles/r1_mac_variants.md)
+// variant (ssr_engine_config::mac_variant), experiments on the Generic kernel
+// (profiles/r1_mac_variants.md):
+//   0 default = bulk-copy (TMA) staged mac_tma_kernel with 5 stages at B >= 1024
+//     (6.78 TB/s on cfg5 under the power cap where the register-staged kernel
+//     reaches 6.37), the register-staged kernel below otherwise
+//   6 / 7 = mac_tma_kernel with 4 / 5 stages
+//   2 = register-staged: 2-stage pipeline, 2 CTAs / SM (128 registers) -- the
+//     default before the bulk-copy kernel existed
 //   1 = 3 stages, 4 = 4 stages (1 CTA / SM), 5 = 2 stages at 1 CTA / SM,
-//   3 = default without L2 eviction hints
+//   3 = variant 2 without L2 eviction hints
 static void* mac_kernel_ptr(int MT, int NV, int variant)
 {
   if (NV == 2 && MT == 4)
@@ -162,6 +167,13 @@ Engine::Engine(const ssr_engine_config& cfg)
   SSR_CUDA(cudaMemset(d_heads.ptr, 0, kMaxInputs * sizeof(int)));
 
   const size_t fft_smem = size_t(2) * B * sizeof(float2);
+  if (mac_tma())
+  {
+    SSR_CUDA(cudaFuncSetAttribute(mac_tma_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          int(mac_tma_smem_bytes<4, 4>())));
+    SSR_CUDA(cudaFuncSetAttribute(mac_tma_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          int(mac_tma_smem_bytes<4, 5>())));
+  }
   if (const char* v = std::getenv("SSR_B200_PDL")) pdl = std::atoi(v) != 0;  // A/B experiments
   if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
   if (2 * fft_smem > 48 * 1024)
@@ -216,11 +228,15 @@ void Engine::unregister_input(int id)
   if (id >= 0 && id < int(inputs.size())) inputs[id] = nullptr;
 }
 
-int Engine::mac_slots() const
+// bulk-copy (TMA) staged MAC for the four-row (Generic) plans at B >= 1024
+bool Engine::mac_tma() const { return (mac_variant == 0 || mac_variant == 6 || mac_variant == 7) && B >= 1024; }
+
+int Engine::mac_slots(int MT) const
 {
+  if (mac_tma() && MT == 4) return sm_count;  // one CTA per SM (shared-memory bound)
   int occ = 0;
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, mac_kernel_ptr(4, 2, mac_variant), kThreads, 0);
+      &occ, mac_kernel_ptr(MT, mac_nv(B), mac_variant), kThreads, 0);
   if (err != cudaSuccess || occ < 1) occ = 1;
   return sm_count * occ;
 }
@@ -301,10 +317,10 @@ void Engine::ensure_partials(size_t nspectra)
   }
 }
 
-void Engine::launch_mac_fn(void* fn, dim3 grid, void** args)
+void Engine::launch_mac_fn(void* fn, dim3 grid, void** args, int threads, size_t smem)
 {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -330,10 +346,20 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   p.wtab_offset = wtab_offset;
   p.partial_offset = partial_offset;
   p.l2_hints = (mac_variant == 3) ? 0 : 1;
-  void* fn = mac_kernel_ptr(plan.MT, mac_nv(B), mac_variant);
   void* args[] = { &p };
   dim3 grid(nwork, mac_ktiles(B), 1);
-  launch_mac_fn(fn, grid, args);
+  if (mac_tma() && plan.MT == 4)
+  {
+    const bool five = mac_variant != 6;
+    void* tfn = five ? (void*)mac_tma_kernel<4, 5> : (void*)mac_tma_kernel<4, 4>;
+    const size_t smem = five ? mac_tma_smem_bytes<4, 5>() : mac_tma_smem_bytes<4, 4>();
+    launch_mac_fn(tfn, grid, args, kTmaThreads, smem);
+  }
+  else
+  {
+    void* fn = mac_kernel_ptr(plan.MT, mac_nv(B), mac_variant);
+    launch_mac_fn(fn, grid, args);
+  }
   count_launch();
   if (cur) cur->mac_launches++;
 }
@@ -1076,7 +1102,7 @@ const float* Output::convolve(float weight)
     }
     else
     {
-      mac.make_work(e->mac_slots());
+      mac.make_work(e->mac_slots(mac.MT));
       mac.upload(e->stream);
       e->ensure_partials(size_t(mac.npartials) * mac.MT);
       inv.entries.host.push_back({0, mac.groups[0].nsplit, 1, 0, 0, 1.0f / float(2 * B)});

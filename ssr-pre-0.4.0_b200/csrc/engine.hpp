@@ -173,7 +173,8 @@ struct Engine
   bool fft1024 = false;            // B == 1024: register/shuffle FFT kernels (fft1024.cuh)
   bool fft1024_always = false;
   bool pdl = true;                 // programmatic dependent launch of the MAC / reduce / inverse kernels
-  void launch_mac_fn(void* fn, dim3 grid, void** args);
+  void launch_mac_fn(void* fn, dim3 grid, void** args, int threads = ssrk::kThreads, size_t smem = 0);
+  bool mac_tma() const;
   bool level1_fused = true;        // Level 1: one launch per convolve() for short term lists
   void launch_level1_fused(const ssrk::FusedParams& p);
   static constexpr int kFft1024MinJobs = 1024;
@@ -214,7 +215,7 @@ struct Engine
   uint64_t dyn_h_seen = 0, dyn_x_seen = 0;
   void upload_weights(const float* w, size_t n);
   void ensure_partials(size_t npartial_spectra);
-  int mac_slots() const;           // CTAs resident at once for the MAC kernel
+  int mac_slots(int MT) const;     // CTAs resident at once for the MAC kernel of MT-row plans
 
   // stats
   bool timing = false;
@@ -490,7 +491,6 @@ struct Renderer
   std::vector<std::pair<const float*, std::unique_ptr<Table<ssrk::FwdJob>>>> fwd_cache;
   Table<ssrk::FwdJob>* fwd = nullptr;
   std::vector<float> wtab_host;
-  int mac_slots_cached = 0;
   DeviceArray<float> d_in, d_out;
   PinnedArray<float> h_in, h_out;
   int inv_key = -1;

@@ -743,6 +743,209 @@ mac_kernel(const MacParams p)
       if (valid[v]) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
 }
 
+// ---------------------------------------------------------------- MAC, bulk-copy staged
+// Variant of mac_kernel for the static (table-driven) plans at B >= 1024: a producer
+// warp streams the X tile and the MT H tiles of every term into a ring of STAGES
+// shared-memory stages with cp.async.bulk (the TMA unit's 1-D bulk copy) completing
+// on mbarriers; the 8 consumer warps read them back with LDS.128.  No registers are
+// spent on load staging and up to (STAGES - 1) x (1 + MT) x 8 KiB stay in flight per
+// SM however the consumers are scheduled.  Selected with ssr_engine_config::
+// mac_variant = 6 (4 stages) / 7 (5 stages); see profiles/ for the A/B.
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+  unsigned done;
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar,
+                                              uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+constexpr int kTmaThreads = kThreads + 32;     // 8 consumer warps + 1 producer warp
+constexpr int kTmaTileVec = 2 * kThreads;      // float4 per 1024-bin tile (8 KiB)
+constexpr int kTmaTileBytes = kTmaTileVec * 16;
+
+template<int MT, int STAGES>
+constexpr size_t mac_tma_smem_bytes()
+{
+  return size_t(STAGES) * (1 + MT) * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + 4) + 128;
+}
+
+template<int MT, int STAGES>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+mac_tma_kernel(const MacParams p)
+{
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ const float4* q_x[kMacTile];          // producer-private staging of a term tile
+  __shared__ const float4* q_h[kMacTile][MT];
+  __shared__ float q_w[kMacTile];
+  float4* buf = reinterpret_cast<float4*>(tma_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tma_smem + size_t(STAGES) * (1 + MT) * kTmaTileBytes);
+  uint64_t* empty = full + STAGES;
+  volatile float* stage_w = reinterpret_cast<volatile float*>(empty + STAGES);
+  volatile int* stage_end = reinterpret_cast<volatile int*>(const_cast<float*>(stage_w) + STAGES);
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int nvec = p.B >> 1;
+  const int tile_off = blockIdx.y * kTmaTileVec;   // B > 1024: blockIdx.y selects a 1024-bin tile
+
+  if (t == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  grid_dependency_wait();
+  const int4 wk = p.work[blockIdx.x];
+
+  if (t >= kThreads)
+  {
+    // ---- producer warp: resolve the terms tile by tile, then one lane feeds the ring
+    const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    int s = 0;
+    unsigned phase = 0;
+    for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+    {
+      const int tile_n = min(kMacTile, wk.y - tb);
+      int count = 0;
+      for (int base = 0; base < tile_n; base += 32)
+      {
+        const int i = base + lane;
+        bool ok = false;
+        MacTermMeta m; float w = 0.f;
+        if (i < tile_n)
+        {
+          m = p.term_meta[tb + i];
+          w = p.wtab[m.wslot + p.wtab_offset];
+          ok = (w != 0.0f);   // a muted source costs no traffic
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (ok)
+        {
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          const int parts = p.xparts[m.input];
+          int slot = p.heads[m.input] - m.p;
+          if (slot < 0) slot += parts;
+          q_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
+          q_w[pos] = w;
+#pragma unroll
+          for (int j = 0; j < MT; ++j) q_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+        }
+        count += __popc(mask);
+      }
+      __syncwarp();
+      if (lane == 0)
+      {
+        for (int i = 0; i < count; ++i)
+        {
+          mbar_wait(empty + s, phase ^ 1u);          // the consumers have released this stage
+          stage_w[s] = q_w[i];
+          stage_end[s] = 0;
+          mbar_arrive_expect_tx(full + s, (1 + MT) * kTmaTileBytes);
+          float4* dst = buf + size_t(s) * (1 + MT) * kTmaTileVec;
+          bulk_copy_g2s(dst, q_x[i] + tile_off, kTmaTileBytes, full + s, pol_x);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            bulk_copy_g2s(dst + size_t(1 + j) * kTmaTileVec, q_h[i][j] + tile_off, kTmaTileBytes, full + s, pol_h);
+          if (++s == STAGES) { s = 0; phase ^= 1u; }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0)
+    {
+      mbar_wait(empty + s, phase ^ 1u);
+      stage_end[s] = 1;                               // no more terms
+      mbar_arrive(full + s);
+    }
+    return;
+  }
+
+  // ---- consumer warps
+  float4 acc[MT][2];
+  float nyq[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+  {
+    nyq[j] = 0.0f;
+    acc[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int tt = tile_off + t;
+  int s = 0;
+  unsigned phase = 0;
+  while (true)
+  {
+    mbar_wait(full + s, phase);
+    if (stage_end[s]) break;
+    const float w = stage_w[s];
+    const float4* sb = buf + size_t(s) * (1 + MT) * kTmaTileVec;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+    {
+      float4 x = sb[t + v * kThreads];
+      x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+#pragma unroll
+      for (int j = 0; j < MT; ++j)
+      {
+        const float4 h = sb[size_t(1 + j) * kTmaTileVec + t + v * kThreads];
+        acc[j][v].x = fmaf(x.x, h.x, acc[j][v].x);
+        acc[j][v].x = fmaf(-x.y, h.y, acc[j][v].x);
+        acc[j][v].y = fmaf(x.x, h.y, acc[j][v].y);
+        acc[j][v].y = fmaf(x.y, h.x, acc[j][v].y);
+        acc[j][v].z = fmaf(x.z, h.z, acc[j][v].z);
+        acc[j][v].z = fmaf(-x.w, h.w, acc[j][v].z);
+        acc[j][v].w = fmaf(x.z, h.w, acc[j][v].w);
+        acc[j][v].w = fmaf(x.w, h.z, acc[j][v].w);
+        if (v == 0 && tt == 0) nyq[j] = fmaf(x.y, h.y, nyq[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);            // this warp is done with the stage
+    if (++s == STAGES) { s = 0; phase ^= 1u; }
+  }
+
+  // bin 0 holds (DC, Nyquist), both real products (convolver.h:510-541)
+  if (tt == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < MT; ++j) { acc[j][0].x += nyq[j]; acc[j][0].y = nyq[j]; }
+  }
+  float4* out = p.partials + size_t(wk.z + p.partial_offset) * MT * nvec;
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
+}
+
 // ---------------------------------------------------------------- inverse
 struct InvEntry
 {

@@ -594,3 +594,32 @@ def test_binaural_multi_partition_hrirs_staggered_switch(capi, co, engine_factor
         y = r.process(x)
         worst = max(worst, maxerr(y, o.process(x)))
     assert worst <= TOL, worst
+
+
+@pytest.mark.parametrize("variant,B", [(0, 1024), (6, 1024), (7, 2048), (2, 1024), (2, 2048), (0, 4096)])
+def test_generic_bulk_copy_staged_mac_variants(capi, co, engine_factory, variant, B):
+    """mac_tma_kernel (ssr_engine_config::mac_variant 0 = default at B >= 1024, 6, 7):
+    X and H tiles staged by cp.async.bulk into a shared-memory ring; variant 2 is the
+    register-staged mac_kernel<4,2,2,2> it replaced as the default -- the same sums
+    either way.  Covers a partial output group (M = 6), all
+    three accumulator kinds (gain change), a muted source (its terms are dropped by
+    the producer) and two spectrum tiles per partition (B = 2048)."""
+    L, N, M = 3 * B + 100, 3, 6
+    rng = np.random.default_rng(variant * 10 + B)
+    e = engine_factory(B, mac_variant=variant)
+    r = capi.Renderer(e, capi.GENERIC, outputs=M)
+    o = co.GenericRendererOracle(B, M)
+    for n in range(N):
+        ir = decaying(rng, L, M, 0.5 / np.sqrt(N * L / 6.9))
+        r.add_source(ir); o.add_source(ir)
+    worst = 0.0
+    for t in range(12):
+        x = rng.uniform(-1, 1, (N, B)).astype(np.float32)
+        if t == 5:
+            r.set_gain(2, 0.3); o.sources[1].gain = 0.3
+        if t == 7:
+            r.set_mute(1, True); o.sources[0].mute = True
+        if t == 10:
+            r.set_mute(1, False); o.sources[0].mute = False
+        worst = max(worst, maxerr(r.process(x), o.process(x)))
+    assert worst <= TOL, worst
