@@ -167,8 +167,12 @@ int ssr_filterset_download(ssr_filterset* fs, int channel, int partition,
 int ssr_input_create(ssr_engine* e, int partitions, ssr_input** out);
 void ssr_input_destroy(ssr_input* in);
 int ssr_input_partitions(const ssr_input* in);
-/* = Input::add_block (convolver.h:324-375): B host floats; H2D + forward FFT
- * are queued asynchronously. */
+/* = Input::add_block (convolver.h:324-375): B host floats.  The block is copied
+ * into the engine's pinned staging buffer (x may be reused on return); its forward
+ * transform runs with the first ssr_output_convolve() on this input (one fused
+ * launch: forward FFT + MAC + inverse), or at the latest with the next add_block /
+ * download, so the delay line advances exactly once per add_block like the
+ * reference's. */
 int ssr_input_add_block(ssr_input* in, const float* x);
 /* parity / debug: spectrum `p` blocks ago (0 = newest) in the reference layout */
 int ssr_input_download(ssr_input* in, int p, float* sorted_out);
@@ -186,7 +190,11 @@ int ssr_output_set_filter(ssr_output* o, const ssr_filterset* fs, int channel);
 int ssr_output_queues_empty(const ssr_output* o);  /* 1 / 0 */
 int ssr_output_rotate_queues(ssr_output* o);
 /* = OutputBase::convolve(weight) (convolver.h:435-465).  *result points at B
- * floats (engine-owned pinned memory), valid until the next convolve() on `o`. */
+ * floats (engine-owned pinned memory), valid until the next convolve() on `o`.
+ * Term lists of up to 64 partitions run as ONE single-CTA launch that reads the
+ * staged input block and writes the result block through mapped host memory
+ * (the call returns when the block has landed); longer ones use the MAC and
+ * inverse kernels of the batched path. */
 int ssr_output_convolve(ssr_output* o, float weight, const float** result);
 
 /* ------------------------- Level 2: renderer block step (the batched path) */
