@@ -630,7 +630,7 @@ const float* Gather::wait()
   return slot_ptr(int(t & 1));
 }
 
-void Gather::release()
+void Gather::release(cudaStream_t s)
 {
   if (!is_root()) throw Error(SSR_ERR_STATE, "ssr_b200: gather: only the root releases");
   if (released == waited) return;
@@ -638,7 +638,7 @@ void Gather::release()
   released = waited;
   if (world > 1)
   {
-    gather_release_kernel<<<1, 1, 0, e->stream>>>(consumed_ptr(), released);
+    gather_release_kernel<<<1, 1, 0, s ? s : e->stream>>>(consumed_ptr(), released);
     SSR_CUDA(cudaGetLastError());
   }
 }

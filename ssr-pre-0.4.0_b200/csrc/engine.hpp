@@ -406,7 +406,8 @@ struct Gather
   ssrk::GatherArgs next_block();
   // root: stream-ordered wait for block (epoch - 1) of every rank; returns its slot
   const float* wait();
-  void release();                                      // root: after the reads of that slot were queued
+  // root: after the reads of that slot were queued (on `s`, default the engine's stream)
+  void release(cudaStream_t s = nullptr);
   int status();                                        // 0 ok, 1 a wait timed out (synchronises)
 };
 
@@ -474,7 +475,10 @@ struct Renderer
   // per-block plans
   MacPlan static_mac;           // generic: built when the source list changes
   bool static_dirty = true;
-  InvPlan inv;
+  InvPlan inv_plans[2];         // inverse tables per output buffer (pipelined submit() alternates)
+  int inv_keys[2] = {-1, -1};
+  int cur_slot = 0;
+  void invalidate_inv();
   // brs / binaural: terms are generated on the device (ssrk::DynTables)
   long long dyn_b = 0;                   // block counter
   int dyn_Pmax = 1, dyn_R = 2, dyn_G = 0;
@@ -491,9 +495,8 @@ struct Renderer
   std::vector<std::pair<const float*, std::unique_ptr<Table<ssrk::FwdJob>>>> fwd_cache;
   Table<ssrk::FwdJob>* fwd = nullptr;
   std::vector<float> wtab_host;
-  DeviceArray<float> d_in, d_out;
+  DeviceArray<float> d_in[2], d_out[2];   // [1] only used by the pipelined submit()
   PinnedArray<float> h_in, h_out;
-  int inv_key = -1;
 
   Source* find(int id);
   int add_source(std::unique_ptr<FilterSet> irs, int channels);
@@ -518,7 +521,7 @@ struct Renderer
   StepDesc prepare_bank(const float* d_input, float* d_output);
   // CUDA graphs of the steady-state kernel sequence of a host-buffer step
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; int seen = 0; int kernels = 0; };
-  GraphEntry graphs[8];                // [kind mask]
+  GraphEntry graphs[2][8];             // [device-buffer slot][kind mask]
   bool use_graphs = true;
   uint64_t graph_launches = 0;
   void drop_graphs();
@@ -539,7 +542,11 @@ struct Renderer
   cudaEvent_t done[2] = {nullptr, nullptr};
   bool slot_direct[2] = {false, false};  // the slot's D2H went straight into the caller's buffer
   void submit(int n, const float* const* in);
-  void submit_block(int n, const float* const* in, float* const* direct_out);
+  void submit_block(int n, const float* const* in, float* const* direct_out, bool pipelined);
+  // copy streams and events of the pipelined submit(): H2D | kernels | D2H
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false};    // a pipelined block has used the slot's buffers before
   void wait(float* const* out);
 };
 

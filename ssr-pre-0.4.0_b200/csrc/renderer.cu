@@ -78,7 +78,7 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
   static_mac.MT = kGenericMT;
-  d_out.resize(size_t(std::max(m_local, 1)) * e->B);
+  for (auto& d : d_out) d.resize(size_t(std::max(m_local, 1)) * e->B);
   h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
 }
 
@@ -88,6 +88,10 @@ Renderer::~Renderer()
   cudaStreamSynchronize(e->stream);
   for (auto ev : done) if (ev) cudaEventDestroy(ev);
   for (auto ev : dyn_copied) if (ev) cudaEventDestroy(ev);
+  if (s_in) { cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_out); }
+  for (auto ev : ev_in) if (ev) cudaEventDestroy(ev);
+  for (auto ev : ev_k) if (ev) cudaEventDestroy(ev);
+  if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_out); }
   drop_graphs();
   g_prof.report("s0 source logic, s1 plan, s2 inv+arena, s3 fwd table, s4 launches");
 }
@@ -124,9 +128,9 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
     // StaticConvolver(*_pre_filter) per input (src/wfsrenderer.h:111-113)
     s->input.reset(new Input(e, partitions));
     M_total = m_local = int(sources.size()) + 1;
-    d_out.resize(size_t(m_local) * e->B);
+    for (auto& d : d_out) d.resize(size_t(m_local) * e->B);
     h_out.resize(size_t(2) * m_local * e->B);
-    inv_key = -1;
+    invalidate_inv();
   }
   else
   {
@@ -138,7 +142,7 @@ int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
   }
   sources.push_back(std::move(s));
   if (metering) { d_levels.release(); (void)level_ptr(0); }
-  inv_key = -1;
+  invalidate_inv();
   static_dirty = true;
   fwd_cache.clear();
   return sources.back()->id;
@@ -152,7 +156,7 @@ void Renderer::rem_source(int id)
     if (sources[i]->id == id)
     {
       sources.erase(sources.begin() + i);
-      if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) { M_total = m_local = int(sources.size()); inv_key = -1; }
+      if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) { M_total = m_local = int(sources.size()); invalidate_inv(); }
       static_dirty = true;
       fwd_cache.clear();
       return;
@@ -181,8 +185,7 @@ void Renderer::set_metering(bool on)
   metering = on;
   if (on) (void)level_ptr(0);
   fwd_cache.clear();
-  inv_key = -1;
-  inv.clear();
+  invalidate_inv();
 }
 
 void Renderer::get_levels(float* pre_fader, float* levels, float* outputs)
@@ -245,6 +248,8 @@ static Mode mode_from_weight(const BlockParameter<float>& f)
 
 Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_output)
 {
+  InvPlan& inv = inv_plans[cur_slot];   // one set of inverse tables per output buffer
+  int& inv_key = inv_keys[cur_slot];
   StepDesc d;
   d.d_input = d_input; d.d_output = d_output;
   const int N = int(sources.size());
@@ -295,7 +300,7 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
     static_mac.upload(e->stream);
     e->ensure_partials(size_t(3) * static_mac.npartials * static_mac.MT);
     static_dirty = false;
-    inv_key = -1;
+    invalidate_inv();
   }
 
   const int key = (kind_active[0] ? 1 : 0) | (kind_active[1] ? 2 : 0) | (kind_active[2] ? 4 : 0);
@@ -352,6 +357,8 @@ static float fwrap(float x, float full)
 // CUDA graph like the static renderers.
 Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_output)
 {
+  InvPlan& inv = inv_plans[cur_slot];   // one set of inverse tables per output buffer
+  int& inv_key = inv_keys[cur_slot];
   StepDesc d;
   d.d_input = d_input; d.d_output = d_output;
   const int N = int(sources.size());
@@ -383,7 +390,7 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     dyn_G = e->dyn_mac_slots();
     e->ensure_partials(size_t(dyn_G) * 2);
     static_dirty = false;
-    inv_key = -1;
+    invalidate_inv();
   }
 
   // layout of the per-block control upload
@@ -590,6 +597,8 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
 // (WfsRenderer::Input::Process, src/wfsrenderer.h:116-120: add_block; convolve()).
 Renderer::StepDesc Renderer::prepare_bank(const float* d_input, float* d_output)
 {
+  InvPlan& inv = inv_plans[cur_slot];   // one set of inverse tables per output buffer
+  int& inv_key = inv_keys[cur_slot];
   StepDesc d;
   d.d_input = d_input; d.d_output = d_output;
   const int N = int(sources.size());
@@ -614,7 +623,7 @@ Renderer::StepDesc Renderer::prepare_bank(const float* d_input, float* d_output)
     static_mac.upload(e->stream);
     e->ensure_partials(size_t(static_mac.npartials) * static_mac.MT);
     static_dirty = false;
-    inv_key = -1;
+    invalidate_inv();
   }
   if (inv_key != 1 || (inv.jobs.host.size() && inv.jobs.host[0].out != d_output))
   {
@@ -664,7 +673,7 @@ void Renderer::bind_gather(Gather* g)
     if (!g->ready()) throw Error(SSR_ERR_STATE, "ssr_b200: gather: buffer not connected (import the root's handle first)");
   }
   gather = g;
-  inv_key = -1;
+  invalidate_inv();
   drop_graphs();
   if (g && g->is_root()) h_out.resize(size_t(2) * M_total * e->B);
   else h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
@@ -684,6 +693,7 @@ Renderer::StepDesc Renderer::prepare(const float* d_input, float* d_output)
 void Renderer::launch(const StepDesc& d)
 {
   const int B = e->B;
+  InvPlan& inv = inv_plans[cur_slot];
   e->stage_begin();
   const bool dynamic = cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS;
   if (dynamic && d.N > 0)
@@ -731,6 +741,7 @@ void Renderer::launch(const StepDesc& d)
 
 void Renderer::step(const float* d_input, float* d_output)
 {
+  cur_slot = 0;
   const StepDesc d = prepare(d_input, d_output);
   g_prof.start();
   launch(d);
@@ -740,11 +751,12 @@ void Renderer::step(const float* d_input, float* d_output)
 
 void Renderer::drop_graphs()
 {
-  for (auto& g : graphs)
-  {
-    if (g.exec) cudaGraphExecDestroy(g.exec);
-    g = GraphEntry();
-  }
+  for (auto& per_slot : graphs)
+    for (auto& g : per_slot)
+    {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      g = GraphEntry();
+    }
 }
 
 // true if the B-float channel blocks behind `ptrs` form one contiguous array in
@@ -757,18 +769,28 @@ static bool contiguous_pinned(Engine* e, const float* const* ptrs, int count, in
   return e->is_pinned(ptrs[0], size_t(count) * B * sizeof(float));
 }
 
+void Renderer::invalidate_inv()
+{
+  for (int i = 0; i < 2; ++i) { inv_keys[i] = -1; inv_plans[i].clear(); }
+}
+
 void Renderer::process(int n, const float* const* in, float* const* out)
 {
   if (outstanding) throw Error(SSR_ERR_STATE, "ssr_b200: process() while submitted blocks are pending");
   // synchronous call: the caller's buffers stay valid until we return, so pinned
-  // contiguous channel arrays are used in place (no staging copies)
-  submit_block(n, in, out);
+  // contiguous channel arrays are used in place (no staging copies); everything
+  // runs on the engine's stream (lowest latency for one block)
+  submit_block(n, in, out, false);
   wait(out);
 }
 
-void Renderer::submit(int n, const float* const* in) { submit_block(n, in, nullptr); }
+// Pipelined: copy-in stream -> engine stream -> copy-out stream, two blocks in
+// flight, so block t+1's H2D and block t-1's D2H overlap block t's kernels
+// (north_star item 5: the reference's per-block thread fan-out,
+// apf/apf/mimoprocessor.h:452-483, becomes a CUDA-stream pipeline).
+void Renderer::submit(int n, const float* const* in) { submit_block(n, in, nullptr, true); }
 
-void Renderer::submit_block(int n, const float* const* in, float* const* direct_out)
+void Renderer::submit_block(int n, const float* const* in, float* const* direct_out, bool pipelined)
 {
   // assert(n == block_size()) (apf/apf/pointer_policy.h:114)
   if (n != e->B) throw Error(SSR_ERR_INVALID, "ssr_b200: audio_callback: n != block size");
@@ -777,9 +799,28 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   const int N = int(sources.size());
   const int B = e->B;
   const size_t in_floats = size_t(std::max(N, 1)) * B;
-  if (h_in.count < 2 * in_floats) { e->sync(); h_in.resize(2 * in_floats); d_in.resize(in_floats); fwd_cache.clear(); }
+  if (h_in.count < 2 * in_floats)
+  {
+    e->sync();
+    h_in.resize(2 * in_floats);
+    for (auto& d : d_in) d.resize(in_floats);
+    fwd_cache.clear();
+  }
   static_assert(sizeof(float) == 4, "");
   const int slot = int(submitted & 1);
+  cur_slot = pipelined ? slot : 0;   // device buffers / inverse tables / graph of this block
+  if (pipelined && !s_in)
+  {
+    SSR_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    SSR_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i)
+    {
+      SSR_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      SSR_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+    }
+  }
+  float* din = d_in[cur_slot].ptr;
+  float* dout = d_out[cur_slot].ptr;
   // with a gather bound the root delivers ALL outputs, the other ranks none
   const int n_host_out = gather ? (gather->is_root() ? M_total : 0) : m_local;
   const float* hin = nullptr;
@@ -799,19 +840,32 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   }
   e->stats.h2d_bytes += uint64_t(N) * B * sizeof(float);
   e->stats.d2h_bytes += uint64_t(n_host_out) * B * sizeof(float);
+  if (!done[slot]) SSR_CUDA(cudaEventCreateWithFlags(&done[slot], cudaEventDisableTiming));
 
-  const StepDesc d = prepare(d_in.ptr, d_out.ptr);
-  if (N > 0)
-    SSR_CUDA(cudaMemcpyAsync(d_in.ptr, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  const StepDesc d = prepare(din, dout);
+  if (pipelined)
+  {
+    // H2D on the copy-in stream, once the kernels of block t-2 (readers of this
+    // input buffer) are through; the engine stream then waits for the copy and for
+    // block t-2's D2H out of this output buffer
+    if (slot_used[slot]) SSR_CUDA(cudaStreamWaitEvent(s_in, ev_k[slot], 0));
+    if (N > 0)
+      SSR_CUDA(cudaMemcpyAsync(din, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    SSR_CUDA(cudaEventRecord(ev_in[slot], s_in));
+    SSR_CUDA(cudaStreamWaitEvent(e->stream, ev_in[slot], 0));
+    if (slot_used[slot]) SSR_CUDA(cudaStreamWaitEvent(e->stream, done[slot], 0));
+  }
+  else if (N > 0)
+    SSR_CUDA(cudaMemcpyAsync(din, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   // Steady state (no table moved or resized since the last blocks): the kernel
   // sequence {forward FFT, MAC passes, [partial reduce], inverse FFT} is replayed
-  // as one CUDA graph per accumulator-kind mask; the two copies stay outside so
-  // that they can use the caller's buffers.  Per-stage event timing needs
-  // separate launches.
+  // as one CUDA graph per device-buffer slot and accumulator-kind mask; the two
+  // copies stay outside so that they can use the caller's buffers.  Per-stage
+  // event timing needs separate launches.
   bool done_by_graph = false;
   if (use_graphs && d.graphable && !e->timing && d.kind_mask > 0 && d.kind_mask < 8)
   {
-    GraphEntry& g = graphs[d.kind_mask];
+    GraphEntry& g = graphs[cur_slot][d.kind_mask];
     const uint64_t epoch = g_layout_epoch.load();
     if (g.exec && g.epoch == epoch)
     {
@@ -843,19 +897,30 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
     else if (g.epoch != epoch) { g.epoch = epoch; g.seen = 0; if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } }
   }
   if (!done_by_graph) launch(d);
+
+  const float* src = dout;
+  size_t out_floats = size_t(m_local) * B;
   if (gather)
   {
+    out_floats = 0;
     if (gather->is_root())
     {
-      const float* all = gather->wait();  // every rank's blocks of this block have arrived
-      SSR_CUDA(cudaMemcpyAsync(hout, all, size_t(M_total) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-      gather->release();
+      src = gather->wait();  // every rank's blocks of this block have arrived (engine stream)
+      out_floats = size_t(M_total) * B;
     }
   }
-  else
-    SSR_CUDA(cudaMemcpyAsync(hout, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-  if (!done[slot]) SSR_CUDA(cudaEventCreateWithFlags(&done[slot], cudaEventDisableTiming));
-  SSR_CUDA(cudaEventRecord(done[slot], e->stream));
+  cudaStream_t copy_stream = e->stream;
+  if (pipelined)
+  {
+    SSR_CUDA(cudaEventRecord(ev_k[slot], e->stream));
+    SSR_CUDA(cudaStreamWaitEvent(s_out, ev_k[slot], 0));
+    copy_stream = s_out;
+  }
+  if (out_floats)
+    SSR_CUDA(cudaMemcpyAsync(hout, src, out_floats * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+  if (gather && gather->is_root()) gather->release(copy_stream);   // after the slot has been read out
+  SSR_CUDA(cudaEventRecord(done[slot], copy_stream));
+  slot_used[slot] = pipelined;
   submitted++;
   outstanding++;
 }
