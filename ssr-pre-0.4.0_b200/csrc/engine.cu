@@ -625,6 +625,7 @@ const float* Gather::wait()
     GatherWaitArgs a{arrived_ptr(0), d_ctas.ptr, world, t, d_error.ptr};
     gather_wait_kernel<<<1, 32, 0, e->stream>>>(a);
     SSR_CUDA(cudaGetLastError());
+    e->count_launch();
   }
   waited = epoch;
   return slot_ptr(int(t & 1));
@@ -640,6 +641,7 @@ void Gather::release(cudaStream_t s)
   {
     gather_release_kernel<<<1, 1, 0, s ? s : e->stream>>>(consumed_ptr(), released);
     SSR_CUDA(cudaGetLastError());
+    e->count_launch();
   }
 }
 
