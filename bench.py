@@ -9,15 +9,19 @@ quoted on -- GenericRenderer MIMO, 128 sources x 512 outputs, 48000-tap IRs
 (P = 47), B = 1024, 48 kHz.  Its 25.2 GB of partition spectra fit one B200, so
 N = 1 runs the full shape; N > 1 shards the outputs across ranks,
 total work fixed => "scaling": "strong".  A step = one audio block (1024 samples
-of all 128 sources) through forward FFT -> MAC -> inverse FFT + crossfade + sum
-[-> NCCL gather of the output blocks to rank 0].
+of all 128 sources) through forward FFT -> MAC -> inverse FFT + crossfade + sum;
+at N > 1 the inverse kernels of the peer ranks store their output blocks straight
+into rank 0's buffer over NVLink peer memory (--gather nccl: NCCL gather instead).
 
   value  device-resident: input blocks already in HBM, steps back to back.
-  e2e    the same through ssr_renderer_process / process_device with HOST
-         buffers: H2D of the block's inputs and D2H of its outputs inside the
-         timed region, one synchronous call per block (also gives p99 latency).
+  e2e    the same through ssr_renderer_process with HOST buffers on every rank:
+         H2D of the block's inputs and D2H of its outputs inside the timed region,
+         one synchronous call per block (also gives p99 latency).
+  e2e_pipelined  the host-buffer path through ssr_renderer_submit / wait, two
+         blocks in flight (copies overlap the neighbouring blocks' kernels).
   roofline  MAC kernel: algorithmic bytes (SURVEY 8d formula, counted by the
-         engine) / CUDA-event time of the MAC launches inside the timed region.
+         engine) / CUDA-event time of the MAC launches inside the timed region
+         (every 8th step carries the events).
   cpu_baseline  the reference's own GenericRenderer (oracle/_ref) on host cores,
          on a bounded output shard of the same workload.
 
