@@ -23,6 +23,14 @@
 // FFT + crossfade + source sum); there is no per-pair convolve() call and no
 // worker-thread fan-out ("threads" is accepted and ignored).
 //
+// Several GPUs in one process (GenericRenderer only): p.set("devices", "0,1,2,3")
+// shards the outputs over one engine per listed device -- the counterpart of the
+// reference spreading its Output items over worker threads
+// (apf/apf/mimoprocessor.h:452-483).  Every control assignment goes to all shards,
+// audio_callback() queues the block on the peer shards and runs it on the first
+// one, whose inverse kernel's peers store their output blocks straight into its
+// gather buffer over NVLink (include/ssr_b200.h, "Multi-GPU output gather").
+//
 // Out of scope and therefore different: GenericRenderer takes its loudspeaker
 // count from the parameter "outputs" (the reference parses the reproduction-setup
 // XML, src/loudspeakerrenderer.h:95-150); IR files are read by the small WAV
@@ -257,13 +265,13 @@ class RendererCore
     class Source
     {
       public:
-        Source(ssr_renderer* r, int id_)
+        Source(RendererCore* c, int id_)
           : id(id_)
-          , position(Position(), [r, id_](const Position& p) { check(ssr_source_set_position(r, id_, p.x, p.y)); })
+          , position(Position(), [c, id_](const Position& p) { c->each([&](ssr_renderer* r) { check(ssr_source_set_position(r, id_, p.x, p.y)); }); })
           , orientation(Orientation(), [](const Orientation&) {})
-          , gain(1.0f, [r, id_](float g) { check(ssr_source_set_gain(r, id_, g)); })
-          , mute(false, [r, id_](bool m) { check(ssr_source_set_mute(r, id_, m)); })
-          , model(point, [r, id_](model_t m) { check(ssr_source_set_model(r, id_, m == plane)); })
+          , gain(1.0f, [c, id_](float g) { c->each([&](ssr_renderer* r) { check(ssr_source_set_gain(r, id_, g)); }); })
+          , mute(false, [c, id_](bool m) { c->each([&](ssr_renderer* r) { check(ssr_source_set_mute(r, id_, m)); }); })
+          , model(point, [c, id_](model_t m) { c->each([&](ssr_renderer* r) { check(ssr_source_set_model(r, id_, m == plane)); }); })
         {}
         const int id;
         Shared<Position, std::function<void(const Position&)>> position;
@@ -275,14 +283,14 @@ class RendererCore
 
     struct State
     {
-      explicit State(ssr_renderer*& r)
-        : reference_position(Position(), [&r](const Position& p) { check(ssr_renderer_set_reference_position(r, p.x, p.y)); })
-        , reference_orientation(Orientation(), [&r](const Orientation& o) { check(ssr_renderer_set_reference_orientation(r, o.azimuth)); })
-        , reference_offset_position(Position(), [&r](const Position& p) { check(ssr_renderer_set_reference_offset_position(r, p.x, p.y)); })
-        , reference_offset_orientation(Orientation(), [&r](const Orientation& o) { check(ssr_renderer_set_reference_offset_orientation(r, o.azimuth)); })
-        , master_volume(1.0f, [&r](float v) { check(ssr_renderer_set_master_volume(r, v)); })
-        , processing(true, [&r](bool v) { check(ssr_renderer_set_processing(r, v)); })
-        , amplitude_reference_distance(3.0f, [&r](float v) { check(ssr_renderer_set_amplitude_reference_distance(r, v)); })
+      explicit State(RendererCore* c)
+        : reference_position(Position(), [c](const Position& p) { c->each([&](ssr_renderer* r) { check(ssr_renderer_set_reference_position(r, p.x, p.y)); }); })
+        , reference_orientation(Orientation(), [c](const Orientation& o) { c->each([&](ssr_renderer* r) { check(ssr_renderer_set_reference_orientation(r, o.azimuth)); }); })
+        , reference_offset_position(Position(), [c](const Position& p) { c->each([&](ssr_renderer* r) { check(ssr_renderer_set_reference_offset_position(r, p.x, p.y)); }); })
+        , reference_offset_orientation(Orientation(), [c](const Orientation& o) { c->each([&](ssr_renderer* r) { check(ssr_renderer_set_reference_offset_orientation(r, o.azimuth)); }); })
+        , master_volume(1.0f, [c](float v) { c->each([&](ssr_renderer* r) { check(ssr_renderer_set_master_volume(r, v)); }); })
+        , processing(true, [c](bool v) { c->each([&](ssr_renderer* r) { check(ssr_renderer_set_processing(r, v)); }); })
+        , amplitude_reference_distance(3.0f, [c](float v) { c->each([&](ssr_renderer* r) { check(ssr_renderer_set_amplitude_reference_distance(r, v)); }); })
       {}
       Shared<Position, std::function<void(const Position&)>> reference_position;
       Shared<Orientation, std::function<void(const Orientation&)>> reference_orientation;
@@ -296,7 +304,12 @@ class RendererCore
     int block_size() const { return _block_size; }
     int sample_rate() const { return _sample_rate; }
     int in_channels() const { return ssr_renderer_sources(_r); }
-    int out_channels() const { return ssr_renderer_local_outputs(_r); }
+    /// outputs audio_callback() delivers (all shards' outputs when sharded)
+    int out_channels() const { return _gathers.empty() ? ssr_renderer_local_outputs(_r) : ssr_gather_total_outputs(_gathers[0]); }
+    int shards() const { return 1 + int(_peer_r.size()); }
+
+    /// f(renderer handle) on every shard (one shard unless "devices" lists several)
+    template<typename F> void each(F f) { f(_r); for (auto r : _peer_r) f(r); }
 
     bool activate() { return true; }
     bool deactivate() { return true; }
@@ -304,7 +317,11 @@ class RendererCore
     /// = pointer_policy::audio_callback (apf/apf/pointer_policy.h:112-122)
     void audio_callback(int n, float* const* in, float* const* out)
     {
+      // sharded: the peers queue the block (their inverse kernels deliver into the
+      // first shard's gather buffer), the first shard runs it and returns all outputs
+      for (auto r : _peer_r) check(ssr_renderer_submit(r, n, in));
       check(ssr_renderer_process(_r, n, in, out));
+      for (auto r : _peer_r) check(ssr_renderer_wait(r, nullptr));
     }
 
     Source* get_source(int id)
@@ -316,8 +333,9 @@ class RendererCore
     void rem_source(Source* s)
     {
       if (!s) return;
-      check(ssr_renderer_rem_source(_r, s->id));
-      _sources.erase(s->id);
+      const int id = s->id;
+      each([&](ssr_renderer* r) { check(ssr_renderer_rem_source(r, id)); });
+      _sources.erase(id);
     }
 
     void rem_all_sources() { while (!_sources.empty()) rem_source(_sources.begin()->second.get()); }
@@ -333,43 +351,108 @@ class RendererCore
 
   protected:
     RendererCore(const apf::parameter_map& p, ssr_renderer_kind kind)
-      : params(p), state(_r)
+      : params(p), state(this)
       , _block_size(p.get<int>("block_size")), _sample_rate(p.get<int>("sample_rate"))
       , _e(nullptr), _r(nullptr)
     {
-      ssr_engine_config ec = ssr_engine_config();
-      ec.device = p.get("device", 0);
-      ec.block_size = _block_size;
-      ec.sample_rate = _sample_rate;
-      check(ssr_engine_create(&ec, &_e));
-      ssr_renderer_config rc = ssr_renderer_config();
-      rc.kind = kind;
-      rc.outputs = kind == SSR_RENDERER_GENERIC ? p.get("outputs", 0) : 2;
-      rc.output_first = p.get("output_first", 0);
-      rc.output_count = p.get("output_count", 0);
-      rc.master_volume_correction_db = float(p.get("master_volume_correction", 0.0));
-      const int rc_ = ssr_renderer_create(_e, &rc, &_r);
-      if (rc_ != SSR_OK) { const std::string m = ssr_last_error(); ssr_engine_destroy(_e); _e = nullptr;
-        throw std::logic_error(m); }
+      // "devices": comma-separated CUDA ordinals, one output shard per entry
+      std::vector<int> devices;
+      {
+        std::stringstream ss(p.get("devices", std::string()));
+        std::string tok;
+        while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(std::atoi(tok.c_str()));
+      }
+      if (devices.empty()) devices.push_back(p.get("device", 0));
+      const int world = int(devices.size());
+      if (world > 1 && kind != SSR_RENDERER_GENERIC)
+        throw std::logic_error("ssr_b200: only the GenericRenderer shards over several devices");
+      const int outputs = kind == SSR_RENDERER_GENERIC ? p.get("outputs", 0) : 2;
+      if (world > 1 && outputs < world) throw std::logic_error("ssr_b200: fewer outputs than devices");
+      std::vector<int> counts(size_t(world), outputs / world);
+      for (int g = 0; g < outputs % world; ++g) counts[size_t(g)]++;
+      try
+      {
+        int first = 0;
+        for (int g = 0; g < world; ++g)
+        {
+          ssr_engine_config ec = ssr_engine_config();
+          ec.device = devices[size_t(g)];
+          ec.block_size = _block_size;
+          ec.sample_rate = _sample_rate;
+          ssr_engine* e = nullptr;
+          check(ssr_engine_create(&ec, &e));
+          (g == 0 ? _e : *_peer_e.insert(_peer_e.end(), nullptr)) = e;
+          ssr_renderer_config rc = ssr_renderer_config();
+          rc.kind = kind;
+          rc.outputs = outputs;
+          rc.output_first = world > 1 ? first : p.get("output_first", 0);
+          rc.output_count = world > 1 ? counts[size_t(g)] : p.get("output_count", 0);
+          rc.master_volume_correction_db = float(p.get("master_volume_correction", 0.0));
+          ssr_renderer* r = nullptr;
+          check(ssr_renderer_create(e, &rc, &r));
+          (g == 0 ? _r : *_peer_r.insert(_peer_r.end(), nullptr)) = r;
+          first += counts[size_t(g)];
+        }
+        if (world > 1)
+        {
+          for (int g = 0; g < world; ++g)
+          {
+            ssr_gather* ga = nullptr;
+            check(ssr_gather_create(g == 0 ? _e : _peer_e[size_t(g - 1)], world, g, 0, counts.data(), &ga));
+            _gathers.push_back(ga);
+            if (g > 0) check(ssr_gather_connect_local(ga, _gathers[0]));
+          }
+          for (int g = 0; g < world; ++g)
+            check(ssr_renderer_bind_gather(g == 0 ? _r : _peer_r[size_t(g - 1)], _gathers[size_t(g)]));
+        }
+      }
+      catch (...) { destroy(); throw; }
     }
 
-    ~RendererCore()
-    {
-      _sources.clear();
-      if (_r) ssr_renderer_destroy(_r);
-      if (_e) ssr_engine_destroy(_e);
-    }
+    ~RendererCore() { destroy(); }
 
     int register_source(int id)
     {
-      _sources[id].reset(new Source(_r, id));
+      _sources[id].reset(new Source(this, id));
+      return id;
+    }
+
+    /// ssr_renderer_add_source on every shard (each picks its own output columns);
+    /// the shards hand out the same id
+    int add_source_all(const float* ir, long frames, int channels)
+    {
+      int id = 0;
+      check(ssr_renderer_add_source(_r, ir, frames, channels, &id));
+      for (auto r : _peer_r)
+      {
+        int pid = 0;
+        check(ssr_renderer_add_source(r, ir, frames, channels, &pid));
+        if (pid != id) throw std::logic_error("ssr_b200: shards disagree on a source id");
+      }
       return id;
     }
 
     const int _block_size, _sample_rate;
     ssr_engine* _e;
-    ssr_renderer* _r;
+    ssr_renderer* _r;                       // the first (host-facing) shard
+    std::vector<ssr_engine*> _peer_e;       // further shards ("devices")
+    std::vector<ssr_renderer*> _peer_r;
+    std::vector<ssr_gather*> _gathers;
     std::map<int, std::unique_ptr<Source>> _sources;
+
+  private:
+    void destroy()
+    {
+      _sources.clear();
+      // renderers first (they only point at their gathers), the peers' gathers before
+      // the root's buffer they map, engines last
+      for (auto r : _peer_r) if (r) ssr_renderer_destroy(r);
+      if (_r) ssr_renderer_destroy(_r);
+      for (size_t g = _gathers.size(); g-- > 0;) if (_gathers[g]) ssr_gather_destroy(_gathers[g]);
+      for (auto e : _peer_e) if (e) ssr_engine_destroy(e);
+      if (_e) ssr_engine_destroy(_e);
+      _peer_r.clear(); _peer_e.clear(); _gathers.clear(); _r = nullptr; _e = nullptr;
+    }
 };
 }  // namespace b200
 
@@ -386,9 +469,7 @@ class GenericRenderer : public b200::RendererCore
     {
       auto ir = b200::load_sndfile(p.get("properties_file", ""), size_t(sample_rate())
           , size_t(params.get("outputs", 0)));
-      int id = 0;
-      b200::check(ssr_renderer_add_source(_r, ir.data.data(), ir.frames, ir.channels, &id));
-      return register_source(id);
+      return register_source(add_source_all(ir.data.data(), long(ir.frames), int(ir.channels)));
     }
 };
 

@@ -228,12 +228,84 @@ static void test_brs_and_binaural(const std::string& dir)
   CHECK(ok);
 }
 
+// "devices" = several CUDA ordinals: the GenericRenderer shards its outputs over
+// one engine per entry (here all on device 0 unless SSR_TEST_DEVICES lists others)
+// and audio_callback() still delivers every output -- the single-process form of
+// the multi-GPU path (the reference spreads its Output items over worker threads,
+// apf/apf/mimoprocessor.h:452-483).
+static void test_generic_sharded(const std::string& dir)
+{
+  const int N = 3, M = 7, L = 150, TT = 8;
+  const char* env = std::getenv("SSR_TEST_DEVICES");
+  for (const std::string devices : {std::string(env ? env : "0,0"), std::string("0,0,0")})
+  {
+    auto p = base_params();
+    p.set("outputs", M);
+    ssr::GenericRenderer whole(p);
+    p.set("devices", devices);
+    ssr::GenericRenderer sharded(p);
+    CHECK(sharded.shards() == (devices.size() + 1) / 2);
+    CHECK(sharded.out_channels() == M && whole.out_channels() == M);
+    std::vector<std::vector<float>> irs(N);
+    for (int n = 0; n < N; ++n)
+    {
+      irs[n].resize(size_t(L) * M);
+      for (auto& v : irs[n]) v = rnd() * 0.1f;
+      const std::string path = dir + "/sharded_ir_" + std::to_string(n) + ".wav";
+      write_wav(path, irs[n], M, FS, false);
+      apf::parameter_map sp;
+      sp.set("properties_file", path);
+      const int a = whole.add_source(sp), b = sharded.add_source(sp);
+      CHECK(a == b);
+    }
+    CHECK(sharded.in_channels() == N);
+    std::vector<std::vector<float>> x(N, std::vector<float>(size_t(TT) * B));
+    for (auto& s : x) for (auto& v : s) v = rnd();
+    double worst = 0, worst_truth = 0;
+    std::vector<std::vector<float>> ys(M, std::vector<float>(size_t(TT) * B)), yw = ys;
+    for (int t = 0; t < TT; ++t)
+    {
+      if (t == 3) { whole.get_source(2)->gain = 0.25f; sharded.get_source(2)->gain = 0.25f; }      // every shard
+      if (t == 5) { whole.state.master_volume = 0.5f; sharded.state.master_volume = 0.5f; }
+      if (t == 6) { whole.rem_source(whole.get_source(1)); sharded.rem_source(sharded.get_source(1)); }
+      const int n_now = t >= 6 ? N - 1 : N;
+      float* in[N]; float* o1[M]; float* o2[M];
+      for (int n = 0; n < n_now; ++n) in[n] = x[t >= 6 ? n + 1 : n].data() + size_t(t) * B;
+      for (int m = 0; m < M; ++m) { o1[m] = yw[m].data() + size_t(t) * B; o2[m] = ys[m].data() + size_t(t) * B; }
+      whole.audio_callback(B, in, o1);
+      sharded.audio_callback(B, in, o2);
+      for (int m = 0; m < M; ++m)
+        for (int i = 0; i < B; ++i) worst = std::fmax(worst, std::fabs(double(o1[m][i]) - double(o2[m][i])));
+    }
+    // blocks 1-2 (constant gains, all sources): against float64 direct convolution
+    for (int m = 0; m < M; ++m)
+    {
+      std::vector<double> truth(size_t(TT) * B, 0.0);
+      for (int n = 0; n < N; ++n)
+      {
+        auto d = direct(x[n], column(irs[n], M, m));
+        for (size_t i = 0; i < truth.size(); ++i) truth[i] += d[i];
+      }
+      for (size_t i = B; i < size_t(3) * B; ++i) worst_truth = std::fmax(worst_truth, std::fabs(truth[i] - ys[m][i]));
+    }
+    std::printf("generic sharded over devices {%s}: max |sharded - whole| %.3g, vs direct convolution %.3g\n",
+        devices.c_str(), worst, worst_truth);
+    CHECK(worst <= 2e-6);
+    CHECK(worst_truth <= 1e-5);
+  }
+  bool ok = false;
+  try { auto p = base_params(); p.set("devices", "0,0"); p.set("hrir_file", "x.wav"); ssr::BrsRenderer r(p); }
+  catch (const std::logic_error&) { ok = true; }
+  CHECK(ok);
+}
+
 int main(int argc, char* argv[])
 {
   const std::string dir = argc > 1 ? argv[1] : "/tmp";
   try
   {
     test_generic(dir);
+    test_generic_sharded(dir);
     test_brs_and_binaural(dir);
   }
   catch (const std::exception& e)
