@@ -13,9 +13,9 @@
 // Differences from the reference: the same return codes for sample-rate (42) and
 // channel (666) mismatches; the last, partial block is zero-padded (the reference
 // leaves the tail of its de-interleaving matrix from the previous block in place);
-// blocks are pipelined two deep through ssr_renderer_submit / ssr_renderer_wait
-// when the processor exposes handle() (north_star item 5), which does not change
-// the result.
+// blocks are pipelined two deep through the processor's submit() / wait()
+// (ssr_renderer_submit / ssr_renderer_wait on every output shard; north_star
+// item 5), which does not change the result.
 #ifndef SSR_B200_APF_MIMOPROCESSOR_FILE_IO_H
 #define SSR_B200_APF_MIMOPROCESSOR_FILE_IO_H
 
@@ -90,20 +90,20 @@ int mimoprocessor_file_io(Processor& processor
   };
 
   // two blocks in flight: block b + 1 is copied and queued while block b computes
-  ssr_renderer* h = processor.handle();
+  // (through the processor, so that a renderer sharded over several devices works too)
   for (long b = 0; b < blocks; ++b)
   {
     load_block(b);
-    ssr::b200::check(ssr_renderer_submit(h, blocksize, in_ptrs.data()));
+    processor.submit(int(blocksize), in_ptrs.data());
     if (b > 0)
     {
-      ssr::b200::check(ssr_renderer_wait(h, out_ptrs.data()));
+      processor.wait(out_ptrs.data());
       store_block(b - 1);
     }
   }
   if (blocks > 0)
   {
-    ssr::b200::check(ssr_renderer_wait(h, out_ptrs.data()));
+    processor.wait(out_ptrs.data());
     store_block(blocks - 1);
   }
 

@@ -324,6 +324,19 @@ class RendererCore
       for (auto r : _peer_r) check(ssr_renderer_wait(r, nullptr));
     }
 
+    /// Pipelined form of audio_callback (offline rendering): submit() queues a block
+    /// and returns, wait() delivers the oldest queued block; at most two in flight.
+    void submit(int n, const float* const* in)
+    {
+      for (auto r : _peer_r) check(ssr_renderer_submit(r, n, in));
+      check(ssr_renderer_submit(_r, n, in));
+    }
+    void wait(float* const* out)
+    {
+      check(ssr_renderer_wait(_r, out));
+      for (auto r : _peer_r) check(ssr_renderer_wait(r, nullptr));
+    }
+
     Source* get_source(int id)
     {
       auto it = _sources.find(id);

@@ -27,7 +27,7 @@ int main(int argc, char* argv[])
 {
   if (argc < 6)
   {
-    std::fprintf(stderr, "usage: %s generic|brs|binaural <block> <in.wav> <out.wav> <ir.wav>... [--azimuth deg]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s generic|brs|binaural <block> <in.wav> <out.wav> <ir.wav>... [--azimuth deg] [--devices 0,1,...]\n", argv[0]);
     return 2;
   }
   const std::string kind = argv[1];
@@ -36,9 +36,11 @@ int main(int argc, char* argv[])
   std::vector<std::string> files;
   float azimuth = 0.0f;
   bool have_az = false;
+  std::string devices;   // generic only: comma-separated CUDA ordinals, one output shard each
   for (int i = 5; i < argc; ++i)
   {
     if (!std::strcmp(argv[i], "--azimuth") && i + 1 < argc) { azimuth = float(std::atof(argv[++i])); have_az = true; }
+    else if (!std::strcmp(argv[i], "--devices") && i + 1 < argc) devices = argv[++i];
     else files.push_back(argv[i]);
   }
   try
@@ -51,6 +53,7 @@ int main(int argc, char* argv[])
     {
       auto first = ssr::b200::load_sndfile(files.at(0), 0, 0);
       p.set("outputs", first.channels);
+      if (!devices.empty()) p.set("devices", devices);
       ssr::GenericRenderer r(p);
       for (auto& f : files) { apf::parameter_map sp; sp.set("properties_file", f); r.add_source(sp); }
       return run(r, in, out);

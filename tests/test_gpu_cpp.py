@@ -69,6 +69,12 @@ def test_offline_file_driver_generic(tmp_path):
     assert np.abs(y[B:] - exp[B:]).max() <= 1e-5
     fade_in = 0.5 * np.cos(np.pi * (B - np.arange(B)) / B) + 0.5
     assert np.abs(y[:B] - exp[:B] * fade_in[:, None]).max() <= 1e-5
+    # the same file rendered by two output shards (two engines; --devices): identical
+    rc, out = run("ssr_b200_render", "generic", str(B), str(tmp_path / "in.wav"), str(tmp_path / "out2.wav"),
+                  *[str(tmp_path / f"ir{n}.wav") for n in range(N)], "--devices", "0,0")
+    assert rc == 0, out
+    _, y2 = wavfile.read(tmp_path / "out2.wav")
+    assert np.array_equal(y, y2)
 
 
 def test_offline_file_driver_rejects_mismatches(tmp_path):
