@@ -280,6 +280,100 @@ def test_live_transform_nested_matches_reference():
             assert np.abs(data - oout.nodes[p].data).max() <= TOL
 
 
+def _decaying(rng, frames, channels, gain):
+    env = np.exp(-6.9 * np.arange(frames) / frames)[:, None]
+    return (rng.uniform(-1, 1, (frames, channels)) * env * gain).astype(np.float32)
+
+
+@needs_ref
+def test_live_brs_sources_added_and_removed_while_the_head_turns():
+    """The scenario of tests/test_gpu_renderers.py::test_brs_unequal_ir_lengths_...: the
+    reference's own BrsRenderer (src/brsrenderer.h, RendererBase::add_source /
+    rem_source src/rendererbase.h:247-314) against the numpy restatement, including its
+    rem_source."""
+    B, A, fs = 64, 10, 48000
+    rng = np.random.default_rng(99)
+    r = ref.Renderer("brs", B, fs)
+    r.load_reproduction_setup()
+    o = co.BrsRendererOracle(B)
+    ids = []
+
+    def add(L):
+        brir = _decaying(rng, L, 2 * A, 0.05)
+        ref.register_sndfile("live_brir", brir, fs)
+        ids.append(r.add_source("live_brir"))
+        ref.unregister_sndfile("live_brir")
+        o.add_source(brir)
+
+    add(40); add(190)
+    r.activate()
+    # pointer_policy keeps the channel index of a removed input (apf/apf/pointer_policy.h:
+    # the remaining inputs still read in[their id]); the oracle's rows are the live ones
+    live = [0, 1]
+    az, worst = 0.0, 0.0
+    for t in range(60):
+        if t == 12:
+            add(300); live.append(2)
+        if t == 31:
+            r.rem_source(ids.pop(1)); o.rem_source(1); live.pop(1)
+        if t == 45:
+            r.set_state("processing", 0); o.processing = False
+        if t == 50:
+            r.set_state("processing", 1); o.processing = True
+        x = rng.uniform(-1, 1, (r.n_in, B)).astype(np.float32)
+        if t < 40 or t % 3 == 0:
+            az += 360.0 / A + 3.0
+        r.set_state("reference_orientation", az); o.reference_orientation = az
+        worst = max(worst, float(np.abs(r.process(x) - o.process(x[live])).max()))
+    assert worst <= TOL, worst
+
+
+@needs_ref
+def test_live_binaural_multi_partition_switches_and_removal():
+    """HRIRs longer than the block (P = 4), moves arriving faster than the staggered
+    switch completes, a mute across a switch and a removal: the reference's own
+    BinauralRenderer (src/binauralrenderer.h:261-389) against the numpy restatement."""
+    B, L, A, N, fs = 64, 250, 16, 3, 48000
+    rng = np.random.default_rng(5)
+    hrir = _decaying(rng, L, 2 * A, 0.5 / np.sqrt(L / 6.9))
+    ref.register_sndfile("live_hrir", hrir, fs)
+    r = ref.Renderer("binaural", B, fs, hrir_file="live_hrir")
+    r.load_reproduction_setup()
+    o = co.BinauralRendererOracle(B, hrir)
+    ids = [r.add_source() for _ in range(N)]
+    for _ in range(N):
+        o.add_source()
+    r.activate()
+
+    def setpos(i, p):
+        r.set_source(ids[i], "position", p[0], p[1])
+        o.sources[i].position = p
+
+    for i, p in enumerate([(0.0, 2.0), (1.5, -1.0), (-2.0, 0.3)]):
+        setpos(i, p)
+    live = list(range(N))   # channel indices of the live sources (see the BRS test)
+    worst = 0.0
+    for t in range(64):
+        if t == 40:
+            r.rem_source(ids.pop(0)); o.rem_source(0); live.pop(0)
+        n = len(ids)
+        x = rng.uniform(-1, 1, (r.n_in, B)).astype(np.float32)
+        if 3 <= t < 18 or t in (25, 27, 44):
+            a = t * 0.45
+            setpos(n - 1, (2 * np.cos(a), 2 * np.sin(a)))
+        if t == 8:
+            r.set_source(ids[1], "mute", 1); o.sources[1].mute = True
+        if t == 10:
+            setpos(1, (0.3, 2.5))
+        if t == 13:
+            r.set_source(ids[1], "mute", 0); o.sources[1].mute = False
+        if t == 50:
+            r.set_state("reference_orientation", 200.0); o.reference_orientation = 200.0
+        worst = max(worst, float(np.abs(r.process(x) - o.process(x[live])).max()))
+    ref.unregister_sndfile("live_hrir")
+    assert worst <= TOL, worst
+
+
 # ---------------------------------------------------------------- 4. reference-independent truth
 @pytest.mark.parametrize("B,L", [(8, 20), (64, 200), (1024, 3000)])
 def test_static_convolver_vs_direct_convolution(B, L):
