@@ -1,0 +1,395 @@
+// inverse.cuh -- partial reduction, inverse transform + crossfade + source sum, the fused multi-GPU output gather and the filter-ring update
+// (part of the kernel set of kernels.cuh; included from there, in this order)
+#pragma once
+
+namespace ssrk
+{
+
+// ---------------------------------------------------------------- inverse
+struct InvEntry
+{
+  int part_first;   // first partial index
+  int part_count;   // number of partials to sum (split count of the group)
+  int part_stride;  // MT of the group
+  int part_row;     // row within the group
+  int fade;         // 0 none, 1 fade-out, 2 fade-in (combine_channels.h:297-335)
+  float scale;      // 1 / (2B) (convolver.h:458) [times a per-row weight]
+};
+
+struct InvJob
+{
+  int first_entry;
+  int n_entries;    // 0 -> output block is zeros (combine_channels.h:126-129)
+  float* out;       // B floats (device)
+  float* level;     // if non-null: max |out| (src/rendererbase.h:468-472)
+};
+
+constexpr int kInvMaxRes = 8;  // B <= 4096: (B/2 float2) / 256 threads
+
+// Multi-GPU output gather fused into the inverse kernel: the output
+// blocks of a rank are stored straight into the host-facing rank's gather buffer
+// over NVLink peer memory (InvJob::out + out_offset points into it), and every
+// CTA then bumps a system-scope arrival counter in that buffer's control block.
+// Two slots alternate by block parity; before storing block t a CTA checks that
+// the root has released block t-2 (`consumed >= need_consumed`).  All pointers
+// null / zero: plain local stores.
+struct GatherArgs
+{
+  long long out_offset;                    // floats added to every InvJob::out (slot * slot stride)
+  const unsigned long long* consumed;      // root's "blocks released" counter (peer memory), or null
+  unsigned long long need_consumed;
+  unsigned long long* arrived;             // this rank's arrival counter on the root (peer memory), or null
+  int* error;                              // local sticky flag: a wait timed out
+};
+
+constexpr unsigned long long kGatherTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// spins until *p >= target; gives up (sticky error flag) after kGatherTimeoutNs so
+// that a dead peer can never hang the GPU
+__device__ __noinline__ void gather_wait_ge(const unsigned long long* p, unsigned long long target, int* error)
+{
+  if (ld_acquire_sys(p) >= target) return;
+  if (error && *reinterpret_cast<volatile int*>(error)) return;
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(p) < target)
+  {
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > kGatherTimeoutNs)
+    {
+      if (error) *reinterpret_cast<volatile int*>(error) = 1;
+      return;
+    }
+  }
+}
+
+// root: wait until every peer rank has delivered its output blocks of block
+// `epoch` (0-based): arrived[g] >= (epoch + 1) * ctas[g].  One thread per rank.
+struct GatherWaitArgs
+{
+  const unsigned long long* arrived;   // [world], 16 counters apart (128 bytes)
+  const int* ctas;                     // [world] CTAs (= output blocks) per rank; 0 for the root itself
+  int world;
+  unsigned long long epoch;
+  int* error;
+};
+constexpr int kGatherCounterStride = 16;  // unsigned long longs between counters (one 128-byte line each)
+
+__global__ void gather_wait_kernel(GatherWaitArgs a)
+{
+  const int g = threadIdx.x;
+  if (g < a.world && a.ctas[g] > 0)
+    gather_wait_ge(a.arrived + size_t(g) * kGatherCounterStride,
+        (a.epoch + 1) * (unsigned long long)a.ctas[g], a.error);
+}
+
+// root: block `epoch` has been read out of its slot -> peers may overwrite it
+__global__ void gather_release_kernel(unsigned long long* consumed, unsigned long long value)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(consumed), "l"(value) : "memory");
+}
+
+// Parallel pre-reduction of the split partial accumulators, used when there are
+// few output blocks but deep splits (Binaural / BRS: 2 outputs; sharded Generic):
+// grid (entries, (B/2)/32); warp w of a CTA sums partials w, w+8, ... for a
+// 64-bin tile, then the 8 warps are combined through shared memory.
+__global__ void __launch_bounds__(kThreads)
+reduce_partials_kernel(const InvEntry* __restrict__ entries, const float4* __restrict__ partials,
+                       float4* __restrict__ reduced, int nvec)
+{
+  __shared__ float4 s_part[kThreads / 32][32];
+  grid_dependency_wait();
+  const InvEntry en = entries[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.y * 32 + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < nvec)
+  {
+    const float4* base = partials + (size_t(en.part_first) * en.part_stride + en.part_row) * nvec + idx;
+    const size_t pstride = size_t(en.part_stride) * nvec;
+#pragma unroll 4
+    for (int c = warp; c < en.part_count; c += kThreads / 32)
+    {
+      const float4 v = __ldcs(base + size_t(c) * pstride);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  s_part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && idx < nvec)
+  {
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w)
+    {
+      const float4 v = s_part[w][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reduced[size_t(blockIdx.x) * nvec + idx] = s;
+  }
+}
+
+// Dynamic renderers: the same pre-reduction with the split derived from the
+// control block (see dyn_split); grid (2 ears x 3 kinds, (B/2)/32).  Entry
+// ear * 3 + kind of `reduced` receives the sum; inactive kinds are skipped (the
+// inverse kernel skips them too).
+__global__ void __launch_bounds__(kThreads)
+dyn_reduce_kernel(const DynCtl* __restrict__ ctl, int Pmax, int G, const float4* __restrict__ partials,
+                  float4* __restrict__ reduced, int nvec)
+{
+  __shared__ float4 s_part[kThreads / 32][32];
+  grid_dependency_wait();
+  const int ear = blockIdx.x / 3, kind = blockIdx.x % 3;
+  const int nn[3] = {ctl->n[0], ctl->n[1], ctl->n[2]};
+  if (nn[kind] == 0) return;
+  int first, count;
+  dyn_split(nn, Pmax, G, kind, first, count);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.y * 32 + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < nvec)
+  {
+    const float4* base = partials + (size_t(first) * 2 + ear) * nvec + idx;
+    const size_t pstride = size_t(2) * nvec;
+#pragma unroll 4
+    for (int c = warp; c < count; c += kThreads / 32)
+    {
+      const float4 v = __ldcs(base + size_t(c) * pstride);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  s_part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && idx < nvec)
+  {
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w)
+    {
+      const float4 v = s_part[w][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reduced[size_t(blockIdx.x) * nvec + idx] = s;
+  }
+}
+
+__device__ __forceinline__ void fwd_ring_update(const FwdRingUpdate& u, int source, int ear)
+{
+  int slot = int(u.ctl->b % u.R);
+  if (slot < 0) slot += u.R;
+  const int row = source * 2 + ear;
+  u.ring[size_t(row) * u.R + slot] = u.upd[row];
+}
+
+// ring[(source, ear)][b mod R] = the filter that is current in block b
+__global__ void dyn_ring_update_kernel(const DynCtl* __restrict__ ctl, const DynRingEntry* __restrict__ upd,
+                                       DynRingEntry* __restrict__ ring, int rows, int R)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  int slot = int(ctl->b % R);
+  if (slot < 0) slot += R;
+  ring[size_t(i) * R + slot] = upd[i];
+}
+
+// One CTA per output block, one kThreads-thread GROUP per accumulator entry of the
+// block (constant / fade-out / fade-in, <= kInvMaxGroups): the up to three inverse
+// transforms of a crossfading output run side by side instead of one after the
+// other; group 0 adds the faded results and stores the block.
+constexpr int kInvMaxGroups = 3;
+
+template<int GROUPS>
+__global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 4 : 1)
+inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
+               const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
+               const float2* __restrict__ tw,
+               const float* __restrict__ fade_out, const float* __restrict__ fade_in,
+               const GatherArgs ga, const int* __restrict__ kind_counts)
+{
+  extern __shared__ float2 smem[];
+  __shared__ float s_max[kThreads / 32];
+  const int g = GROUPS == 1 ? 0 : threadIdx.x / kThreads;  // entry group
+  const int t = threadIdx.x - g * kThreads;                // thread within the group
+  constexpr int ngroups = GROUPS;
+  float2* a = smem + size_t(g) * 2 * B;
+  float2* b = a + B;
+  const InvJob job = jobs[blockIdx.x];
+  const int half = B >> 1;
+  // twiddle table -> shared memory, once for all groups
+  float2* stw = smem + size_t(GROUPS) * 2 * B;
+  stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);  // constants: may overlap the predecessor's tail
+  grid_dependency_wait();
+  __syncthreads();
+  // flow control of the fused gather: the slot this block goes to must have been
+  // read out by the root (checked by one thread while the others start loading)
+  if (ga.consumed && threadIdx.x == 0) gather_wait_ge(ga.consumed, ga.need_consumed, ga.error);
+
+  float2 res[kInvMaxRes];
+#pragma unroll
+  for (int q = 0; q < kInvMaxRes; ++q) res[q] = make_float2(0.f, 0.f);
+
+  // entries beyond the launched groups are handled by the last group in turn
+  for (int e = g; e < job.n_entries; e += ngroups)
+  {
+    const InvEntry en = entries[job.first_entry + e];
+    // dynamic renderers: accumulator kinds without sources this block are skipped
+    if (kind_counts && kind_counts[en.fade] == 0) continue;
+    // A[k] = sum over split partials
+    // (float4 = two bins per thread; the loop over partials is unrolled so that
+    // 8 independent loads are in flight per thread)
+    if (reduced)
+    {
+      const float4* r = reinterpret_cast<const float4*>(reduced) + size_t(job.first_entry + e) * (B >> 1);
+      for (int k = t; k < (B >> 1); k += kThreads) reinterpret_cast<float4*>(a)[k] = __ldcs(r + k);
+    }
+    else
+    {
+      const float4* pbase = reinterpret_cast<const float4*>(partials)
+          + (size_t(en.part_first) * en.part_stride + en.part_row) * (B >> 1);
+      const size_t pstride = size_t(en.part_stride) * (B >> 1);
+      for (int k = t; k < (B >> 1); k += kThreads)
+      {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        int c = 0;
+        for (; c + 8 <= en.part_count; c += 8)
+        {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(pbase + size_t(c + u) * pstride + k);
+#pragma unroll
+          for (int u = 0; u < 8; u += 2)
+          {
+            s0.x += v[u].x; s0.y += v[u].y; s0.z += v[u].z; s0.w += v[u].w;
+            s1.x += v[u + 1].x; s1.y += v[u + 1].y; s1.z += v[u + 1].z; s1.w += v[u + 1].w;
+          }
+        }
+        for (; c < en.part_count; ++c)
+        {
+          const float4 v = __ldcs(pbase + size_t(c) * pstride + k);
+          s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+        }
+        reinterpret_cast<float4*>(a)[k] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+      }
+    }
+    group_sync(g + 1);
+    // Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k])
+    for (int k = t; k <= half; k += kThreads)
+    {
+      if (k == 0)
+      {
+        const float2 x0 = a[0];  // (DC, Nyquist)
+        b[0] = make_float2(x0.x + x0.y, x0.x - x0.y);
+      }
+      else
+      {
+        const int k2 = B - k;
+        const float2 xk = a[k], xk2 = a[k2];
+        const float er = xk.x + xk2.x, ei = xk.y - xk2.y;
+        const float dr = xk.x - xk2.x, di = xk.y + xk2.y;
+        float2 w = stw[k];
+        w.y = -w.y;  // w^{-k}
+        const float tr = -(dr * w.y + di * w.x), ti = dr * w.x - di * w.y;
+        b[k] = make_float2(er + tr, ei + ti);
+        if (k2 != k) b[k2] = make_float2(er - tr, -(ei - ti));
+      }
+    }
+    group_sync(g + 1);
+    const float2* z = fft_smem<true, true>(b, a, B, stw, t, g + 1);
+    // keep the second half: time index i = 2j, 2j+1 with j >= B/2
+#pragma unroll
+    for (int q = 0; q < kInvMaxRes; ++q)
+    {
+      const int jj = t + q * kThreads;  // j - half
+      if (jj < half)
+      {
+        const float2 v = z[half + jj];
+        float f0 = en.scale, f1 = en.scale;
+        if (en.fade == 1) { f0 *= __ldg(fade_out + 2 * jj); f1 *= __ldg(fade_out + 2 * jj + 1); }
+        else if (en.fade == 2) { f0 *= __ldg(fade_in + 2 * jj); f1 *= __ldg(fade_in + 2 * jj + 1); }
+        res[q].x = fmaf(v.x, f0, res[q].x);
+        res[q].y = fmaf(v.y, f1, res[q].y);
+      }
+    }
+    group_sync(g + 1);  // z (smem) is rewritten by the group's next entry / the hand-over below
+  }
+
+  // groups 1.. hand their faded blocks to group 0 through their own smem region
+  if (ngroups > 1)
+  {
+    if (g > 0)
+    {
+#pragma unroll
+      for (int q = 0; q < kInvMaxRes; ++q)
+      {
+        const int jj = t + q * kThreads;
+        if (jj < half) a[jj] = res[q];
+      }
+    }
+    __syncthreads();
+    if (g == 0)
+      for (int gg = 1; gg < ngroups; ++gg)
+      {
+        const float2* other = smem + size_t(gg) * 2 * B;
+#pragma unroll
+        for (int q = 0; q < kInvMaxRes; ++q)
+        {
+          const int jj = t + q * kThreads;
+          if (jj < half) { const float2 v = other[jj]; res[q].x += v.x; res[q].y += v.y; }
+        }
+      }
+  }
+
+  if (ga.consumed) __syncthreads();  // thread 0's slot check precedes every store
+  if (g == 0)
+  {
+    float m = 0.0f;
+    float2* out = reinterpret_cast<float2*>(job.out + ga.out_offset);
+#pragma unroll
+    for (int q = 0; q < kInvMaxRes; ++q)
+    {
+      const int jj = t + q * kThreads;
+      if (jj < half)
+      {
+        out[jj] = res[q];
+        m = fmaxf(m, fmaxf(fabsf(res[q].x), fabsf(res[q].y)));
+      }
+    }
+    if (job.level)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((t & 31) == 0) s_max[t >> 5] = m;
+      group_sync(1);
+      if (t < 32)
+      {
+        m = t < kThreads / 32 ? s_max[t] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (t == 0) *job.level = m;
+      }
+    }
+  }
+  if (ga.arrived)
+  {
+    // all stores of this CTA (peer memory, over NVLink) -> fence -> arrival count
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      __threadfence_system();
+      atomicAdd_system(ga.arrived, 1ull);
+    }
+  }
+}
+
+}  // namespace ssrk

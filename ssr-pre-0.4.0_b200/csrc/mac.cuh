@@ -1,0 +1,542 @@
+// mac.cuh -- the spectral multiply-accumulate kernels: register-staged (table-driven or generated terms) and bulk-copy (TMA) staged
+// (part of the kernel set of kernels.cuh; included from there, in this order)
+#pragma once
+
+namespace ssrk
+{
+
+// ---------------------------------------------------------------- MAC
+// A "term" is one partition-MAC shared by the MT rows of a group:
+//   acc[row j] += w * X[input, partition p blocks ago] * H_j
+struct MacTermMeta { int input; int p; int wslot; int pad; };
+
+// Dynamic renderers (Binaural / BRS): the term list is not uploaded, it is GENERATED
+// by the MAC kernel from a few hundred bytes of per-block control data.
+//
+// Staggered filter switch (apf/apf/convolver.h:618-699): partition p of a filter
+// installed in block b_set becomes active in block b_set + p.  Equivalently, in
+// block b partition p uses "the filter that was current in block b - p".  So the
+// device keeps, per (source, ear), a ring of the current filter by block index;
+// the state after this block's switch reads ring[b - p], the state before it
+// ("old", crossfaded out) reads ring[b - 1 - p].
+struct DynRingEntry
+{
+  const float4* base;            // partition 0 of the filter channel (null: empty, convolver.h:415)
+  const unsigned char* flags;    // per partition: 1 = carries data (0: fft_node::zero); null = all of them
+  int nparts;                    // partitions of that filter; beyond -> empty (convolver.h:650-656)
+  int pad;
+};
+
+struct DynCtl                    // uploaded once per block
+{
+  long long b;                   // block index of the state AFTER this block's switch
+  int n[3];                      // sources in the constant / old / new accumulator group
+  int pad;
+};
+
+struct DynTables
+{
+  const DynCtl* ctl;
+  const int* lists;              // [3][nsrc] source slots per group
+  const DynRingEntry* ring;      // [nsrc][2 ears][R]
+  const int* src_input;          // [nsrc] input id (X ring) of a source slot
+  const int* src_parts;          // [nsrc] partitions of its delay line
+  unsigned long long* stats;     // [2]: H partitions read, X partitions read (or null)
+  int nsrc, R, Pmax;
+};
+
+// CTAs [first, first + count) of a G-CTA launch work on group k; proportional to
+// the group sizes, at least one CTA per non-empty group.  Every CTA (and the
+// reduction that follows) evaluates this identically from the control block.
+constexpr int kDynMinTermsPerCta = 4;  // small problems use fewer CTAs (fewer partials to sum)
+
+__host__ __device__ __forceinline__ void dyn_split(const int* n, int Pmax, int G, int k, int& first, int& count)
+{
+  const int tot = n[0] + n[1] + n[2];
+  const int A = (n[0] > 0) + (n[1] > 0) + (n[2] > 0);
+  first = 0; count = 0;
+  int off = 0;
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+  {
+    int g = n[q] > 0 ? 1 + int((long long)(G - A) * n[q] / tot) : 0;
+    const int cap = (n[q] * Pmax + kDynMinTermsPerCta - 1) / kDynMinTermsPerCta;
+    if (g > cap) g = cap;
+    if (q == k) { first = off; count = g; }
+    off += g;
+  }
+}
+
+struct MacParams
+{
+  const MacTermMeta* term_meta;      // [nterms]
+  const float4* const* term_h;       // [nterms][MT] partition spectra (never null:
+                                     //  "empty" partitions point at a zero partition)
+  const int4* work;                  // per CTA: x = term_begin, y = term_end, z = partial index
+  const float* wtab;                 // weights by slot
+  const float4* const* xring;        // per input: ring base
+  const int* xparts;                 // per input: ring length
+  const int* heads;                  // per input: ring head
+  float4* partials;                  // [npartials][MT][B/2] float4
+  int B;
+  int wtab_offset;                   // added to wslot (selects the weight "kind")
+  int partial_offset;                // added to work.z
+  int l2_hints;                      // 1: evict-first for H, evict-last for X
+  const float4* zero;                // an all-zero partition
+  DynTables dyn;                     // mac_kernel<..., DYN = true>: generated terms
+};
+
+constexpr int kMacTile = 64;
+
+// STAGES = depth of the register software pipeline (loads of term i + STAGES - 1
+// are issued before term i is consumed); MINB = CTAs per SM asked of ptxas.
+// DYN: terms generated from MacParams::dyn (dynamic renderers, MT == 2 = the ears)
+template<int MT, int NV, int STAGES = 2, int MINB = 1, bool DYN = false>
+__global__ void __launch_bounds__(kThreads, MINB)
+mac_kernel(const MacParams p)
+{
+  __shared__ const float4* s_x[kMacTile];
+  __shared__ const float4* s_h[kMacTile][MT];
+  __shared__ float s_w[kMacTile];
+  __shared__ int s_count;
+
+  grid_dependency_wait();
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int nvec = p.B >> 1;  // float4 per partition
+  static_assert(!DYN || MT == 2, "generated terms: rows are the two ears");
+  int4 wk;
+  int kind = 0;
+  if constexpr (DYN)
+  {
+    // generated work: which group this CTA serves and its slice of the group's
+    // (source, partition) terms
+    const int n0 = p.dyn.ctl->n[0], n1 = p.dyn.ctl->n[1], n2 = p.dyn.ctl->n[2];
+    const int nn[3] = {n0, n1, n2};
+    int first = 0, count = 0;
+    kind = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+      int f, c;
+      dyn_split(nn, p.dyn.Pmax, gridDim.x, k, f, c);
+      if (int(blockIdx.x) >= f && int(blockIdx.x) < f + c) { kind = k; first = f; count = c; }
+    }
+    if (kind < 0) return;
+    const int terms = nn[kind] * p.dyn.Pmax;
+    const int chunk = (terms + count - 1) / count;
+    const int s = int(blockIdx.x) - first;
+    wk = make_int4(min(terms, s * chunk), min(terms, (s + 1) * chunk), int(blockIdx.x), 0);
+  }
+  else wk = p.work[blockIdx.x];
+  // B > 1024: blockIdx.y selects a 1024-bin tile of the spectrum
+  const int tile_off = blockIdx.y * (NV * kThreads);
+  const int tt = tile_off + t;
+  const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+  const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+
+  float4 acc[MT][NV];
+  float nyq[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+  {
+    nyq[j] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  bool valid[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) valid[v] = (tt + v * kThreads) < nvec;
+
+  for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+  {
+    const int tile_n = min(kMacTile, wk.y - tb);
+    __syncthreads();  // previous tile fully consumed
+    if (t < 32)
+    {
+      // warp 0 stages the tile and compacts away terms with zero weight
+      int count = 0;
+      for (int base = 0; base < tile_n; base += 32)
+      {
+        const int i = base + lane;
+        bool ok = false;
+        MacTermMeta m; float w = 0.f;
+        const float4* hgen[2] = {nullptr, nullptr};
+        if (i < tile_n)
+        {
+          if constexpr (DYN)
+          {
+            {
+              const int src = p.dyn.lists[kind * p.dyn.nsrc + (tb + i) / p.dyn.Pmax];
+              m.input = p.dyn.src_input[src];
+              m.p = (tb + i) % p.dyn.Pmax;
+              w = p.wtab[kind * p.dyn.nsrc + src];
+              if (m.p < p.dyn.src_parts[src] && w != 0.0f)
+              {
+                long long time = p.dyn.ctl->b - (kind == 1 ? 1 : 0) - m.p;
+                int slot = int(time % p.dyn.R);
+                if (slot < 0) slot += p.dyn.R;
+#pragma unroll
+                for (int ear = 0; ear < 2; ++ear)
+                {
+                  const DynRingEntry en = p.dyn.ring[(size_t(src) * 2 + ear) * p.dyn.R + slot];
+                  if (en.base && m.p < en.nparts && (!en.flags || en.flags[m.p])) hgen[ear] = en.base + size_t(m.p) * nvec;
+                }
+                ok = hgen[0] || hgen[1];
+              }
+            }
+          }
+          else
+          {
+            m = p.term_meta[tb + i];
+            w = p.wtab[m.wslot + p.wtab_offset];
+            ok = (w != 0.0f);
+          }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (ok)
+        {
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          const int parts = p.xparts[m.input];
+          int slot = p.heads[m.input] - m.p;
+          if (slot < 0) slot += parts;
+          s_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
+          s_w[pos] = w;
+          if constexpr (DYN)
+          {
+            s_h[pos][0] = hgen[0] ? hgen[0] : p.zero;
+            s_h[pos][1] = hgen[1] ? hgen[1] : p.zero;
+          }
+          else
+          {
+#pragma unroll
+            for (int j = 0; j < MT; ++j) s_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+          }
+        }
+        count += __popc(mask);
+        if (DYN && p.dyn.stats && blockIdx.y == 0)
+        {
+          // traffic accounting: H and X partitions this CTA reads
+          const int nh = __popc(__ballot_sync(0xffffffffu, hgen[0] != nullptr))
+              + __popc(__ballot_sync(0xffffffffu, hgen[1] != nullptr));
+          if (lane == 0 && nh)
+          {
+            atomicAdd(p.dyn.stats, (unsigned long long)nh);
+            // X[n, p] counts once: the old-state group re-reads it from L2
+            if (kind != 1) atomicAdd(p.dyn.stats + 1, (unsigned long long)__popc(mask));
+          }
+        }
+      }
+      if (lane == 0) s_count = count;
+    }
+    __syncthreads();
+    const int n = s_count;
+
+    // software pipeline: loads of term i + STAGES - 1 are in flight while term i
+    // is consumed (buffer indices are compile-time after unrolling)
+    float4 xb[STAGES][NV];
+    float4 hb[STAGES][MT][NV];
+
+#define SSR_MAC_LOAD(buf, i) \
+    { \
+      const float4* xp = s_x[i]; \
+      _Pragma("unroll") for (int v = 0; v < NV; ++v) \
+        if (valid[v]) xb[buf][v] = ldg_stream_hint(xp + tt + v * kThreads, pol_x); \
+      _Pragma("unroll") for (int j = 0; j < MT; ++j) \
+      { \
+        const float4* hp = s_h[i][j]; \
+        _Pragma("unroll") for (int v = 0; v < NV; ++v) \
+          if (valid[v]) hb[buf][j][v] = ldg_stream_hint(hp + tt + v * kThreads, pol_h); \
+      } \
+    }
+
+#define SSR_MAC_FMA(buf, i) \
+    { \
+      const float w = s_w[i]; \
+      _Pragma("unroll") for (int v = 0; v < NV; ++v) \
+      { \
+        if (valid[v]) \
+        { \
+          float4 x = xb[buf][v]; \
+          x.x *= w; x.y *= w; x.z *= w; x.w *= w; \
+          _Pragma("unroll") for (int j = 0; j < MT; ++j) \
+          { \
+            const float4 h = hb[buf][j][v]; \
+            acc[j][v].x = fmaf(x.x, h.x, acc[j][v].x); \
+            acc[j][v].x = fmaf(-x.y, h.y, acc[j][v].x); \
+            acc[j][v].y = fmaf(x.x, h.y, acc[j][v].y); \
+            acc[j][v].y = fmaf(x.y, h.x, acc[j][v].y); \
+            acc[j][v].z = fmaf(x.z, h.z, acc[j][v].z); \
+            acc[j][v].z = fmaf(-x.w, h.w, acc[j][v].z); \
+            acc[j][v].w = fmaf(x.z, h.w, acc[j][v].w); \
+            acc[j][v].w = fmaf(x.w, h.z, acc[j][v].w); \
+            if (v == 0 && tt == 0) nyq[j] = fmaf(x.y, h.y, nyq[j]); \
+          } \
+        } \
+      } \
+    }
+
+    if constexpr (STAGES == 2)
+    {
+      // hand-scheduled double buffer (measurably better code than the generic
+      // loop below: 6.3 vs 5.1 TB/s at one CTA per SM)
+      if (n > 0) SSR_MAC_LOAD(0, 0)
+      int i = 0;
+      for (; i + 1 < n; i += 2)
+      {
+        SSR_MAC_LOAD(1, i + 1)
+        SSR_MAC_FMA(0, i)
+        if (i + 2 < n) SSR_MAC_LOAD(0, i + 2)
+        SSR_MAC_FMA(1, i + 1)
+      }
+      if (i < n) SSR_MAC_FMA(0, i)
+    }
+    else
+    {
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; ++st)
+      if (st < n) SSR_MAC_LOAD(st, st)
+    for (int i = 0; i < n; i += STAGES)
+    {
+#pragma unroll
+      for (int st = 0; st < STAGES; ++st)
+      {
+        const int curi = i + st;
+        if (curi < n)
+        {
+          const int nxt = curi + STAGES - 1;
+          if (nxt < n) SSR_MAC_LOAD((st + STAGES - 1) % STAGES, nxt)
+          SSR_MAC_FMA(st, curi)
+        }
+      }
+    }
+    }
+#undef SSR_MAC_LOAD
+#undef SSR_MAC_FMA
+  }
+
+  // bin 0 holds (DC, Nyquist), both real products (convolver.h:510-541):
+  // acc.x = sum(xr*hr - xi*hi) -> DC = acc.x + nyq ; Nyquist = nyq
+  if (tt == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < MT; ++j)
+    {
+      acc[j][0].x += nyq[j];
+      acc[j][0].y = nyq[j];
+    }
+  }
+
+  float4* out = p.partials + size_t(wk.z + p.partial_offset) * MT * nvec;
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (valid[v]) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
+}
+
+// ---------------------------------------------------------------- MAC, bulk-copy staged
+// Variant of mac_kernel for the static (table-driven) plans at B >= 1024: a producer
+// warp streams the X tile and the MT H tiles of every term into a ring of STAGES
+// shared-memory stages with cp.async.bulk (the TMA unit's 1-D bulk copy) completing
+// on mbarriers; the 8 consumer warps read them back with LDS.128.  No registers are
+// spent on load staging and up to (STAGES - 1) x (1 + MT) x 8 KiB stay in flight per
+// SM however the consumers are scheduled.  Selected with ssr_engine_config::
+// mac_variant = 6 (4 stages) / 7 (5 stages); see profiles/ for the A/B.
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+  unsigned done;
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar,
+                                              uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+constexpr int kTmaThreads = kThreads + 32;     // 8 consumer warps + 1 producer warp
+constexpr int kTmaTileVec = 2 * kThreads;      // float4 per 1024-bin tile (8 KiB)
+constexpr int kTmaTileBytes = kTmaTileVec * 16;
+
+template<int MT, int STAGES>
+constexpr size_t mac_tma_smem_bytes()
+{
+  return size_t(STAGES) * (1 + MT) * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + 4) + 128;
+}
+
+template<int MT, int STAGES>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+mac_tma_kernel(const MacParams p)
+{
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ const float4* q_x[kMacTile];          // producer-private staging of a term tile
+  __shared__ const float4* q_h[kMacTile][MT];
+  __shared__ float q_w[kMacTile];
+  float4* buf = reinterpret_cast<float4*>(tma_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tma_smem + size_t(STAGES) * (1 + MT) * kTmaTileBytes);
+  uint64_t* empty = full + STAGES;
+  volatile float* stage_w = reinterpret_cast<volatile float*>(empty + STAGES);
+  volatile int* stage_end = reinterpret_cast<volatile int*>(const_cast<float*>(stage_w) + STAGES);
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int nvec = p.B >> 1;
+  const int tile_off = blockIdx.y * kTmaTileVec;   // B > 1024: blockIdx.y selects a 1024-bin tile
+
+  if (t == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  grid_dependency_wait();
+  const int4 wk = p.work[blockIdx.x];
+
+  if (t >= kThreads)
+  {
+    // ---- producer warp: resolve the terms tile by tile, then one lane feeds the ring
+    const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    int s = 0;
+    unsigned phase = 0;
+    for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+    {
+      const int tile_n = min(kMacTile, wk.y - tb);
+      int count = 0;
+      for (int base = 0; base < tile_n; base += 32)
+      {
+        const int i = base + lane;
+        bool ok = false;
+        MacTermMeta m; float w = 0.f;
+        if (i < tile_n)
+        {
+          m = p.term_meta[tb + i];
+          w = p.wtab[m.wslot + p.wtab_offset];
+          ok = (w != 0.0f);   // a muted source costs no traffic
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (ok)
+        {
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          const int parts = p.xparts[m.input];
+          int slot = p.heads[m.input] - m.p;
+          if (slot < 0) slot += parts;
+          q_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
+          q_w[pos] = w;
+#pragma unroll
+          for (int j = 0; j < MT; ++j) q_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+        }
+        count += __popc(mask);
+      }
+      __syncwarp();
+      if (lane == 0)
+      {
+        for (int i = 0; i < count; ++i)
+        {
+          mbar_wait(empty + s, phase ^ 1u);          // the consumers have released this stage
+          stage_w[s] = q_w[i];
+          stage_end[s] = 0;
+          mbar_arrive_expect_tx(full + s, (1 + MT) * kTmaTileBytes);
+          float4* dst = buf + size_t(s) * (1 + MT) * kTmaTileVec;
+          bulk_copy_g2s(dst, q_x[i] + tile_off, kTmaTileBytes, full + s, pol_x);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            bulk_copy_g2s(dst + size_t(1 + j) * kTmaTileVec, q_h[i][j] + tile_off, kTmaTileBytes, full + s, pol_h);
+          if (++s == STAGES) { s = 0; phase ^= 1u; }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0)
+    {
+      mbar_wait(empty + s, phase ^ 1u);
+      stage_end[s] = 1;                               // no more terms
+      mbar_arrive(full + s);
+    }
+    return;
+  }
+
+  // ---- consumer warps
+  float4 acc[MT][2];
+  float nyq[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+  {
+    nyq[j] = 0.0f;
+    acc[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int tt = tile_off + t;
+  int s = 0;
+  unsigned phase = 0;
+  while (true)
+  {
+    mbar_wait(full + s, phase);
+    if (stage_end[s]) break;
+    const float w = stage_w[s];
+    const float4* sb = buf + size_t(s) * (1 + MT) * kTmaTileVec;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+    {
+      float4 x = sb[t + v * kThreads];
+      x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+#pragma unroll
+      for (int j = 0; j < MT; ++j)
+      {
+        const float4 h = sb[size_t(1 + j) * kTmaTileVec + t + v * kThreads];
+        acc[j][v].x = fmaf(x.x, h.x, acc[j][v].x);
+        acc[j][v].x = fmaf(-x.y, h.y, acc[j][v].x);
+        acc[j][v].y = fmaf(x.x, h.y, acc[j][v].y);
+        acc[j][v].y = fmaf(x.y, h.x, acc[j][v].y);
+        acc[j][v].z = fmaf(x.z, h.z, acc[j][v].z);
+        acc[j][v].z = fmaf(-x.w, h.w, acc[j][v].z);
+        acc[j][v].w = fmaf(x.z, h.w, acc[j][v].w);
+        acc[j][v].w = fmaf(x.w, h.z, acc[j][v].w);
+        if (v == 0 && tt == 0) nyq[j] = fmaf(x.y, h.y, nyq[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);            // this warp is done with the stage
+    if (++s == STAGES) { s = 0; phase ^= 1u; }
+  }
+
+  // bin 0 holds (DC, Nyquist), both real products (convolver.h:510-541)
+  if (tt == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < MT; ++j) { acc[j][0].x += nyq[j]; acc[j][0].y = nyq[j]; }
+  }
+  float4* out = p.partials + size_t(wk.z + p.partial_offset) * MT * nvec;
+#pragma unroll
+  for (int j = 0; j < MT; ++j)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
+}
+
+}  // namespace ssrk

@@ -1,4 +1,4 @@
-// Unity translation unit: the kernels in kernels.cuh are defined once and every
+// Unity translation unit: the kernels (kernels.cuh and the headers it includes) are defined once and every
 // host file sees the same instantiations (one cubin, one set of symbols).
 #include "engine.cu"
 #include "renderer.cu"

@@ -11,7 +11,7 @@ Two implementations of that step:
   * connect_peer_gather(): the product path.  The root's gather buffer is mapped
     into every rank (CUDA IPC handle broadcast with torch.distributed); each
     rank's inverse-FFT kernel stores its output blocks straight into it over
-    NVLink peer memory and signals arrival (csrc/kernels.cuh GatherArgs), so no
+    NVLink peer memory and signals arrival (csrc/inverse.cuh GatherArgs), so no
     collective runs per block.
   * gather_outputs(): a plain torch.distributed gather (NCCL on GPUs, gloo in the
     CPU tests) -- the fallback when peer mapping is unavailable, and the A/B

@@ -6,7 +6,7 @@
 //  * MacPlan::make_work: every term of every group is covered exactly once by
 //    contiguous chunks, partial indices are unique, chunks are balanced;
 //  * the rule the dynamic renderers' device-side term generation rests on
-//    (kernels.cuh, DynTables): with the renderers' protocol (old state, rotate
+//    (mac.cuh, DynTables): with the renderers' protocol (old state, rotate
 //    while the queues are not empty, set_filter), in block b partition p uses the
 //    filter that was current in block b - p, the state before the switch is the
 //    previous block's state, and queues_empty() <=> b >= b_set + P;
