@@ -516,144 +516,6 @@ bool Engine::is_pinned(const void* p, size_t bytes)
   return pinned;
 }
 
-// ------------------------------------------------------------------ Gather
-Gather::Gather(Engine* e_, int world_, int rank_, int root_, const int* outputs_per_rank)
-  : e(e_), world(world_), rank(rank_), root(root_)
-{
-  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || root < 0 || root >= world || !outputs_per_rank)
-    throw Error(SSR_ERR_INVALID, "ssr_b200: gather: bad world / rank / root");
-  for (int g = 0; g < world; ++g)
-  {
-    if (outputs_per_rank[g] < 0) throw Error(SSR_ERR_INVALID, "ssr_b200: gather: negative output count");
-    firsts.push_back(M_total);
-    counts.push_back(outputs_per_rank[g]);
-    M_total += outputs_per_rank[g];
-  }
-  if (M_total == 0) throw Error(SSR_ERR_INVALID, "ssr_b200: gather: no outputs");
-  e->use_device();
-  d_error.resize(1);
-  SSR_CUDA(cudaMemset(d_error.ptr, 0, sizeof(int)));
-  if (is_root())
-  {
-    void* p = nullptr;
-    cudaError_t err = cudaMalloc(&p, total_bytes());
-    if (err != cudaSuccess)
-      throw Error(err == cudaErrorMemoryAllocation ? SSR_ERR_NOMEM : SSR_ERR_CUDA,
-          std::string("cudaMalloc (gather buffer): ") + cudaGetErrorString(err));
-    base = static_cast<unsigned char*>(p);
-    owns = true;
-    SSR_CUDA(cudaMemset(base, 0, total_bytes()));
-    std::vector<int> ctas(counts);
-    ctas[root] = 0;  // the root's own blocks are ordered by its stream
-    d_ctas.resize(world);
-    SSR_CUDA(cudaMemcpy(d_ctas.ptr, ctas.data(), world * sizeof(int), cudaMemcpyHostToDevice));
-  }
-}
-
-Gather::~Gather()
-{
-  cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
-  if (owns && base) cudaFree(base);
-  else if (ipc_mapped && base) cudaIpcCloseMemHandle(base);
-}
-
-void Gather::export_handle(void* handle64) const
-{
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  if (!is_root() || !base) throw Error(SSR_ERR_STATE, "ssr_b200: gather: only the root exports its buffer");
-  e->use_device();
-  cudaIpcMemHandle_t h;
-  SSR_CUDA(cudaIpcGetMemHandle(&h, base));
-  std::memcpy(handle64, &h, sizeof(h));
-}
-
-void Gather::import_handle(const void* handle64)
-{
-  if (is_root() || base) throw Error(SSR_ERR_STATE, "ssr_b200: gather: buffer already present");
-  e->use_device();
-  cudaIpcMemHandle_t h;
-  std::memcpy(&h, handle64, sizeof(h));
-  void* p = nullptr;
-  SSR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-  base = static_cast<unsigned char*>(p);
-  ipc_mapped = true;
-}
-
-void Gather::import_pointer(void* root_base, int root_device)
-{
-  if (is_root() || base) throw Error(SSR_ERR_STATE, "ssr_b200: gather: buffer already present");
-  if (!root_base) throw Error(SSR_ERR_INVALID, "ssr_b200: gather: null buffer");
-  e->use_device();
-  if (root_device != e->device)
-  {
-    int can = 0;
-    SSR_CUDA(cudaDeviceCanAccessPeer(&can, e->device, root_device));
-    if (!can) throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: gather: no peer access to the root device");
-    cudaError_t err = cudaDeviceEnablePeerAccess(root_device, 0);
-    if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-    else SSR_CUDA(err);
-  }
-  base = static_cast<unsigned char*>(root_base);
-}
-
-GatherArgs Gather::next_block()
-{
-  if (!base) throw Error(SSR_ERR_STATE, "ssr_b200: gather: buffer not connected (import the root's handle first)");
-  GatherArgs ga{};
-  const uint64_t t = epoch++;
-  // InvJob::out holds the offset of the output inside a slot (see Renderer)
-  ga.out_offset = (long long)((t & 1) * slot_floats());
-  ga.error = d_error.ptr;
-  if (!is_root())
-  {
-    ga.consumed = consumed_ptr();
-    ga.need_consumed = t >= 2 ? t - 1 : 0;   // block t-2 (same slot) released
-    ga.arrived = arrived_ptr(rank);
-  }
-  return ga;
-}
-
-const float* Gather::wait()
-{
-  if (!is_root()) throw Error(SSR_ERR_STATE, "ssr_b200: gather: only the root waits");
-  if (epoch == 0 || waited == epoch) throw Error(SSR_ERR_STATE, "ssr_b200: gather: no rendered block to wait for");
-  e->use_device();
-  const uint64_t t = epoch - 1;
-  if (world > 1)
-  {
-    GatherWaitArgs a{arrived_ptr(0), d_ctas.ptr, world, t, d_error.ptr};
-    gather_wait_kernel<<<1, 32, 0, e->stream>>>(a);
-    SSR_CUDA(cudaGetLastError());
-    e->count_launch();
-  }
-  waited = epoch;
-  return slot_ptr(int(t & 1));
-}
-
-void Gather::release(cudaStream_t s)
-{
-  if (!is_root()) throw Error(SSR_ERR_STATE, "ssr_b200: gather: only the root releases");
-  if (released == waited) return;
-  e->use_device();
-  released = waited;
-  if (world > 1)
-  {
-    gather_release_kernel<<<1, 1, 0, s ? s : e->stream>>>(consumed_ptr(), released);
-    SSR_CUDA(cudaGetLastError());
-    e->count_launch();
-  }
-}
-
-int Gather::status()
-{
-  e->use_device();
-  e->sync();
-  int flag = 0;
-  SSR_CUDA(cudaMemcpy(&flag, d_error.ptr, sizeof(int), cudaMemcpyDeviceToHost));
-  return flag;
-}
-
 void Engine::upload_weights(const float* w, size_t n)
 {
   if (n == 0) return;
