@@ -523,6 +523,7 @@ struct Renderer
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; int seen = 0; int kernels = 0; };
   GraphEntry graphs[2][8];             // [device-buffer slot][kind mask]
   bool use_graphs = true;
+  bool zero_copy = true;               // process(): inverse kernel stores into the caller's pinned array
   uint64_t graph_launches = 0;
   void drop_graphs();
   // level meters

@@ -77,6 +77,7 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   // apf::math::dB2linear (src/rendererbase.h:234-235)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
+  if (const char* v = std::getenv("SSR_B200_ZEROCOPY_OUT")) zero_copy = std::atoi(v) != 0;
   static_mac.MT = kGenericMT;
   for (auto& d : d_out) d.resize(size_t(std::max(m_local, 1)) * e->B);
   h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
@@ -841,6 +842,11 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   e->stats.h2d_bytes += uint64_t(N) * B * sizeof(float);
   e->stats.d2h_bytes += uint64_t(n_host_out) * B * sizeof(float);
   if (!done[slot]) SSR_CUDA(cudaEventCreateWithFlags(&done[slot], cudaEventDisableTiming));
+  // Synchronous call into the caller's page-locked output array: the inverse kernel
+  // stores its blocks straight into it (mapped host memory, posted PCIe writes that
+  // overlap the kernel) instead of a device buffer + D2H copy afterwards.
+  const bool zero_copy_out = zero_copy && !pipelined && !gather && slot_direct[slot];
+  if (zero_copy_out) dout = hout;
 
   const StepDesc d = prepare(din, dout);
   if (pipelined)
@@ -916,7 +922,7 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
     SSR_CUDA(cudaStreamWaitEvent(s_out, ev_k[slot], 0));
     copy_stream = s_out;
   }
-  if (out_floats)
+  if (out_floats && !zero_copy_out)
     SSR_CUDA(cudaMemcpyAsync(hout, src, out_floats * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
   if (gather && gather->is_root()) gather->release(copy_stream);   // after the slot has been read out
   SSR_CUDA(cudaEventRecord(done[slot], copy_stream));
