@@ -845,8 +845,13 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   // Synchronous call into the caller's page-locked output array: the inverse kernel
   // stores its blocks straight into it (mapped host memory, posted PCIe writes that
   // overlap the kernel) instead of a device buffer + D2H copy afterwards.
-  const bool zero_copy_out = zero_copy && !pipelined && !gather && slot_direct[slot];
-  if (zero_copy_out) dout = hout;
+  bool zero_copy_out = zero_copy && !pipelined && !gather && slot_direct[slot];
+  if (zero_copy_out)
+  {
+    void* mapped = nullptr;  // the device's view of the array (the same address under UVA)
+    if (cudaHostGetDevicePointer(&mapped, hout, 0) == cudaSuccess && mapped) dout = static_cast<float*>(mapped);
+    else { cudaGetLastError(); zero_copy_out = false; }
+  }
 
   const StepDesc d = prepare(din, dout);
   if (pipelined)
