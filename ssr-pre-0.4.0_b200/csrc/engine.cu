@@ -461,7 +461,6 @@ void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
 {
   const int njobs = int(plan.jobs.uploaded);
   if (njobs == 0) return;
-  const size_t smem = size_t(2) * B * sizeof(float2);
   // few output blocks with deep splits: reduce the partials in parallel first
   const int nentries = int(plan.entries.uploaded);
   int max_count = 0;

@@ -114,7 +114,7 @@ __device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* tile,
 __device__ __forceinline__ void fwd1024_warp(const FwdJob& job, float2* tile,
                                              const float2* __restrict__ tw, int lane)
 {
-  constexpr int B = 1024, half = 512;
+  constexpr int B = 1024;
   int new_head = 0;
   if (!job.dst)
   {

@@ -237,14 +237,14 @@ static void test_generic_sharded(const std::string& dir)
 {
   const int N = 3, M = 7, L = 150, TT = 8;
   const char* env = std::getenv("SSR_TEST_DEVICES");
-  for (const std::string devices : {std::string(env ? env : "0,0"), std::string("0,0,0")})
+  for (const std::string& devices : {std::string(env ? env : "0,0"), std::string("0,0,0")})
   {
     auto p = base_params();
     p.set("outputs", M);
     ssr::GenericRenderer whole(p);
     p.set("devices", devices);
     ssr::GenericRenderer sharded(p);
-    CHECK(sharded.shards() == (devices.size() + 1) / 2);
+    CHECK(sharded.shards() == int((devices.size() + 1) / 2));
     CHECK(sharded.out_channels() == M && whole.out_channels() == M);
     std::vector<std::vector<float>> irs(N);
     for (int n = 0; n < N; ++n)
