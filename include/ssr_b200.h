@@ -160,6 +160,12 @@ int ssr_filterset_lerp(ssr_filterset* dst, int dch, const ssr_filterset* a, int 
  * the zero flag. */
 int ssr_filterset_download(ssr_filterset* fs, int channel, int partition,
                            float* sorted_out, int* zero);
+/* The inverse: writes one partition spectrum given in the reference's layout, or
+ * (zero != 0, sorted_in may be NULL) sets its zero flag.  Load-time tooling: the
+ * C++ facade's transform_nested with an arbitrary host functor
+ * (apf/apf/convolver.h:773-817) is download -> functor -> upload. */
+int ssr_filterset_upload(ssr_filterset* fs, int channel, int partition,
+                         const float* sorted_in, int zero);
 
 /* ------------------------------------------- Level 1: apf::conv class API */
 

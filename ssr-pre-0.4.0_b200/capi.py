@@ -75,6 +75,7 @@ SIGNATURES = {
     "ssr_synth_uniform": (None, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_long, _f32p]),
     "ssr_filterset_lerp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float]),
     "ssr_filterset_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]),
+    "ssr_filterset_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]),
     "ssr_input_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "ssr_input_destroy": (None, [C.c_void_p]),
     "ssr_input_partitions": (C.c_int, [C.c_void_p]),

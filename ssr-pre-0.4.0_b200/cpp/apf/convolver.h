@@ -6,15 +6,17 @@
 //
 //   namespace apf::conv { min_partitions, Filter, Transform, Input, Output,
 //                         StaticOutput, Convolver, StaticConvolver,
-//                         transform_nested (lerp functor only) }
+//                         transform_nested }
 //
 // Deviations from the reference (all documented in INTEGRATION.md):
 //  * Filter does not expose host fft_node storage (spectra are device resident);
 //    Filter::download() returns a partition in the reference's sorted layout.
 //  * Transform::prepare_partition takes (first, last, filter, index) instead of
 //    a fft_node&.
-//  * transform_nested accepts apf::conv::lerp(t) -- the one functor the renderers
-//    use (src/binauralrenderer.h:372-377) -- not arbitrary host callables.
+//  * transform_nested with apf::conv::lerp(t) -- the one functor the renderers
+//    use (src/binauralrenderer.h:372-377) -- runs as a kernel; any other binary
+//    host callable works too, through a host round trip of the spectra (it is
+//    host code; a load-time operation in the reference as well).
 //  * block sizes must be powers of two in [8, 4096]; other multiples of 8 throw
 //    std::logic_error with a different message.
 //  * One engine per (device, block size) is created lazily; the device ordinal
@@ -356,10 +358,36 @@ struct lerp
   float t;
 };
 
-/// transform_nested (convolver.h:773-817) for the lerp functor
+/// transform_nested (convolver.h:773-817) for the lerp functor: one kernel
 inline void transform_nested(const Filter& in1, const Filter& in2, Filter& out, lerp f)
 {
   detail::check(ssr_filterset_lerp(out.handle(), 0, in1.handle(), 0, in2.handle(), 0, f.t));
+}
+
+/// transform_nested (convolver.h:773-817) for any binary host callable
+/// float(float, float): out[p] = f(in1[p], in2[p]) element by element, with the
+/// reference's zero-flag rules -- both inputs zero-flagged (or past their end) ->
+/// result zero-flagged; one of them -> f(x, 0) resp. f(0, x).  The spectra make a
+/// host round trip in the reference's layout (f is host code).
+template<typename BinaryFunction>
+void transform_nested(const Filter& in1, const Filter& in2, Filter& out, BinaryFunction f)
+{
+  if (in1.block_size() != out.block_size() || in2.block_size() != out.block_size())
+    throw std::logic_error("transform_nested: block sizes differ");
+  const size_t n = out.partition_size();
+  std::vector<float> a(n), b(n), r(n);
+  for (size_t p = 0; p < out.partitions(); ++p)
+  {
+    const bool zero1 = p >= in1.partitions() || in1.download(p, a.data());
+    const bool zero2 = p >= in2.partitions() || in2.download(p, b.data());
+    if (zero1 && zero2)
+    {
+      detail::check(ssr_filterset_upload(out.handle(), 0, int(p), nullptr, 1));
+      continue;
+    }
+    for (size_t i = 0; i < n; ++i) r[i] = f(zero1 ? 0.0f : a[i], zero2 ? 0.0f : b[i]);
+    detail::check(ssr_filterset_upload(out.handle(), 0, int(p), r.data(), 0));
+  }
 }
 
 }  // namespace conv

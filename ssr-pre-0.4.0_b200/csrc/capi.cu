@@ -175,6 +175,14 @@ int ssr_filterset_download(ssr_filterset* fs, int channel, int partition, float*
   });
 }
 
+int ssr_filterset_upload(ssr_filterset* fs, int channel, int partition, const float* sorted_in, int zero)
+{
+  return guarded([&] {
+    require(fs != nullptr, "filterset_upload: null argument");
+    fs->impl.upload(channel, partition, sorted_in, zero);
+  });
+}
+
 /* ----------------------------------------------------------------- Level 1 */
 
 int ssr_input_create(ssr_engine* e, int partitions, ssr_input** out)

@@ -748,6 +748,39 @@ static void packed_to_sorted(const float2* packed, int B, float* sorted)
   }
 }
 
+// the inverse mapping (filterset_upload)
+static void sorted_to_packed(const float* sorted, int B, float2* packed)
+{
+  for (int k = 0; k < B; ++k)
+  {
+    const int g = k >> 2, j = k & 3;
+    packed[k] = make_float2(sorted[8 * g + j], sorted[8 * g + 4 + j]);
+  }
+}
+
+// writes one partition spectrum given in the reference's layout (transform_nested
+// with a host functor, parity tooling); zero != 0 sets the zero flag instead
+void FilterSet::upload(int ch, int p, const float* sorted_in, int zero)
+{
+  if (ch < 0 || ch >= channels || p < 0 || p >= partitions || (!zero && !sorted_in))
+    throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_upload: bad arguments");
+  e->use_device();
+  flags_dirty = true;
+  if (zero) { flags[size_t(ch) * partitions + p] = 0; }
+  else
+  {
+    const int B = e->B;
+    std::vector<float2> tmp(B);
+    sorted_to_packed(sorted_in, B, tmp.data());
+    e->sync();  // kernels in flight may still read the partition
+    SSR_CUDA(cudaMemcpy(part(ch, p), tmp.data(), B * sizeof(float2), cudaMemcpyHostToDevice));
+    flags[size_t(ch) * partitions + p] = 1;
+  }
+  int v = 0;
+  for (int q = 0; q < partitions; ++q) if (flags[size_t(ch) * partitions + q]) v = q + 1;
+  valid[ch] = v;
+}
+
 void FilterSet::download(int ch, int p, float* sorted_out, int* zero)
 {
   if (ch < 0 || ch >= channels || p < 0 || p >= partitions)

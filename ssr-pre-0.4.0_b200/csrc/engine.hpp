@@ -268,6 +268,7 @@ struct FilterSet
                 const float* envelope, float scale);
   void lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t);
   void download(int ch, int p, float* sorted_out, int* zero);
+  void upload(int ch, int p, const float* sorted_in, int zero);
 };
 
 // pointer table + staggered switch queues of one dynamic Output

@@ -188,6 +188,32 @@ static void section_errors_and_extras()
   float* y = out.convolve(2.0f);
   float exp[8] = { 1.5f, 0.5f, 0, 0, 0, 0, 0, 0 };
   CHECK_RANGE(y, exp, 8);
+
+  // transform_nested with an arbitrary binary host callable (convolver.h:773-817):
+  // element-wise on the spectra, zero-flag rules for unequal lengths.  in1 has two
+  // partitions, in2 one, out three: partition 0 = f(a, b), partition 1 = f(a, 0),
+  // partition 2 is zero-flagged.  With the linear f(u, v) = 2u - 3v the result is
+  // the filter 2 * ha - 3 * hb.
+  float ha[16], hb[8];
+  for (int i = 0; i < 16; ++i) ha[i] = 0.01f * float(i + 1);
+  for (int i = 0; i < 8; ++i) hb[i] = 0.05f * float(8 - i);
+  c::Filter f1(8, ha, ha + 16), f2(8, hb, hb + 8), res(8, 3);
+  c::transform_nested(f1, f2, res, [](float u, float v) { return 2.0f * u - 3.0f * v; });
+  std::vector<float> spec(16);
+  CHECK(!res.download(0, spec.data()));
+  CHECK(!res.download(1, spec.data()));
+  CHECK(res.download(2, spec.data()));   // both inputs past their end -> zero flag
+  c::Input in2(8, 3);
+  c::StaticOutput out2(in2, res);
+  in2.add_block(x);                      // unit impulse -> the impulse response, block by block
+  float* y0 = out2.convolve();
+  float exp0[8], exp1[8];
+  for (int i = 0; i < 8; ++i) { exp0[i] = 2.0f * ha[i] - 3.0f * hb[i]; exp1[i] = 2.0f * ha[8 + i]; }
+  CHECK_RANGE(y0, exp0, 8);
+  float zeros[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  in2.add_block(zeros);
+  float* y1 = out2.convolve();
+  CHECK_RANGE(y1, exp1, 8);
 }
 
 int main()
