@@ -137,6 +137,103 @@ def golden_binaural():
     np.savez_compressed(os.path.join(HERE, "binaural.npz"), B=B, hrir=hrir, x=x, pos=pos, y=y)
 
 
+def golden_brs_dynamic():
+    """BRS: sources of different lengths (P = 1, 3, 5), one added and one removed while
+    the head turns in (almost) every block, processing switched off and on.  `channel`
+    records, per block, which input channel of x carries each live source (the
+    reference's pointer_policy keeps the channel index of a removed input)."""
+    rng = np.random.default_rng(424)
+    B, A, T, fs = 64, 10, 60, 48000
+    lengths = [40, 190, 300]
+    brirs = [decaying(rng, L, 2 * A, 0.05) for L in lengths]
+    r = ref.Renderer("brs", B, fs, threads=1)
+    r.load_reproduction_setup()
+    ids = []
+
+    def add(k):
+        ref.register_sndfile("gb", brirs[k], fs)
+        ids.append(r.add_source("gb"))
+        ref.unregister_sndfile("gb")
+
+    add(0); add(1)
+    r.activate()
+    live = [0, 1]
+    x = rng.uniform(-1, 1, (T, 3, B)).astype(np.float32)
+    y = np.zeros((T, 2, B), np.float32)
+    az = np.zeros(T, np.float32)
+    channel = np.full((T, 3), -1, np.int64)
+    a = 0.0
+    for t in range(T):
+        if t == 12:
+            add(2); live.append(2)
+        if t == 31:
+            r.rem_source(ids.pop(1)); live.pop(1)
+        if t == 45:
+            r.set_state("processing", 0)
+        if t == 50:
+            r.set_state("processing", 1)
+        if t < 40 or t % 3 == 0:
+            a += 360.0 / A + 3.0
+        az[t] = a
+        r.set_state("reference_orientation", a)
+        channel[t, :len(live)] = live
+        y[t] = r.process(x[t, :r.n_in])
+    pad = np.zeros((3, max(lengths), 2 * A), np.float32)
+    for k, b in enumerate(brirs):
+        pad[k, :b.shape[0]] = b
+    np.savez_compressed(os.path.join(HERE, "brs_dynamic.npz"), B=B, brirs=pad, lengths=np.array(lengths),
+                        x=x, az=az, y=y, channel=channel)
+
+
+def golden_binaural_multipartition():
+    """Binaural with HRIRs longer than the block (P = 4): moves arriving faster than the
+    staggered switch completes, a mute across a switch, a removal, a head turn."""
+    rng = np.random.default_rng(525)
+    B, L, A, N, T, fs = 64, 250, 16, 3, 64, 48000
+    hrir = decaying(rng, L, 2 * A, 0.5 / np.sqrt(L / 6.9))
+    ref.register_sndfile("gh", hrir, fs)
+    r = ref.Renderer("binaural", B, fs, threads=1, hrir_file="gh")
+    r.load_reproduction_setup()
+    ids = [r.add_source() for _ in range(N)]
+    r.activate()
+    live = list(range(N))
+    x = rng.uniform(-1, 1, (T, N, B)).astype(np.float32)
+    y = np.zeros((T, 2, B), np.float32)
+    pos = np.zeros((T, N, 2), np.float32)          # by ORIGINAL source index
+    mute = np.zeros((T, N), np.int64)
+    channel = np.full((T, N), -1, np.int64)
+    ref_az = np.zeros(T, np.float32)
+    cur = {0: (0.0, 2.0), 1: (1.5, -1.0), 2: (-2.0, 0.3)}
+    muted = {0: 0, 1: 0, 2: 0}
+    az = 0.0
+    for t in range(T):
+        if t == 40:
+            r.rem_source(ids.pop(0)); live.pop(0)
+        if 3 <= t < 18 or t in (25, 27, 44):
+            ang = t * 0.45
+            cur[live[-1]] = (2 * np.cos(ang), 2 * np.sin(ang))
+        if t == 8:
+            muted[1] = 1
+        if t == 10:
+            cur[1] = (0.3, 2.5)
+        if t == 13:
+            muted[1] = 0
+        if t == 50:
+            az = 200.0
+        for j, k in enumerate(live):
+            r.set_source(ids[j], "position", float(cur[k][0]), float(cur[k][1]))
+            r.set_source(ids[j], "mute", muted[k])
+        r.set_state("reference_orientation", az)
+        for k in range(N):
+            pos[t, k] = cur[k]; mute[t, k] = muted[k]
+        ref_az[t] = az
+        channel[t, :len(live)] = live
+        y[t] = r.process(x[t, :r.n_in])
+    ref.unregister_sndfile("gh")
+    np.savez_compressed(os.path.join(HERE, "binaural_multipartition.npz"), B=B, hrir=hrir, x=x, pos=pos, mute=mute,
+                        az=ref_az, y=y, channel=channel)
+
+
 def golden_hrirs_fabian():
     """Real-data fixture: the reference's shipped HRIR set
     (data/impulse_responses/hrirs/hrirs_fabian.wav, 720 ch x 512 frames, 44.1 kHz,
@@ -158,6 +255,8 @@ if __name__ == "__main__":
     golden_generic()
     golden_brs()
     golden_binaural()
+    golden_brs_dynamic()
+    golden_binaural_multipartition()
     golden_hrirs_fabian()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -88,6 +88,51 @@ def test_golden_binaural(capi, engine_factory):
         assert np.abs(r.process(g["x"][t]) - g["y"][t]).max() <= TOL
 
 
+def test_golden_brs_dynamic(capi, engine_factory):
+    """The reference's own BrsRenderer output for sources of unequal length added and
+    removed while the head turns (tests/golden/make_golden.py::golden_brs_dynamic):
+    exercises the device-side filter ring against the reference's switch queues."""
+    g = np.load(os.path.join(GOLDEN, "brs_dynamic.npz"))
+    e = engine_factory(int(g["B"]))
+    r = capi.Renderer(e, capi.BRS)
+    brirs = [g["brirs"][k, :int(g["lengths"][k])] for k in range(3)]
+    ids = [r.add_source(brirs[0]), r.add_source(brirs[1])]
+    for t in range(g["x"].shape[0]):
+        if t == 12:
+            ids.append(r.add_source(brirs[2]))
+        if t == 31:
+            r.rem_source(ids.pop(1))
+        if t == 45:
+            r.set_processing(False)
+        if t == 50:
+            r.set_processing(True)
+        r.set_reference_orientation(float(g["az"][t]))
+        live = [int(c) for c in g["channel"][t] if c >= 0]
+        assert np.abs(r.process(g["x"][t][live]) - g["y"][t]).max() <= TOL, t
+
+
+def test_golden_binaural_multipartition(capi, engine_factory):
+    """The reference's own BinauralRenderer output with HRIRs of four partitions
+    (golden_binaural_multipartition): overlapping staggered switches, a mute across a
+    switch, a removal."""
+    g = np.load(os.path.join(GOLDEN, "binaural_multipartition.npz"))
+    e = engine_factory(int(g["B"]))
+    r = capi.Renderer(e, capi.BINAURAL)
+    r.load_hrirs(g["hrir"])
+    N = g["x"].shape[1]
+    ids = [r.add_source() for _ in range(N)]
+    live = list(range(N))
+    for t in range(g["x"].shape[0]):
+        now = [int(c) for c in g["channel"][t] if c >= 0]
+        while len(live) > len(now):
+            r.rem_source(ids.pop(0)); live.pop(0)
+        for j, k in enumerate(live):
+            r.set_position(ids[j], float(g["pos"][t, k, 0]), float(g["pos"][t, k, 1]))
+            r.set_mute(ids[j], bool(g["mute"][t, k]))
+        r.set_reference_orientation(float(g["az"][t]))
+        assert np.abs(r.process(g["x"][t][now]) - g["y"][t]).max() <= TOL, t
+
+
 def test_golden_real_hrirs_fabian_spectra(capi, engine_factory):
     g = np.load(os.path.join(GOLDEN, "hrirs_fabian_4ch.npz"))
     B = int(g["B"])

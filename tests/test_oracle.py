@@ -215,6 +215,55 @@ def test_golden_binaural():
         assert np.abs(o.process(g["x"][t]) - g["y"][t]).max() <= TOL
 
 
+def _play_brs_dynamic(g, make, add, rem, set_az, set_processing, process):
+    """Replays tests/golden/brs_dynamic.npz (made by the reference itself) on any
+    implementation; returns the worst deviation from the reference's output."""
+    brirs = [g["brirs"][k, :int(g["lengths"][k])] for k in range(3)]
+    add(brirs[0]); add(brirs[1])
+    worst = 0.0
+    for t in range(g["x"].shape[0]):
+        if t == 12:
+            add(brirs[2])
+        if t == 31:
+            rem(1)
+        if t == 45:
+            set_processing(False)
+        if t == 50:
+            set_processing(True)
+        set_az(float(g["az"][t]))
+        live = [int(c) for c in g["channel"][t] if c >= 0]
+        worst = max(worst, float(np.abs(process(g["x"][t][live]) - g["y"][t]).max()))
+    return worst
+
+
+def test_golden_brs_dynamic():
+    g = np.load(os.path.join(GOLDEN, "brs_dynamic.npz"))
+    o = co.BrsRendererOracle(int(g["B"]))
+    worst = _play_brs_dynamic(
+        g, None, o.add_source, o.rem_source,
+        lambda a: setattr(o, "reference_orientation", a),
+        lambda v: setattr(o, "processing", v), o.process)
+    assert worst <= TOL, worst
+
+
+def test_golden_binaural_multipartition():
+    g = np.load(os.path.join(GOLDEN, "binaural_multipartition.npz"))
+    o = co.BinauralRendererOracle(int(g["B"]), g["hrir"])
+    N = g["x"].shape[1]
+    for _ in range(N):
+        o.add_source()
+    live = list(range(N))
+    for t in range(g["x"].shape[0]):
+        now = [int(c) for c in g["channel"][t] if c >= 0]
+        while len(live) > len(now):   # the fixture removes from the front
+            o.rem_source(0); live.pop(0)
+        for j, k in enumerate(live):
+            o.sources[j].position = (float(g["pos"][t, k, 0]), float(g["pos"][t, k, 1]))
+            o.sources[j].mute = bool(g["mute"][t, k])
+        o.reference_orientation = float(g["az"][t])
+        assert np.abs(o.process(g["x"][t][now]) - g["y"][t]).max() <= TOL
+
+
 def test_golden_real_hrirs_fabian_spectra():
     g = np.load(os.path.join(GOLDEN, "hrirs_fabian_4ch.npz"))
     assert int(g["channels"]) == 720 and int(g["frames"]) == 512 and int(g["fs"]) == 44100
