@@ -585,6 +585,30 @@ def main_ours(args):
             pipe_ms_total = max_over_ranks((time.perf_counter() - t_start) * 1e3)
         pipelined_value = (B / w.fs) / (pipe_ms_total / K * 1e-3)
 
+    # ---- OFFLINE rendering (reported separately): ssr_renderer_process_batch renders
+    # 4 consecutive blocks per pass over the filter spectra; host buffers, H2D/D2H inside
+    offline_value, offline_batched = None, 0
+    if world == 1 and w.kind == "generic" and B >= 1024:
+        TB = 4
+        def batch_ptrs(t0):
+            ins = (f32p * (TB * w.sources))(*[ctypes.cast(host_in[(t0 + t) % nring].data_ptr() + 4 * B * i, f32p)
+                                              for t in range(TB) for i in range(w.sources)])
+            return ins
+        host_out_b = torch.empty((TB, n_out_total, B), dtype=torch.float32).pin_memory()
+        outs_b = (f32p * (TB * n_out_total))(*[ctypes.cast(host_out_b.data_ptr() + 4 * B * (t * n_out_total + m), f32p)
+                                               for t in range(TB) for m in range(n_out_total)])
+        in_sets = [batch_ptrs(t0) for t0 in range(0, nring, TB)]
+        for nb in (max(2, W // TB), max(1, K // TB)):
+            torch.cuda.synchronize()
+            t_start = time.perf_counter()
+            for b in range(nb):
+                rc = lib.ssr_renderer_process_batch(ren.h, B, TB, in_sets[b % len(in_sets)], outs_b)
+                if rc != 0:
+                    raise RuntimeError(lib.ssr_last_error().decode())
+            off_ms = (time.perf_counter() - t_start) * 1e3
+        offline_value = (B / w.fs) * (nb * TB) / (off_ms * 1e-3)
+        offline_batched = ren.batched_blocks
+
     # ---- roofline of the MAC kernel (this rank)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -646,6 +670,10 @@ def main_ours(args):
             "e2e_pipelined": {"value": pipelined_value, "unit": UNIT,
                               "mode": "ssr_renderer_submit / ssr_renderer_wait, two blocks in flight "
                                       "(H2D | kernels | D2H on three streams), host buffers"},
+            "offline_batched": {"value": offline_value, "unit": UNIT, "blocks_through_the_batched_pass": offline_batched,
+                                "mode": "ssr_renderer_process_batch: 4 blocks per pass over the filter spectra "
+                                        "(every H tile read once for 4 time steps); NOT the real-time path, "
+                                        "reported separately (SURVEY 8d); host buffers"},
             "p99_block_ms": p99,
             "gpu_launches": launches,
             "roofline": roofline,

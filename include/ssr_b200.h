@@ -292,6 +292,19 @@ int ssr_renderer_get_levels(ssr_renderer* r, float* source_pre_fader, float* sou
  * when `out` is filled. */
 int ssr_renderer_process(ssr_renderer* r, int n, const float* const* in, float* const* out);
 
+/* OFFLINE rendering of `nblocks` consecutive blocks in one call (the use case of
+ * apf::mimoprocessor_file_io, apf/apf/mimoprocessor_file_io.h:40-117, where every
+ * input block is known in advance): in[t * sources + i] / out[t * outputs + m] are
+ * the channel pointers of block t.  Results are those of `nblocks` calls of
+ * ssr_renderer_process.  Runs of 4 blocks during which no control changes (Generic
+ * renderer, B >= 1024) are rendered by ONE pass over the filter spectra -- every H
+ * tile is read once for 4 time steps -- which is not possible in real time, where
+ * block t + 1 does not exist yet when block t is due.  Everything else
+ * falls back to ssr_renderer_process block by block.
+ * ssr_renderer_batched_blocks: how many blocks went through the batched pass. */
+int ssr_renderer_process_batch(ssr_renderer* r, int n, int nblocks, const float* const* in, float* const* out);
+int ssr_renderer_batched_blocks(const ssr_renderer* r, uint64_t* blocks);
+
 /* Same step on DEVICE buffers, asynchronous on the engine's stream: d_in is
  * sources x B floats, d_out is local_outputs x B floats (both contiguous).
  * Used by the multi-GPU driver, which owns the buffers and the NCCL gather. */

@@ -111,6 +111,8 @@ SIGNATURES = {
     "ssr_renderer_set_level_metering": (C.c_int, [C.c_void_p, C.c_int]),
     "ssr_renderer_get_levels": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "ssr_renderer_process": (C.c_int, [C.c_void_p, C.c_int, _pp, _pp]),
+    "ssr_renderer_process_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _pp, _pp]),
+    "ssr_renderer_batched_blocks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ssr_renderer_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_renderer_submit": (C.c_int, [C.c_void_p, C.c_int, _pp]),
     "ssr_renderer_wait": (C.c_int, [C.c_void_p, _pp]),
@@ -518,6 +520,25 @@ class Renderer:
         ins, outs = self._ptr_arrays(x, y)
         _check(lib().ssr_renderer_process(self.h, B, ins, outs))
         return y
+
+    def process_batch(self, x) -> np.ndarray:
+        """Offline: x (blocks, sources, B) -> (blocks, outputs, B); = `blocks` calls of
+        process(), runs of constant-control blocks sharing one pass over the filters."""
+        B = self.engine.block_size
+        x = _f32(x)
+        T, N = x.shape[0], x.shape[1]
+        M = self.host_outputs
+        y = np.empty((T, M, B), np.float32)
+        ins = (_f32p * max(1, T * N))(*[x[t, i].ctypes.data_as(_f32p) for t in range(T) for i in range(N)])
+        outs = (_f32p * max(1, T * M))(*[y[t, m].ctypes.data_as(_f32p) for t in range(T) for m in range(M)])
+        _check(lib().ssr_renderer_process_batch(self.h, B, T, ins, outs))
+        return y
+
+    @property
+    def batched_blocks(self) -> int:
+        v = C.c_uint64(0)
+        _check(lib().ssr_renderer_batched_blocks(self.h, C.byref(v)))
+        return int(v.value)
 
     def submit(self, x):
         B = self.engine.block_size

@@ -465,6 +465,20 @@ int ssr_renderer_process(ssr_renderer* r, int n, const float* const* in, float* 
   });
 }
 
+int ssr_renderer_process_batch(ssr_renderer* r, int n, int nblocks, const float* const* in, float* const* out)
+{
+  return guarded([&] {
+    require(r && out, "renderer_process_batch: null argument");
+    require(in || r->impl.sources.empty(), "renderer_process_batch: null input array");
+    r->impl.process_batch(n, nblocks, in, out);
+  });
+}
+
+int ssr_renderer_batched_blocks(const ssr_renderer* r, uint64_t* blocks)
+{
+  return guarded([&] { require(r && blocks, "null argument"); *blocks = r->impl.batched_blocks; });
+}
+
 int ssr_renderer_process_device(ssr_renderer* r, const float* d_in, float* d_out)
 {
   return guarded([&] {

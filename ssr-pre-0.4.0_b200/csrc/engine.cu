@@ -169,6 +169,8 @@ Engine::Engine(const ssr_engine_config& cfg)
   const size_t fft_smem = size_t(2) * B * sizeof(float2);
   if (mac_tma())
   {
+    SSR_CUDA(cudaFuncSetAttribute(mac_tma_batch_kernel<4, Input::kTimeBatch, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          int(mac_tma_batch_smem_bytes<4, Input::kTimeBatch, 3>())));
     SSR_CUDA(cudaFuncSetAttribute(mac_tma_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
           int(mac_tma_smem_bytes<4, 4>())));
     SSR_CUDA(cudaFuncSetAttribute(mac_tma_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -215,7 +217,7 @@ int Engine::register_input(Input* in)
   }
   inputs[id] = in;
   const float4* ring = reinterpret_cast<const float4*>(in->ring.ptr);
-  const int parts = in->P, zero = 0;
+  const int parts = in->slots, zero = 0;
   SSR_CUDA(cudaMemcpyAsync(d_xring.ptr + id, &ring, sizeof(ring), cudaMemcpyHostToDevice, stream));
   SSR_CUDA(cudaMemcpyAsync(d_xparts.ptr + id, &parts, sizeof(int), cudaMemcpyHostToDevice, stream));
   SSR_CUDA(cudaMemcpyAsync(d_heads.ptr + id, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -415,6 +417,32 @@ void Engine::launch_dyn_ring_update(const DynCtl* ctl, const DynRingEntry* upd, 
   if (rows <= 0) return;
   dyn_ring_update_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(ctl, upd, ring, rows, R);
   SSR_CUDA(cudaGetLastError());
+}
+
+void Engine::launch_mac_batch(const MacPlan& plan, int wtab_offset)
+{
+  const int nwork = int(plan.work.uploaded);
+  if (nwork == 0) return;
+  if (!mac_tma() || plan.MT != 4) throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: time-batched MAC needs the four-row bulk-copy plan (B >= 1024)");
+  MacParams p{};
+  p.term_meta = plan.meta.device();
+  p.term_h = plan.hptr.device();
+  p.work = plan.work.device();
+  p.wtab = wtab.device();
+  p.xring = d_xring.ptr;
+  p.xparts = d_xparts.ptr;
+  p.heads = d_heads.ptr;
+  p.partials = partials.ptr;
+  p.B = B;
+  p.wtab_offset = wtab_offset;
+  p.partial_offset = 0;
+  p.l2_hints = 1;
+  void* args[] = { &p };
+  dim3 grid(nwork, mac_ktiles(B), 1);
+  launch_mac_fn((void*)mac_tma_batch_kernel<4, Input::kTimeBatch, 3>, grid, args, kTmaThreads,
+      mac_tma_batch_smem_bytes<4, Input::kTimeBatch, 3>());
+  count_launch();
+  if (cur) cur->mac_launches++;
 }
 
 void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights)
@@ -887,15 +915,15 @@ bool FilterPtrTable::references(const float2* lo, const float2* hi) const
 
 // ------------------------------------------------------------------ Input
 Input::Input(Engine* e_, int partitions)
-  : e(e_), id(-1), P(partitions)
+  : e(e_), id(-1), P(partitions), slots(partitions + kTimeBatch - 1)
 {
   if (partitions <= 0) throw Error(SSR_ERR_INVALID, "ssr_b200: Input needs partitions > 0");
   e->use_device();
   const int B = e->B;
-  ring.resize(size_t(P) * B);
+  ring.resize(size_t(slots) * B);
   prev.resize(B); cur.resize(B);
   stage.resize(B);
-  SSR_CUDA(cudaMemsetAsync(ring.ptr, 0, size_t(P) * B * sizeof(float2), e->stream));
+  SSR_CUDA(cudaMemsetAsync(ring.ptr, 0, size_t(slots) * B * sizeof(float2), e->stream));
   SSR_CUDA(cudaMemsetAsync(prev.ptr, 0, B * sizeof(float), e->stream));
   id = e->register_input(this);
   job.host.assign(1, make_job(cur.ptr));
@@ -913,7 +941,7 @@ FwdJob Input::make_job(const float* d_cur)
   j.dst = nullptr;
   j.ring = ring.ptr;
   j.head = e->d_heads.ptr + id;
-  j.parts = P;
+  j.parts = slots;
   j.save_second = prev.ptr;
   j.level = nullptr;
   return j;
@@ -951,7 +979,7 @@ void Input::download(int p, float* sorted_out)
   e->sync();
   int head = 0;
   SSR_CUDA(cudaMemcpy(&head, e->d_heads.ptr + id, sizeof(int), cudaMemcpyDeviceToHost));
-  int slot = head - p; if (slot < 0) slot += P;
+  int slot = head - p; if (slot < 0) slot += slots;
   std::vector<float2> tmp(e->B);
   SSR_CUDA(cudaMemcpy(tmp.data(), ring.ptr + size_t(slot) * e->B, e->B * sizeof(float2), cudaMemcpyDeviceToHost));
   packed_to_sorted(tmp.data(), e->B, sorted_out);

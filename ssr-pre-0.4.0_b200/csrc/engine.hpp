@@ -174,6 +174,8 @@ struct Engine
   bool fft1024_always = false;
   bool pdl = true;                 // programmatic dependent launch of the MAC / reduce / inverse kernels
   void launch_mac_fn(void* fn, dim3 grid, void** args, int threads = ssrk::kThreads, size_t smem = 0);
+  // offline: kTimeBatch blocks per launch (mac_tma_batch_kernel); partials [CTA][t][row][B]
+  void launch_mac_batch(const MacPlan& plan, int wtab_offset);
   bool mac_tma() const;
   bool level1_fused = true;        // Level 1: one launch per convolve() for short term lists
   void launch_level1_fused(const ssrk::FusedParams& p);
@@ -327,7 +329,11 @@ struct Input
   ~Input();
   Engine* e;
   int id, P;
-  DeviceArray<float2> ring;          // [P][B]
+  // delay-line slots: P partitions + (kTimeBatch - 1) spare ones, so that the
+  // offline time-batched MAC can read kTimeBatch consecutive blocks' spectra
+  static constexpr int kTimeBatch = 4;
+  int slots;
+  DeviceArray<float2> ring;          // [slots][B]
   DeviceArray<float> prev, cur;      // B floats each
   PinnedArray<float> stage;
   Table<ssrk::FwdJob> job;
@@ -535,6 +541,17 @@ struct Renderer
   void get_levels(float* pre_fader, float* levels, float* outputs);
   void build_fwd(const float* d_input);
   void process(int n, const float* const* in, float* const* out);
+  // Offline: `nblocks` consecutive blocks (in[t * sources + i], out[t * outputs + m]);
+  // runs of Input::kTimeBatch blocks with constant controls go through the
+  // time-batched MAC, everything else through process()
+  void process_batch(int n, int nblocks, const float* const* in, float* const* out);
+  bool batch_eligible();
+  void run_batch(const float* const* in, float* const* out);
+  InvPlan inv_batch;
+  int inv_batch_key = -1;
+  DeviceArray<float> d_in_batch, d_out_batch;
+  PinnedArray<float> h_in_batch, h_out_batch;
+  uint64_t batched_blocks = 0;
   // multi-GPU: output blocks go to a Gather (not owned) instead of d_output
   Gather* gather = nullptr;
   void bind_gather(Gather* g);

@@ -539,4 +539,191 @@ mac_tma_kernel(const MacParams p)
     for (int v = 0; v < 2; ++v) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
 }
 
+// ---------------------------------------------------------------- MAC, time-batched (offline)
+// Offline rendering knows every input block in advance (apf::mimoprocessor_file_io).
+// TB consecutive blocks are then rendered per launch: every H tile is read ONCE and
+// multiplied with the TB delay-line spectra X[n, p] of the TB time steps, so the
+// H stream -- the whole cost of the streaming MAC -- is amortised over TB blocks
+// ("an offline batched mode may be reported separately"; it is not the
+// real-time path, where block t + 1 does not exist yet when block t is due).
+// Same producer / consumer structure as mac_tma_kernel; a stage holds the MT H tiles
+// and the TB X tiles of one term.  For time step t of the batch the term (n, p)
+// reads the delay-line slot of block (last - (TB - 1 - t)) - p, i.e. TB consecutive
+// slots; the ring therefore has TB - 1 spare slots (Input::slots).
+// Partials: [CTA][t][row][B].
+template<int MT, int TB, int STAGES>
+constexpr size_t mac_tma_batch_smem_bytes()
+{
+  return size_t(STAGES) * (TB + MT) * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + 4) + 128;
+}
+
+template<int MT, int TB, int STAGES>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+mac_tma_batch_kernel(const MacParams p)
+{
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ const float4* q_x[kMacTile][TB];
+  __shared__ const float4* q_h[kMacTile][MT];
+  __shared__ float q_w[kMacTile];
+  constexpr int kStageVec = (TB + MT) * kTmaTileVec;
+  float4* buf = reinterpret_cast<float4*>(tma_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tma_smem + size_t(STAGES) * (TB + MT) * kTmaTileBytes);
+  uint64_t* empty = full + STAGES;
+  volatile float* stage_w = reinterpret_cast<volatile float*>(empty + STAGES);
+  volatile int* stage_end = reinterpret_cast<volatile int*>(const_cast<float*>(stage_w) + STAGES);
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int nvec = p.B >> 1;
+  const int tile_off = blockIdx.y * kTmaTileVec;
+
+  if (t == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  grid_dependency_wait();
+  const int4 wk = p.work[blockIdx.x];
+
+  if (t >= kThreads)
+  {
+    const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    int s = 0;
+    unsigned phase = 0;
+    for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+    {
+      const int tile_n = min(kMacTile, wk.y - tb);
+      int count = 0;
+      for (int base = 0; base < tile_n; base += 32)
+      {
+        const int i = base + lane;
+        bool ok = false;
+        MacTermMeta m; float w = 0.f;
+        if (i < tile_n)
+        {
+          m = p.term_meta[tb + i];
+          w = p.wtab[m.wslot + p.wtab_offset];
+          ok = (w != 0.0f);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (ok)
+        {
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          const int parts = p.xparts[m.input];
+          const int head = p.heads[m.input];   // slot of the LAST block of the batch
+#pragma unroll
+          for (int ts = 0; ts < TB; ++ts)
+          {
+            int slot = head - (TB - 1 - ts) - m.p;
+            while (slot < 0) slot += parts;
+            q_x[pos][ts] = p.xring[m.input] + size_t(slot) * nvec;
+          }
+          q_w[pos] = w;
+#pragma unroll
+          for (int j = 0; j < MT; ++j) q_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+        }
+        count += __popc(mask);
+      }
+      __syncwarp();
+      if (lane == 0)
+      {
+        for (int i = 0; i < count; ++i)
+        {
+          mbar_wait(empty + s, phase ^ 1u);
+          stage_w[s] = q_w[i];
+          stage_end[s] = 0;
+          mbar_arrive_expect_tx(full + s, (TB + MT) * kTmaTileBytes);
+          float4* dst = buf + size_t(s) * kStageVec;
+#pragma unroll
+          for (int ts = 0; ts < TB; ++ts)
+            bulk_copy_g2s(dst + size_t(ts) * kTmaTileVec, q_x[i][ts] + tile_off, kTmaTileBytes, full + s, pol_x);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            bulk_copy_g2s(dst + size_t(TB + j) * kTmaTileVec, q_h[i][j] + tile_off, kTmaTileBytes, full + s, pol_h);
+          if (++s == STAGES) { s = 0; phase ^= 1u; }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0)
+    {
+      mbar_wait(empty + s, phase ^ 1u);
+      stage_end[s] = 1;
+      mbar_arrive(full + s);
+    }
+    return;
+  }
+
+  // ---- consumers: acc[time step][row][2 float4]
+  float4 acc[TB][MT][2];
+  float nyq[TB][MT];
+#pragma unroll
+  for (int ts = 0; ts < TB; ++ts)
+#pragma unroll
+    for (int j = 0; j < MT; ++j)
+    {
+      nyq[ts][j] = 0.0f;
+      acc[ts][j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[ts][j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  const int tt = tile_off + t;
+  int s = 0;
+  unsigned phase = 0;
+  while (true)
+  {
+    mbar_wait(full + s, phase);
+    if (stage_end[s]) break;
+    const float w = stage_w[s];
+    const float4* sb = buf + size_t(s) * kStageVec;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+    {
+      float4 h[MT];
+#pragma unroll
+      for (int j = 0; j < MT; ++j) h[j] = sb[size_t(TB + j) * kTmaTileVec + t + v * kThreads];
+#pragma unroll
+      for (int ts = 0; ts < TB; ++ts)
+      {
+        float4 x = sb[size_t(ts) * kTmaTileVec + t + v * kThreads];
+        x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+        {
+          acc[ts][j][v].x = fmaf(x.x, h[j].x, acc[ts][j][v].x);
+          acc[ts][j][v].x = fmaf(-x.y, h[j].y, acc[ts][j][v].x);
+          acc[ts][j][v].y = fmaf(x.x, h[j].y, acc[ts][j][v].y);
+          acc[ts][j][v].y = fmaf(x.y, h[j].x, acc[ts][j][v].y);
+          acc[ts][j][v].z = fmaf(x.z, h[j].z, acc[ts][j][v].z);
+          acc[ts][j][v].z = fmaf(-x.w, h[j].w, acc[ts][j][v].z);
+          acc[ts][j][v].w = fmaf(x.z, h[j].w, acc[ts][j][v].w);
+          acc[ts][j][v].w = fmaf(x.w, h[j].z, acc[ts][j][v].w);
+          if (v == 0 && tt == 0) nyq[ts][j] = fmaf(x.y, h[j].y, nyq[ts][j]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    if (++s == STAGES) { s = 0; phase ^= 1u; }
+  }
+
+  if (tt == 0)
+  {
+#pragma unroll
+    for (int ts = 0; ts < TB; ++ts)
+#pragma unroll
+      for (int j = 0; j < MT; ++j) { acc[ts][j][0].x += nyq[ts][j]; acc[ts][j][0].y = nyq[ts][j]; }
+  }
+  float4* out = p.partials + size_t(wk.z + p.partial_offset) * TB * MT * nvec;
+#pragma unroll
+  for (int ts = 0; ts < TB; ++ts)
+#pragma unroll
+    for (int j = 0; j < MT; ++j)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) out[(size_t(ts) * MT + j) * nvec + tt + v * kThreads] = acc[ts][j][v];
+}
+
 }  // namespace ssrk

@@ -770,6 +770,116 @@ static bool contiguous_pinned(Engine* e, const float* const* ptrs, int count, in
   return e->is_pinned(ptrs[0], size_t(count) * B * sizeof(float));
 }
 
+// ------------------------------------------------------------------ offline, time-batched
+// Would this block leave every source's weight as it is (and non-fading)?  Then
+// kTimeBatch such blocks can share one pass over the filter spectra.
+bool Renderer::batch_eligible()
+{
+  if (cfg.kind != SSR_RENDERER_GENERIC || gather || static_dirty || sources.empty()) return false;
+  if (!e->mac_tma() || static_mac.MT != kGenericMT || e->timing || metering) return false;
+  for (auto& sp : sources)
+  {
+    Source& s = *sp;
+    const float next = (!processing || s.mute) ? 0.0f : s.gain * master_volume * mvc;  // base_weight()
+    if (next != s.weighting_factor.get() || next != s.w.get() || s.w.changed()) return false;
+  }
+  return true;
+}
+
+void Renderer::run_batch(const float* const* in, float* const* out)
+{
+  constexpr int T = Input::kTimeBatch;
+  e->use_device();
+  const int N = int(sources.size());
+  const int B = e->B;
+  const size_t in_floats = size_t(T) * N * B, out_floats = size_t(T) * m_local * B;
+  if (d_in_batch.count < in_floats || d_out_batch.count < out_floats)
+  {
+    e->sync();
+    d_in_batch.resize(in_floats); h_in_batch.resize(in_floats);
+    d_out_batch.resize(out_floats); h_out_batch.resize(out_floats);
+    fwd_cache.clear();
+    inv_batch_key = -1;
+  }
+  for (int t = 0; t < T; ++t)
+    for (int i = 0; i < N; ++i)
+      std::memcpy(h_in_batch.ptr + (size_t(t) * N + i) * B, in[size_t(t) * N + i], B * sizeof(float));
+  SSR_CUDA(cudaMemcpyAsync(d_in_batch.ptr, h_in_batch.ptr, in_floats * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  e->stats.h2d_bytes += in_floats * sizeof(float);
+  e->stats.d2h_bytes += out_floats * sizeof(float);
+
+  // the per-block state updates of T constant blocks (src/genericrenderer.h:122-129)
+  wtab_host.assign(size_t(3) * N, 0.0f);
+  for (int t = 0; t < T; ++t)
+    for (int n = 0; n < N; ++n)
+    {
+      Source& s = *sources[n];
+      base_weight(s);
+      s.w.assign(s.weighting_factor.get());
+      s.mode = mode_from_weight(s.w);
+      wtab_host[n] = s.w.get();   // constant accumulator kind; zero weights are dropped by the kernel
+    }
+  e->upload_weights(wtab_host.data(), wtab_host.size());
+
+  // T forward transforms (each advances the delay line by one block)
+  for (int t = 0; t < T; ++t)
+  {
+    build_fwd(d_in_batch.ptr + size_t(t) * N * B);
+    e->launch_fwd(fwd->device(), N);
+  }
+  // one pass over the filter spectra for all T blocks
+  e->ensure_partials(size_t(static_mac.npartials) * T * static_mac.MT);
+  e->launch_mac_batch(static_mac, 0);
+  // T x outputs inverse transforms; partial layout [CTA][t][row]
+  const int key = static_mac.npartials * 131 + m_local;
+  if (inv_batch_key != key || (inv_batch.jobs.host.size() && inv_batch.jobs.host[0].out != d_out_batch.ptr))
+  {
+    inv_batch.clear();
+    const float scale = 1.0f / float(2 * B);
+    for (int t = 0; t < T; ++t)
+      for (int m = 0; m < m_local; ++m)
+      {
+        const int g = m / kGenericMT, row = m % kGenericMT;
+        const auto& grp = static_mac.groups[g];
+        inv_batch.entries.host.push_back({grp.partial_first, grp.nsplit, T * kGenericMT, t * kGenericMT + row, 0, scale});
+        inv_batch.jobs.host.push_back(InvJob{int(inv_batch.entries.host.size()) - 1, 1,
+            d_out_batch.ptr + (size_t(t) * m_local + m) * B, nullptr});
+      }
+    inv_batch.upload(e->stream);
+    inv_batch_key = key;
+  }
+  e->launch_inv(inv_batch);
+  SSR_CUDA(cudaMemcpyAsync(h_out_batch.ptr, d_out_batch.ptr, out_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  e->sync();
+  for (int t = 0; t < T; ++t)
+    for (int m = 0; m < m_local; ++m)
+      std::memcpy(out[size_t(t) * m_local + m], h_out_batch.ptr + (size_t(t) * m_local + m) * B, B * sizeof(float));
+  batched_blocks += T;
+}
+
+void Renderer::process_batch(int n, int nblocks, const float* const* in, float* const* out)
+{
+  if (outstanding) throw Error(SSR_ERR_STATE, "ssr_b200: process_batch() while submitted blocks are pending");
+  if (n != e->B) throw Error(SSR_ERR_INVALID, "ssr_b200: audio_callback: n != block size");
+  if (nblocks < 0) throw Error(SSR_ERR_INVALID, "ssr_b200: process_batch: negative block count");
+  const int N = int(sources.size());
+  const int n_out = gather ? (gather->is_root() ? M_total : 0) : m_local;
+  int t = 0;
+  while (t < nblocks)
+  {
+    if (nblocks - t >= Input::kTimeBatch && batch_eligible())
+    {
+      run_batch(in + size_t(t) * N, out + size_t(t) * n_out);
+      t += Input::kTimeBatch;
+    }
+    else
+    {
+      process(n, in + size_t(t) * N, out + size_t(t) * n_out);
+      t += 1;
+    }
+  }
+}
+
 void Renderer::invalidate_inv()
 {
   for (int i = 0; i < 2; ++i) { inv_keys[i] = -1; inv_plans[i].clear(); }

@@ -623,3 +623,50 @@ def test_generic_bulk_copy_staged_mac_variants(capi, co, engine_factory, variant
             r.set_mute(1, False); o.sources[0].mute = False
         worst = max(worst, maxerr(r.process(x), o.process(x)))
     assert worst <= TOL, worst
+
+
+@pytest.mark.parametrize("B", [1024, 2048])
+def test_offline_time_batched_blocks_equal_block_by_block(capi, co, engine_factory, B):
+    """ssr_renderer_process_batch: runs of 4 constant-control blocks share ONE pass over
+    the filter spectra (mac_tma_batch_kernel); the results are those of block-by-block
+    process() calls (and of the reference).  Fade-in, a gain change and a mute fall
+    back to single blocks in between."""
+    L, N, M = 3 * B + 100, 3, 6
+    rng = np.random.default_rng(B)
+    irs = [decaying(rng, L, M, 0.5 / np.sqrt(N * L / 6.9)) for _ in range(N)]
+    r1 = capi.Renderer(engine_factory(B), capi.GENERIC, outputs=M)
+    r2 = capi.Renderer(engine_factory(B), capi.GENERIC, outputs=M)
+    o = co.GenericRendererOracle(B, M)
+    for ir in irs:
+        r1.add_source(ir); r2.add_source(ir); o.add_source(ir)
+    x = rng.uniform(-1, 1, (27, N, B)).astype(np.float32)
+
+    class OracleControls:   # the same two setters on the oracle
+        def set_gain(self, sid, g): o.sources[sid - 1].gain = g
+        def set_mute(self, sid, m): o.sources[sid - 1].mute = m
+
+    def script(t, targets):
+        for r in targets:
+            if t == 11:
+                r.set_gain(2, 0.3)
+            if t == 20:
+                r.set_mute(1, True)
+
+    want, truth = [], []
+    for t in range(27):
+        script(t, (r1, OracleControls()))
+        want.append(r1.process(x[t]))
+        truth.append(o.process(x[t]))
+    got = []
+    for lo, hi in ((0, 11), (11, 20), (20, 27)):   # controls change between the calls
+        script(lo, (r2,))
+        got.extend(r2.process_batch(x[lo:hi]))
+    # a block is batchable once the block before it left every weight unchanged:
+    # 0 fade-in, 1 single, 2-9 batched, 10 single | 11 change, 12 single, 13-16 batched, 17-19 single |
+    # 20 fade-out, 21 single, 22-25 batched, 26 single
+    assert r2.batched_blocks == 8 + 4 + 4
+    assert r1.batched_blocks == 0
+    worst = max(float(np.abs(g - w).max()) for g, w in zip(got, want))
+    worst_truth = max(float(np.abs(g - w).max()) for g, w in zip(got, truth))
+    assert worst <= 2e-6, worst
+    assert worst_truth <= TOL, worst_truth
