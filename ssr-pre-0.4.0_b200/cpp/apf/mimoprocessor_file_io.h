@@ -89,6 +89,44 @@ int mimoprocessor_file_io(Processor& processor
       for (long i = 0; i < n; ++i) result[size_t(first + i) * nout + c] = out_ptrs[c][i];
   };
 
+  if (processor.batchable())
+  {
+    // Every block is known in advance: hand the engine chunks of blocks, so that runs of
+    // constant-control blocks share one pass over the filter spectra
+    // (ssr_renderer_process_batch; same results as block by block).
+    const long chunk = 16;
+    std::vector<std::vector<float>> ibuf(size_t(chunk) * nin, std::vector<float>(size_t(blocksize)));
+    std::vector<std::vector<float>> obuf(size_t(chunk) * nout, std::vector<float>(size_t(blocksize)));
+    std::vector<const float*> ip(ibuf.size());
+    std::vector<float*> op(obuf.size());
+    for (size_t i = 0; i < ibuf.size(); ++i) ip[i] = ibuf[i].data();
+    for (size_t i = 0; i < obuf.size(); ++i) op[i] = obuf[i].data();
+    for (long b0 = 0; b0 < blocks; b0 += chunk)
+    {
+      const long nb = std::min<long>(chunk, blocks - b0);
+      for (long k = 0; k < nb; ++k)
+      {
+        const long first = (b0 + k) * blocksize;
+        const long n = std::min<long>(blocksize, in.frames - first);
+        for (int c = 0; c < nin; ++c)
+        {
+          float* dst = ibuf[size_t(k) * nin + c].data();
+          for (long i = 0; i < n; ++i) dst[i] = in.data[size_t(first + i) * nin + c];
+          for (long i = n; i < blocksize; ++i) dst[i] = 0.0f;
+        }
+      }
+      processor.audio_callback_batch(int(blocksize), int(nb), ip.data(), op.data());
+      for (long k = 0; k < nb; ++k)
+      {
+        const long first = (b0 + k) * blocksize;
+        const long n = std::min<long>(blocksize, in.frames - first);
+        for (int c = 0; c < nout; ++c)
+          for (long i = 0; i < n; ++i) result[size_t(first + i) * nout + c] = obuf[size_t(k) * nout + c][i];
+      }
+    }
+  }
+  else
+  {
   // two blocks in flight: block b + 1 is copied and queued while block b computes
   // (through the processor, so that a renderer sharded over several devices works too)
   for (long b = 0; b < blocks; ++b)
@@ -105,6 +143,8 @@ int mimoprocessor_file_io(Processor& processor
   {
     processor.wait(out_ptrs.data());
     store_block(blocks - 1);
+  }
+
   }
 
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

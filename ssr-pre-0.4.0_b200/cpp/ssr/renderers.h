@@ -307,6 +307,8 @@ class RendererCore
     /// outputs audio_callback() delivers (all shards' outputs when sharded)
     int out_channels() const { return _gathers.empty() ? ssr_renderer_local_outputs(_r) : ssr_gather_total_outputs(_gathers[0]); }
     int shards() const { return 1 + int(_peer_r.size()); }
+    /// can audio_callback_batch() share passes over the filters between blocks?
+    bool batchable() const { return _peer_r.empty() && _kind == SSR_RENDERER_GENERIC && _block_size >= 1024; }
 
     /// f(renderer handle) on every shard (one shard unless "devices" lists several)
     template<typename F> void each(F f) { f(_r); for (auto r : _peer_r) f(r); }
@@ -322,6 +324,15 @@ class RendererCore
       for (auto r : _peer_r) check(ssr_renderer_submit(r, n, in));
       check(ssr_renderer_process(_r, n, in, out));
       for (auto r : _peer_r) check(ssr_renderer_wait(r, nullptr));
+    }
+
+    /// Offline: `nblocks` consecutive blocks in one call (in[t * in_channels() + i],
+    /// out[t * out_channels() + m]); runs of constant-control blocks share one pass
+    /// over the filter spectra (ssr_renderer_process_batch).  Unsharded renderers only.
+    void audio_callback_batch(int n, int nblocks, const float* const* in, float* const* out)
+    {
+      if (!_peer_r.empty()) throw std::logic_error("ssr_b200: audio_callback_batch on a sharded renderer");
+      check(ssr_renderer_process_batch(_r, n, nblocks, in, out));
     }
 
     /// Pipelined form of audio_callback (offline rendering): submit() queues a block
@@ -366,7 +377,7 @@ class RendererCore
     RendererCore(const apf::parameter_map& p, ssr_renderer_kind kind)
       : params(p), state(this)
       , _block_size(p.get<int>("block_size")), _sample_rate(p.get<int>("sample_rate"))
-      , _e(nullptr), _r(nullptr)
+      , _kind(kind), _e(nullptr), _r(nullptr)
     {
       // "devices": comma-separated CUDA ordinals, one output shard per entry
       std::vector<int> devices;
@@ -446,6 +457,7 @@ class RendererCore
     }
 
     const int _block_size, _sample_rate;
+    const ssr_renderer_kind _kind;
     ssr_engine* _e;
     ssr_renderer* _r;                       // the first (host-facing) shard
     std::vector<ssr_engine*> _peer_e;       // further shards ("devices")
