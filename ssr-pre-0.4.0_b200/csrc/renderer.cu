@@ -801,10 +801,17 @@ void Renderer::run_batch(const float* const* in, float* const* out)
     fwd_cache.clear();
     inv_batch_key = -1;
   }
-  for (int t = 0; t < T; ++t)
-    for (int i = 0; i < N; ++i)
-      std::memcpy(h_in_batch.ptr + (size_t(t) * N + i) * B, in[size_t(t) * N + i], B * sizeof(float));
-  SSR_CUDA(cudaMemcpyAsync(d_in_batch.ptr, h_in_batch.ptr, in_floats * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  // page-locked arrays laid out [t][channel][B] are used in place, like process() does
+  const float* hin = h_in_batch.ptr;
+  if (contiguous_pinned(e, in, T * N, B)) hin = in[0];
+  else
+    for (int t = 0; t < T; ++t)
+      for (int i = 0; i < N; ++i)
+        std::memcpy(h_in_batch.ptr + (size_t(t) * N + i) * B, in[size_t(t) * N + i], B * sizeof(float));
+  float* hout = h_out_batch.ptr;
+  const bool out_in_place = contiguous_pinned(e, out, T * m_local, B);
+  if (out_in_place) hout = out[0];
+  SSR_CUDA(cudaMemcpyAsync(d_in_batch.ptr, hin, in_floats * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->stats.h2d_bytes += in_floats * sizeof(float);
   e->stats.d2h_bytes += out_floats * sizeof(float);
 
@@ -849,11 +856,12 @@ void Renderer::run_batch(const float* const* in, float* const* out)
     inv_batch_key = key;
   }
   e->launch_inv(inv_batch);
-  SSR_CUDA(cudaMemcpyAsync(h_out_batch.ptr, d_out_batch.ptr, out_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  SSR_CUDA(cudaMemcpyAsync(hout, d_out_batch.ptr, out_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   e->sync();
-  for (int t = 0; t < T; ++t)
-    for (int m = 0; m < m_local; ++m)
-      std::memcpy(out[size_t(t) * m_local + m], h_out_batch.ptr + (size_t(t) * m_local + m) * B, B * sizeof(float));
+  if (!out_in_place)
+    for (int t = 0; t < T; ++t)
+      for (int m = 0; m < m_local; ++m)
+        std::memcpy(out[size_t(t) * m_local + m], h_out_batch.ptr + (size_t(t) * m_local + m) * B, B * sizeof(float));
   batched_blocks += T;
 }
 
