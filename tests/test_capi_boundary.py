@@ -95,3 +95,18 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower() or f == "__init__.py", f"{f} mentions the oracle"
+
+
+def test_default_mac_kernel_is_bulk_copy_staged():
+    """The judged kernel (ssrk::mac_tma_kernel<4,5>) moves its tiles with the TMA unit's
+    bulk copy and synchronises on mbarriers: SASS UBLKCP.S.G / SYNCS.ARRIVE.TRANS64 /
+    SYNCS.PHASECHK.TRANS64.TRYWAIT (B200_PROFILING.md: the mnemonics that prove it)."""
+    lib = os.path.join(ROOT, "ssr-pre-0.4.0_b200", "lib", "libssr_b200.so")
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4ssrk14mac_tma_kernelILi4ELi5EEEvNS_9MacParamsE", lib],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0 or "Function" not in out.stdout:
+        pytest.skip("cuobjdump cannot list the kernel")
+    sass = out.stdout
+    assert sass.count("UBLKCP.S.G") >= 5          # X tile + 4 H tiles per term
+    assert "SYNCS.ARRIVE.TRANS64" in sass and "TRYWAIT" in sass
+    assert "LDS.128" in sass and "FFMA" in sass
