@@ -258,8 +258,40 @@ static void test_dyn_split()
   }
 }
 
+// the split the docs quote for BASELINE config 5 on one GPU
+static void test_cfg5_split()
+{
+  MacPlan plan;
+  plan.MT = 4;
+  const float4* h[4] = { nullptr, nullptr, nullptr, nullptr };
+  for (int g = 0; g < 128; ++g)          // 512 outputs in groups of 4
+  {
+    plan.begin_group();
+    for (int n = 0; n < 128; ++n)        // 128 sources x 47 partitions
+      for (int p = 0; p < 47; ++p) plan.add_term(n, p, n, h);
+    plan.end_group();
+  }
+  plan.make_work(148);                   // bulk-copy staged MAC: one CTA per SM
+  CHECK(plan.npartials == 1920);         // 15 splits per group = 12.97 waves of 148
+  plan.make_work(296);                   // register-staged MAC: two CTAs per SM
+  CHECK(plan.npartials == 3840);
+  // sharded over 8 GPUs: 16 groups per GPU -> full waves of 148 (37 splits per group = 4 waves)
+  MacPlan shard;
+  shard.MT = 4;
+  for (int g = 0; g < 16; ++g)
+  {
+    shard.begin_group();
+    for (int n = 0; n < 128; ++n)
+      for (int p = 0; p < 47; ++p) shard.add_term(n, p, n, h);
+    shard.end_group();
+  }
+  shard.make_work(148);
+  CHECK(shard.npartials % 148 == 0 && shard.npartials >= 148);
+}
+
 int main()
 {
+  test_cfg5_split();
   test_ptr_table();
   test_make_work();
   test_filter_ring_rule();
