@@ -12,7 +12,7 @@ namespace ssr_b200
 using namespace ssrk;
 
 // ------------------------------------------------------------------ MacPlan
-void MacPlan::make_work(int slots)
+void MacPlan::make_work(int slots, int fixed_cost)
 {
   work.host.clear();
   npartials = 0;
@@ -23,7 +23,7 @@ void MacPlan::make_work(int slots)
   const long avg = std::max<long>(1, (total + G - 1) / G);
   // pick the split count S (per average group) that minimises
   //   waves(G*S) * (chunk length + fixed cost of a CTA in term units)
-  const long c0 = 2;
+  const long c0 = fixed_cost;  // cost of one more CTA, in units of one term
   long bestS = 1; double best = 1e300;
   const long Smax = std::min<long>(avg, 512);
   for (long S = 1; S <= Smax; ++S)
@@ -232,6 +232,15 @@ void Engine::unregister_input(int id)
 
 // bulk-copy (TMA) staged MAC for the four-row (Generic) plans at B >= 1024
 bool Engine::mac_tma() const { return (mac_variant == 0 || mac_variant == 6 || mac_variant == 7) && B >= 1024; }
+
+// Fixed cost of a CTA in units of one term, for MacPlan::make_work: staging and the
+// partial spectra it writes (and the inverse kernel sums); the bulk-copy kernel also
+// fills its 5-stage ring before the first FMA.  SSR_B200_SPLIT_COST overrides (experiments).
+int Engine::split_cost(int MT) const
+{
+  if (const char* v = std::getenv("SSR_B200_SPLIT_COST")) return std::max(0, std::atoi(v));
+  return (mac_tma() && MT == 4) ? kSplitCostTma : 2;
+}
 
 int Engine::mac_slots(int MT) const
 {
@@ -1026,7 +1035,7 @@ const float* Output::convolve(float weight)
     }
     else
     {
-      mac.make_work(e->mac_slots(mac.MT));
+      mac.make_work(e->mac_slots(mac.MT), e->split_cost(mac.MT));
       mac.upload(e->stream);
       e->ensure_partials(size_t(mac.npartials) * mac.MT);
       inv.entries.host.push_back({0, mac.groups[0].nsplit, 1, 0, 0, 1.0f / float(2 * B)});

@@ -149,7 +149,7 @@ struct MacPlan
   }
   void end_group() { groups.back().term_end = int(meta.host.size()); }
   // split every group's terms into equal chunks; `slots` = CTAs resident at once
-  void make_work(int slots);
+  void make_work(int slots, int fixed_cost = 2);
   void upload(cudaStream_t s) { meta.upload(s); hptr.upload(s); work.upload(s); }
 };
 
@@ -218,6 +218,8 @@ struct Engine
   void upload_weights(const float* w, size_t n);
   void ensure_partials(size_t npartial_spectra);
   int mac_slots(int MT) const;     // CTAs resident at once for the MAC kernel of MT-row plans
+  static constexpr int kSplitCostTma = 8;
+  int split_cost(int MT) const;    // see MacPlan::make_work
 
   // stats
   bool timing = false;

@@ -297,7 +297,7 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
       }
       static_mac.end_group();
     }
-    static_mac.make_work(e->mac_slots(static_mac.MT));
+    static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT));
     static_mac.upload(e->stream);
     e->ensure_partials(size_t(3) * static_mac.npartials * static_mac.MT);
     static_dirty = false;
@@ -620,7 +620,7 @@ Renderer::StepDesc Renderer::prepare_bank(const float* d_input, float* d_output)
       }
       static_mac.end_group();
     }
-    static_mac.make_work(e->mac_slots(static_mac.MT));
+    static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT));
     static_mac.upload(e->stream);
     e->ensure_partials(size_t(static_mac.npartials) * static_mac.MT);
     static_dirty = false;

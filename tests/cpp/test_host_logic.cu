@@ -271,11 +271,13 @@ static void test_cfg5_split()
       for (int p = 0; p < 47; ++p) plan.add_term(n, p, n, h);
     plan.end_group();
   }
-  plan.make_work(148);                   // bulk-copy staged MAC: one CTA per SM
-  CHECK(plan.npartials == 1920);         // 15 splits per group = 12.97 waves of 148
-  plan.make_work(296);                   // register-staged MAC: two CTAs per SM
+  plan.make_work(148, Engine::kSplitCostTma);  // bulk-copy staged MAC: one CTA per SM
+  CHECK(plan.npartials == 1024);         // 8 splits per group = 6.92 waves of 148
+  plan.make_work(148, 2);
+  CHECK(plan.npartials == 1920);         // (the split before the fixed cost was raised: 12.97 waves)
+  plan.make_work(296, 2);                // register-staged MAC: two CTAs per SM
   CHECK(plan.npartials == 3840);
-  // sharded over 8 GPUs: 16 groups per GPU -> full waves of 148 (37 splits per group = 4 waves)
+  // sharded over 8 GPUs: 16 groups per GPU -> one wave (9 splits per group)
   MacPlan shard;
   shard.MT = 4;
   for (int g = 0; g < 16; ++g)
@@ -285,8 +287,10 @@ static void test_cfg5_split()
       for (int p = 0; p < 47; ++p) shard.add_term(n, p, n, h);
     shard.end_group();
   }
-  shard.make_work(148);
-  CHECK(shard.npartials % 148 == 0 && shard.npartials >= 148);
+  shard.make_work(148, Engine::kSplitCostTma);
+  CHECK(shard.npartials == 144);
+  shard.make_work(148, 2);
+  CHECK(shard.npartials == 592);         // four waves, four pipeline fills and 4x the partials
 }
 
 int main()
