@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--outputs", type=int, default=0)
     ap.add_argument("--taps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the float64 parity phase (development only)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--mac-variant", type=int, default=0)
     ap.add_argument("--static-head", action="store_true", help="Binaural/BRS: no head rotation")
@@ -71,6 +72,9 @@ def parse_args():
     ap.add_argument("--no-stage-timing", action="store_true",
                     help="device-resident loop without any stage events; roofline is then taken from a "
                          "separate pass that does not count towards `value`")
+    ap.add_argument("--no-host-direct", action="store_true",
+                    help="N > 1: the host-buffer call delivers through the peer-memory gather + one D2H copy "
+                         "on rank 0 (the round-1 path) instead of the shared host segment (A/B)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: output blocks reach rank 0 by peer-memory stores fused into the "
                          "inverse kernel (default) or by an NCCL gather (A/B baseline)")
@@ -212,7 +216,7 @@ def run_reference_dynamic(w, n_sources: int, blocks: int, warm: int, threads: in
         r.load_reproduction_setup()
         for i in range(n_sources):
             sid = r.add_source()
-            a = 2 * np.pi * i / w.sources
+            a = 2 * np.pi * (i + 0.25) / w.sources   # same positions as the GPU arm
             r.set_source(sid, "position", float(2 * np.cos(a)), float(2 * np.sin(a)))
     r.activate()
     x = np.stack([wl.signal_block(w, t, n_sources) for t in range(4)])
@@ -337,6 +341,27 @@ def main_reference(args):
     return 0
 
 
+
+# ----------------------------------------------------------------- parity (outside every timed region)
+PARITY_TOL = 1e-5   # of full scale (BASELINE.json north_star)
+
+
+def parity_truth(x, irs):
+    """float64 FFT convolution: x (N, T) float32, irs[i] = list of N float32 IRs (one
+    per source) for sampled output i -> (len(irs), T) float64."""
+    from numpy.fft import irfft, rfft
+    N, T = x.shape
+    taps = max(len(h) for hs in irs for h in hs)
+    nfft = 1 << int(np.ceil(np.log2(T + taps)))
+    X = rfft(x.astype(np.float64), nfft, axis=1)
+    out = np.empty((len(irs), T))
+    for i, hs in enumerate(irs):
+        acc = np.zeros(nfft // 2 + 1, np.complex128)
+        for n, h in enumerate(hs):
+            acc += X[n] * rfft(np.asarray(h, np.float64), nfft)
+        out[i] = irfft(acc, nfft)[:T]
+    return out
+
 # ----------------------------------------------------------------- our arm
 def main_ours(args):
     import torch
@@ -404,7 +429,7 @@ def main_ours(args):
         ren.generate_hrirs(w.channels, w.taps, w.ir_seed, envelope=env, scale=scale)
         ids = [ren.add_source() for _ in range(w.sources)]
         for i, sid in enumerate(ids):  # sources on a 2 m circle around the listener
-            a = 2 * np.pi * i / w.sources
+            a = 2 * np.pi * (i + 0.25) / w.sources   # (+ 0.25: away from the filter-index rounding boundaries)
             ren.set_position(sid, float(2 * np.cos(a)), float(2 * np.sin(a)))
     else:
         raise SystemExit(f"workload kind {w.kind}: use ssr-pre-0.4.0_b200/lib/perf_static_convolver")
@@ -438,12 +463,39 @@ def main_ours(args):
     # NVLink.  Default: fused into the inverse kernel (peer-memory stores + arrival
     # counters, no collective per block); --gather nccl or a failed peer mapping:
     # NCCL gather after the inverse kernel.
-    peer = None
+    peer = hostg = None
     if world > 1 and args.gather == "peer":
-        peer = mg.connect_peer_gather(capi, eng, ren, w.outputs, world, rank, dev)
+        peer = mg.connect_peer_gather(capi, eng, ren, w.outputs, world, rank, dev)   # binds it
+        if peer is not None and not args.no_host_direct:
+            # the HOST-buffer call: every rank's inverse kernel stores its blocks into one
+            # shared page-locked host segment over its own PCIe link (csrc/hostgather.cu)
+            hostg = mg.connect_host_gather(capi, eng, w.outputs, world, rank, dev)
     gather_mode = "single GPU" if world == 1 else (
         "peer-memory stores fused into the inverse kernel (CUDA IPC over NVLink)" if peer is not None
         else "NCCL gather")
+    bound = ["peer" if peer is not None else None]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def bind(mode):
+        """Which exchange path the renderer delivers through: "peer" (device-resident and
+        pipelined runs) or "host" (the synchronous host-buffer call)."""
+        if mode == bound[0] or (mode == "host" and hostg is None) or (mode == "peer" and peer is None):
+            return
+        barrier()   # no rank rebinds while another one still renders
+        if bound[0] == "peer":
+            ren.bind_gather(None)
+        elif bound[0] == "host":
+            ren.bind_hostgather(None)
+        if mode == "peer":
+            ren.bind_gather(peer)
+        else:
+            ren.bind_hostgather(hostg)
+        bound[0] = mode
+        barrier()
 
     def gather():
         if world == 1:
@@ -471,19 +523,31 @@ def main_ours(args):
         in_ptr_sets.append((f32p * w.sources)(*[ctypes.cast(base + 4 * B * i, f32p) for i in range(w.sources)]))
     out_ptrs = (f32p * n_out_total)(*[ctypes.cast(host_out.data_ptr() + 4 * B * i, f32p)
                                       for i in range(n_out_total)])
+    # host-direct delivery: the root reads the blocks in place in the segment's two slots
+    slot_ptrs, slot_views = [None, None], [None, None]
+    if hostg is not None and rank == 0:
+        for sl in range(2):
+            a = hostg.slot_address(sl)
+            slot_ptrs[sl] = (f32p * n_out_total)(*[ctypes.cast(a + 4 * B * i, f32p) for i in range(n_out_total)])
+            slot_views[sl] = hostg.slot_array(sl)
     lib = capi.lib()
 
-    def step_e2e(t):
+    def host_block(in_ptrs, host_block_in):
+        """One block through the host-buffer path; returns rank 0's (outputs, B) result view."""
+        if bound[0] == "host":
+            sl = hostg.next_slot
+            rc = lib.ssr_renderer_process(ren.h, B, in_ptrs, slot_ptrs[sl] if rank == 0 else None)
+            if rc != 0:
+                raise RuntimeError(lib.ssr_last_error().decode())
+            return slot_views[sl]
         if world == 1 or peer is not None:
             # the reference-facing call on every rank; with the gather bound, rank 0's
             # `out` receives ALL outputs and the other ranks deliver none
-            control(t)
-            rc = lib.ssr_renderer_process(ren.h, B, in_ptr_sets[t % nring], out_ptrs)
+            rc = lib.ssr_renderer_process(ren.h, B, in_ptrs, out_ptrs)
             if rc != 0:
                 raise RuntimeError(lib.ssr_last_error().decode())
-            return
-        control(t)
-        d_in_step.copy_(host_in[t % nring], non_blocking=True)           # H2D (pinned)
+            return host_out.numpy()
+        d_in_step.copy_(host_block_in, non_blocking=True)               # H2D (pinned)
         ren.process_device(d_in_step.data_ptr(), d_out.data_ptr())
         gather()
         if rank == 0:
@@ -492,11 +556,93 @@ def main_ours(args):
             else:
                 host_out.copy_(d_out, non_blocking=True)                 # D2H
         torch.cuda.synchronize()
+        return host_out.numpy()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step_e2e(t):
+        control(t)
+        host_block(in_ptr_sets[t % nring], host_in[t % nring])
+
+    # ---- PARITY, before anything is timed: the first blocks of the workload's noise
+    # through the host-buffer path (at N > 1: through the output gather), sampled
+    # outputs from EVERY rank's shard against float64 FFT convolution of the
+    # host-regenerated IRs (truth independent of the engine and of the oracle).
+    parity = None
+    if not args.no_parity:
+        nb = w.partitions + 9
+        T = nb * B
+        x_all = np.stack([wl.synth_uniform(w.signal_seed, n, 0, T) for n in range(w.sources)])
+        par_in = torch.empty((w.sources, B), dtype=torch.float32).pin_memory()
+        par_ptrs = (f32p * w.sources)(*[ctypes.cast(par_in.data_ptr() + 4 * B * i, f32p) for i in range(w.sources)])
+        if w.kind == "generic":
+            per = w.outputs // world
+            outs = sorted({g * per + (7 * g + 3) % per for g in range(world)} | {0, w.outputs - 1})
+        else:
+            outs = [0, 1]
+        ndev_blocks = 4 if (world > 1 and peer is not None) else 0   # then through the device-buffer path
+        y = np.zeros((len(outs), T), np.float32)
+        control(0)
+        bind("host")
+        host_path = bound[0]
+        for t in range(nb - ndev_blocks):
+            par_in.copy_(torch.from_numpy(x_all[:, t * B:(t + 1) * B]))
+            res = host_block(par_ptrs, par_in)
+            if rank == 0:
+                y[:, t * B:(t + 1) * B] = res[outs]
+        if ndev_blocks:
+            # ... and the last blocks through ssr_renderer_process_device + the peer-memory
+            # gather (the path `value` times): rank 0 reads the gathered slot back
+            bind("peer")
+            cudart = ctypes.CDLL("libcudart.so.12")
+            par_dev = torch.empty((w.sources, B), dtype=torch.float32, device=dev)
+            slot_host = np.empty((n_out_total, B), np.float32)
+            for t in range(nb - ndev_blocks, nb):
+                par_dev.copy_(torch.from_numpy(x_all[:, t * B:(t + 1) * B]))
+                ren.process_device(par_dev.data_ptr(), d_out.data_ptr())
+                if rank == 0:
+                    ptr = peer.wait()
+                    torch.cuda.synchronize()
+                    rcm = cudart.cudaMemcpy(ctypes.c_void_p(slot_host.ctypes.data), ctypes.c_void_p(ptr),
+                                            ctypes.c_size_t(slot_host.nbytes), 2)
+                    assert rcm == 0, f"cudaMemcpy from the gather slot failed ({rcm})"
+                    peer.release()
+                    y[:, t * B:(t + 1) * B] = slot_host[outs]
+                barrier()
+        if rank == 0:
+            if w.kind == "generic":
+                irs = [[wl.synth_ir(w.ir_seed, n * w.outputs + m, w.taps, env, scale) for n in range(w.sources)]
+                       for m in outs]
+                gains = np.ones(w.sources)
+            elif w.kind == "brs":
+                # head at azimuth 0: index = size_t(wrap((0 - 90) * angles / 360 + 0.5, angles)) (src/brsrenderer.h:147-155)
+                idx = int(np.fmod(np.float32(-90.0) * np.float32(angles) / np.float32(360.0) + np.float32(0.5), angles) + angles) % angles
+                irs = [[wl.synth_ir(w.ir_seed, n * w.channels + 2 * idx + ear, w.taps, env, scale)
+                        for n in range(w.sources)] for ear in outs]
+                gains = np.ones(w.sources)
+            else:
+                # source i at 2 m, azimuth (i + 0.25) * 360 / N: weight 0.5 / 2, index = round(az * angles / 360)
+                # (src/binauralrenderer.h:273-314)
+                irs = []
+                for ear in outs:
+                    hs = []
+                    for i in range(w.sources):
+                        az = (i + 0.25) * 360.0 / w.sources
+                        idx = int(az * angles / 360.0 + 0.5) % angles
+                        hs.append(wl.synth_ir(w.ir_seed, 2 * idx + ear, w.taps, env, scale))
+                    irs.append(hs)
+                gains = np.full(w.sources, 0.25)
+            truth = parity_truth(x_all * gains[:, None].astype(np.float32), irs)
+            # block 0 is the fade-in from weight 0 (src/rendererbase.h:379); compare from block 1 on
+            err = float(np.abs(y[:, B:] - truth[:, B:]).max())
+            parity = {"max_err": err, "tolerance": PARITY_TOL, "ok": bool(err <= PARITY_TOL),
+                      "outputs_checked": [int(m) for m in outs], "blocks": nb,
+                      "truth_rms": float(truth[:, B:].std()),
+                      "path": (("ssr_renderer_process on every rank, "
+                                + ("host-direct delivery into the shared host segment" if host_path == "host"
+                                   else "peer-memory output gather bound")
+                                + f"; last {ndev_blocks} blocks: ssr_renderer_process_device + peer-memory gather")
+                               if (world > 1 and peer is not None)
+                               else ("process_device + NCCL gather" if world > 1 else "ssr_renderer_process")),
+                      "truth": "float64 FFT convolution of the workload's noise with the host-regenerated IRs"}
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -508,6 +654,7 @@ def main_ours(args):
     K, W = args.steps, max(args.warmup, 3)
 
     # ---- device-resident throughput (`value`)
+    bind("peer")
     for t in range(W):
         step_device(t)
     barrier()
@@ -541,7 +688,32 @@ def main_ours(args):
         st = eng.stats(reset=True)
         eng.set_timing(False)
 
+    # ---- L2-resident working sets (cfg4 sharded, cfg2): the same device-resident step with the
+    # L2 flushed before every step, each step timed with its own event pair (the flush is outside)
+    spectra_bytes = ((w.sources * m_local if w.kind == "generic" else
+                      (w.sources if w.kind == "brs" else 1) * w.channels) * w.partitions * 8 * B)
+    mac_read_bytes = (w.sources * m_local if w.kind == "generic" else w.sources * 2) * w.partitions * 8 * B
+    l2_resident = mac_read_bytes < 126e6
+    l2_cold = None
+    if l2_resident:
+        flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        nflush = min(K, 200)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nflush)]
+        barrier()
+        for t in range(nflush):
+            flush_buf.fill_(t & 0xff)
+            evs[t][0].record()
+            step_device(W + K + t)
+            evs[t][1].record()
+        barrier()
+        cold_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in evs])))
+        l2_cold = {"value": (B / w.fs) / (cold_ms * 1e-3), "unit": UNIT, "ms_per_step": cold_ms, "steps": nflush,
+                   "mode": "device-resident step after a 256 MB L2 flush, one CUDA-event pair per step"}
+        del flush_buf
+
     # ---- end to end through the host-buffer call (`e2e`), synchronous per block
+    bind("host")
+    e2e_path = bound[0]
     for t in range(W):
         step_e2e(t)
     barrier()
@@ -561,6 +733,7 @@ def main_ours(args):
     # t+1's H2D and block t-1's D2H overlap block t's kernels.  Reported next to `e2e`
     # (which stays the synchronous per-block call, the one that has a block latency).
     pipelined_value = None
+    bind("peer")
     if world == 1 or peer is not None:
         def submit(t):
             control(t)
@@ -637,7 +810,7 @@ def main_ours(args):
         "ifft_ms_per_step": st["ms_ifft"] / max(1, st["blocks"]),
         "fft_gflops": (w.sources * 56320 / 1e9) / max(1e-12, st["ms_fft"] / max(1, st["blocks"]) * 1e-3),
         "ifft_gflops": (m_local * 56320 / 1e9) / max(1e-12, st["ms_ifft"] / max(1, st["blocks"]) * 1e-3),
-        "l2_resident": bool(st["mac_bytes"] / max(1, st["mac_launches"]) < 100e6),
+        "l2_resident": bool(l2_resident),
     }
     line = None
     if rank == 0:
@@ -651,7 +824,11 @@ def main_ours(args):
                        "head_rotation": ("one filter step per block" if rotate else "none") if w.kind != "generic" else "n/a",
                        "outputs_per_gpu": m_local, "gather": gather_mode,
                        "stage_timing": ("separate pass" if args.no_stage_timing else
-                                        f"inside the timed region, every {args.stage_timing_every}th step"), "l2": "inputs>L2 (spectra per GPU >> 126 MB)",
+                                        f"inside the timed region, every {args.stage_timing_every}th step"),
+                       "l2": ("inputs>L2 (every step streams %.0f MB of spectra per GPU through the 126 MB L2)" % (mac_read_bytes / 1e6)
+                              if not l2_resident else
+                              "L2-RESIDENT: a step reads %.1f MB of spectra per GPU < 126 MB L2, so `value` is not an "
+                              "HBM figure; `l2_cold` is the same step after an L2 flush" % (mac_read_bytes / 1e6)),
                        "filter_load_s": load_s,
                        "spectra_gb_per_gpu": (w.sources * m_local if w.kind == "generic" else
                                               (w.sources if w.kind == "brs" else 1) * w.channels)
@@ -662,8 +839,12 @@ def main_ours(args):
                     "ms_per_step": e2e_ms_total / K,
                     "mode": ("ssr_renderer_process (C ABI, host channel pointers), synchronous per block"
                              if world == 1 else
-                             ("per rank: ssr_renderer_process (C ABI, host channel pointers) with the output "
-                              "gather bound; rank 0 receives all outputs; synchronous per block"
+                             (("per rank: ssr_renderer_process (C ABI, host channel pointers); every rank's inverse "
+                               "kernel stores its blocks into one shared page-locked host segment over its own PCIe "
+                               "link (host-direct), rank 0 returns when all flags are in; synchronous per block"
+                               if e2e_path == "host" else
+                               "per rank: ssr_renderer_process (C ABI, host channel pointers) with the peer-memory output "
+                               "gather bound; rank 0 receives all outputs (one D2H copy); synchronous per block")
                               if peer is not None else
                               "per rank: pinned H2D -> ssr_renderer_process_device -> NCCL gather -> D2H on "
                               "rank 0, synchronous per block"))},
@@ -678,6 +859,8 @@ def main_ours(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "clocks": clocks,
+            "parity": parity,
+            "l2_cold": l2_cold,
         }
 
     # ---- CPU baseline (rank 0, N = 1 only)
@@ -696,16 +879,23 @@ def main_ours(args):
         peer.check()   # a timed-out wait would have produced garbage: fail loudly
     if rank == 0:
         print(json.dumps(line))
+    rc = 0
+    if rank == 0 and parity is not None and not parity["ok"]:
+        print(f"bench.py: PARITY FAILED: max |gpu - float64 truth| = {parity['max_err']:.3e} > {PARITY_TOL}",
+              file=sys.stderr)
+        rc = 3
     if world > 1:
         dist.barrier()  # the root's gather buffer outlives every peer's last store
     ren.close()
+    if hostg is not None:
+        hostg.close()
     if peer is not None:
         peer.close()
     eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

@@ -54,6 +54,7 @@ typedef struct ssr_input ssr_input;
 typedef struct ssr_output ssr_output;
 typedef struct ssr_renderer ssr_renderer;
 typedef struct ssr_gather ssr_gather;
+typedef struct ssr_hostgather ssr_hostgather;
 
 const char* ssr_last_error(void);
 int ssr_abi_version(void);
@@ -344,8 +345,20 @@ int ssr_renderer_local_outputs(const ssr_renderer* r);
  * With ssr_renderer_process_device() (d_out ignored) the root calls
  * ssr_gather_wait() -> device pointer to total_outputs x B floats of this
  * block, valid until ssr_gather_release(), both stream-ordered; the root must
- * release every block (peers wait for it, with a 20 s time-out that sets a
- * sticky error reported by ssr_gather_status()). */
+ * release every block (peers wait for it).
+ *
+ * Failure behaviour: every device-side wait gives up after 20 s
+ * (SSR_B200_GATHER_TIMEOUT_MS overrides).  A peer that times out stores nothing;
+ * the rank that timed out keeps a sticky flag, and from then on
+ * ssr_renderer_process / ssr_renderer_wait on that rank return SSR_ERR_STATE
+ * instead of delivering a stale block (ssr_gather_status() reports the same flag).
+ *
+ * One rank per device is the deployment shape.  Ranks that SHARE a device and
+ * are driven by ONE host thread (single-GPU test rigs) must queue the root's
+ * block last: the root's wait kernel spins on the device, and a peer's host
+ * work that synchronises the device (a growing table) would otherwise wait for
+ * it.  The host-direct path below (ssr_hostgather_*) never spins on a device
+ * and has no such rule. */
 #define SSR_GATHER_HANDLE_BYTES 64
 int ssr_gather_create(ssr_engine* e, int world, int rank, int root, const int* outputs_per_rank,
                       ssr_gather** out);
@@ -358,6 +371,40 @@ int ssr_gather_wait(ssr_gather* g, const float** d_block);
 int ssr_gather_release(ssr_gather* g);
 int ssr_gather_status(ssr_gather* g);  /* SSR_OK, or SSR_ERR_STATE after a time-out (synchronises) */
 int ssr_gather_total_outputs(const ssr_gather* g);
+
+/* ------------------------------------------------------------------------
+ * Host-direct output delivery for a sharded renderer (the HOST-buffer call).
+ *
+ * In the reference every Output item writes the caller's host channel itself
+ * (apf/apf/pointer_policy.h:112-122, apf/apf/mimoprocessor.h:452-483).  The
+ * same holds here across GPUs: all ranks map ONE page-locked POSIX shared-memory
+ * segment ("/name", created by the root) and rank g's inverse kernel stores its
+ * output blocks straight into it over that GPU's own PCIe link; the CTA that
+ * finishes last publishes the rank's flag behind the data.  No GPU waits for
+ * another GPU, nothing funnels through the root's device, and no D2H copy runs.
+ *
+ *   every rank: ssr_hostgather_create(e, world, rank, root, counts, "/name", &g)
+ *               (peers wait up to the time-out for the root's segment to appear)
+ *               ssr_renderer_bind_hostgather(renderer, g)
+ *   per block:  ssr_renderer_process(r, n, in, out) on every rank.  On the root
+ *               it returns once every rank's blocks of this block have landed;
+ *               `out` has one pointer per output of the WHOLE renderer.  When
+ *               out[m] == slot + m * B with slot = ssr_hostgather_slot(g,
+ *               ssr_hostgather_next_slot(g)) the caller reads the blocks in place
+ *               (no copy at all); any other pointers receive a host memcpy.  On
+ *               the other ranks `out` is ignored (may be NULL).
+ * Two slots alternate by block parity: a slot's blocks stay valid until the
+ * root's second-next ssr_renderer_process.  A rank that waits longer than the
+ * time-out (20 s, SSR_B200_GATHER_TIMEOUT_MS) fails its call with SSR_ERR_STATE.
+ * ssr_renderer_process_device / submit / wait are not served by this path (they
+ * use the peer-memory gather above). */
+int ssr_hostgather_create(ssr_engine* e, int world, int rank, int root, const int* outputs_per_rank,
+                          const char* shm_name, ssr_hostgather** out);
+void ssr_hostgather_destroy(ssr_hostgather* g);
+int ssr_renderer_bind_hostgather(ssr_renderer* r, ssr_hostgather* g /* NULL: unbind */);
+int ssr_hostgather_total_outputs(const ssr_hostgather* g);
+int ssr_hostgather_slot(ssr_hostgather* g, int slot /* 0 | 1 */, float** host_blocks);
+int ssr_hostgather_next_slot(const ssr_hostgather* g);
 
 #ifdef __cplusplus
 }

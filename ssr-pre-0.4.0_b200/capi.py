@@ -127,6 +127,13 @@ SIGNATURES = {
     "ssr_gather_release": (C.c_int, [C.c_void_p]),
     "ssr_gather_status": (C.c_int, [C.c_void_p]),
     "ssr_gather_total_outputs": (C.c_int, [C.c_void_p]),
+    "ssr_hostgather_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_char_p,
+                                        C.POINTER(C.c_void_p)]),
+    "ssr_hostgather_destroy": (None, [C.c_void_p]),
+    "ssr_renderer_bind_hostgather": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_hostgather_total_outputs": (C.c_int, [C.c_void_p]),
+    "ssr_hostgather_slot": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_f32p)]),
+    "ssr_hostgather_next_slot": (C.c_int, [C.c_void_p]),
 }
 GATHER_HANDLE_BYTES = 64
 
@@ -414,6 +421,50 @@ class Gather:
         self.close()
 
 
+class HostGather:
+    """Host-direct output delivery of a sharded renderer (include/ssr_b200.h): every
+    rank's inverse kernel stores its blocks into one shared, page-locked host segment."""
+
+    def __init__(self, engine: Engine, world: int, rank: int, outputs_per_rank: Sequence[int], name: str,
+                 root: int = 0):
+        self.engine = engine
+        self.world, self.rank, self.root = world, rank, root
+        counts = (C.c_int * world)(*[int(c) for c in outputs_per_rank])
+        h = C.c_void_p()
+        _check(lib().ssr_hostgather_create(engine.h, world, rank, root, counts, name.encode(), C.byref(h)))
+        self.h = h
+        engine._adopt(self, "ssr_hostgather_destroy")
+
+    @property
+    def is_root(self) -> bool:
+        return self.rank == self.root
+
+    @property
+    def total_outputs(self) -> int:
+        return lib().ssr_hostgather_total_outputs(self.h)
+
+    @property
+    def next_slot(self) -> int:
+        return lib().ssr_hostgather_next_slot(self.h)
+
+    def slot_address(self, slot: int) -> int:
+        p = _f32p()
+        _check(lib().ssr_hostgather_slot(self.h, slot, C.byref(p)))
+        return C.cast(p, C.c_void_p).value
+
+    def slot_array(self, slot: int) -> np.ndarray:
+        """(total_outputs, B) float32 view of a slot of the shared segment (no copy)."""
+        p = _f32p()
+        _check(lib().ssr_hostgather_slot(self.h, slot, C.byref(p)))
+        return np.ctypeslib.as_array(p, shape=(self.total_outputs, self.engine.block_size))
+
+    def close(self):
+        self.engine._release(self, "ssr_hostgather_destroy")
+
+    def __del__(self):
+        self.close()
+
+
 class Renderer:
     def __init__(self, engine: Engine, kind: int, outputs: int = 2, output_first: int = 0,
                  output_count: int = 0, master_volume_correction_db: float = 0.0):
@@ -438,12 +489,32 @@ class Renderer:
         _check(lib().ssr_renderer_bind_gather(self.h, gather.h if gather is not None else None))
         self.gather = gather
 
+    def bind_hostgather(self, hg: Optional["HostGather"]):
+        """Multi-GPU, host-buffer call: blocks go straight into the shared host segment."""
+        _check(lib().ssr_renderer_bind_hostgather(self.h, hg.h if hg is not None else None))
+        self.gather = hg
+
     @property
     def host_outputs(self) -> int:
         """Output blocks process()/wait() deliver on this rank."""
         if self.gather is None:
             return self.local_outputs
         return self.gather.total_outputs if self.gather.is_root else 0
+
+    def process_in_place(self, x) -> np.ndarray:
+        """Root of a host-direct gather: renders the block and returns a VIEW of the
+        segment's slot (valid until the second-next call); other ranks: empty array."""
+        B = self.engine.block_size
+        x = _f32(x).reshape(-1, B)
+        ins = (_f32p * max(1, x.shape[0]))(*[x[i].ctypes.data_as(_f32p) for i in range(x.shape[0])])
+        hg = self.gather
+        if not hg.is_root:
+            _check(lib().ssr_renderer_process(self.h, B, ins, None))
+            return np.empty((0, B), np.float32)
+        y = hg.slot_array(hg.next_slot)
+        outs = (_f32p * y.shape[0])(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
+        _check(lib().ssr_renderer_process(self.h, B, ins, outs))
+        return y
 
     @property
     def n_sources(self) -> int:

@@ -13,6 +13,7 @@ struct ssr_filterset { FilterSet impl; ssr_filterset(Engine* e, int c, int p) : 
 struct ssr_input { Input impl; ssr_input(Engine* e, int p) : impl(e, p) {} };
 struct ssr_output { Output impl; ssr_output(Input* i, ssr_output_kind k) : impl(i, k) {} };
 struct ssr_gather { Gather impl; ssr_gather(Engine* e, int w, int r, int root, const int* c) : impl(e, w, r, root, c) {} };
+struct ssr_hostgather { HostGather impl; ssr_hostgather(Engine* e, int w, int r, int root, const int* c, const char* n) : impl(e, w, r, root, c, n) {} };
 struct ssr_renderer { Renderer impl; ssr_renderer(Engine* e, const ssr_renderer_config& c) : impl(e, c) {} };
 
 namespace
@@ -459,7 +460,7 @@ int ssr_renderer_process(ssr_renderer* r, int n, const float* const* in, float* 
   return guarded([&] {
     require(r != nullptr, "renderer_process: null argument");
     // a non-root rank of a gather delivers no output blocks: out may be null there
-    require(out || (r->impl.gather && !r->impl.gather->is_root()), "renderer_process: null output array");
+    require(out || r->impl.host_outputs() == 0, "renderer_process: null output array");
     require(in || r->impl.sources.empty(), "renderer_process: null input array");
     r->impl.process(n, in, out);
   });
@@ -496,7 +497,7 @@ int ssr_renderer_wait(ssr_renderer* r, float* const* out)
 {
   return guarded([&] {
     require(r != nullptr, "renderer_wait: null argument");
-    require(out || (r->impl.gather && !r->impl.gather->is_root()), "renderer_wait: null output array");
+    require(out || r->impl.host_outputs() == 0, "renderer_wait: null output array");
     r->impl.wait(out);
   });
 }
@@ -564,5 +565,37 @@ int ssr_gather_status(ssr_gather* g)
 }
 
 int ssr_gather_total_outputs(const ssr_gather* g) { return g ? g->impl.M_total : 0; }
+
+/* ------------------------------------------------------------- hostgather */
+
+int ssr_hostgather_create(ssr_engine* e, int world, int rank, int root, const int* outputs_per_rank,
+                          const char* shm_name, ssr_hostgather** out)
+{
+  return guarded([&] {
+    require(e && out && shm_name, "hostgather_create: null argument");
+    *out = nullptr;
+    *out = new ssr_hostgather(&e->impl, world, rank, root, outputs_per_rank, shm_name);
+  });
+}
+
+void ssr_hostgather_destroy(ssr_hostgather* g) { delete g; }
+
+int ssr_renderer_bind_hostgather(ssr_renderer* r, ssr_hostgather* g)
+{
+  return guarded([&] { require(r, "null renderer"); r->impl.bind_hostgather(g ? &g->impl : nullptr); });
+}
+
+int ssr_hostgather_total_outputs(const ssr_hostgather* g) { return g ? g->impl.M_total : 0; }
+
+int ssr_hostgather_slot(ssr_hostgather* g, int slot, float** host_blocks)
+{
+  return guarded([&] {
+    require(g && host_blocks, "hostgather_slot: null argument");
+    require(slot == 0 || slot == 1, "hostgather_slot: slot must be 0 or 1");
+    *host_blocks = g->impl.slot_ptr(slot);
+  });
+}
+
+int ssr_hostgather_next_slot(const ssr_hostgather* g) { return g ? int(g->impl.epoch & 1) : 0; }
 
 }  // extern "C"

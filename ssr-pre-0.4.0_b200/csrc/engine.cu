@@ -517,7 +517,7 @@ void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
   if (cur) cur->ifft_launches++;
     red = reinterpret_cast<const float2*>(reduced.ptr);
   }
-  const bool gathering = ga.out_offset != 0 || ga.consumed || ga.arrived;
+  const bool gathering = ga.out_offset != 0 || ga.consumed || ga.arrived || ga.host_flag;
   if (fft1024 && !gathering && (njobs >= kFft1024MinJobs || fft1024_always))
   {
     const int ctas = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;

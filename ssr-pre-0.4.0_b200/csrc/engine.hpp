@@ -394,7 +394,14 @@ struct Gather
   static constexpr int kMaxWorld = 24;
   unsigned char* base = nullptr;     // root: own allocation; peer: mapped pointer
   bool owns = false, ipc_mapped = false;
-  DeviceArray<int> d_error;          // local sticky timeout flag
+  // local sticky time-out flag in MAPPED PINNED host memory: written by the waiting
+  // kernels, read by the host after a block's completion event at no cost
+  PinnedArray<int> h_error;
+  int* d_error = nullptr;            // the device's view of h_error
+  bool timed_out() const { return h_error.ptr && *reinterpret_cast<volatile int*>(h_error.ptr) != 0; }
+  // ranks driven by one host thread on ONE device (single-GPU tests): see ssr_b200.h
+  bool shares_root_device = false;
+  unsigned long long timeout_ns = 0;  // 0: ssrk::kGatherTimeoutNs (20 s)
   DeviceArray<int> d_ctas;           // root: CTAs per rank (0 for the root)
   uint64_t epoch = 0;                // blocks rendered into the buffer so far
   uint64_t waited = 0, released = 0; // root bookkeeping
@@ -418,6 +425,54 @@ struct Gather
   // root: after the reads of that slot were queued (on `s`, default the engine's stream)
   void release(cudaStream_t s = nullptr);
   int status();                                        // 0 ok, 1 a wait timed out (synchronises)
+};
+
+// ------------------------------------------------------------ host-direct output delivery
+// Second realisation of the path's exchange step, for the HOST-buffer call
+// (pointer_policy::audio_callback, apf/apf/pointer_policy.h:112-122, where the
+// reference's Output items write the caller's host channels directly): one POSIX
+// shared-memory segment, page-locked and device-mapped in every rank
+//   [control 4 KiB: consumed | flag[rank] (one 128-byte line each)]
+//   [slot 0: M_total x B floats][slot 1: M_total x B floats]
+// Rank g's inverse kernel stores its M/G x B blocks into slot (t & 1) over ITS OWN
+// PCIe link (posted writes that overlap the kernel) and its last CTA then writes
+// flag[g] = t + 1.  The root's host thread returns from the block when every flag
+// is in; no GPU ever waits for another one, no 2 MB D2H copy funnels through the
+// root's link, and the caller reads the output blocks in place (hostgather.cu).
+struct HostGather
+{
+  HostGather(Engine* e, int world, int rank, int root, const int* outputs_per_rank, const char* shm_name);
+  ~HostGather();
+  HostGather(const HostGather&) = delete;
+  HostGather& operator=(const HostGather&) = delete;
+  Engine* e;
+  int world, rank, root;
+  std::string name;
+  std::vector<int> counts, firsts;
+  int M_total = 0;
+  bool is_root() const { return rank == root; }
+
+  static constexpr size_t kControlBytes = 4096;
+  static constexpr int kMaxWorld = 24;
+  unsigned char* base = nullptr;     // host mapping of the segment
+  unsigned char* d_base = nullptr;   // the device's view of it
+  size_t bytes = 0;
+  bool created = false, registered = false, failed = false;
+  double timeout_ms = 20000.0;
+  DeviceArray<unsigned> d_counter;   // CTAs of the running inverse launch that have stored their block
+  uint64_t epoch = 0;                // blocks rendered into the segment so far
+
+  size_t slot_floats() const { return size_t(M_total) * e->B; }
+  float* slot_ptr(int slot) const { return reinterpret_cast<float*>(base + kControlBytes) + size_t(slot) * slot_floats(); }
+  float* d_slot_ptr(int slot) const { return reinterpret_cast<float*>(d_base + kControlBytes) + size_t(slot) * slot_floats(); }
+  unsigned long long* consumed_ptr() const { return reinterpret_cast<unsigned long long*>(base); }
+  volatile unsigned long long* flag_ptr(int g) const
+  { return reinterpret_cast<volatile unsigned long long*>(base) + size_t(1 + g) * ssrk::kGatherCounterStride; }
+
+  ssrk::GatherArgs next_block(int ctas);
+  void publish_consumed(uint64_t t);
+  void wait_slot_free(uint64_t t);
+  void wait_all(uint64_t t);
 };
 
 // ------------------------------------------------------------ Level 2
@@ -557,11 +612,22 @@ struct Renderer
   // multi-GPU: output blocks go to a Gather (not owned) instead of d_output
   Gather* gather = nullptr;
   void bind_gather(Gather* g);
+  // ... or straight to the shared host segment of a HostGather (not owned)
+  HostGather* hostgather = nullptr;
+  void bind_hostgather(HostGather* g);
+  // output blocks the host call delivers on this rank
+  int host_outputs() const
+  {
+    if (gather) return gather->is_root() ? M_total : 0;
+    if (hostgather) return hostgather->is_root() ? M_total : 0;
+    return m_local;
+  }
   // pipelined
   int outstanding = 0;
   uint64_t submitted = 0;
   cudaEvent_t done[2] = {nullptr, nullptr};
   bool slot_direct[2] = {false, false};  // the slot's D2H went straight into the caller's buffer
+  uint64_t slot_epoch[2] = {0, 0};       // host-direct gather: block index the slot's call rendered
   void submit(int n, const float* const* in);
   void submit_block(int n, const float* const* in, float* const* direct_out, bool pipelined);
   // copy streams and events of the pipelined submit(): H2D | kernels | D2H

@@ -3,6 +3,9 @@
 // per-block kernel arguments, the root's wait / release launches.
 #include "engine.hpp"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace ssr_b200
 {
 
@@ -23,8 +26,16 @@ Gather::Gather(Engine* e_, int world_, int rank_, int root_, const int* outputs_
   }
   if (M_total == 0) throw Error(SSR_ERR_INVALID, "ssr_b200: gather: no outputs");
   e->use_device();
-  d_error.resize(1);
-  SSR_CUDA(cudaMemset(d_error.ptr, 0, sizeof(int)));
+  // SSR_B200_GATHER_TIMEOUT_MS: how long a rank waits for another one before it gives up
+  if (const char* v = std::getenv("SSR_B200_GATHER_TIMEOUT_MS"))
+    timeout_ns = (unsigned long long)(std::max(1.0, std::atof(v)) * 1e6);
+  h_error.resize(16);
+  h_error.ptr[0] = 0;
+  {
+    void* mapped = nullptr;
+    SSR_CUDA(cudaHostGetDevicePointer(&mapped, h_error.ptr, 0));
+    d_error = static_cast<int*>(mapped);
+  }
   if (is_root())
   {
     void* p = nullptr;
@@ -86,6 +97,7 @@ void Gather::import_pointer(void* root_base, int root_device)
     if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
     else SSR_CUDA(err);
   }
+  else shares_root_device = true;
   base = static_cast<unsigned char*>(root_base);
 }
 
@@ -96,7 +108,8 @@ GatherArgs Gather::next_block()
   const uint64_t t = epoch++;
   // InvJob::out holds the offset of the output inside a slot (see Renderer)
   ga.out_offset = (long long)((t & 1) * slot_floats());
-  ga.error = d_error.ptr;
+  ga.error = d_error;
+  ga.timeout_ns = timeout_ns;
   if (!is_root())
   {
     ga.consumed = consumed_ptr();
@@ -114,7 +127,7 @@ const float* Gather::wait()
   const uint64_t t = epoch - 1;
   if (world > 1)
   {
-    GatherWaitArgs a{arrived_ptr(0), d_ctas.ptr, world, t, d_error.ptr};
+    GatherWaitArgs a{arrived_ptr(0), d_ctas.ptr, world, t, d_error, timeout_ns};
     gather_wait_kernel<<<1, 32, 0, e->stream>>>(a);
     SSR_CUDA(cudaGetLastError());
     e->count_launch();
@@ -141,9 +154,7 @@ int Gather::status()
 {
   e->use_device();
   e->sync();
-  int flag = 0;
-  SSR_CUDA(cudaMemcpy(&flag, d_error.ptr, sizeof(int), cudaMemcpyDeviceToHost));
-  return flag;
+  return timed_out() ? 1 : 0;
 }
 
 }  // namespace ssr_b200

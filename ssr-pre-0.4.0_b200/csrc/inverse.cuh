@@ -40,6 +40,13 @@ struct GatherArgs
   unsigned long long need_consumed;
   unsigned long long* arrived;             // this rank's arrival counter on the root (peer memory), or null
   int* error;                              // local sticky flag: a wait timed out
+  unsigned long long timeout_ns;           // 0: kGatherTimeoutNs
+  // host-direct delivery (HostGather): InvJob::out points into a device-mapped host
+  // segment; the CTA that finishes last writes flag_value to host_flag
+  unsigned* cta_counter;                   // device-local, zero between launches
+  unsigned cta_total;
+  unsigned long long* host_flag;           // mapped host memory, or null
+  unsigned long long flag_value;
 };
 
 constexpr unsigned long long kGatherTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
@@ -58,22 +65,27 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// spins until *p >= target; gives up (sticky error flag) after kGatherTimeoutNs so
-// that a dead peer can never hang the GPU
-__device__ __noinline__ void gather_wait_ge(const unsigned long long* p, unsigned long long target, int* error)
+// spins until *p >= target; gives up (sticky error flag, false) after kGatherTimeoutNs
+// so that a dead peer can never hang the GPU.  `error` lives in mapped host memory:
+// the host reads it after the block's completion event (Renderer::wait) and fails
+// the call with SSR_ERR_STATE instead of delivering a stale block.
+__device__ __noinline__ bool gather_wait_ge(const unsigned long long* p, unsigned long long target, int* error,
+                                            unsigned long long timeout_ns)
 {
-  if (ld_acquire_sys(p) >= target) return;
-  if (error && *reinterpret_cast<volatile int*>(error)) return;
+  if (timeout_ns == 0) timeout_ns = kGatherTimeoutNs;
+  if (ld_acquire_sys(p) >= target) return true;
+  if (error && *reinterpret_cast<volatile int*>(error)) return false;
   const unsigned long long t0 = globaltimer_ns();
   while (ld_acquire_sys(p) < target)
   {
     __nanosleep(200);
-    if (globaltimer_ns() - t0 > kGatherTimeoutNs)
+    if (globaltimer_ns() - t0 > timeout_ns)
     {
-      if (error) *reinterpret_cast<volatile int*>(error) = 1;
-      return;
+      if (error) { *reinterpret_cast<volatile int*>(error) = 1; __threadfence_system(); }
+      return false;
     }
   }
+  return true;
 }
 
 // root: wait until every peer rank has delivered its output blocks of block
@@ -85,6 +97,7 @@ struct GatherWaitArgs
   int world;
   unsigned long long epoch;
   int* error;
+  unsigned long long timeout_ns;
 };
 constexpr int kGatherCounterStride = 16;  // unsigned long longs between counters (one 128-byte line each)
 
@@ -93,7 +106,7 @@ __global__ void gather_wait_kernel(GatherWaitArgs a)
   const int g = threadIdx.x;
   if (g < a.world && a.ctas[g] > 0)
     gather_wait_ge(a.arrived + size_t(g) * kGatherCounterStride,
-        (a.epoch + 1) * (unsigned long long)a.ctas[g], a.error);
+        (a.epoch + 1) * (unsigned long long)a.ctas[g], a.error, a.timeout_ns);
 }
 
 // root: block `epoch` has been read out of its slot -> peers may overwrite it
@@ -219,6 +232,7 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
 {
   extern __shared__ float2 smem[];
   __shared__ float s_max[kThreads / 32];
+  __shared__ int s_slot_ok;
   const int g = GROUPS == 1 ? 0 : threadIdx.x / kThreads;  // entry group
   const int t = threadIdx.x - g * kThreads;                // thread within the group
   constexpr int ngroups = GROUPS;
@@ -233,7 +247,7 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
   __syncthreads();
   // flow control of the fused gather: the slot this block goes to must have been
   // read out by the root (checked by one thread while the others start loading)
-  if (ga.consumed && threadIdx.x == 0) gather_wait_ge(ga.consumed, ga.need_consumed, ga.error);
+  if (ga.consumed && threadIdx.x == 0) s_slot_ok = gather_wait_ge(ga.consumed, ga.need_consumed, ga.error, ga.timeout_ns) ? 1 : 0;
 
   float2 res[kInvMaxRes];
 #pragma unroll
@@ -350,7 +364,11 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
       }
   }
 
-  if (ga.consumed) __syncthreads();  // thread 0's slot check precedes every store
+  if (ga.consumed)
+  {
+    __syncthreads();          // thread 0's slot check precedes every store
+    if (!s_slot_ok) return;   // timed out: the slot still holds an unread block -- store nothing, signal nothing
+  }
   if (g == 0)
   {
     float m = 0.0f;
@@ -388,6 +406,24 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
     {
       __threadfence_system();
       atomicAdd_system(ga.arrived, 1ull);
+    }
+  }
+  if (ga.host_flag)
+  {
+    // all stores of this CTA (host memory, posted writes over PCIe) -> fence -> count
+    // on a device-local counter; the CTA that comes last publishes the rank's flag
+    // behind everybody's stores (fence cumulativity; PCIe keeps posted writes in order)
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      __threadfence_system();
+      const unsigned prev = atomicAdd(ga.cta_counter, 1u);
+      if (prev + 1 == ga.cta_total)
+      {
+        *ga.cta_counter = 0;   // every other CTA has counted in: ready for the next launch
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(ga.host_flag), "l"(ga.flag_value) : "memory");
+      }
     }
   }
 }

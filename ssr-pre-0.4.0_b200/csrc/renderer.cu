@@ -338,7 +338,7 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
     d.xparts[k] = active_parts[k];
   }
   d.nrows = m_local;
-  d.graphable = gather == nullptr;  // the gather's kernel arguments change every block
+  d.graphable = gather == nullptr && hostgather == nullptr;  // a gather's kernel arguments change every block
   return d;
 }
 
@@ -666,6 +666,7 @@ void Renderer::bind_gather(Gather* g)
   e->sync();
   if (g)
   {
+    if (hostgather) throw Error(SSR_ERR_STATE, "ssr_b200: a host-direct gather is bound; unbind it first");
     if (cfg.kind != SSR_RENDERER_GENERIC)
       throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: only the Generic renderer shards its outputs (Binaural/BRS: replicas only)");
     if (g->e != e) throw Error(SSR_ERR_INVALID, "ssr_b200: gather belongs to another engine");
@@ -680,11 +681,33 @@ void Renderer::bind_gather(Gather* g)
   else h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
 }
 
+// Multi-GPU, host-buffer call: the inverse kernel stores this rank's output blocks
+// into the shared host segment (HostGather) through its device mapping.
+void Renderer::bind_hostgather(HostGather* g)
+{
+  if (outstanding) throw Error(SSR_ERR_STATE, "ssr_b200: bind_hostgather() while submitted blocks are pending");
+  e->use_device();
+  e->sync();
+  if (g)
+  {
+    if (gather) throw Error(SSR_ERR_STATE, "ssr_b200: a peer-memory gather is bound; unbind it first");
+    if (cfg.kind != SSR_RENDERER_GENERIC)
+      throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: only the Generic renderer shards its outputs (Binaural/BRS: replicas only)");
+    if (g->e != e) throw Error(SSR_ERR_INVALID, "ssr_b200: hostgather belongs to another engine");
+    if (g->M_total != M_total || g->counts[g->rank] != m_local || g->firsts[g->rank] != m_first)
+      throw Error(SSR_ERR_INVALID, "ssr_b200: hostgather layout does not match the renderer's output shard");
+  }
+  hostgather = g;
+  invalidate_inv();
+  drop_graphs();
+}
+
 Renderer::StepDesc Renderer::prepare(const float* d_input, float* d_output)
 {
   e->use_device();
   // slot 0 of the gather buffer; the kernel adds the slot offset of the block
   if (gather) d_output = gather->slot_ptr(0) + size_t(m_first) * e->B;
+  if (hostgather) d_output = hostgather->d_slot_ptr(0) + size_t(m_first) * e->B;
   if (cfg.kind == SSR_RENDERER_GENERIC) return prepare_generic(d_input, d_output);
   if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) return prepare_bank(d_input, d_output);
   return prepare_dynamic(d_input, d_output);
@@ -735,6 +758,13 @@ void Renderer::launch(const StepDesc& d)
   if (cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS)
     e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G);
   else if (gather) e->launch_inv(inv, gather->next_block());
+  else if (hostgather)
+  {
+    // the slot this block goes to must have been read out on the root (host-side wait;
+    // forward transform and MAC are already queued and run meanwhile)
+    hostgather->wait_slot_free(hostgather->epoch);
+    e->launch_inv(inv, hostgather->next_block(int(inv.jobs.uploaded)));
+  }
   else e->launch_inv(inv);
   e->stage_mark(3);
   e->stage_end();
@@ -742,6 +772,9 @@ void Renderer::launch(const StepDesc& d)
 
 void Renderer::step(const float* d_input, float* d_output)
 {
+  if (hostgather)
+    throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: the device-buffer step delivers through the peer-memory gather "
+        "(ssr_gather_*); a host-direct gather serves ssr_renderer_process");
   cur_slot = 0;
   const StepDesc d = prepare(d_input, d_output);
   g_prof.start();
@@ -775,7 +808,7 @@ static bool contiguous_pinned(Engine* e, const float* const* ptrs, int count, in
 // kTimeBatch such blocks can share one pass over the filter spectra.
 bool Renderer::batch_eligible()
 {
-  if (cfg.kind != SSR_RENDERER_GENERIC || gather || static_dirty || sources.empty()) return false;
+  if (cfg.kind != SSR_RENDERER_GENERIC || gather || hostgather || static_dirty || sources.empty()) return false;
   if (!e->mac_tma() || static_mac.MT != kGenericMT || e->timing || metering) return false;
   for (auto& sp : sources)
   {
@@ -871,7 +904,7 @@ void Renderer::process_batch(int n, int nblocks, const float* const* in, float* 
   if (n != e->B) throw Error(SSR_ERR_INVALID, "ssr_b200: audio_callback: n != block size");
   if (nblocks < 0) throw Error(SSR_ERR_INVALID, "ssr_b200: process_batch: negative block count");
   const int N = int(sources.size());
-  const int n_out = gather ? (gather->is_root() ? M_total : 0) : m_local;
+  const int n_out = host_outputs();
   int t = 0;
   while (t < nblocks)
   {
@@ -941,7 +974,9 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   float* din = d_in[cur_slot].ptr;
   float* dout = d_out[cur_slot].ptr;
   // with a gather bound the root delivers ALL outputs, the other ranks none
-  const int n_host_out = gather ? (gather->is_root() ? M_total : 0) : m_local;
+  const int n_host_out = host_outputs();
+  if (hostgather && pipelined) throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: submit()/wait() with a host-direct gather: use process()");
+  if (hostgather && hostgather->is_root()) hostgather->publish_consumed(hostgather->epoch);
   const float* hin = nullptr;
   if (direct_out && N > 0 && contiguous_pinned(e, in, N, B)) hin = in[0];
   else
@@ -950,9 +985,17 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
     for (int i = 0; i < N; ++i) std::memcpy(stage + size_t(i) * B, in[i], B * sizeof(float));
     hin = stage;
   }
-  float* hout = h_out.ptr + size_t(slot) * n_host_out * B;
+  float* hout = hostgather ? nullptr : h_out.ptr + size_t(slot) * n_host_out * B;
   slot_direct[slot] = false;
-  if (direct_out && n_host_out > 0 && contiguous_pinned(e, direct_out, n_host_out, B))
+  if (hostgather)
+  {
+    // the caller reads the blocks in place when `out` points at the segment's slot of this block
+    const float* want = hostgather->slot_ptr(int(hostgather->epoch & 1));
+    bool in_place = direct_out && n_host_out > 0;
+    for (int m = 0; in_place && m < n_host_out; ++m) in_place = direct_out[m] == want + size_t(m) * B;
+    slot_direct[slot] = in_place;
+  }
+  else if (direct_out && n_host_out > 0 && contiguous_pinned(e, direct_out, n_host_out, B))
   {
     hout = direct_out[0];
     slot_direct[slot] = true;
@@ -963,7 +1006,7 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   // Synchronous call into the caller's page-locked output array: the inverse kernel
   // stores its blocks straight into it (mapped host memory, posted PCIe writes that
   // overlap the kernel) instead of a device buffer + D2H copy afterwards.
-  bool zero_copy_out = zero_copy && !pipelined && !gather && slot_direct[slot];
+  bool zero_copy_out = zero_copy && !pipelined && !gather && !hostgather && slot_direct[slot];
   if (zero_copy_out)
   {
     void* mapped = nullptr;  // the device's view of the array (the same address under UVA)
@@ -1029,6 +1072,11 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
 
   const float* src = dout;
   size_t out_floats = size_t(m_local) * B;
+  if (hostgather)
+  {
+    out_floats = 0;   // the inverse kernel delivered the blocks; no copy on any rank
+    slot_epoch[slot] = hostgather->epoch - 1;
+  }
   if (gather)
   {
     out_floats = 0;
@@ -1061,10 +1109,24 @@ void Renderer::wait(float* const* out)
   const int B = e->B;
   const int slot = int((submitted - outstanding) & 1);
   SSR_CUDA(cudaEventSynchronize(done[slot]));
-  const int n_host_out = gather ? (gather->is_root() ? M_total : 0) : m_local;
+  const int n_host_out = host_outputs();
+  if (gather && gather->timed_out())
+  {
+    // a wait on another rank gave up (inverse.cuh, gather_wait_ge): the slot holds a
+    // stale or partial block -- fail the call instead of delivering it
+    outstanding--;
+    throw Error(SSR_ERR_STATE, "ssr_b200: gather: a wait on a peer rank timed out; the output block is not valid");
+  }
+  if (hostgather && hostgather->is_root())
+  {
+    // our own kernels are through; now every other rank's flag (host memory)
+    try { hostgather->wait_all(slot_epoch[slot]); }
+    catch (...) { outstanding--; throw; }
+  }
   if (!slot_direct[slot])
   {
-    const float* hout = h_out.ptr + size_t(slot) * n_host_out * B;
+    const float* hout = hostgather ? hostgather->slot_ptr(int(slot_epoch[slot] & 1))
+                                   : h_out.ptr + size_t(slot) * n_host_out * B;
     for (int m = 0; m < n_host_out; ++m) std::memcpy(out[m], hout + size_t(m) * B, B * sizeof(float));
   }
   outstanding--;

@@ -2,5 +2,6 @@
 // host file sees the same instantiations (one cubin, one set of symbols).
 #include "engine.cu"
 #include "gather.cu"
+#include "hostgather.cu"
 #include "renderer.cu"
 #include "capi.cu"

@@ -7,7 +7,12 @@ block and forward-transforms it itself).  The only exchange step is bringing the
 M/G x B output blocks to the host-facing rank.  No reduction, no exchange of
 spectra.  One process per GPU.
 
-Two implementations of that step:
+Three implementations of that step:
+  * connect_host_gather(): the HOST-buffer call's path.  All ranks map one
+    page-locked shared-memory segment and every rank's inverse-FFT kernel stores
+    its blocks straight into it over its own PCIe link (csrc/hostgather.cu); the
+    root's host thread returns when every rank's flag is in.  No D2H copy, no
+    device-side waiting.
   * connect_peer_gather(): the product path.  The root's gather buffer is mapped
     into every rank (CUDA IPC handle broadcast with torch.distributed); each
     rank's inverse-FFT kernel stores its output blocks straight into it over
@@ -90,3 +95,39 @@ def connect_peer_gather(capi, engine, renderer, outputs: int, world: int, rank: 
     if world > 1:
         dist.barrier()  # nobody renders into the buffer before every rank is bound
     return gather
+
+
+def connect_host_gather(capi, engine, outputs: int, world: int, rank: int, device):
+    """Creates the rank's ssr_hostgather on one shared host segment whose name rank 0
+    picks and broadcasts.  Collective: every rank must call it.  Returns the
+    capi.HostGather (not yet bound to a renderer), or None on ALL ranks if any rank
+    failed to map the segment."""
+    import os
+    import uuid
+    import torch
+    import torch.distributed as dist
+    _, count = shard_outputs(outputs, world, rank)
+    names = [f"/ssr_b200_{os.getpid()}_{uuid.uuid4().hex[:10]}" if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(names, src=0)
+    hg, ok = None, 1
+    try:
+        if rank == 0:
+            hg = capi.HostGather(engine, world, rank, [count] * world, names[0])
+    except capi.SsrError:
+        ok = 0
+    if world > 1:
+        dist.barrier()  # the segment exists (or rank 0 failed) before the peers look for it
+    if rank != 0:
+        try:
+            hg = capi.HostGather(engine, world, rank, [count] * world, names[0])
+        except capi.SsrError:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if hg is not None:
+            hg.close()
+        return None
+    return hg

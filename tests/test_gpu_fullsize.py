@@ -75,6 +75,56 @@ def test_cfg4_generic_64x64_impulse_responses_and_linearity(capi, engine_factory
     assert worst <= TOL
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_cfg4_sharded_over_ranks_equals_the_unsharded_renderer(capi, engine_factory, world):
+    """BASELINE config 4 "at 1/2/4/8 GPUs": `world` ranks (one engine each, on distinct
+    devices when the box has them) render output shards through the fused gather; the
+    root's blocks equal the unsharded renderer's and the synthetic IRs' impulse responses."""
+    import torch
+    wl = _wl()
+    w = wl.WORKLOADS["cfg4"]
+    env = wl.envelope(w.taps)
+    scale = wl.ir_scale(w.sources, env)
+    ndev = torch.cuda.device_count()
+    per = w.outputs // world
+    engines, rens, gathers = [], [], []
+    for g in range(world):
+        e = engine_factory(w.block, device=g % ndev)
+        r = capi.Renderer(e, capi.GENERIC, outputs=w.outputs, output_first=g * per, output_count=per)
+        for n in range(w.sources):
+            r.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
+                                   envelope=env, scale=scale)
+        engines.append(e); rens.append(r); gathers.append(capi.Gather(e, world, g, [per] * world))
+    for g in range(1, world):
+        gathers[g].connect_local(gathers[0])
+    for g in range(world):
+        rens[g].bind_gather(gathers[g])
+    full = capi.Renderer(engines[0], capi.GENERIC, outputs=w.outputs)
+    for n in range(w.sources):
+        full.add_source_synthetic(w.taps, w.outputs, w.ir_seed, channel_id_offset=n * w.outputs,
+                                  envelope=env, scale=scale)
+    nb = w.partitions + 4
+    worst = 0.0
+    ys = []
+    for t in range(nb):
+        x = wl.signal_block(w, t)
+        if t == 5:
+            for r in rens + [full]:
+                r.set_gain(3, 0.4)      # a crossfading block through the gather
+        for r in rens[1:]:
+            r.submit(x)                 # peers first: ranks may share a device here (ssr_b200.h)
+        rens[0].submit(x)
+        y = rens[0].wait()
+        for r in rens[1:]:
+            r.wait()
+        ys.append(y)
+        worst = max(worst, float(np.abs(y - full.process(x)).max()))
+    for ga in gathers:
+        ga.check()
+    assert worst <= 2e-6, worst          # float32 summation order differs between the plans
+    assert float(np.abs(np.stack(ys)).max(axis=(0, 2)).min()) > 1e-3   # no dead output
+
+
 def test_cfg5_generic_128x512_x48000_impulse_responses(capi, engine_factory):
     wl = _wl()
     w = wl.WORKLOADS["cfg5"]                                        # 25.2 GB of spectra
