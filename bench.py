@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the float64 parity phase (development only)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--reference-budget-s", type=float, default=150.0,
+                    help="--impl reference: time budget of the measured blocks (3 repeats)")
     ap.add_argument("--mac-variant", type=int, default=0)
     ap.add_argument("--static-head", action="store_true", help="Binaural/BRS: no head rotation")
     ap.add_argument("--stage-timing-every", type=int, default=8,
@@ -160,32 +162,40 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------- reference arm
-def run_reference_renderer(w, out_shard: int, blocks: int, warm: int, threads: int):
+def run_reference_renderer(w, out_shard: int, blocks: int, warm: int, threads: int, repeats: int = 1):
     """The reference's own GenericRenderer (oracle/_ref/libssr_ref.so) on host
     cores: `out_shard` of the workload's outputs, all sources, full taps.
-    Returns (seconds for `blocks` blocks, per-block ms)."""
+    Returns (list of seconds for `blocks` blocks, one per repeat; per-block ms of all repeats)."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import ref
     import ssr_b200.workloads as wl
     env = wl.envelope(w.taps)
     scale = wl.ir_scale(w.sources, env)
     r = ref.Renderer("generic", w.block, w.fs, threads=threads)
     r.add_outputs(out_shard)
-    import ssr_b200.capi as capi
-    for n in range(w.sources):
-        # same synthetic IRs as the GPU run (host twin of the device generator)
-        ir = np.stack([capi.synth_ir(w.ir_seed, n * w.outputs + m, w.taps, env, scale)
-                       for m in range(out_shard)], axis=1)
-        name = f"bench_ir_{n}"
-        ref.register_sndfile(name, ir, w.fs)
-        r.add_source(name)
-        ref.unregister_sndfile(name)
+    # same synthetic IRs as the GPU run: the pure-numpy twin of the device generator
+    # (workloads.synth_ir, pinned bit for bit to the library's by a CPU test) -- this arm
+    # never loads the product library.  numpy releases the GIL: one task per IR column.
+    with ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1)) as pool:
+        for n in range(w.sources):
+            cols = list(pool.map(lambda m: wl.synth_ir(w.ir_seed, n * w.outputs + m, w.taps, env, scale),
+                                 range(out_shard)))
+            ir = np.stack(cols, axis=1)
+            name = f"bench_ir_{n}"
+            ref.register_sndfile(name, ir, w.fs)
+            r.add_source(name)
+            ref.unregister_sndfile(name)
     r.activate()
     nin = 4
     x = np.stack([wl.signal_block(w, t) for t in range(nin)])
     if warm > 0:
         r.run(x, warm, want_output=False)
-    _, secs, times = r.run(x, blocks, want_output=False, want_times=True)
-    return secs, times
+    secs_all, times_all = [], []
+    for _ in range(max(1, repeats)):
+        _, secs, times = r.run(x, blocks, want_output=False, want_times=True)
+        secs_all.append(secs)
+        times_all.append(times)
+    return secs_all, np.concatenate(times_all)
 
 
 def run_reference_dynamic(w, n_sources: int, blocks: int, warm: int, threads: int, rotate: bool):
@@ -193,14 +203,13 @@ def run_reference_dynamic(w, n_sources: int, blocks: int, warm: int, threads: in
     `n_sources` of the workload's sources and the head rotating one filter step
     per block (the same control script as the GPU run)."""
     from oracle import ref
-    import ssr_b200.capi as capi
     import ssr_b200.workloads as wl
     env = wl.envelope(w.taps)
     scale = wl.ir_scale(w.sources, env)
     angles = w.channels // 2
 
     def ir_set(offset):
-        cols = [capi.synth_ir(w.ir_seed, offset + c, w.taps, env, scale) for c in range(w.channels)]
+        cols = [wl.synth_ir(w.ir_seed, offset + c, w.taps, env, scale) for c in range(w.channels)]
         return np.stack(cols, axis=1)
 
     if w.kind == "brs":
@@ -233,7 +242,6 @@ def port_sample(w, steps: int, warmup: int):
     (oracle/conv_oracle.py, kind "port", one core) on ONE output of a Generic
     workload / one source of a Binaural/BRS workload, scaled to the full shape."""
     from oracle import conv_oracle as co
-    import ssr_b200.capi as capi
     import ssr_b200.workloads as wl
     env = wl.envelope(w.taps)
     scale = wl.ir_scale(w.sources, env)
@@ -242,12 +250,12 @@ def port_sample(w, steps: int, warmup: int):
         nsrc = min(w.sources, 8)
         o = co.GenericRendererOracle(w.block, 1)
         for n in range(nsrc):
-            o.add_source(capi.synth_ir(w.ir_seed, n * w.outputs, w.taps, env, scale)[:, None])
+            o.add_source(wl.synth_ir(w.ir_seed, n * w.outputs, w.taps, env, scale)[:, None])
         factor = (w.sources / nsrc) * w.outputs
         what = f"{nsrc} of {w.sources} src x 1 of {w.outputs} outputs"
     else:
         nsrc = 1
-        cols = np.stack([capi.synth_ir(w.ir_seed, c, w.taps, env, scale) for c in range(w.channels)], axis=1)
+        cols = np.stack([wl.synth_ir(w.ir_seed, c, w.taps, env, scale) for c in range(w.channels)], axis=1)
         if w.kind == "brs":
             o = co.BrsRendererOracle(w.block)
             o.add_source(cols)
@@ -270,76 +278,131 @@ def port_sample(w, steps: int, warmup: int):
     return float(times.mean()), times, 1, sample, "port"
 
 
-def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, rotate: bool = True):
-    """Runs the reference CPU arm on a bounded sample of workload `w`.
-    Returns (full-workload ms per block, per-block ms scaled, cores used, sample text, kind)."""
+def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, rotate: bool = True,
+                     repeats: int = 1):
+    """Runs the reference CPU arm on a bounded sample of workload `w`: `repeats` runs of
+    `steps` blocks, the MEDIAN run is reported (one noisy run used to move the number by
+    tens of percent).  Returns (full-workload ms per block, per-block ms scaled, cores
+    used, sample text, kind)."""
     from oracle import ref
     if not ref.available():
         return port_sample(w, steps, warmup)
     if w.kind == "generic":
-        shard = reference_plan(w, steps, warmup, budget_s, threads)
+        shard, why = reference_plan(w, steps, warmup, budget_s, threads, repeats)
         used = max(1, min(threads, shard))  # items are spread round-robin over outputs
-        secs, times = run_reference_renderer(w, shard, steps, warmup, used)
+        secs_all, times = run_reference_renderer(w, shard, steps, warmup, used, repeats)
         factor = w.outputs / shard
-        what = f"{w.sources} src x {shard} of {w.outputs} outputs x {w.taps} taps"
+        what = f"{w.sources} src x {shard} of {w.outputs} outputs x {w.taps} taps ({why})"
     else:
         # cost ~ sources * 2 ears * partitions * (1 or 2 evaluations)
         per_src = 2 * w.partitions * (2 if rotate else 1) * 1.6e-6 * 1.6
         nsrc = w.sources
-        while nsrc > 1 and (per_src * nsrc / max(1, min(threads, nsrc)) * (steps + warmup) > budget_s
-                            or nsrc * w.channels * (w.partitions * 8 * w.block + 4 * w.taps) > 24e9):
+        while nsrc > 1 and (per_src * nsrc / max(1, min(threads, nsrc)) * (steps + warmup) * repeats > budget_s
+                            or nsrc * w.channels * (w.partitions * 8 * w.block + 4 * w.taps) > 0.5 * host_ram_available()):
             nsrc //= 2
         used = max(1, min(threads, nsrc))
-        secs, times = run_reference_dynamic(w, nsrc, steps, warmup, used, rotate)
+        secs_all, times_all = [], []
+        for _ in range(max(1, repeats)):
+            secs, times = run_reference_dynamic(w, nsrc, steps, warmup, used, rotate)
+            secs_all.append(secs)
+            times_all.append(times)
+        times = np.concatenate(times_all)
         factor = w.sources / nsrc
         what = (f"{nsrc} of {w.sources} src x 2 ears, {w.channels}-channel {w.taps}-tap set, "
                 f"head {'rotating one step per block' if rotate else 'static'}")
+    secs = float(np.median(secs_all))
     full_ms = secs / steps * 1e3 * factor
-    sample = (f"reference {w.name}: {what}; {steps} blocks after {warmup} warm-up; block time scaled "
-              f"x{factor:g} to the full workload{' (extrapolated)' if factor != 1 else ''}; {ref.describe()}")
+    spread = (max(secs_all) - min(secs_all)) / secs if secs > 0 else 0.0
+    sample = (f"reference {w.name}: {what}; {steps} blocks after {warmup} warm-up"
+              + (f", median of {len(secs_all)} runs (spread {spread * 100:.0f}%)" if len(secs_all) > 1 else "")
+              + (f"; block time scaled x{factor:g} to the full workload (extrapolated)" if factor != 1 else
+                 "; FULL shape, no extrapolation")
+              + f"; {ref.describe()}")
     return full_ms, times * factor, used, sample, "reference"
 
 
-def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int):
-    """Pick the output shard so that (steps + warmup) blocks fit the budget.
-    Cost model from SURVEY 0.7: ~1.6 us per partition-MAC per core."""
-    per_out_block = w.sources * w.partitions * 1.6e-6 / max(1, min(threads, 64)) * 1.6
-    shard = w.outputs
-    while shard > 1 and per_out_block * shard * (steps + warmup) > budget_s:
-        shard //= 2
-    # host memory: spectra + time-domain IRs
-    while shard > 1 and w.sources * shard * (w.partitions * 8 * w.block + 4 * w.taps) > 24e9:
-        shard //= 2
-    return max(1, shard)
+def host_ram_available() -> float:
+    try:
+        import psutil
+        return float(psutil.virtual_memory().available)
+    except Exception:
+        return 32e9
+
+
+def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int, repeats: int = 1):
+    """Pick the output shard of a Generic workload: the FULL shape when it fits in host
+    memory and (steps + warmup) x repeats blocks fit the time budget,
+    else the largest multiple of the thread count that does.  The per-block cost is
+    MEASURED on a probe (one output per thread, 1/8 of the sources), not modelled."""
+    from oracle import ref
+    import copy
+    # host memory per output: partition spectra + Output buffers, plus the transient
+    # time-domain IR matrix of one source
+    per_out = w.sources * (w.partitions * 8 * w.block + 8 * w.block + 16 * w.partitions) + 8 * w.taps
+    mem_shard = int(0.55 * host_ram_available() / per_out)
+    probe_w = copy.copy(w)
+    probe_w.sources = max(1, w.sources // 8)
+    probe_out = max(1, min(threads, w.outputs))
+    secs_all, _ = run_reference_renderer(probe_w, probe_out, 3, 2, probe_out)
+    per_round = secs_all[0] / 3 * (w.sources / probe_w.sources)   # one output per thread, all sources
+    rounds = max(1, int(budget_s / (max(1, repeats) * (steps + warmup) * per_round)))
+    time_shard = rounds * probe_out
+    shard = min(w.outputs, mem_shard, time_shard)
+    if shard >= w.outputs:
+        return w.outputs, "full shape"
+    shard = max(probe_out if shard >= probe_out else 1, (shard // probe_out) * probe_out)
+    why = "host memory" if mem_shard < time_shard else f"time budget {budget_s:.0f} s"
+    return max(1, shard), f"shard bounded by {why}"
+
+
+def make_config(w, reduced: bool, world: int, rotate: bool):
+    """`config` of the JSON line: a function of the workload and N only, so that both
+    arms print the same object (impl-specific facts go to `details`)."""
+    m_local = w.outputs // world if w.kind == "generic" else 2
+    mac_read_bytes = (w.sources * m_local if w.kind == "generic" else w.sources * 2) * w.partitions * 8 * w.block
+    l2_resident = mac_read_bytes < 126e6
+    return {
+        "workload": w.label() + (" [REDUCED]" if reduced else ""), "block": w.block,
+        "sample_rate": w.fs, "partitions": w.partitions,
+        "parallelism": f"outputs sharded x{world}" if world > 1 else "single GPU",
+        "head_rotation": ("one filter step per block" if rotate else "none") if w.kind != "generic" else "n/a",
+        "outputs_per_gpu": m_local,
+        "l2": ("inputs>L2 (every step streams %.0f MB of spectra per GPU through the 126 MB L2)" % (mac_read_bytes / 1e6)
+               if not l2_resident else
+               "L2-RESIDENT: a step reads %.1f MB of spectra per GPU < 126 MB L2, so `value` is not an "
+               "HBM figure; `l2_cold` is the same step after an L2 flush" % (mac_read_bytes / 1e6)),
+        "spectra_gb_per_gpu": (w.sources * m_local if w.kind == "generic" else
+                               (w.sources if w.kind == "brs" else 1) * w.channels) * w.partitions * 8 * w.block / 1e9,
+    }, l2_resident
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    w, reduced = get_workload(args)
-    from oracle import ref
+    w, reduced = get_workload(args)   # (imports the package's numpy workload module only, never the .so)
     threads = os.cpu_count() or 1
     steps, warmup = args.steps, args.warmup
-    entry.load_package()
-    full_ms, times, threads_used, sample, kind = reference_sample(w, steps, warmup, 150.0, threads,
-                                                                  rotate=not args.static_head)
+    rotate = w.kind != "generic" and not args.static_head
+    full_ms, times, threads_used, sample, kind = reference_sample(w, steps, warmup, args.reference_budget_s, threads,
+                                                                  rotate=rotate, repeats=3)
     value = (w.block / w.fs) / (full_ms * 1e-3)
+    config, _ = make_config(w, reduced, max(1, args.gpus), rotate)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": full_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.label() + (" [REDUCED]" if reduced else ""), "block": w.block,
-                   "sample_rate": w.fs, "partitions": w.partitions},
+        "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads_used, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "p99_block_ms": float(np.percentile(times, 99)),
         "gpu_launches": 0,
+        "details": {"note": "the reference's own CPU renderer on the host cores; no GPU, product library not loaded",
+                    "product_so_loaded": "ssr_b200.capi" in sys.modules},
     }
     print(json.dumps(line))
     return 0
-
 
 
 # ----------------------------------------------------------------- parity (outside every timed region)
@@ -690,10 +753,7 @@ def main_ours(args):
 
     # ---- L2-resident working sets (cfg4 sharded, cfg2): the same device-resident step with the
     # L2 flushed before every step, each step timed with its own event pair (the flush is outside)
-    spectra_bytes = ((w.sources * m_local if w.kind == "generic" else
-                      (w.sources if w.kind == "brs" else 1) * w.channels) * w.partitions * 8 * B)
-    mac_read_bytes = (w.sources * m_local if w.kind == "generic" else w.sources * 2) * w.partitions * 8 * B
-    l2_resident = mac_read_bytes < 126e6
+    config, l2_resident = make_config(w, reduced, world, rotate)
     l2_cold = None
     if l2_resident:
         flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -818,21 +878,13 @@ def main_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.label() + (" [REDUCED]" if reduced else ""), "block": B,
-                       "sample_rate": w.fs, "partitions": w.partitions,
-                       "parallelism": f"outputs sharded x{world}" if world > 1 else "single GPU",
-                       "head_rotation": ("one filter step per block" if rotate else "none") if w.kind != "generic" else "n/a",
-                       "outputs_per_gpu": m_local, "gather": gather_mode,
-                       "stage_timing": ("separate pass" if args.no_stage_timing else
-                                        f"inside the timed region, every {args.stage_timing_every}th step"),
-                       "l2": ("inputs>L2 (every step streams %.0f MB of spectra per GPU through the 126 MB L2)" % (mac_read_bytes / 1e6)
-                              if not l2_resident else
-                              "L2-RESIDENT: a step reads %.1f MB of spectra per GPU < 126 MB L2, so `value` is not an "
-                              "HBM figure; `l2_cold` is the same step after an L2 flush" % (mac_read_bytes / 1e6)),
-                       "filter_load_s": load_s,
-                       "spectra_gb_per_gpu": (w.sources * m_local if w.kind == "generic" else
-                                              (w.sources if w.kind == "brs" else 1) * w.channels)
-                       * w.partitions * 8 * B / 1e9},
+            "config": config,
+            "details": {"gather": gather_mode,
+                        "stage_timing": ("separate pass" if args.no_stage_timing else
+                                         f"inside the timed region, every {args.stage_timing_every}th step"),
+                        "filter_load_s": load_s,
+                        "forward_under_mac": os.environ.get("SSR_B200_FWD_OVERLAP", "1") != "0",
+                        "env": {k: v for k, v in os.environ.items() if k.startswith("SSR_B200_")}},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": w.sources * B * 4 * world,
                     "d2h_bytes_per_step": n_out_total * B * 4,

@@ -12,43 +12,61 @@ namespace ssr_b200
 using namespace ssrk;
 
 // ------------------------------------------------------------------ MacPlan
-void MacPlan::make_work(int slots, int fixed_cost)
+void MacPlan::make_work(int slots, int fixed_cost, int waves)
 {
   work.host.clear();
-  npartials = 0;
-  const int G = int(groups.size());
+  cta_first.host.clear();
+  npartials = 0; ncta = 0;
   long total = 0;
-  for (auto& g : groups) total += g.term_end - g.term_begin;
-  if (G == 0) return;
-  const long avg = std::max<long>(1, (total + G - 1) / G);
-  // pick the split count S (per average group) that minimises
-  //   waves(G*S) * (chunk length + fixed cost of a CTA in term units)
-  const long c0 = fixed_cost;  // cost of one more CTA, in units of one term
-  long bestS = 1; double best = 1e300;
-  const long Smax = std::min<long>(avg, 512);
-  for (long S = 1; S <= Smax; ++S)
+  for (auto& g : groups) { total += g.term_end - g.term_begin; g.partial_first = 0; g.nsplit = 0; }
+  if (groups.empty()) return;
+  // Number of CTAs: one full wave of the resident CTAs.  Every extra wave costs each SM
+  // another pipeline fill and another set of partials (waves x (share + fixed cost) only
+  // grows), and since shares may straddle group boundaries nothing forces more; small
+  // problems use fewer CTAs so that a share is worth its fixed cost.
+  const long min_share = std::max<long>(1, fixed_cost / 2);
+  long C = std::min<long>(long(slots) * std::max(1, waves), (total + min_share - 1) / min_share);
+  C = std::max<long>(C, 1);
+  // groups without terms still own one (empty) segment: their accumulators are zeros
+  std::vector<int4> segs;
+  std::vector<int> first;
+  size_t g = 0;
+  for (long c = 0; c < C; ++c)
   {
-    const long ctas = long(G) * S;
-    const long waves = (ctas + slots - 1) / slots;
-    const long chunk = (avg + S - 1) / S;
-    const double cost = double(waves) * double(chunk + c0);
-    if (cost < best - 1e-9) { best = cost; bestS = S; }
-  }
-  const long chunk = std::max<long>(1, (avg + bestS - 1) / bestS);
-  for (auto& g : groups)
-  {
-    const int n = g.term_end - g.term_begin;
-    int S = std::max(1, int((n + chunk - 1) / chunk));
-    g.partial_first = npartials;
-    g.nsplit = S;
-    for (int s = 0; s < S; ++s)
+    const long b = total * c / C, e = total * (c + 1) / C;   // share of CTA c in the term table
+    first.push_back(int(segs.size()));
+    long pos = b;
+    while (pos < e)
     {
-      const int b = g.term_begin + int((long(n) * s) / S);
-      const int e = g.term_begin + int((long(n) * (s + 1)) / S);
-      work.host.push_back(make_int4(b, e, npartials + s, 0));
+      while (groups[g].term_end <= pos) ++g;                  // (terms of all groups are back to back)
+      const long stop = std::min<long>(e, groups[g].term_end);
+      segs.push_back(make_int4(int(pos), int(stop), int(g), 0));
+      pos = stop;
     }
-    npartials += S;
   }
+  first.push_back(int(segs.size()));
+  // partial indices in term order (so a group's partials are consecutive) ...
+  for (size_t i = 0; i < segs.size(); ++i)
+  {
+    Group& grp = groups[size_t(segs[i].z)];
+    if (grp.nsplit == 0) grp.partial_first = int(i);
+    grp.nsplit++;
+    segs[i].z = int(i);
+  }
+  npartials = int(segs.size());
+  // ... and the longest segment of every CTA first: the bulk-copy kernel overlaps its
+  // first segment's p != 0 terms with the block's forward transform
+  for (long c = 0; c < C; ++c)
+  {
+    const int lo = first[size_t(c)], hi = first[size_t(c) + 1];
+    int best = lo;
+    for (int i = lo + 1; i < hi; ++i)
+      if (segs[size_t(i)].y - segs[size_t(i)].x > segs[size_t(best)].y - segs[size_t(best)].x) best = i;
+    if (best != lo) std::swap(segs[size_t(lo)], segs[size_t(best)]);
+  }
+  work.host = segs;
+  cta_first.host = first;
+  ncta = int(C);
 }
 
 // ------------------------------------------------------------------ launches
@@ -176,7 +194,15 @@ Engine::Engine(const ssr_engine_config& cfg)
     SSR_CUDA(cudaFuncSetAttribute(mac_tma_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
           int(mac_tma_smem_bytes<4, 5>())));
   }
+  // the overlapped forward kernel shares its SM with a MAC CTA (205 KiB of shared memory):
+  // both must run under the same (maximal) shared-memory carve-out to be co-resident
+  SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        int(cudaSharedmemCarveoutMaxShared)));
   if (const char* v = std::getenv("SSR_B200_PDL")) pdl = std::atoi(v) != 0;  // A/B experiments
+  if (const char* v = std::getenv("SSR_B200_FWD_OVERLAP")) fwd_overlap = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SSR_B200_MAC_WAVES")) mac_waves = std::max(0, std::atoi(v));
+  if (const char* v = std::getenv("SSR_B200_PREREDUCE_MIN")) prereduce_min = std::max(1, std::atoi(v));
+  fwd_overlap = fwd_overlap && pdl;
   if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
   if (2 * fft_smem > 48 * 1024)
   {
@@ -184,6 +210,7 @@ Engine::Engine(const ssr_engine_config& cfg)
     SSR_CUDA(cudaFuncSetAttribute(level1_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
   }
   // the inverse kernel runs up to kInvMaxGroups transforms side by side (3 x 16 KiB
   // at B = 1024, which with its static shared memory already exceeds 48 KiB)
@@ -252,14 +279,20 @@ int Engine::mac_slots(int MT) const
   return sm_count * occ;
 }
 
-void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ring_update)
+void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ring_update, bool overlap)
 {
   if (njobs <= 0) return;
   FwdRingUpdate ru{nullptr, nullptr, nullptr, 0};
   // One warp per transform wins on throughput (2.2x at filter load), one CTA per
   // transform on latency; the block loop rarely has enough transforms to fill
   // the machine (profiles/r1_fft_kernels.md)
-  if (fft1024 && (njobs >= kFft1024MinJobs || fft1024_always))
+  if (overlap)
+  {
+    if (ring_update) { ru = *ring_update; ring_update = nullptr; }
+    launch_kernel(fwd_fft_overlap_kernel, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
+        d_jobs, B, static_cast<const float2*>(tw.ptr), ru);
+  }
+  else if (fft1024 && (njobs >= kFft1024MinJobs || fft1024_always))
   {
     const int ctas = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
     fwd_fft1024_kernel<<<ctas, kWarpsPerCta * 32, 0, stream>>>(d_jobs, njobs, tw.ptr);
@@ -340,14 +373,17 @@ void Engine::launch_mac_fn(void* fn, dim3 grid, void** args, int threads, size_t
   SSR_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
 }
 
-void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights)
+void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights,
+                        bool overlap)
 {
-  const int nwork = int(plan.work.uploaded);
+  const int nwork = plan.work.uploaded ? plan.ncta : 0;
   if (nwork == 0) return;
   MacParams p{};
   p.term_meta = plan.meta.device();
   p.term_h = plan.hptr.device();
   p.work = plan.work.device();
+  p.cta_first = plan.cta_first.device();
+  p.head_bias = overlap ? 1 : 0;
   p.wtab = weights ? weights : wtab.device();
   p.xring = d_xring.ptr;
   p.xparts = d_xparts.ptr;
@@ -395,19 +431,19 @@ int Engine::inv_groups(int max_entries) const
 }
 
 void Engine::launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const float2* red,
-                               const GatherArgs& ga, const int* kind_counts)
+                               const GatherArgs& ga, const int* kind_counts, const HeadCommit& hc)
 {
   const size_t smem = size_t(2) * B * sizeof(float2) * (groups + 1);
   const float2* part = reinterpret_cast<const float2*>(partials.ptr);
   if (groups == 3)
     launch_kernel(inv_fft_kernel<3>, dim3(njobs), dim3(kThreads * 3), smem, stream, pdl, plan.jobs.device(),
-        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts, hc);
   else if (groups == 2)
     launch_kernel(inv_fft_kernel<2>, dim3(njobs), dim3(kThreads * 2), smem, stream, pdl, plan.jobs.device(),
-        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts, hc);
   else
     launch_kernel(inv_fft_kernel<1>, dim3(njobs), dim3(kThreads), smem, stream, pdl, plan.jobs.device(),
-        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts);
+        plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts, hc);
 }
 
 void Engine::launch_level1_fused(const FusedParams& p)
@@ -430,13 +466,14 @@ void Engine::launch_dyn_ring_update(const DynCtl* ctl, const DynRingEntry* upd, 
 
 void Engine::launch_mac_batch(const MacPlan& plan, int wtab_offset)
 {
-  const int nwork = int(plan.work.uploaded);
+  const int nwork = plan.work.uploaded ? plan.ncta : 0;
   if (nwork == 0) return;
   if (!mac_tma() || plan.MT != 4) throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: time-batched MAC needs the four-row bulk-copy plan (B >= 1024)");
   MacParams p{};
   p.term_meta = plan.meta.device();
   p.term_h = plan.hptr.device();
   p.work = plan.work.device();
+  p.cta_first = plan.cta_first.device();
   p.wtab = wtab.device();
   p.xring = d_xring.ptr;
   p.xparts = d_xparts.ptr;
@@ -494,15 +531,19 @@ void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, in
   if (cur) cur->ifft_launches++;
 }
 
-void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
+void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga, const HeadCommit& hc)
 {
   const int njobs = int(plan.jobs.uploaded);
-  if (njobs == 0) return;
+  if (njobs == 0)
+  {
+    if (hc.n) throw Error(SSR_ERR_STATE, "ssr_b200: an overlapped forward launch needs an inverse launch to commit the ring heads");
+    return;
+  }
   // few output blocks with deep splits: reduce the partials in parallel first
   const int nentries = int(plan.entries.uploaded);
   int max_count = 0;
   for (auto& en : plan.entries.host) max_count = std::max(max_count, en.part_count);
-  const bool pre_reduce = nentries > 0 && max_count >= 8 && njobs < 2 * sm_count;
+  const bool pre_reduce = nentries > 0 && max_count >= prereduce_min && njobs < 2 * sm_count;
   const float2* red = nullptr;
   if (pre_reduce)
   {
@@ -518,7 +559,7 @@ void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
     red = reinterpret_cast<const float2*>(reduced.ptr);
   }
   const bool gathering = ga.out_offset != 0 || ga.consumed || ga.arrived || ga.host_flag;
-  if (fft1024 && !gathering && (njobs >= kFft1024MinJobs || fft1024_always))
+  if (fft1024 && !gathering && !hc.n && (njobs >= kFft1024MinJobs || fft1024_always))
   {
     const int ctas = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
     inv_fft1024_kernel<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.jobs.device(), njobs, plan.entries.device(),
@@ -528,7 +569,7 @@ void Engine::launch_inv(const InvPlan& plan, const GatherArgs& ga)
   {
     int max_entries = 1;
     for (auto& j : plan.jobs.host) max_entries = std::max(max_entries, j.n_entries);
-    launch_inv_kernel(inv_groups(max_entries), njobs, plan, red, ga, nullptr);
+    launch_inv_kernel(inv_groups(max_entries), njobs, plan, red, ga, nullptr, hc);
   }
   SSR_CUDA(cudaGetLastError());
   count_launch();
@@ -1035,7 +1076,7 @@ const float* Output::convolve(float weight)
     }
     else
     {
-      mac.make_work(e->mac_slots(mac.MT), e->split_cost(mac.MT));
+      mac.make_work(e->mac_slots(mac.MT), e->split_cost(mac.MT), e->mac_waves);
       mac.upload(e->stream);
       e->ensure_partials(size_t(mac.npartials) * mac.MT);
       inv.entries.host.push_back({0, mac.groups[0].nsplit, 1, 0, 0, 1.0f / float(2 * B)});

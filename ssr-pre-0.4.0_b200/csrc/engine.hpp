@@ -136,11 +136,18 @@ struct MacPlan
   int MT = 1;
   Table<ssrk::MacTermMeta> meta;
   Table<const float4*> hptr;   // [nterms][MT]
-  Table<int4> work;            // one per CTA
-  int npartials = 0;           // partial spectra groups written per launch (= CTAs)
+  // The term table (all groups back to back) is cut into `ncta` equal shares, one per
+  // CTA; a share that straddles a group boundary becomes two (or more) SEGMENTS, each
+  // with its own partial spectra.  work = segments, CTA c owns segments
+  // [cta_first[c], cta_first[c + 1]) -- its longest one first.
+  Table<int4> work;            // x = term_begin, y = term_end, z = partial index
+  Table<int> cta_first;        // [ncta + 1]
+  int ncta = 0;
+  int npartials = 0;           // partial spectra groups written per launch (= segments)
   struct Group { int term_begin, term_end, partial_first, nsplit; };
   std::vector<Group> groups;
-  void clear() { meta.host.clear(); hptr.host.clear(); work.host.clear(); groups.clear(); npartials = 0; }
+  void clear()
+  { meta.host.clear(); hptr.host.clear(); work.host.clear(); cta_first.host.clear(); groups.clear(); npartials = 0; ncta = 0; }
   int begin_group() { groups.push_back({int(meta.host.size()), 0, 0, 0}); return int(groups.size()) - 1; }
   void add_term(int input, int p, int wslot, const float4* const* h)
   {
@@ -148,9 +155,10 @@ struct MacPlan
     for (int j = 0; j < MT; ++j) hptr.host.push_back(h[j]);
   }
   void end_group() { groups.back().term_end = int(meta.host.size()); }
-  // split every group's terms into equal chunks; `slots` = CTAs resident at once
-  void make_work(int slots, int fixed_cost = 2);
-  void upload(cudaStream_t s) { meta.upload(s); hptr.upload(s); work.upload(s); }
+  // `slots` = CTAs resident at once; `fixed_cost` = cost of one more CTA in units of one
+  // term (pipeline fill, partials); `waves` > 0 forces waves x slots CTAs (experiments)
+  void make_work(int slots, int fixed_cost = 2, int waves = 0);
+  void upload(cudaStream_t s) { meta.upload(s); hptr.upload(s); work.upload(s); cta_first.upload(s); }
 };
 
 struct InvPlan
@@ -200,10 +208,19 @@ struct Engine
   DeviceArray<float4> reduced;     // pre-reduced accumulators (see reduce_partials_kernel)
 
   // launches (all asynchronous on `stream`)
-  void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs, const ssrk::FwdRingUpdate* ring_update = nullptr);
+  // overlap: the launch takes part in the programmatic-dependent-launch chain of a block
+  // loop and leaves the ring heads to be committed by the block's inverse kernel
+  // (ssrk::HeadCommit), so that the MAC launched behind it may run concurrently
+  void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs, const ssrk::FwdRingUpdate* ring_update = nullptr,
+                  bool overlap = false);
   void launch_fwd_batch(const ssrk::FwdBatch& batch, int nparts, int nchannels);
-  void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr);
-  void launch_inv(const InvPlan& plan, const ssrk::GatherArgs& ga = ssrk::GatherArgs{});
+  void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr,
+                  bool fwd_overlap = false);
+  void launch_inv(const InvPlan& plan, const ssrk::GatherArgs& ga = ssrk::GatherArgs{},
+                  const ssrk::HeadCommit& hc = ssrk::HeadCommit{});
+  bool fwd_overlap = true;         // forward transform under the MAC (SSR_B200_FWD_OVERLAP=0: off)
+  int mac_waves = 0;               // SSR_B200_MAC_WAVES: CTAs of a MAC launch = waves x resident CTAs
+  int prereduce_min = 16;          // partials per accumulator from which a separate reduction launch pays
   // dynamic renderers: terms generated on the device (ssrk::DynTables), static launch shapes
   void launch_mac_dyn(const ssrk::DynTables& dyn, int G, const float* weights);
   void launch_inv_dyn(const InvPlan& plan, const ssrk::DynCtl* ctl, int Pmax, int G);
@@ -212,7 +229,8 @@ struct Engine
   int dyn_mac_slots() const;
   int inv_groups(int max_entries) const;
   void launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const float2* red,
-                         const ssrk::GatherArgs& ga, const int* kind_counts);       // CTAs resident at once for the generated-terms MAC kernel
+                         const ssrk::GatherArgs& ga, const int* kind_counts,
+                         const ssrk::HeadCommit& hc = ssrk::HeadCommit{});       // CTAs resident at once for the generated-terms MAC kernel
   DeviceArray<unsigned long long> d_dyn_stats;  // [2] H / X partitions read by generated-terms launches
   uint64_t dyn_h_seen = 0, dyn_x_seen = 0;
   void upload_weights(const float* w, size_t n);

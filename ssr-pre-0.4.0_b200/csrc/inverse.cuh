@@ -49,6 +49,15 @@ struct GatherArgs
   unsigned long long flag_value;
 };
 
+// Ring heads left untouched by a forward launch that the MAC overlapped
+// (fwd_fft_overlap_kernel): CTA 0 of the block's inverse kernel advances them once the
+// MAC -- their last reader -- is complete.
+struct HeadCommit
+{
+  const FwdJob* jobs;   // the forward launch's job table (head pointer + ring length per input)
+  int n;                // 0: nothing to commit
+};
+
 constexpr unsigned long long kGatherTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -228,7 +237,7 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
                const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
                const float2* __restrict__ tw,
                const float* __restrict__ fade_out, const float* __restrict__ fade_in,
-               const GatherArgs ga, const int* __restrict__ kind_counts)
+               const GatherArgs ga, const int* __restrict__ kind_counts, const HeadCommit hc)
 {
   extern __shared__ float2 smem[];
   __shared__ float s_max[kThreads / 32];
@@ -244,6 +253,14 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
   float2* stw = smem + size_t(GROUPS) * 2 * B;
   stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);  // constants: may overlap the predecessor's tail
   grid_dependency_wait();
+  if (hc.n && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < hc.n; i += kThreads * GROUPS)
+    {
+      int* head = hc.jobs[i].head;
+      int h = *head + 1;
+      if (h >= hc.jobs[i].parts) h = 0;
+      *head = h;
+    }
   __syncthreads();
   // flow control of the fused gather: the slot this block goes to must have been
   // read out by the root (checked by one thread while the others start loading)

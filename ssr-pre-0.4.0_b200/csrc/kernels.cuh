@@ -67,6 +67,14 @@ __device__ __forceinline__ void grid_dependency_wait()
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Lets the next kernel of the stream (launched with the programmatic attribute) start
+// once every CTA of this grid has got here or exited; its own griddepcontrol.wait
+// still waits for this grid's completion.
+__device__ __forceinline__ void grid_launch_dependents()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -265,7 +273,9 @@ __device__ __forceinline__ float fwd_sample(const FwdHalf& h, int i)
 
 // One CTA per transform.  B = block size = complex FFT size; smem = 2 * B float2
 // (TWS: + 2 * B float2 for the staged twiddle table).
-template<bool TWS = false>
+// DEFER_HEAD: the new ring head is NOT published (the block's inverse kernel commits it,
+// HeadCommit) so that a MAC launch running concurrently sees a stable value.
+template<bool TWS = false, bool DEFER_HEAD = false>
 __device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const float2* __restrict__ tw_global)
 {
   extern __shared__ float2 smem[];
@@ -344,7 +354,7 @@ __device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const flo
   // Every thread read the old head before the first __syncthreads above, so
   // thread 0 may publish the new one now.  No other CTA of this launch touches
   // this ring; the next kernel in stream order (MAC) sees the new value.
-  if (!job.dst && t == 0) *job.head = new_head;
+  if (!DEFER_HEAD && !job.dst && t == 0) *job.head = new_head;
 }
 
 // Dynamic renderers: CTA n (= source slot n) also records the two ears' current
@@ -366,6 +376,23 @@ fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict_
   const FwdJob job = jobs[blockIdx.x];
   if (ru.ctl && threadIdx.x < 2) fwd_ring_update(ru, blockIdx.x, threadIdx.x);
   fwd_fft_body<true>(job, B, tw);
+}
+
+// The block loop's forward launch when the MAC behind it overlaps it (Engine::fwd_overlap):
+// part of the programmatic-dependent-launch chain inverse(t-1) -> forward(t) -> MAC(t).
+// It waits for the previous block's inverse kernel (which commits the ring heads and is
+// the last reader of the partial accumulators), THEN lets the MAC start: the MAC's CTAs
+// move in next to ours (16 KiB of shared memory here, no staged twiddles, leaves room
+// for the MAC's 205 KiB ring) and stream every term that does not need this block's
+// spectrum while we compute it.  The ring heads stay untouched (DEFER_HEAD).
+__global__ void __launch_bounds__(kThreads)
+fwd_fft_overlap_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru)
+{
+  grid_dependency_wait();
+  grid_launch_dependents();
+  const FwdJob job = jobs[blockIdx.x];
+  if (ru.ctl && threadIdx.x < 2) fwd_ring_update(ru, blockIdx.x, threadIdx.x);
+  fwd_fft_body<false, true>(job, B, tw);
 }
 
 // Filter-set loading: one launch transforms `channels x nvalid` partitions described

@@ -72,7 +72,11 @@ struct MacParams
   const MacTermMeta* term_meta;      // [nterms]
   const float4* const* term_h;       // [nterms][MT] partition spectra (never null:
                                      //  "empty" partitions point at a zero partition)
-  const int4* work;                  // per CTA: x = term_begin, y = term_end, z = partial index
+  const int4* work;                  // SEGMENTS: x = term_begin, y = term_end, z = partial index; a segment
+                                     //  never crosses a group boundary
+  const int* cta_first;              // [CTAs + 1]: CTA c works through segments [cta_first[c], cta_first[c + 1])
+                                     //  (usually one; two or more where its share of the term list straddles
+                                     //  a group boundary -- that is what lets 16 groups fill all 148 SMs)
   const float* wtab;                 // weights by slot
   const float4* const* xring;        // per input: ring base
   const int* xparts;                 // per input: ring length
@@ -83,6 +87,9 @@ struct MacParams
   int partial_offset;                // added to work.z
   int l2_hints;                      // 1: evict-first for H, evict-last for X
   const float4* zero;                // an all-zero partition
+  int head_bias;                     // 1: the forward transform of this block runs CONCURRENTLY (it has not
+                                     //  published the ring heads yet): newest slot = heads[] + 1, and terms with
+                                     //  p == 0 are issued last, behind griddepcontrol.wait (mac_tma_kernel)
   DynTables dyn;                     // mac_kernel<..., DYN = true>: generated terms
 };
 
@@ -128,13 +135,21 @@ mac_kernel(const MacParams p)
     const int s = int(blockIdx.x) - first;
     wk = make_int4(min(terms, s * chunk), min(terms, (s + 1) * chunk), int(blockIdx.x), 0);
   }
-  else wk = p.work[blockIdx.x];
+  int seg = 0, seg_end = 1;
+  if constexpr (!DYN) { seg = p.cta_first[blockIdx.x]; seg_end = p.cta_first[blockIdx.x + 1]; }
   // B > 1024: blockIdx.y selects a 1024-bin tile of the spectrum
   const int tile_off = blockIdx.y * (NV * kThreads);
   const int tt = tile_off + t;
   const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
   const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
 
+  bool valid[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) valid[v] = (tt + v * kThreads) < nvec;
+
+  for (; seg < seg_end; ++seg)
+  {
+  if constexpr (!DYN) wk = p.work[seg];
   float4 acc[MT][NV];
   float nyq[MT];
 #pragma unroll
@@ -144,10 +159,6 @@ mac_kernel(const MacParams p)
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-
-  bool valid[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) valid[v] = (tt + v * kThreads) < nvec;
 
   for (int tb = wk.x; tb < wk.y; tb += kMacTile)
   {
@@ -199,8 +210,9 @@ mac_kernel(const MacParams p)
         {
           const int pos = count + __popc(mask & ((1u << lane) - 1u));
           const int parts = p.xparts[m.input];
-          int slot = p.heads[m.input] - m.p;
+          int slot = p.heads[m.input] + p.head_bias - m.p;
           if (slot < 0) slot += parts;
+          if (slot >= parts) slot -= parts;
           s_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
           s_w[pos] = w;
           if constexpr (DYN)
@@ -334,6 +346,7 @@ mac_kernel(const MacParams p)
 #pragma unroll
     for (int v = 0; v < NV; ++v)
       if (valid[v]) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
+  }  // segments
 }
 
 // ---------------------------------------------------------------- MAC, bulk-copy staged
@@ -385,7 +398,81 @@ constexpr int kTmaTileBytes = kTmaTileVec * 16;
 template<int MT, int STAGES>
 constexpr size_t mac_tma_smem_bytes()
 {
-  return size_t(STAGES) * (1 + MT) * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + 4) + 128;
+  return size_t(STAGES) * (1 + MT) * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + 4 + 4) + 128;
+}
+
+// Stage markers the producer hands to the consumers next to the data stages
+constexpr int kStageData = 0, kStageDone = 1, kStageFlush = 2;
+
+// Producer side, shared by the streaming and the time-batched kernel: resolves the
+// 64-term tile [tb, tb + tile_n) of the term table into (x pointer(s), h pointers, weight)
+// records in shared memory, dropping terms with zero weight (a muted source costs no
+// traffic).  Returns the number of records.
+// defer_count != null (forward transform still running, MacParams::head_bias): terms with
+// p == 0 -- the only ones that read the spectrum the forward transform is producing -- go
+// to the side list d_* instead (at most `defer_cap` of them; *defer_count is updated; the
+// caller checks the room beforehand).
+constexpr int kMacDeferCap = 64;
+
+template<int MT, int TB>
+__device__ __forceinline__ int mac_tma_resolve_tile(const MacParams& p, int tb, int tile_n, int lane, int nvec,
+                                                    const float4* (*q_x)[TB], const float4* (*q_h)[MT], float* q_w,
+                                                    int* defer_count = nullptr, const float4** d_x = nullptr,
+                                                    const float4* (*d_h)[MT] = nullptr, float* d_w = nullptr)
+{
+  int count = 0;
+  int dcount = defer_count ? *defer_count : 0;
+  for (int base = 0; base < tile_n; base += 32)
+  {
+    const int i = base + lane;
+    bool ok = false, late = false;
+    MacTermMeta m; float w = 0.f;
+    if (i < tile_n)
+    {
+      m = p.term_meta[tb + i];
+      w = p.wtab[m.wslot + p.wtab_offset];
+      ok = (w != 0.0f);
+      late = ok && defer_count && m.p == 0;
+    }
+    const unsigned mask_late = __ballot_sync(0xffffffffu, late);
+    const unsigned mask = __ballot_sync(0xffffffffu, ok && !late);
+    if (ok)
+    {
+      const int parts = p.xparts[m.input];
+      const int head = p.heads[m.input] + p.head_bias;   // slot of the LAST block of the launch
+      const float4* xp[TB];
+#pragma unroll
+      for (int ts = 0; ts < TB; ++ts)
+      {
+        int slot = head - (TB - 1 - ts) - m.p;
+        while (slot < 0) slot += parts;
+        if (slot >= parts) slot -= parts;
+        xp[ts] = p.xring[m.input] + size_t(slot) * nvec;
+      }
+      if (late)
+      {
+        const int pos = dcount + __popc(mask_late & ((1u << lane) - 1u));
+        d_x[pos] = xp[0];
+        d_w[pos] = w;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) d_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+      }
+      else
+      {
+        const int pos = count + __popc(mask & ((1u << lane) - 1u));
+#pragma unroll
+        for (int ts = 0; ts < TB; ++ts) q_x[pos][ts] = xp[ts];
+        q_w[pos] = w;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) q_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+      }
+    }
+    count += __popc(mask);
+    dcount += __popc(mask_late);
+  }
+  if (defer_count) *defer_count = dcount;
+  __syncwarp();
+  return count;
 }
 
 template<int MT, int STAGES>
@@ -393,14 +480,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 mac_tma_kernel(const MacParams p)
 {
   extern __shared__ __align__(128) unsigned char tma_smem[];
-  __shared__ const float4* q_x[kMacTile];          // producer-private staging of a term tile
+  __shared__ const float4* q_x[kMacTile][1];       // producer-private staging of a term tile
   __shared__ const float4* q_h[kMacTile][MT];
   __shared__ float q_w[kMacTile];
+  __shared__ const float4* d_x[kMacDeferCap];      // p == 0 terms held back until the forward transform is done
+  __shared__ const float4* d_h[kMacDeferCap][MT];
+  __shared__ float d_w[kMacDeferCap];
   float4* buf = reinterpret_cast<float4*>(tma_smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(tma_smem + size_t(STAGES) * (1 + MT) * kTmaTileBytes);
   uint64_t* empty = full + STAGES;
   volatile float* stage_w = reinterpret_cast<volatile float*>(empty + STAGES);
-  volatile int* stage_end = reinterpret_cast<volatile int*>(const_cast<float*>(stage_w) + STAGES);
+  volatile int* stage_kind = reinterpret_cast<volatile int*>(const_cast<float*>(stage_w) + STAGES);
+  volatile int* stage_aux = stage_kind + STAGES;   // kStageFlush: partial index the accumulators go to
 
   const int t = threadIdx.x;
   const int lane = t & 31;
@@ -415,8 +506,12 @@ mac_tma_kernel(const MacParams p)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  grid_dependency_wait();
-  const int4 wk = p.work[blockIdx.x];
+  // head_bias: this block's forward transform may still be running (programmatic dependent
+  // launch); everything it does not produce -- the term tables, the weights, the delay-line
+  // slots of EARLIER blocks, the filter spectra -- may be read already.  Only the producer
+  // warp reads global memory; it waits before its first p == 0 term.
+  if (!p.head_bias) grid_dependency_wait();
+  const int seg_first = p.cta_first[blockIdx.x], seg_last = p.cta_first[blockIdx.x + 1];
 
   if (t >= kThreads)
   {
@@ -425,60 +520,68 @@ mac_tma_kernel(const MacParams p)
     const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     int s = 0;
     unsigned phase = 0;
-    for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+    bool waited = !p.head_bias;
+    auto issue = [&](const float4* x, const float4* const* h, float w)
     {
-      const int tile_n = min(kMacTile, wk.y - tb);
-      int count = 0;
-      for (int base = 0; base < tile_n; base += 32)
-      {
-        const int i = base + lane;
-        bool ok = false;
-        MacTermMeta m; float w = 0.f;
-        if (i < tile_n)
-        {
-          m = p.term_meta[tb + i];
-          w = p.wtab[m.wslot + p.wtab_offset];
-          ok = (w != 0.0f);   // a muted source costs no traffic
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, ok);
-        if (ok)
-        {
-          const int pos = count + __popc(mask & ((1u << lane) - 1u));
-          const int parts = p.xparts[m.input];
-          int slot = p.heads[m.input] - m.p;
-          if (slot < 0) slot += parts;
-          q_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
-          q_w[pos] = w;
+      mbar_wait(empty + s, phase ^ 1u);              // the consumers have released this stage
+      stage_w[s] = w;
+      stage_kind[s] = kStageData;
+      mbar_arrive_expect_tx(full + s, (1 + MT) * kTmaTileBytes);
+      float4* dst = buf + size_t(s) * (1 + MT) * kTmaTileVec;
+      bulk_copy_g2s(dst, x + tile_off, kTmaTileBytes, full + s, pol_x);
 #pragma unroll
-          for (int j = 0; j < MT; ++j) q_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
-        }
-        count += __popc(mask);
-      }
+      for (int j = 0; j < MT; ++j)
+        bulk_copy_g2s(dst + size_t(1 + j) * kTmaTileVec, h[j] + tile_off, kTmaTileBytes, full + s, pol_h);
+      if (++s == STAGES) { s = 0; phase ^= 1u; }
+    };
+    auto feed = [&](int count)
+    {
+      if (lane == 0)
+        for (int i = 0; i < count; ++i) issue(q_x[i][0], q_h[i], q_w[i]);
       __syncwarp();
+    };
+    auto marker = [&](int kind, int aux)
+    {
       if (lane == 0)
       {
-        for (int i = 0; i < count; ++i)
-        {
-          mbar_wait(empty + s, phase ^ 1u);          // the consumers have released this stage
-          stage_w[s] = q_w[i];
-          stage_end[s] = 0;
-          mbar_arrive_expect_tx(full + s, (1 + MT) * kTmaTileBytes);
-          float4* dst = buf + size_t(s) * (1 + MT) * kTmaTileVec;
-          bulk_copy_g2s(dst, q_x[i] + tile_off, kTmaTileBytes, full + s, pol_x);
-#pragma unroll
-          for (int j = 0; j < MT; ++j)
-            bulk_copy_g2s(dst + size_t(1 + j) * kTmaTileVec, q_h[i][j] + tile_off, kTmaTileBytes, full + s, pol_h);
-          if (++s == STAGES) { s = 0; phase ^= 1u; }
-        }
+        mbar_wait(empty + s, phase ^ 1u);
+        stage_kind[s] = kind;
+        stage_aux[s] = aux;
+        mbar_arrive(full + s);
+        if (++s == STAGES) { s = 0; phase ^= 1u; }
       }
       __syncwarp();
-    }
-    if (lane == 0)
+    };
+    // Until the forward transform of this block is known to be complete, terms with
+    // p == 0 are resolved but held back in the side list; everything else streams.  The
+    // wait comes when the CTA's first segment ends or the side list is full.
+    int deferred = 0;
+    auto release_deferred = [&]()
     {
-      mbar_wait(empty + s, phase ^ 1u);
-      stage_end[s] = 1;                               // no more terms
-      mbar_arrive(full + s);
+      grid_dependency_wait();                        // the forward transform of this block is complete
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      waited = true;
+      if (lane == 0)
+        for (int i = 0; i < deferred; ++i) issue(d_x[i], d_h[i], d_w[i]);
+      __syncwarp();
+      deferred = 0;
+    };
+    for (int seg = seg_first; seg < seg_last; ++seg)
+    {
+      const int4 wk = p.work[seg];
+      for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+      {
+        const int tile_n = min(kMacTile, wk.y - tb);
+        if (!waited && deferred + tile_n > kMacDeferCap) release_deferred();
+        const int count = waited
+            ? mac_tma_resolve_tile<MT, 1>(p, tb, tile_n, lane, nvec, q_x, q_h, q_w)
+            : mac_tma_resolve_tile<MT, 1>(p, tb, tile_n, lane, nvec, q_x, q_h, q_w, &deferred, d_x, d_h, d_w);
+        feed(count);
+      }
+      if (!waited) release_deferred();               // the side list belongs to this segment's accumulators
+      marker(kStageFlush, wk.z + p.partial_offset);
     }
+    marker(kStageDone, 0);
     return;
   }
 
@@ -498,45 +601,60 @@ mac_tma_kernel(const MacParams p)
   while (true)
   {
     mbar_wait(full + s, phase);
-    if (stage_end[s]) break;
-    const float w = stage_w[s];
-    const float4* sb = buf + size_t(s) * (1 + MT) * kTmaTileVec;
-#pragma unroll
-    for (int v = 0; v < 2; ++v)
+    const int kind = stage_kind[s];
+    if (kind == kStageDone) break;
+    if (kind == kStageFlush)
     {
-      float4 x = sb[t + v * kThreads];
-      x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+      // end of a segment: the accumulators go to its partial spectra
+      // (bin 0 holds (DC, Nyquist), both real products, convolver.h:510-541)
+      const int pidx = stage_aux[s];
+      if (tt == 0)
+      {
+#pragma unroll
+        for (int j = 0; j < MT; ++j) { acc[j][0].x += nyq[j]; acc[j][0].y = nyq[j]; }
+      }
+      float4* out = p.partials + size_t(pidx) * MT * nvec;
 #pragma unroll
       for (int j = 0; j < MT; ++j)
       {
-        const float4 h = sb[size_t(1 + j) * kTmaTileVec + t + v * kThreads];
-        acc[j][v].x = fmaf(x.x, h.x, acc[j][v].x);
-        acc[j][v].x = fmaf(-x.y, h.y, acc[j][v].x);
-        acc[j][v].y = fmaf(x.x, h.y, acc[j][v].y);
-        acc[j][v].y = fmaf(x.y, h.x, acc[j][v].y);
-        acc[j][v].z = fmaf(x.z, h.z, acc[j][v].z);
-        acc[j][v].z = fmaf(-x.w, h.w, acc[j][v].z);
-        acc[j][v].w = fmaf(x.z, h.w, acc[j][v].w);
-        acc[j][v].w = fmaf(x.w, h.z, acc[j][v].w);
-        if (v == 0 && tt == 0) nyq[j] = fmaf(x.y, h.y, nyq[j]);
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+        {
+          out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
+          acc[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        nyq[j] = 0.0f;
+      }
+    }
+    else
+    {
+      const float w = stage_w[s];
+      const float4* sb = buf + size_t(s) * (1 + MT) * kTmaTileVec;
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+      {
+        float4 x = sb[t + v * kThreads];
+        x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+        {
+          const float4 h = sb[size_t(1 + j) * kTmaTileVec + t + v * kThreads];
+          acc[j][v].x = fmaf(x.x, h.x, acc[j][v].x);
+          acc[j][v].x = fmaf(-x.y, h.y, acc[j][v].x);
+          acc[j][v].y = fmaf(x.x, h.y, acc[j][v].y);
+          acc[j][v].y = fmaf(x.y, h.x, acc[j][v].y);
+          acc[j][v].z = fmaf(x.z, h.z, acc[j][v].z);
+          acc[j][v].z = fmaf(-x.w, h.w, acc[j][v].z);
+          acc[j][v].w = fmaf(x.z, h.w, acc[j][v].w);
+          acc[j][v].w = fmaf(x.w, h.z, acc[j][v].w);
+          if (v == 0 && tt == 0) nyq[j] = fmaf(x.y, h.y, nyq[j]);
+        }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);            // this warp is done with the stage
     if (++s == STAGES) { s = 0; phase ^= 1u; }
   }
-
-  // bin 0 holds (DC, Nyquist), both real products (convolver.h:510-541)
-  if (tt == 0)
-  {
-#pragma unroll
-    for (int j = 0; j < MT; ++j) { acc[j][0].x += nyq[j]; acc[j][0].y = nyq[j]; }
-  }
-  float4* out = p.partials + size_t(wk.z + p.partial_offset) * MT * nvec;
-#pragma unroll
-  for (int j = 0; j < MT; ++j)
-#pragma unroll
-    for (int v = 0; v < 2; ++v) out[size_t(j) * nvec + tt + v * kThreads] = acc[j][v];
 }
 
 // ---------------------------------------------------------------- MAC, time-batched (offline)
@@ -554,7 +672,7 @@ mac_tma_kernel(const MacParams p)
 template<int MT, int TB, int STAGES>
 constexpr size_t mac_tma_batch_smem_bytes()
 {
-  return size_t(STAGES) * (TB + MT) * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + 4) + 128;
+  return size_t(STAGES) * (TB + MT) * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + 4 + 4) + 128;
 }
 
 template<int MT, int TB, int STAGES>
@@ -570,7 +688,8 @@ mac_tma_batch_kernel(const MacParams p)
   uint64_t* full = reinterpret_cast<uint64_t*>(tma_smem + size_t(STAGES) * (TB + MT) * kTmaTileBytes);
   uint64_t* empty = full + STAGES;
   volatile float* stage_w = reinterpret_cast<volatile float*>(empty + STAGES);
-  volatile int* stage_end = reinterpret_cast<volatile int*>(const_cast<float*>(stage_w) + STAGES);
+  volatile int* stage_kind = reinterpret_cast<volatile int*>(const_cast<float*>(stage_w) + STAGES);
+  volatile int* stage_aux = stage_kind + STAGES;
 
   const int t = threadIdx.x;
   const int lane = t & 31;
@@ -586,7 +705,7 @@ mac_tma_batch_kernel(const MacParams p)
   }
   __syncthreads();
   grid_dependency_wait();
-  const int4 wk = p.work[blockIdx.x];
+  const int seg_first = p.cta_first[blockIdx.x], seg_last = p.cta_first[blockIdx.x + 1];
 
   if (t >= kThreads)
   {
@@ -594,66 +713,46 @@ mac_tma_batch_kernel(const MacParams p)
     const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     int s = 0;
     unsigned phase = 0;
-    for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+    for (int seg = seg_first; seg <= seg_last; ++seg)
     {
-      const int tile_n = min(kMacTile, wk.y - tb);
-      int count = 0;
-      for (int base = 0; base < tile_n; base += 32)
+      int4 wk = make_int4(0, 0, 0, 0);
+      if (seg < seg_last)
       {
-        const int i = base + lane;
-        bool ok = false;
-        MacTermMeta m; float w = 0.f;
-        if (i < tile_n)
+        wk = p.work[seg];
+        for (int tb = wk.x; tb < wk.y; tb += kMacTile)
         {
-          m = p.term_meta[tb + i];
-          w = p.wtab[m.wslot + p.wtab_offset];
-          ok = (w != 0.0f);
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, ok);
-        if (ok)
-        {
-          const int pos = count + __popc(mask & ((1u << lane) - 1u));
-          const int parts = p.xparts[m.input];
-          const int head = p.heads[m.input];   // slot of the LAST block of the batch
-#pragma unroll
-          for (int ts = 0; ts < TB; ++ts)
+          const int count = mac_tma_resolve_tile<MT, TB>(p, tb, min(kMacTile, wk.y - tb), lane, nvec, q_x, q_h, q_w);
+          if (lane == 0)
           {
-            int slot = head - (TB - 1 - ts) - m.p;
-            while (slot < 0) slot += parts;
-            q_x[pos][ts] = p.xring[m.input] + size_t(slot) * nvec;
-          }
-          q_w[pos] = w;
+            for (int i = 0; i < count; ++i)
+            {
+              mbar_wait(empty + s, phase ^ 1u);
+              stage_w[s] = q_w[i];
+              stage_kind[s] = kStageData;
+              mbar_arrive_expect_tx(full + s, (TB + MT) * kTmaTileBytes);
+              float4* dst = buf + size_t(s) * kStageVec;
 #pragma unroll
-          for (int j = 0; j < MT; ++j) q_h[pos][j] = p.term_h[size_t(tb + i) * MT + j];
+              for (int ts = 0; ts < TB; ++ts)
+                bulk_copy_g2s(dst + size_t(ts) * kTmaTileVec, q_x[i][ts] + tile_off, kTmaTileBytes, full + s, pol_x);
+#pragma unroll
+              for (int j = 0; j < MT; ++j)
+                bulk_copy_g2s(dst + size_t(TB + j) * kTmaTileVec, q_h[i][j] + tile_off, kTmaTileBytes, full + s, pol_h);
+              if (++s == STAGES) { s = 0; phase ^= 1u; }
+            }
+          }
+          __syncwarp();
         }
-        count += __popc(mask);
       }
-      __syncwarp();
       if (lane == 0)
       {
-        for (int i = 0; i < count; ++i)
-        {
-          mbar_wait(empty + s, phase ^ 1u);
-          stage_w[s] = q_w[i];
-          stage_end[s] = 0;
-          mbar_arrive_expect_tx(full + s, (TB + MT) * kTmaTileBytes);
-          float4* dst = buf + size_t(s) * kStageVec;
-#pragma unroll
-          for (int ts = 0; ts < TB; ++ts)
-            bulk_copy_g2s(dst + size_t(ts) * kTmaTileVec, q_x[i][ts] + tile_off, kTmaTileBytes, full + s, pol_x);
-#pragma unroll
-          for (int j = 0; j < MT; ++j)
-            bulk_copy_g2s(dst + size_t(TB + j) * kTmaTileVec, q_h[i][j] + tile_off, kTmaTileBytes, full + s, pol_h);
-          if (++s == STAGES) { s = 0; phase ^= 1u; }
-        }
+        // end of a segment (flush the accumulators to its partials) / end of the work
+        mbar_wait(empty + s, phase ^ 1u);
+        stage_kind[s] = seg < seg_last ? kStageFlush : kStageDone;
+        stage_aux[s] = wk.z + p.partial_offset;
+        mbar_arrive(full + s);
+        if (++s == STAGES) { s = 0; phase ^= 1u; }
       }
       __syncwarp();
-    }
-    if (lane == 0)
-    {
-      mbar_wait(empty + s, phase ^ 1u);
-      stage_end[s] = 1;
-      mbar_arrive(full + s);
     }
     return;
   }
@@ -676,32 +775,55 @@ mac_tma_batch_kernel(const MacParams p)
   while (true)
   {
     mbar_wait(full + s, phase);
-    if (stage_end[s]) break;
-    const float w = stage_w[s];
-    const float4* sb = buf + size_t(s) * kStageVec;
-#pragma unroll
-    for (int v = 0; v < 2; ++v)
+    const int kind = stage_kind[s];
+    if (kind == kStageDone) break;
+    if (kind == kStageFlush)
     {
-      float4 h[MT];
-#pragma unroll
-      for (int j = 0; j < MT; ++j) h[j] = sb[size_t(TB + j) * kTmaTileVec + t + v * kThreads];
+      const int pidx = stage_aux[s];
+      float4* out = p.partials + size_t(pidx) * TB * MT * nvec;   // partials: [segment][t][row][B]
 #pragma unroll
       for (int ts = 0; ts < TB; ++ts)
-      {
-        float4 x = sb[size_t(ts) * kTmaTileVec + t + v * kThreads];
-        x.x *= w; x.y *= w; x.z *= w; x.w *= w;
 #pragma unroll
         for (int j = 0; j < MT; ++j)
         {
-          acc[ts][j][v].x = fmaf(x.x, h[j].x, acc[ts][j][v].x);
-          acc[ts][j][v].x = fmaf(-x.y, h[j].y, acc[ts][j][v].x);
-          acc[ts][j][v].y = fmaf(x.x, h[j].y, acc[ts][j][v].y);
-          acc[ts][j][v].y = fmaf(x.y, h[j].x, acc[ts][j][v].y);
-          acc[ts][j][v].z = fmaf(x.z, h[j].z, acc[ts][j][v].z);
-          acc[ts][j][v].z = fmaf(-x.w, h[j].w, acc[ts][j][v].z);
-          acc[ts][j][v].w = fmaf(x.z, h[j].w, acc[ts][j][v].w);
-          acc[ts][j][v].w = fmaf(x.w, h[j].z, acc[ts][j][v].w);
-          if (v == 0 && tt == 0) nyq[ts][j] = fmaf(x.y, h[j].y, nyq[ts][j]);
+          if (tt == 0) { acc[ts][j][0].x += nyq[ts][j]; acc[ts][j][0].y = nyq[ts][j]; }
+#pragma unroll
+          for (int v = 0; v < 2; ++v)
+          {
+            out[(size_t(ts) * MT + j) * nvec + tt + v * kThreads] = acc[ts][j][v];
+            acc[ts][j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          nyq[ts][j] = 0.0f;
+        }
+    }
+    else
+    {
+      const float w = stage_w[s];
+      const float4* sb = buf + size_t(s) * kStageVec;
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+      {
+        float4 h[MT];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) h[j] = sb[size_t(TB + j) * kTmaTileVec + t + v * kThreads];
+#pragma unroll
+        for (int ts = 0; ts < TB; ++ts)
+        {
+          float4 x = sb[size_t(ts) * kTmaTileVec + t + v * kThreads];
+          x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+          {
+            acc[ts][j][v].x = fmaf(x.x, h[j].x, acc[ts][j][v].x);
+            acc[ts][j][v].x = fmaf(-x.y, h[j].y, acc[ts][j][v].x);
+            acc[ts][j][v].y = fmaf(x.x, h[j].y, acc[ts][j][v].y);
+            acc[ts][j][v].y = fmaf(x.y, h[j].x, acc[ts][j][v].y);
+            acc[ts][j][v].z = fmaf(x.z, h[j].z, acc[ts][j][v].z);
+            acc[ts][j][v].z = fmaf(-x.w, h[j].w, acc[ts][j][v].z);
+            acc[ts][j][v].w = fmaf(x.z, h[j].w, acc[ts][j][v].w);
+            acc[ts][j][v].w = fmaf(x.w, h[j].z, acc[ts][j][v].w);
+            if (v == 0 && tt == 0) nyq[ts][j] = fmaf(x.y, h[j].y, nyq[ts][j]);
+          }
         }
       }
     }
@@ -709,21 +831,6 @@ mac_tma_batch_kernel(const MacParams p)
     if (lane == 0) mbar_arrive(empty + s);
     if (++s == STAGES) { s = 0; phase ^= 1u; }
   }
-
-  if (tt == 0)
-  {
-#pragma unroll
-    for (int ts = 0; ts < TB; ++ts)
-#pragma unroll
-      for (int j = 0; j < MT; ++j) { acc[ts][j][0].x += nyq[ts][j]; acc[ts][j][0].y = nyq[ts][j]; }
-  }
-  float4* out = p.partials + size_t(wk.z + p.partial_offset) * TB * MT * nvec;
-#pragma unroll
-  for (int ts = 0; ts < TB; ++ts)
-#pragma unroll
-    for (int j = 0; j < MT; ++j)
-#pragma unroll
-      for (int v = 0; v < 2; ++v) out[(size_t(ts) * MT + j) * nvec + tt + v * kThreads] = acc[ts][j][v];
 }
 
 }  // namespace ssrk

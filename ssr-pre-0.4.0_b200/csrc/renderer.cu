@@ -297,7 +297,7 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
       }
       static_mac.end_group();
     }
-    static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT));
+    static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT), e->mac_waves);
     static_mac.upload(e->stream);
     e->ensure_partials(size_t(3) * static_mac.npartials * static_mac.MT);
     static_dirty = false;
@@ -620,7 +620,7 @@ Renderer::StepDesc Renderer::prepare_bank(const float* d_input, float* d_output)
       }
       static_mac.end_group();
     }
-    static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT));
+    static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT), e->mac_waves);
     static_mac.upload(e->stream);
     e->ensure_partials(size_t(static_mac.npartials) * static_mac.MT);
     static_dirty = false;
@@ -720,20 +720,24 @@ void Renderer::launch(const StepDesc& d)
   InvPlan& inv = inv_plans[cur_slot];
   e->stage_begin();
   const bool dynamic = cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS;
+  // Generic plans on the bulk-copy MAC: the forward transform runs UNDER the MAC (only the
+  // p == 0 terms need its result); the ring heads are then committed by the inverse kernel
+  const bool overlap = e->fwd_overlap && cfg.kind == SSR_RENDERER_GENERIC && e->mac_tma()
+      && static_mac.MT == kGenericMT && d.N > 0;
   if (dynamic && d.N > 0)
   {
     // the forward kernel's CTA n also records source n's current filters in the ring
     const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
     e->launch_fwd(fwd->device(), d.N, &ru);
   }
-  else e->launch_fwd(fwd->device(), d.N);
+  else e->launch_fwd(fwd->device(), d.N, nullptr, overlap);
   e->stage_mark(1);
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
     for (int k = 0; k < 3; ++k)
     {
       if (!(d.kind_mask & (1 << k))) continue;
-      e->launch_mac(static_mac, k * d.N, k * static_mac.npartials);
+      e->launch_mac(static_mac, k * d.N, k * static_mac.npartials, nullptr, overlap);
       if (e->cur)
       {
         e->cur->mac_bytes += uint64_t(8) * B * (d.hparts[k] + d.xparts[k] + uint64_t(d.nrows));
@@ -755,17 +759,18 @@ void Renderer::launch(const StepDesc& d)
     }
   }
   e->stage_mark(2);
+  const HeadCommit hc{overlap ? fwd->device() : nullptr, overlap ? d.N : 0};
   if (cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS)
     e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G);
-  else if (gather) e->launch_inv(inv, gather->next_block());
+  else if (gather) e->launch_inv(inv, gather->next_block(), hc);
   else if (hostgather)
   {
     // the slot this block goes to must have been read out on the root (host-side wait;
     // forward transform and MAC are already queued and run meanwhile)
     hostgather->wait_slot_free(hostgather->epoch);
-    e->launch_inv(inv, hostgather->next_block(int(inv.jobs.uploaded)));
+    e->launch_inv(inv, hostgather->next_block(int(inv.jobs.uploaded)), hc);
   }
-  else e->launch_inv(inv);
+  else e->launch_inv(inv, GatherArgs{}, hc);
   e->stage_mark(3);
   e->stage_end();
 }

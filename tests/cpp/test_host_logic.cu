@@ -140,32 +140,62 @@ static void test_make_work()
       plan.end_group();
     }
     const int slots = 148 * (1 + int(rnd() % 2));
-    plan.make_work(slots);
+    const int fixed = (rnd() % 2) ? 2 : 8;
+    const int waves = int(rnd() % 3);   // 0 = default (one wave)
+    plan.make_work(slots, fixed, waves);
     CHECK(int(plan.work.host.size()) == plan.npartials);
+    CHECK(int(plan.cta_first.host.size()) == plan.ncta + 1);
+    CHECK(plan.ncta >= 1 && plan.ncta <= slots * std::max(1, waves));
+    // every segment lies inside one group, carries a unique partial index, and the
+    // segments of a group cover its terms exactly once with CONSECUTIVE partial indices
+    std::vector<int4> by_partial(plan.work.host.size());
     std::set<int> partial_ids;
-    size_t w = 0;
     bool ok = true;
-    int max_chunk = 0, min_chunk = 1 << 30;
+    for (auto& item : plan.work.host)
+    {
+      ok = ok && item.z >= 0 && item.z < plan.npartials && item.y > item.x;
+      if (!ok) break;
+      partial_ids.insert(item.z);
+      by_partial[size_t(item.z)] = item;
+    }
+    CHECK(ok);
+    CHECK(int(partial_ids.size()) == plan.npartials);
     for (auto& g : plan.groups)
     {
-      ok = ok && g.nsplit >= 1 && g.partial_first == int(w);
       int pos = g.term_begin;
-      for (int s = 0; s < g.nsplit; ++s, ++w)
+      ok = ok && (g.nsplit >= 1 || g.term_end == g.term_begin);
+      for (int s = 0; ok && s < g.nsplit; ++s)
       {
-        const int4 item = plan.work.host[w];
-        ok = ok && item.x == pos && item.y >= item.x && item.z == g.partial_first + s;
-        partial_ids.insert(item.z);
+        const int4 item = by_partial[size_t(g.partial_first + s)];
+        ok = ok && item.x == pos && item.y <= g.term_end;
         pos = item.y;
-        if (g.term_end > g.term_begin) { max_chunk = std::max(max_chunk, item.y - item.x); min_chunk = std::min(min_chunk, item.y - item.x); }
       }
       ok = ok && pos == g.term_end;
     }
     CHECK(ok);
-    CHECK(w == plan.work.host.size());
-    CHECK(int(partial_ids.size()) == plan.npartials);
-    if (uniform && total < 200000) CHECK(max_chunk - min_chunk <= 1);  // balanced
-    // no pathological over-splitting: at most one CTA per term (plus empty groups)
-    CHECK(plan.npartials <= total + G);
+    // CTA shares: contiguous, balanced to within one term, longest segment first
+    long lo = 1 << 30, hi = 0, covered = 0;
+    for (int c = 0; c < plan.ncta; ++c)
+    {
+      const int a = plan.cta_first.host[size_t(c)], b = plan.cta_first.host[size_t(c) + 1];
+      ok = ok && a <= b;
+      long share = 0;
+      int first_len = 0, max_len = 0;
+      for (int i = a; i < b; ++i)
+      {
+        const int len = plan.work.host[size_t(i)].y - plan.work.host[size_t(i)].x;
+        if (i == a) first_len = len;
+        max_len = std::max(max_len, len);
+        share += len;
+      }
+      ok = ok && first_len == max_len;
+      lo = std::min(lo, share); hi = std::max(hi, share); covered += share;
+    }
+    CHECK(ok);
+    CHECK(covered == total);
+    if (total >= plan.ncta) CHECK(hi - lo <= 1);
+    // no pathological over-splitting: a CTA adds at most one segment per group it touches
+    CHECK(plan.npartials <= plan.ncta + G);
   }
 }
 
@@ -271,13 +301,16 @@ static void test_cfg5_split()
       for (int p = 0; p < 47; ++p) plan.add_term(n, p, n, h);
     plan.end_group();
   }
-  plan.make_work(148, Engine::kSplitCostTma);  // bulk-copy staged MAC: one CTA per SM
-  CHECK(plan.npartials == 1024);         // 8 splits per group = 6.92 waves of 148
-  plan.make_work(148, 2);
-  CHECK(plan.npartials == 1920);         // (the split before the fixed cost was raised: 12.97 waves)
-  plan.make_work(296, 2);                // register-staged MAC: two CTAs per SM
-  CHECK(plan.npartials == 3840);
-  // sharded over 8 GPUs: 16 groups per GPU -> one wave (9 splits per group)
+  // bulk-copy staged MAC, one CTA per SM: one wave of 148 equal shares of the 770 048 terms
+  // (5203 each); 124 of the 127 group boundaries fall inside a share (3 coincide with share
+  // boundaries: 128 / 148 = 32 / 37) -> 272 partial spectra groups
+  // (round 1 cut every group into 8: 1024 CTAs = 6.92 waves, 1024 partials)
+  plan.make_work(148, Engine::kSplitCostTma);
+  CHECK(plan.ncta == 148);
+  CHECK(plan.npartials == 148 + 124);
+  plan.make_work(148, Engine::kSplitCostTma, 7);   // SSR_B200_MAC_WAVES=7
+  CHECK(plan.ncta == 1036);
+  // sharded over 8 GPUs: 16 groups per GPU -> all 148 SMs (round 1: 16 x 9 = 144 CTAs)
   MacPlan shard;
   shard.MT = 4;
   for (int g = 0; g < 16; ++g)
@@ -288,9 +321,17 @@ static void test_cfg5_split()
     shard.end_group();
   }
   shard.make_work(148, Engine::kSplitCostTma);
-  CHECK(shard.npartials == 144);
-  shard.make_work(148, 2);
-  CHECK(shard.npartials == 592);         // four waves, four pipeline fills and 4x the partials
+  CHECK(shard.ncta == 148);
+  CHECK(shard.npartials == 148 + 12);
+  int longest = 0;
+  for (int c = 0; c < shard.ncta; ++c)
+  {
+    int share = 0;
+    for (int i = shard.cta_first.host[size_t(c)]; i < shard.cta_first.host[size_t(c) + 1]; ++i)
+      share += shard.work.host[size_t(i)].y - shard.work.host[size_t(i)].x;
+    longest = std::max(longest, share);
+  }
+  CHECK(longest == 651);                 // 96 256 terms / 148 (round 1: 6016 / 9 = 669)
 }
 
 int main()
