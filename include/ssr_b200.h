@@ -20,7 +20,9 @@
  *    valid until the next call that produces a result for the same object.
  *  - threading: one engine is used by one host thread at a time (the reference
  *    gives the same guarantee per convolver object, apf/apf/convolver.h:53 and
- *    the list barrier apf/apf/mimoprocessor.h:476-482).
+ *    the list barrier apf/apf/mimoprocessor.h:476-482) -- EXCEPT the control
+ *    setters ssr_source_set_* / ssr_renderer_set_*, which any thread may call at
+ *    any time (command queue, see "Control inputs").
  */
 #ifndef SSR_B200_H
 #define SSR_B200_H
@@ -261,13 +263,25 @@ int ssr_renderer_add_source_synthetic(ssr_renderer* r, long taps, int channels, 
 int ssr_renderer_rem_source(ssr_renderer* r, int id);
 int ssr_renderer_sources(const ssr_renderer* r);
 
-/* per-source control inputs (src/rendererbase.h:419-423) */
+/* Control inputs.  THREAD-SAFE HAND-OFF: these setters may be called from any thread,
+ * also while another thread is inside ssr_renderer_process / submit / wait (the GUI,
+ * network and tracker threads of the reference, src/rendersubscriber.h:164-169).  Like
+ * apf::SharedData::operator= (apf/apf/shareddata.h:57-60) they do not touch the
+ * renderer: they queue a command (apf::CommandQueue::push, apf/apf/commandqueue.h:
+ * 185-210; 4096 slots, several control threads are serialised internally), and the
+ * audio thread executes everything queued, in order, at the start of its next block
+ * (apf/apf/mimoprocessor.h:374).  A command for a source that has been removed
+ * meanwhile is dropped.  SSR_ERR_STATE: the queue stayed full for 0.2 s (no thread
+ * is rendering blocks).  Adding / removing sources, loading filters and the level
+ * meters remain calls of the thread that owns the audio callback.
+ *
+ * per-source (src/rendererbase.h:419-423) */
 int ssr_source_set_gain(ssr_renderer* r, int id, float gain);
 int ssr_source_set_mute(ssr_renderer* r, int id, int mute);
 int ssr_source_set_position(ssr_renderer* r, int id, float x, float y);
 int ssr_source_set_model(ssr_renderer* r, int id, int plane);  /* 0 point, 1 plane */
 
-/* global control inputs (RendererBase::State, src/rendererbase.h:84-103) */
+/* global (RendererBase::State, src/rendererbase.h:84-103) */
 int ssr_renderer_set_reference_position(ssr_renderer* r, float x, float y);
 int ssr_renderer_set_reference_orientation(ssr_renderer* r, float azimuth_deg);
 int ssr_renderer_set_reference_offset_position(ssr_renderer* r, float x, float y);
@@ -275,6 +289,28 @@ int ssr_renderer_set_reference_offset_orientation(ssr_renderer* r, float azimuth
 int ssr_renderer_set_master_volume(ssr_renderer* r, float v);
 int ssr_renderer_set_processing(ssr_renderer* r, int on);
 int ssr_renderer_set_amplitude_reference_distance(ssr_renderer* r, float d);
+
+/* The state the audio thread rendered its LAST block with (= SharedData::get() on the
+ * audio side; queued commands are not visible before the block that applies them).
+ * To be called by the thread that owns the audio callback. */
+typedef struct ssr_renderer_state
+{
+  float reference_x, reference_y, reference_azimuth;
+  float reference_offset_x, reference_offset_y, reference_offset_azimuth;
+  float master_volume, amplitude_reference_distance;
+  int processing;
+  int pending_commands;      /* queued, not applied yet */
+  uint64_t blocks;           /* blocks started so far */
+  int reserved[4];
+} ssr_renderer_state;
+typedef struct ssr_source_state
+{
+  float gain; int mute; float x, y; int plane;
+  float weighting_factor;    /* RendererBase::Source::weighting_factor of the last block */
+  int reserved[4];
+} ssr_source_state;
+int ssr_renderer_get_state(ssr_renderer* r, ssr_renderer_state* out);
+int ssr_source_get_state(ssr_renderer* r, int id, ssr_source_state* out);
 
 /* Level meters = the reference's apf::enable_queries policy
  * (src/rendererbase.h:431-437, 468-474; shown by the GUI, src/controller.h:406-528):

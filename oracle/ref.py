@@ -17,7 +17,11 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libssr_ref.so")
+# SSR_REF_LIB selects another build of the same harness: _ref/libssr_ref_gpu.so is the
+# reference's unmodified renderers compiled against the GPU engine's facade of
+# apf/convolver.h (oracle/Makefile; tests/test_gpu_dropin.py) -- single-threaded only
+LIB_PATH = os.environ.get("SSR_REF_LIB") or os.path.join(_HERE, "_ref", "libssr_ref.so")
+GPU_LIB_PATH = os.path.join(_HERE, "_ref", "libssr_ref_gpu.so")
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)

@@ -234,9 +234,15 @@ int ref_filter_partitions(void* f)
 /* copies the sorted spectrum of partition p; returns the zero flag */
 int ref_filter_get(void* f, int p, float* out)
 {
+#ifdef SSR_REF_GPU_FACADE
+  // built against ssr-pre-0.4.0_b200/cpp/apf/convolver.h (the GPU engine's facade of
+  // the same class API): spectra live in HBM, fetched in the reference's layout
+  return static_cast<c::Filter*>(f)->download(size_t(p), out) ? 1 : 0;
+#else
   auto& node = (*static_cast<c::Filter*>(f))[size_t(p)];
   std::copy(node.begin(), node.end(), out);
   return node.zero ? 1 : 0;
+#endif
 }
 
 void ref_filter_delete(void* f) { delete static_cast<c::Filter*>(f); }
@@ -272,10 +278,15 @@ int ref_input_partitions(void* in)
 /* spectrum p of the FDL (0 = newest); returns zero flag */
 int ref_input_get(void* in, int p, float* out)
 {
+#ifdef SSR_REF_GPU_FACADE
+  if (ssr_input_download(static_cast<c::Input*>(in)->handle(), p, out) != SSR_OK) return -1;
+  return 0;   // the engine keeps no zero flag for delay-line spectra (an all-zero block is stored as zeros)
+#else
   auto it = static_cast<c::Input*>(in)->spectra.begin();
   std::advance(it, p);
   std::copy(it->begin(), it->end(), out);
   return it->zero ? 1 : 0;
+#endif
 }
 
 void ref_input_delete(void* in) { delete static_cast<c::Input*>(in); }

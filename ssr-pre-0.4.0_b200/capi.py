@@ -45,6 +45,19 @@ class RendererConfig(C.Structure):
                 ("reserved", C.c_int * 8)]
 
 
+class RendererState(C.Structure):
+    _fields_ = [("reference_x", C.c_float), ("reference_y", C.c_float), ("reference_azimuth", C.c_float),
+                ("reference_offset_x", C.c_float), ("reference_offset_y", C.c_float),
+                ("reference_offset_azimuth", C.c_float), ("master_volume", C.c_float),
+                ("amplitude_reference_distance", C.c_float), ("processing", C.c_int),
+                ("pending_commands", C.c_int), ("blocks", C.c_uint64), ("reserved", C.c_int * 4)]
+
+
+class SourceState(C.Structure):
+    _fields_ = [("gain", C.c_float), ("mute", C.c_int), ("x", C.c_float), ("y", C.c_float), ("plane", C.c_int),
+                ("weighting_factor", C.c_float), ("reserved", C.c_int * 4)]
+
+
 class SsrError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"[{code}] {msg}")
@@ -108,6 +121,8 @@ SIGNATURES = {
     "ssr_renderer_set_master_volume": (C.c_int, [C.c_void_p, C.c_float]),
     "ssr_renderer_set_processing": (C.c_int, [C.c_void_p, C.c_int]),
     "ssr_renderer_set_amplitude_reference_distance": (C.c_int, [C.c_void_p, C.c_float]),
+    "ssr_renderer_get_state": (C.c_int, [C.c_void_p, C.POINTER(RendererState)]),
+    "ssr_source_get_state": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SourceState)]),
     "ssr_renderer_set_level_metering": (C.c_int, [C.c_void_p, C.c_int]),
     "ssr_renderer_get_levels": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "ssr_renderer_process": (C.c_int, [C.c_void_p, C.c_int, _pp, _pp]),
@@ -563,6 +578,17 @@ class Renderer:
     def set_master_volume(self, v): _check(lib().ssr_renderer_set_master_volume(self.h, v))
     def set_processing(self, on): _check(lib().ssr_renderer_set_processing(self.h, int(on)))
     def set_amplitude_reference_distance(self, d): _check(lib().ssr_renderer_set_amplitude_reference_distance(self.h, d))
+
+    def get_state(self) -> RendererState:
+        """State the audio thread rendered its last block with."""
+        st = RendererState()
+        _check(lib().ssr_renderer_get_state(self.h, C.byref(st)))
+        return st
+
+    def get_source_state(self, sid: int) -> SourceState:
+        st = SourceState()
+        _check(lib().ssr_source_get_state(self.h, sid, C.byref(st)))
+        return st
 
     def set_level_metering(self, on: bool):
         _check(lib().ssr_renderer_set_level_metering(self.h, int(on)))

@@ -40,6 +40,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -130,75 +131,123 @@ struct SoundFile
 inline uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (uint32_t(p[3]) << 24); }
 inline uint16_t rd16(const unsigned char* p) { return uint16_t(p[0] | (p[1] << 8)); }
 
-/// Replaces apf::load_sndfile (apf/apf/sndfiletools.h:43-90), same checks and
-/// std::logic_error messages.
-inline SoundFile load_sndfile(const std::string& name, size_t sample_rate, size_t channels)
+/// Streaming WAV reader: the header is parsed on open(), frames are converted to float
+/// as they are read (what libsndfile's SndfileHandle::readf does for the reference,
+/// apf/apf/mimoprocessor_file_io.h:80-110) -- a long multichannel file is never held
+/// in memory as a whole.
+class WavReader
 {
-  if (name == "") throw std::logic_error("apf::load_sndfile(): Empty file name!");
-  SoundFile sf;
-  std::FILE* f = std::fopen(name.c_str(), "rb");
-  auto fail = [&] { if (f) std::fclose(f);
-    throw std::logic_error("apf::load_sndfile(): \"" + name + "\" couldn't be loaded!"); };
-  if (!f) fail();
-  unsigned char hdr[12];
-  if (std::fread(hdr, 1, 12, f) != 12 || std::memcmp(hdr, "RIFF", 4) || std::memcmp(hdr + 8, "WAVE", 4)) fail();
-  int format = 0, bits = 0;
-  bool have_fmt = false;
-  for (;;)
-  {
-    unsigned char ch[8];
-    if (std::fread(ch, 1, 8, f) != 8) fail();
-    const uint32_t size = rd32(ch + 4);
-    if (!std::memcmp(ch, "fmt ", 4))
+  public:
+    WavReader() {}
+    WavReader(const WavReader&) = delete;
+    WavReader& operator=(const WavReader&) = delete;
+    ~WavReader() { close(); }
+
+    int channels = 0, samplerate = 0;
+    long frames = 0;
+    int format = 3, bits = 32;  // WAV format tag (1 PCM, 3 IEEE float) and sample width
+
+    /// false: not a readable WAV file
+    bool open(const std::string& name)
     {
-      std::vector<unsigned char> fmt(size);
-      if (size < 16 || std::fread(fmt.data(), 1, size, f) != size) fail();
-      format = rd16(fmt.data());
-      sf.channels = rd16(fmt.data() + 2);
-      sf.samplerate = int(rd32(fmt.data() + 4));
-      bits = rd16(fmt.data() + 14);
-      if (format == 0xFFFE && size >= 26) format = rd16(fmt.data() + 24);  // WAVE_FORMAT_EXTENSIBLE
-      have_fmt = true;
-      if (size & 1) std::fseek(f, 1, SEEK_CUR);
-    }
-    else if (!std::memcmp(ch, "data", 4))
-    {
-      if (!have_fmt || sf.channels <= 0 || bits % 8 != 0) fail();
-      const size_t bps = size_t(bits) / 8;
-      std::vector<unsigned char> raw(size);
-      const size_t got = std::fread(raw.data(), 1, size, f);
-      const size_t n = got / bps;
-      sf.frames = long(n / size_t(sf.channels));
-      sf.data.resize(size_t(sf.frames) * sf.channels);
-      for (size_t i = 0; i < sf.data.size(); ++i)
+      close();
+      _f = std::fopen(name.c_str(), "rb");
+      if (!_f) return false;
+      unsigned char hdr[12];
+      if (std::fread(hdr, 1, 12, _f) != 12 || std::memcmp(hdr, "RIFF", 4) || std::memcmp(hdr + 8, "WAVE", 4))
+        return fail();
+      bool have_fmt = false;
+      for (;;)
       {
-        const unsigned char* p = raw.data() + i * bps;
+        unsigned char ch[8];
+        if (std::fread(ch, 1, 8, _f) != 8) return fail();
+        const uint32_t size = rd32(ch + 4);
+        if (!std::memcmp(ch, "fmt ", 4))
+        {
+          std::vector<unsigned char> fmt(size);
+          if (size < 16 || std::fread(fmt.data(), 1, size, _f) != size) return fail();
+          format = rd16(fmt.data());
+          channels = rd16(fmt.data() + 2);
+          samplerate = int(rd32(fmt.data() + 4));
+          bits = rd16(fmt.data() + 14);
+          if (format == 0xFFFE && size >= 26) format = rd16(fmt.data() + 24);  // WAVE_FORMAT_EXTENSIBLE
+          have_fmt = true;
+          if (size & 1) std::fseek(_f, 1, SEEK_CUR);
+        }
+        else if (!std::memcmp(ch, "data", 4))
+        {
+          if (!have_fmt || channels <= 0 || bits % 8 != 0) return fail();
+          const bool known = (format == 1 && (bits == 8 || bits == 16 || bits == 24 || bits == 32))
+              || (format == 3 && (bits == 32 || bits == 64));
+          if (!known) return fail();
+          // a truncated file delivers what is there (libsndfile does the same)
+          const long here = std::ftell(_f);
+          std::fseek(_f, 0, SEEK_END);
+          const long avail = std::ftell(_f) - here;
+          std::fseek(_f, here, SEEK_SET);
+          const size_t bytes = std::min<size_t>(size, size_t(std::max<long>(avail, 0)));
+          frames = long(bytes / (size_t(bits) / 8) / size_t(channels));
+          _left = frames;
+          return true;
+        }
+        else std::fseek(_f, long(size + (size & 1)), SEEK_CUR);
+      }
+    }
+
+    /// reads up to `n` frames, interleaved (frames x channels) floats; returns the frames read
+    long read(float* out, long n)
+    {
+      n = std::min(n, _left);
+      if (n <= 0 || !_f) return 0;
+      const size_t bps = size_t(bits) / 8;
+      const size_t count = size_t(n) * channels;
+      _raw.resize(count * bps);
+      const size_t got = std::fread(_raw.data(), bps, count, _f) / size_t(channels);
+      for (size_t i = 0; i < got * channels; ++i)
+      {
+        const unsigned char* p = _raw.data() + i * bps;
         float v = 0.0f;
         if (format == 1)  // PCM, scaled like libsndfile's float conversion
         {
           if (bits == 8) v = (float(p[0]) - 128.0f) / 128.0f;
           else if (bits == 16) v = float(int16_t(rd16(p))) / 32768.0f;
           else if (bits == 24) v = float(int32_t((p[0] << 8) | (p[1] << 16) | (uint32_t(p[2]) << 24)) >> 8) / 8388608.0f;
-          else if (bits == 32) v = float(double(int32_t(rd32(p))) / 2147483648.0);
-          else fail();
+          else v = float(double(int32_t(rd32(p))) / 2147483648.0);
         }
-        else if (format == 3)
+        else
         {
           if (bits == 32) { uint32_t u = rd32(p); std::memcpy(&v, &u, 4); }
-          else if (bits == 64) { double d; std::memcpy(&d, p, 8); v = float(d); }
-          else fail();
+          else { double d; std::memcpy(&d, p, 8); v = float(d); }
         }
-        else fail();
-        sf.data[i] = v;
+        out[i] = v;
       }
-      break;
+      _left -= long(got);
+      return long(got);
     }
-    else std::fseek(f, long(size + (size & 1)), SEEK_CUR);
-  }
-  std::fclose(f);
-  f = nullptr;
-  sf.format = format; sf.bits = bits;
-  if (!sf.channels) fail();
+
+    void close() { if (_f) std::fclose(_f); _f = nullptr; _left = 0; }
+
+  private:
+    bool fail() { close(); return false; }
+    std::FILE* _f = nullptr;
+    long _left = 0;
+    std::vector<unsigned char> _raw;
+};
+
+/// Replaces apf::load_sndfile (apf/apf/sndfiletools.h:43-90), same checks and
+/// std::logic_error messages.  (Impulse-response sets are loaded as a whole, as in the
+/// reference.)
+inline SoundFile load_sndfile(const std::string& name, size_t sample_rate, size_t channels)
+{
+  if (name == "") throw std::logic_error("apf::load_sndfile(): Empty file name!");
+  WavReader rd;
+  if (!rd.open(name) || !rd.channels)
+    throw std::logic_error("apf::load_sndfile(): \"" + name + "\" couldn't be loaded!");
+  SoundFile sf;
+  sf.channels = rd.channels; sf.samplerate = rd.samplerate; sf.format = rd.format; sf.bits = rd.bits;
+  sf.data.resize(size_t(rd.frames) * rd.channels);
+  sf.frames = rd.read(sf.data.data(), rd.frames);
+  sf.data.resize(size_t(sf.frames) * rd.channels);
   if (sample_rate && sample_rate != size_t(sf.samplerate))
     throw std::logic_error("apf::load_sndfile(): \"" + name + "\" has sample rate "
         + std::to_string(sf.samplerate) + " instead of " + std::to_string(sample_rate) + "!");
@@ -208,38 +257,82 @@ inline SoundFile load_sndfile(const std::string& name, size_t sample_rate, size_
   return sf;
 }
 
-/// Writes interleaved float samples as WAV (PCM 16/24/32 or IEEE float 32).
+/// Streaming WAV writer (PCM 16/24/32 or IEEE float 32): header first, frames as they
+/// come, sizes patched on close().
+class WavWriter
+{
+  public:
+    WavWriter() {}
+    WavWriter(const WavWriter&) = delete;
+    WavWriter& operator=(const WavWriter&) = delete;
+    ~WavWriter() { close(); }
+
+    void open(const std::string& name, int channels, int samplerate, int format = 3, int bits = 32)
+    {
+      close();
+      if (!((format == 1 && (bits == 16 || bits == 24 || bits == 32)) || (format == 3 && bits == 32)))
+      { format = 3; bits = 32; }
+      _f = std::fopen(name.c_str(), "wb");
+      if (!_f) throw std::runtime_error("write_wav(): cannot open \"" + name + "\"");
+      _channels = channels; _format = format; _bits = bits; _bytes = 0;
+      const uint32_t bps = uint32_t(bits) / 8;
+      std::fwrite("RIFF", 1, 4, _f); put32(36); std::fwrite("WAVE", 1, 4, _f);
+      std::fwrite("fmt ", 1, 4, _f); put32(16); put16(uint16_t(format)); put16(uint16_t(channels));
+      put32(uint32_t(samplerate)); put32(uint32_t(samplerate) * channels * bps);
+      put16(uint16_t(channels * bps)); put16(uint16_t(bits));
+      std::fwrite("data", 1, 4, _f); put32(0);
+    }
+
+    void write(const float* data, long frames)
+    {
+      if (!_f || frames <= 0) return;
+      const size_t n = size_t(frames) * _channels;
+      const uint32_t bps = uint32_t(_bits) / 8;
+      if (_format == 3) std::fwrite(data, 4, n, _f);
+      else
+      {
+        const double full = _bits == 16 ? 32768.0 : (_bits == 24 ? 8388608.0 : 2147483648.0);
+        _raw.resize(n * bps);
+        for (size_t i = 0; i < n; ++i)
+        {
+          double v = std::floor(double(data[i]) * full + 0.5);
+          if (v > full - 1) v = full - 1;
+          if (v < -full) v = -full;
+          const int32_t q = int32_t(v);
+          std::memcpy(_raw.data() + i * bps, &q, bps);  // little endian host
+        }
+        std::fwrite(_raw.data(), 1, _raw.size(), _f);
+      }
+      _bytes += uint64_t(n) * bps;
+    }
+
+    void close()
+    {
+      if (!_f) return;
+      const uint32_t bytes = uint32_t(_bytes);
+      std::fseek(_f, 4, SEEK_SET); put32(36 + bytes);
+      std::fseek(_f, 40, SEEK_SET); put32(bytes);
+      std::fclose(_f);
+      _f = nullptr;
+    }
+
+  private:
+    void put32(uint32_t v) { std::fwrite(&v, 4, 1, _f); }
+    void put16(uint16_t v) { std::fwrite(&v, 2, 1, _f); }
+    std::FILE* _f = nullptr;
+    int _channels = 0, _format = 3, _bits = 32;
+    uint64_t _bytes = 0;
+    std::vector<unsigned char> _raw;
+};
+
+/// Writes interleaved float samples as WAV in one go.
 inline void write_wav(const std::string& name, const float* data, long frames, int channels
     , int samplerate, int format = 3, int bits = 32)
 {
-  if (!((format == 1 && (bits == 16 || bits == 24 || bits == 32)) || (format == 3 && bits == 32)))
-  { format = 3; bits = 32; }
-  std::FILE* f = std::fopen(name.c_str(), "wb");
-  if (!f) throw std::runtime_error("write_wav(): cannot open \"" + name + "\"");
-  const uint32_t bps = uint32_t(bits) / 8;
-  const uint32_t bytes = uint32_t(size_t(frames) * channels * bps);
-  auto put32 = [f](uint32_t v) { std::fwrite(&v, 4, 1, f); };
-  auto put16 = [f](uint16_t v) { std::fwrite(&v, 2, 1, f); };
-  std::fwrite("RIFF", 1, 4, f); put32(36 + bytes); std::fwrite("WAVE", 1, 4, f);
-  std::fwrite("fmt ", 1, 4, f); put32(16); put16(uint16_t(format)); put16(uint16_t(channels));
-  put32(uint32_t(samplerate)); put32(uint32_t(samplerate) * channels * bps);
-  put16(uint16_t(channels * bps)); put16(uint16_t(bits));
-  std::fwrite("data", 1, 4, f); put32(bytes);
-  const size_t n = size_t(frames) * channels;
-  if (format == 3) std::fwrite(data, 4, n, f);
-  else
-  {
-    const double full = bits == 16 ? 32768.0 : (bits == 24 ? 8388608.0 : 2147483648.0);
-    for (size_t i = 0; i < n; ++i)
-    {
-      double v = std::floor(double(data[i]) * full + 0.5);
-      if (v > full - 1) v = full - 1;
-      if (v < -full) v = -full;
-      const int32_t q = int32_t(v);
-      std::fwrite(&q, bps, 1, f);  // little endian host
-    }
-  }
-  std::fclose(f);
+  WavWriter w;
+  w.open(name, channels, samplerate, format, bits);
+  w.write(data, frames);
+  w.close();
 }
 
 /// Assignable control value forwarding to a C setter (stands in for

@@ -423,24 +423,59 @@ int ssr_renderer_rem_source(ssr_renderer* r, int id)
 int ssr_renderer_sources(const ssr_renderer* r) { return r ? int(r->impl.sources.size()) : 0; }
 int ssr_renderer_local_outputs(const ssr_renderer* r) { return r ? r->impl.m_local : 0; }
 
-#define SSR_SOURCE_SETTER(name, stmt) \
-  return guarded([&] { require(r, "null renderer"); Renderer::Source* s = r->impl.find(id); stmt; })
+// Control inputs: callable from any thread, also while another thread is inside
+// ssr_renderer_process.  They queue a command (apf::SharedData::operator= ->
+// CommandQueue::push, apf/apf/shareddata.h:57-60); the audio thread applies the queue
+// at the start of its next block.
+static int push_control(ssr_renderer* r, int kind, int id, float a, float b, bool source)
+{
+  return guarded([&] {
+    require(r, "null renderer");
+    // (reads the source list: adding / removing sources stays a call of the audio thread's owner)
+    if (source) (void)r->impl.find(id);
+    if (!r->impl.control.push(ControlQueue::Cmd{kind, id, a, b}))
+      throw Error(SSR_ERR_STATE, "ssr_b200: control queue full (4096 commands pending): is the audio thread rendering blocks?");
+  });
+}
 
-int ssr_source_set_gain(ssr_renderer* r, int id, float gain) { SSR_SOURCE_SETTER(gain, s->gain = gain); }
-int ssr_source_set_mute(ssr_renderer* r, int id, int mute) { SSR_SOURCE_SETTER(mute, s->mute = mute != 0); }
-int ssr_source_set_position(ssr_renderer* r, int id, float x, float y) { SSR_SOURCE_SETTER(position, (s->px = x, s->py = y)); }
-int ssr_source_set_model(ssr_renderer* r, int id, int plane) { SSR_SOURCE_SETTER(model, s->plane = plane != 0); }
+int ssr_source_set_gain(ssr_renderer* r, int id, float gain) { return push_control(r, ControlQueue::SRC_GAIN, id, gain, 0, true); }
+int ssr_source_set_mute(ssr_renderer* r, int id, int mute) { return push_control(r, ControlQueue::SRC_MUTE, id, mute ? 1.0f : 0.0f, 0, true); }
+int ssr_source_set_position(ssr_renderer* r, int id, float x, float y) { return push_control(r, ControlQueue::SRC_POSITION, id, x, y, true); }
+int ssr_source_set_model(ssr_renderer* r, int id, int plane) { return push_control(r, ControlQueue::SRC_MODEL, id, plane ? 1.0f : 0.0f, 0, true); }
 
-#define SSR_STATE_SETTER(stmt) \
-  return guarded([&] { require(r, "null renderer"); Renderer& R = r->impl; stmt; })
+int ssr_renderer_set_reference_position(ssr_renderer* r, float x, float y) { return push_control(r, ControlQueue::REF_POSITION, 0, x, y, false); }
+int ssr_renderer_set_reference_orientation(ssr_renderer* r, float az) { return push_control(r, ControlQueue::REF_ORIENTATION, 0, az, 0, false); }
+int ssr_renderer_set_reference_offset_position(ssr_renderer* r, float x, float y) { return push_control(r, ControlQueue::OFF_POSITION, 0, x, y, false); }
+int ssr_renderer_set_reference_offset_orientation(ssr_renderer* r, float az) { return push_control(r, ControlQueue::OFF_ORIENTATION, 0, az, 0, false); }
+int ssr_renderer_set_master_volume(ssr_renderer* r, float v) { return push_control(r, ControlQueue::MASTER_VOLUME, 0, v, 0, false); }
+int ssr_renderer_set_processing(ssr_renderer* r, int on) { return push_control(r, ControlQueue::PROCESSING, 0, on ? 1.0f : 0.0f, 0, false); }
+int ssr_renderer_set_amplitude_reference_distance(ssr_renderer* r, float d) { return push_control(r, ControlQueue::AMP_REF_DISTANCE, 0, d, 0, false); }
 
-int ssr_renderer_set_reference_position(ssr_renderer* r, float x, float y) { SSR_STATE_SETTER((R.ref_x = x, R.ref_y = y)); }
-int ssr_renderer_set_reference_orientation(ssr_renderer* r, float az) { SSR_STATE_SETTER(R.ref_az = az); }
-int ssr_renderer_set_reference_offset_position(ssr_renderer* r, float x, float y) { SSR_STATE_SETTER((R.off_x = x, R.off_y = y)); }
-int ssr_renderer_set_reference_offset_orientation(ssr_renderer* r, float az) { SSR_STATE_SETTER(R.off_az = az); }
-int ssr_renderer_set_master_volume(ssr_renderer* r, float v) { SSR_STATE_SETTER(R.master_volume = v); }
-int ssr_renderer_set_processing(ssr_renderer* r, int on) { SSR_STATE_SETTER(R.processing = on != 0); }
-int ssr_renderer_set_amplitude_reference_distance(ssr_renderer* r, float d) { SSR_STATE_SETTER(R.amplitude_reference_distance = d); }
+int ssr_renderer_get_state(ssr_renderer* r, ssr_renderer_state* out)
+{
+  return guarded([&] {
+    require(r && out, "renderer_get_state: null argument");
+    const Renderer& R = r->impl;
+    *out = ssr_renderer_state{};
+    out->reference_x = R.ref_x; out->reference_y = R.ref_y; out->reference_azimuth = R.ref_az;
+    out->reference_offset_x = R.off_x; out->reference_offset_y = R.off_y; out->reference_offset_azimuth = R.off_az;
+    out->master_volume = R.master_volume; out->amplitude_reference_distance = R.amplitude_reference_distance;
+    out->processing = R.processing ? 1 : 0;
+    out->blocks = R.blocks_started;
+    out->pending_commands = int(R.control.tail.load() - R.control.head.load());
+  });
+}
+
+int ssr_source_get_state(ssr_renderer* r, int id, ssr_source_state* out)
+{
+  return guarded([&] {
+    require(r && out, "source_get_state: null argument");
+    const Renderer::Source* s = r->impl.find(id);
+    *out = ssr_source_state{};
+    out->gain = s->gain; out->mute = s->mute ? 1 : 0; out->x = s->px; out->y = s->py; out->plane = s->plane ? 1 : 0;
+    out->weighting_factor = s->weighting_factor.get();
+  });
+}
 
 int ssr_renderer_set_level_metering(ssr_renderer* r, int on)
 {

@@ -196,8 +196,10 @@ Engine::Engine(const ssr_engine_config& cfg)
   }
   // the overlapped forward kernel shares its SM with a MAC CTA (205 KiB of shared memory):
   // both must run under the same (maximal) shared-memory carve-out to be co-resident
-  SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+  SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout,
         int(cudaSharedmemCarveoutMaxShared)));
+  // (the generated-terms MAC of Binaural / BRS keeps the default carve-out -- with the
+  // maximal one it loses 20 % (profiles/r2_ab) -- and so does the forward kernel next to it)
   if (const char* v = std::getenv("SSR_B200_PDL")) pdl = std::atoi(v) != 0;  // A/B experiments
   if (const char* v = std::getenv("SSR_B200_FWD_OVERLAP")) fwd_overlap = std::atoi(v) != 0;
   if (const char* v = std::getenv("SSR_B200_MAC_WAVES")) mac_waves = std::max(0, std::atoi(v));
@@ -210,7 +212,8 @@ Engine::Engine(const ssr_engine_config& cfg)
     SSR_CUDA(cudaFuncSetAttribute(level1_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(fwd_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
-    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
   }
   // the inverse kernel runs up to kInvMaxGroups transforms side by side (3 x 16 KiB
   // at B = 1024, which with its static shared memory already exceeds 48 KiB)
@@ -289,8 +292,12 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
   if (overlap)
   {
     if (ring_update) { ru = *ring_update; ring_update = nullptr; }
-    launch_kernel(fwd_fft_overlap_kernel, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
-        d_jobs, B, static_cast<const float2*>(tw.ptr), ru);
+    if (ru.ctl)
+      launch_kernel(fwd_fft_overlap_kernel<1>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru);
+    else
+      launch_kernel(fwd_fft_overlap_kernel<0>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru);
   }
   else if (fft1024 && (njobs >= kFft1024MinJobs || fft1024_always))
   {
@@ -414,7 +421,7 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
 int Engine::dyn_mac_slots() const
 {
   int occ = 0;
-  void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 1, true> : (void*)mac_kernel<2, 1, 2, 1, true>;
+  void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 2, true> : (void*)mac_kernel<2, 1, 2, 2, true>;
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0);
   if (err != cudaSuccess || occ < 1) occ = 1;
   return sm_count * occ;
@@ -491,9 +498,10 @@ void Engine::launch_mac_batch(const MacPlan& plan, int wtab_offset)
   if (cur) cur->mac_launches++;
 }
 
-void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights)
+void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights, bool overlap)
 {
   MacParams p{};
+  p.head_bias = overlap ? 1 : 0;
   p.wtab = weights;
   p.xring = d_xring.ptr;
   p.xparts = d_xparts.ptr;
@@ -504,7 +512,7 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights)
   p.zero = reinterpret_cast<const float4*>(zero_part.ptr);
   p.dyn = dyn;
   p.dyn.stats = cur ? d_dyn_stats.ptr : nullptr;
-  void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 1, true> : (void*)mac_kernel<2, 1, 2, 1, true>;
+  void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 2, true> : (void*)mac_kernel<2, 1, 2, 2, true>;
   void* args[] = { &p };
   dim3 grid(G, mac_ktiles(B), 1);
   launch_mac_fn(fn, grid, args);
@@ -513,7 +521,7 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights)
 }
 
 // reduce the generated-terms partials per (ear, kind), then one inverse CTA per ear
-void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, int G)
+void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, int G, const HeadCommit& hc)
 {
   const int njobs = int(plan.jobs.uploaded);
   if (njobs == 0) return;
@@ -525,7 +533,7 @@ void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, in
   SSR_CUDA(cudaGetLastError());
   count_launch();
   if (cur) cur->ifft_launches++;
-  launch_inv_kernel(inv_groups(3), njobs, plan, reinterpret_cast<const float2*>(reduced.ptr), GatherArgs{}, ctl->n);
+  launch_inv_kernel(inv_groups(3), njobs, plan, reinterpret_cast<const float2*>(reduced.ptr), GatherArgs{}, ctl->n, hc);
   SSR_CUDA(cudaGetLastError());
   count_launch();
   if (cur) cur->ifft_launches++;
@@ -661,6 +669,12 @@ FilterSet::FilterSet(Engine* e_, int channels_, int partitions_)
   flags.assign(size_t(channels) * partitions, 0);
 }
 
+void FilterSet::touch_flags()
+{
+  flags_dirty = true;
+  ++e->flags_epoch;
+}
+
 const unsigned char* FilterSet::device_flags()
 {
   if (flags_dirty || !d_flags.ptr)
@@ -720,7 +734,7 @@ void FilterSet::load_time(int first_channel, int nch, const float* host, long fr
     const int ch = first_channel + c;
     valid[ch] = nvalid;
     for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
-    flags_dirty = true;
+    touch_flags();
   }
   FwdBatch batch{};
   batch.time = d_time.ptr;
@@ -741,7 +755,7 @@ void FilterSet::set_partition_time(int ch, int p, const float* taps, int n)
   {
     // chunk == 0 -> zero flag, no FFT (convolver.h:218-221)
     flags[size_t(ch) * partitions + p] = 0;
-    flags_dirty = true;
+    touch_flags();
     return;
   }
   DeviceArray<float> d{size_t(n)};
@@ -753,7 +767,7 @@ void FilterSet::set_partition_time(int ch, int p, const float* taps, int n)
   jobs[0].dst = part(ch, p);
   run_fwd_jobs(e, jobs);
   flags[size_t(ch) * partitions + p] = 1;
-  flags_dirty = true;
+  touch_flags();
   valid[ch] = std::max(valid[ch], p + 1);
 }
 
@@ -777,7 +791,7 @@ void FilterSet::generate(int first_channel, int nch, long taps, uint64_t seed, u
     const int ch = first_channel + c;
     valid[ch] = nvalid;
     for (int p = 0; p < partitions; ++p) flags[size_t(ch) * partitions + p] = p < nvalid;
-    flags_dirty = true;
+    touch_flags();
   }
   FwdBatch batch{};
   batch.time = d_env.ptr;
@@ -789,27 +803,37 @@ void FilterSet::generate(int first_channel, int nch, long taps, uint64_t seed, u
   e->sync();  // d_env goes out of scope
 }
 
-void FilterSet::lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t)
+void FilterSet::lerp_plan(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t,
+                          std::vector<LerpJob>& jobs)
 {
   if (dch < 0 || dch >= channels || ach < 0 || ach >= a.channels || bch < 0 || bch >= b.channels)
     throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_lerp: bad channel");
-  e->use_device();
-  std::vector<LerpJob> jobs;
+  bool changed = false;
   for (int p = 0; p < partitions; ++p)
   {
     const float2* pa = a.part_or_null(ach, p);
     const float2* pb = b.part_or_null(bch, p);
-    flags_dirty = true;
-    if (!pa && !pb) { flags[size_t(dch) * partitions + p] = 0; continue; }
-    flags[size_t(dch) * partitions + p] = 1;
+    const uint8_t flag = (pa || pb) ? 1 : 0;
+    uint8_t& cur = flags[size_t(dch) * partitions + p];
+    changed |= (cur != flag);
+    cur = flag;
+    if (!flag) continue;
     jobs.push_back({reinterpret_cast<const float4*>(pa), reinterpret_cast<const float4*>(pb),
-        reinterpret_cast<float4*>(part(dch, p))});
+        reinterpret_cast<float4*>(part(dch, p)), 1.0f - t, t});
   }
+  if (changed) touch_flags();
+}
+
+void FilterSet::lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t)
+{
+  e->use_device();
+  std::vector<LerpJob> jobs;
+  lerp_plan(dch, a, ach, b, bch, t, jobs);
   if (jobs.empty()) return;
   DeviceArray<LerpJob> d(jobs.size());
   SSR_CUDA(cudaMemcpyAsync(d.ptr, jobs.data(), jobs.size() * sizeof(LerpJob),
         cudaMemcpyHostToDevice, e->stream));
-  lerp_kernel<<<int(jobs.size()), kThreads, 0, e->stream>>>(d.ptr, e->B / 2, 1.0f - t, t);
+  lerp_kernel<<<int(jobs.size()), kThreads, 0, e->stream>>>(d.ptr, e->B / 2);
   SSR_CUDA(cudaGetLastError());
   e->sync();  // `jobs` / `d` go out of scope
 }
@@ -843,7 +867,7 @@ void FilterSet::upload(int ch, int p, const float* sorted_in, int zero)
   if (ch < 0 || ch >= channels || p < 0 || p >= partitions || (!zero && !sorted_in))
     throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_upload: bad arguments");
   e->use_device();
-  flags_dirty = true;
+  touch_flags();
   if (zero) { flags[size_t(ch) * partitions + p] = 0; }
   else
   {
@@ -876,20 +900,21 @@ void FilterSet::download(int ch, int p, float* sorted_out, int* zero)
 
 // ------------------------------------------------------------------ FilterPtrTable
 FilterPtrTable::FilterPtrTable(int partitions)
-  : P(partitions), base_ptrs(partitions, nullptr)
+  : P(partitions)
 {}
 
 void FilterPtrTable::set_static(const FilterSet& fs, int ch)
 {
-  std::vector<const float2*> parts(size_t(fs.partitions));
-  for (int p = 0; p < fs.partitions; ++p) parts[p] = fs.part_or_null(ch, p);
-  set_static_ptrs(parts);
+  // fewer partitions given -> the rest is empty; more -> ignored (convolver.h:733-738)
+  base = Event{0, fs.part(ch, 0), size_t(fs.e->B), fs.flags.data() + size_t(ch) * fs.partitions,
+               fs.partitions, nullptr};
+  events.clear();
+  ++version;
 }
 
 void FilterPtrTable::set_static_ptrs(const std::vector<const float2*>& parts)
 {
-  // fewer partitions given -> the rest is empty; more -> ignored (convolver.h:733-738)
-  for (int p = 0; p < P; ++p) base_ptrs[p] = p < int(parts.size()) ? parts[p] : nullptr;
+  base = Event{0, nullptr, 0, nullptr, 0, std::make_shared<std::vector<const float2*>>(parts)};
   events.clear();
   ++version;
 }
@@ -934,7 +959,7 @@ void FilterPtrTable::rotate_queues()
   if (fold >= 0)
   {
     // partitions for which a newer event already qualifies are taken from it in current()
-    for (int p = 0; p < P; ++p) base_ptrs[p] = events[fold].part(p);
+    base = events[fold];
     events.erase(events.begin(), events.begin() + fold + 1);
   }
   ++version;
@@ -949,7 +974,7 @@ const std::vector<const float2*>& FilterPtrTable::current()
   {
     // t_set + p grows with p, so the newest qualifying event only moves backwards
     while (idx >= 0 && events[idx].t_set + uint64_t(p) > T) --idx;
-    _ptrs[p] = idx >= 0 ? events[idx].part(p) : base_ptrs[p];
+    _ptrs[p] = idx >= 0 ? events[idx].part(p) : base.part(p);
   }
   _ptrs_version = version;
   return _ptrs;
@@ -957,7 +982,7 @@ const std::vector<const float2*>& FilterPtrTable::current()
 
 bool FilterPtrTable::references(const float2* lo, const float2* hi) const
 {
-  for (auto p : base_ptrs) if (p >= lo && p < hi) return true;
+  for (int p = 0; p < P; ++p) { const float2* q = base.part(p); if (q >= lo && q < hi) return true; }
   for (auto& ev : events)
     for (int p = 0; p < P; ++p) { const float2* q = ev.part(p); if (q >= lo && q < hi) return true; }
   return false;
@@ -1053,6 +1078,14 @@ const float* Output::convolve(float weight)
   // The MAC / inverse tables only depend on the pointer table: rebuild them when
   // set_filter / rotate_queues / bind changed it, otherwise relaunch as they are.
   const bool zero = (weight == 0.0f);
+  if (planned_flags_epoch != e->flags_epoch)
+  {
+    // a filter of this engine was edited in place (prepare_partition, upload, transform_nested
+    // into a filter that is bound or queued here): zero flags are read live, like the
+    // reference's _multiply_spectra does
+    ++table.version;
+    planned_flags_epoch = e->flags_epoch;
+  }
   if (planned_version != table.version || planned_zero != zero)
   {
     mac.clear();

@@ -10,6 +10,10 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <deque>
@@ -35,10 +39,18 @@ struct Error : std::runtime_error
     throw ::ssr_b200::Error(SSR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
-// Bumped whenever a device buffer moves or a device table changes its length:
-// anything a captured CUDA graph has baked in (pointers, grid sizes).  Table
-// CONTENT may change without invalidating a graph.
-inline std::atomic<uint64_t> g_layout_epoch{1};
+// "Layout epoch": bumped whenever a device buffer moves or a device table changes its
+// length -- anything a captured CUDA graph has baked in (pointers, grid sizes).  Table
+// CONTENT may change without invalidating a graph.  The counter is PER ENGINE: every
+// entry point selects its engine with Engine::use_device(), which sets this thread's
+// epoch slot, so one engine's allocations never invalidate another engine's graphs
+// (engines beyond 63 share slots, which is only conservative).  Allocations made outside
+// any engine scope count on slot 0, which every graph checks as well.
+constexpr int kEpochSlots = 64;
+inline std::atomic<uint64_t> g_layout_epochs[kEpochSlots];
+inline std::atomic<unsigned> g_next_epoch_slot{0};
+inline thread_local int t_epoch_slot = 0;
+inline void bump_layout_epoch() { ++g_layout_epochs[t_epoch_slot]; }
 
 // ------------------------------------------------------------ memory helpers
 template<typename T>
@@ -51,12 +63,12 @@ struct DeviceArray
   DeviceArray(const DeviceArray&) = delete;
   DeviceArray& operator=(const DeviceArray&) = delete;
   ~DeviceArray() { release(); }
-  void release() { if (ptr) { cudaFree(ptr); ++g_layout_epoch; } ptr = nullptr; count = 0; }
+  void release() { if (ptr) { cudaFree(ptr); bump_layout_epoch(); } ptr = nullptr; count = 0; }
   void resize(size_t n)
   {
     release();
     if (n == 0) return;
-    ++g_layout_epoch;
+    bump_layout_epoch();
     cudaError_t err = cudaMalloc(&ptr, n * sizeof(T));
     if (err != cudaSuccess)
       throw Error(err == cudaErrorMemoryAllocation ? SSR_ERR_NOMEM : SSR_ERR_CUDA,
@@ -107,7 +119,7 @@ struct Table
   // already queued may still read the old table.
   void upload(cudaStream_t s)
   {
-    if (uploaded != host.size()) ++g_layout_epoch;
+    if (uploaded != host.size()) bump_layout_epoch();
     uploaded = host.size();
     if (host.empty()) return;
     if (staged) SSR_CUDA(cudaEventSynchronize(staged));
@@ -203,6 +215,9 @@ struct Engine
   int register_input(Input* in);
   void unregister_input(int id);
 
+  // bumped whenever a zero flag of any filter set of this engine may have changed; plans
+  // that snapshot "partition present / absent" (Output::convolve) key on it
+  uint64_t flags_epoch = 1;
   Table<float> wtab;               // weight slots
   DeviceArray<float4> partials;
   DeviceArray<float4> reduced;     // pre-reduced accumulators (see reduce_partials_kernel)
@@ -222,8 +237,9 @@ struct Engine
   int mac_waves = 0;               // SSR_B200_MAC_WAVES: CTAs of a MAC launch = waves x resident CTAs
   int prereduce_min = 16;          // partials per accumulator from which a separate reduction launch pays
   // dynamic renderers: terms generated on the device (ssrk::DynTables), static launch shapes
-  void launch_mac_dyn(const ssrk::DynTables& dyn, int G, const float* weights);
-  void launch_inv_dyn(const InvPlan& plan, const ssrk::DynCtl* ctl, int Pmax, int G);
+  void launch_mac_dyn(const ssrk::DynTables& dyn, int G, const float* weights, bool fwd_overlap = false);
+  void launch_inv_dyn(const InvPlan& plan, const ssrk::DynCtl* ctl, int Pmax, int G,
+                      const ssrk::HeadCommit& hc = ssrk::HeadCommit{});
   void launch_dyn_ring_update(const ssrk::DynCtl* ctl, const ssrk::DynRingEntry* upd,
                               ssrk::DynRingEntry* ring, int rows, int R);
   int dyn_mac_slots() const;
@@ -253,7 +269,9 @@ struct Engine
   void stage_end();
   void fold_stats();
   void sync() { SSR_CUDA(cudaStreamSynchronize(stream)); }
-  void use_device() { SSR_CUDA(cudaSetDevice(device)); }
+  const int epoch_slot = 1 + int(g_next_epoch_slot++ % unsigned(kEpochSlots - 1));
+  uint64_t graph_epoch() const { return g_layout_epochs[epoch_slot].load() + g_layout_epochs[0].load(); }
+  void use_device() { SSR_CUDA(cudaSetDevice(device)); t_epoch_slot = epoch_slot; }
 
   // Is [p, p + bytes) page-locked host memory (cudaMallocHost / cudaHostRegister)?
   // Answers are cached by address: a stale "pinned" answer only costs speed, since
@@ -274,6 +292,7 @@ struct FilterSet
   std::vector<uint8_t> flags;        // per (channel, partition): 1 = non-zero-flagged
   DeviceArray<unsigned char> d_flags;  // device mirror of `flags` (generated MAC terms read it)
   bool flags_dirty = true;
+  void touch_flags();                  // a zero flag may have changed: device mirror and cached plans are stale
   const unsigned char* device_flags(); // uploads when stale (stream-ordered)
   std::vector<uint8_t> all_set;        // per channel: no zero-flagged partition
   // device flags of one channel, or null when every partition carries data
@@ -289,6 +308,11 @@ struct FilterSet
   void generate(int first_channel, int nch, long taps, uint64_t seed, uint64_t id_offset,
                 const float* envelope, float scale);
   void lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t);
+  // host half of lerp_from: zero flags + one job per partition appended to `jobs`; the caller
+  // launches ssrk::lerp_kernel over them (the renderers batch a block's interpolations
+  // into one stream-ordered launch, no allocation, no synchronisation)
+  void lerp_plan(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t,
+                 std::vector<ssrk::LerpJob>& jobs);
   void download(int ch, int p, float* sorted_out, int* zero);
   void upload(int ch, int p, const float* sorted_in, int zero);
 };
@@ -320,7 +344,10 @@ struct FilterPtrTable
     }
   };
   uint64_t T = 0;                                  // rotate_queues() calls so far
-  std::vector<const float2*> base_ptrs;            // table before / below all pending events
+  // table before / below all pending events: a filter (evaluated LIVE, so that a zero
+  // flag flipped in place after binding is seen -- the reference reads fft_node::zero in
+  // every _multiply_spectra, convolver.h:556-561), or nothing (all partitions empty)
+  Event base{0, nullptr, 0, nullptr, 0, nullptr};
   std::vector<Event> events;                       // ascending t_set, at most one per T
 
   void set_static(const FilterSet& fs, int ch);    // StaticOutput::_set_filter :729-739
@@ -377,6 +404,7 @@ struct Output
   MacPlan mac;
   InvPlan inv;
   uint64_t planned_version = ~uint64_t(0);   // table.version the cached plan was built from
+  uint64_t planned_flags_epoch = 0;          // Engine::flags_epoch it was built under
   int planned_terms = 0;
   bool planned_zero = false;
   DeviceArray<float> d_res;
@@ -508,6 +536,58 @@ struct BlockParameter  // apf::BlockParameter (apf/apf/misc.h:94-195)
 
 enum Mode { NOTHING = 0, CONSTANT = 1, CHANGE = 2, FADE_IN = 3, FADE_OUT = 4 };
 
+// SSR_B200_PROFILE_HOST=1: wall time of the host-side sections of a block,
+// printed when the renderer is destroyed (development aid)
+struct HostProfile
+{
+  bool on = std::getenv("SSR_B200_PROFILE_HOST") != nullptr;
+  double acc[8] = {0}; uint64_t n = 0;
+  std::chrono::steady_clock::time_point t;
+  void start() { if (on) t = std::chrono::steady_clock::now(); }
+  void lap(int i)
+  {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  void report(const char* what)
+  {
+    if (!on || !n) return;
+    std::printf("[ssr_b200 host profile] %s: %llu blocks; us/block:", what, (unsigned long long)n);
+    for (int i = 0; i < 8; ++i) if (acc[i] > 0) std::printf(" s%d=%.1f", i, acc[i] / n);
+    std::printf("\n");
+  }
+};
+
+
+// Control hand-off from non-realtime threads to the audio thread = apf::CommandQueue +
+// apf::SharedData (apf/apf/commandqueue.h:141-153,185-210, apf/apf/shareddata.h:35-83):
+// a setter called from a control thread (GUI, network, tracker; src/rendersubscriber.h:
+// 164-169) does not touch the renderer's state, it queues a SetCommand; the audio thread
+// executes everything queued, in order, at the START of its next block
+// (apf/apf/mimoprocessor.h:374).  Single consumer (the thread inside process()), any
+// number of producers (serialised by a mutex, like the reference's scoped lock).
+struct ControlQueue
+{
+  enum Kind { SRC_GAIN, SRC_MUTE, SRC_POSITION, SRC_MODEL, REF_POSITION, REF_ORIENTATION, OFF_POSITION,
+              OFF_ORIENTATION, MASTER_VOLUME, PROCESSING, AMP_REF_DISTANCE };
+  struct Cmd { int kind; int id; float a, b; };
+  static constexpr uint32_t kCapacity = 4096;     // (the reference's "fifo_size" defaults to 1024)
+  Cmd ring[kCapacity];
+  std::atomic<uint32_t> head{0}, tail{0};          // consumer / producer positions (free-running)
+  std::mutex producers;
+  // false: still full after ~0.2 s (nobody is rendering blocks)
+  bool push(const Cmd& c);
+  template<typename F> void drain(F apply)
+  {
+    uint32_t h = head.load(std::memory_order_relaxed);
+    const uint32_t t = tail.load(std::memory_order_acquire);
+    for (; h != t; ++h) apply(ring[h % kCapacity]);
+    head.store(h, std::memory_order_release);
+  }
+};
+
 struct Renderer
 {
   Renderer(Engine* e, const ssr_renderer_config& cfg);
@@ -577,10 +657,17 @@ struct Renderer
   std::vector<std::pair<const float*, std::unique_ptr<Table<ssrk::FwdJob>>>> fwd_cache;
   Table<ssrk::FwdJob>* fwd = nullptr;
   std::vector<float> wtab_host;
+  Table<ssrk::LerpJob> lerp_tab;          // Binaural: this block's Dirac interpolations (one launch)
   DeviceArray<float> d_in[2], d_out[2];   // [1] only used by the pipelined submit()
   PinnedArray<float> h_in, h_out;
 
+  HostProfile prof;                      // per renderer (development aid, off by default)
+  ControlQueue control;
+  void apply_controls();                 // audio thread, start of every block
+  uint64_t blocks_started = 0;
+  bool controls_applied = false;         // process_batch() already ran apply_controls() for the next block
   Source* find(int id);
+  Source* find_or_null(int id);
   int add_source(std::unique_ptr<FilterSet> irs, int channels);
   void rem_source(int id);
   void base_weight(Source& s);

@@ -11,6 +11,21 @@ namespace ssr_b200
 
 using namespace ssrk;
 
+// one-CTA helper kernels, launched into the programmatic-dependent-launch chain of the
+// block loop (their launch latency overlaps the predecessor's tail)
+template<typename... KArgs, typename... Args>
+static void launch_small(void (*kernel)(KArgs...), int threads, cudaStream_t stream, bool pdl, Args&&... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SSR_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 // ------------------------------------------------------------------ Gather
 Gather::Gather(Engine* e_, int world_, int rank_, int root_, const int* outputs_per_rank)
   : e(e_), world(world_), rank(rank_), root(root_)
@@ -128,8 +143,7 @@ const float* Gather::wait()
   if (world > 1)
   {
     GatherWaitArgs a{arrived_ptr(0), d_ctas.ptr, world, t, d_error, timeout_ns};
-    gather_wait_kernel<<<1, 32, 0, e->stream>>>(a);
-    SSR_CUDA(cudaGetLastError());
+    launch_small(gather_wait_kernel, 32, e->stream, e->pdl, a);
     e->count_launch();
   }
   waited = epoch;
@@ -144,8 +158,7 @@ void Gather::release(cudaStream_t s)
   released = waited;
   if (world > 1)
   {
-    gather_release_kernel<<<1, 1, 0, s ? s : e->stream>>>(consumed_ptr(), released);
-    SSR_CUDA(cudaGetLastError());
+    launch_small(gather_release_kernel, 1, s ? s : e->stream, e->pdl, consumed_ptr(), (unsigned long long)released);
     e->count_launch();
   }
 }

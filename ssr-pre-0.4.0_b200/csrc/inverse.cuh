@@ -112,6 +112,10 @@ constexpr int kGatherCounterStride = 16;  // unsigned long longs between counter
 
 __global__ void gather_wait_kernel(GatherWaitArgs a)
 {
+  // (programmatic dependent launch: the root's own inverse kernel -- whose blocks go to the
+  // same slot -- must be complete when this kernel is)
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int g = threadIdx.x;
   if (g < a.world && a.ctas[g] > 0)
     gather_wait_ge(a.arrived + size_t(g) * kGatherCounterStride,
@@ -121,6 +125,7 @@ __global__ void gather_wait_kernel(GatherWaitArgs a)
 // root: block `epoch` has been read out of its slot -> peers may overwrite it
 __global__ void gather_release_kernel(unsigned long long* consumed, unsigned long long value)
 {
+  grid_dependency_wait();   // everything queued before (the readers of the slot) is complete
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(consumed), "l"(value) : "memory");
 }
 

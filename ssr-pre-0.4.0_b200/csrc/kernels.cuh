@@ -385,6 +385,9 @@ fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict_
 // move in next to ours (16 KiB of shared memory here, no staged twiddles, leaves room
 // for the MAC's 205 KiB ring) and stream every term that does not need this block's
 // spectrum while we compute it.  The ring heads stay untouched (DEFER_HEAD).
+// (VARIANT only separates the function attributes: 0 runs next to the bulk-copy MAC under the
+// maximal shared-memory carve-out, 1 next to the generated-terms MAC under the default one)
+template<int VARIANT>
 __global__ void __launch_bounds__(kThreads)
 fwd_fft_overlap_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru)
 {
@@ -457,12 +460,13 @@ namespace ssrk
 // dst = ca * a + cb * b over one partition spectrum (transform_nested lerp,
 // convolver.h:773-817 with src/binauralrenderer.h:372-377); a / b may be null
 // (zero-flagged partition).  grid.x = partitions.
-struct LerpJob { const float4* a; const float4* b; float4* dst; };
+struct LerpJob { const float4* a; const float4* b; float4* dst; float ca, cb; };
 
 __global__ void __launch_bounds__(kThreads)
-lerp_kernel(const LerpJob* __restrict__ jobs, int nvec, float ca, float cb)
+lerp_kernel(const LerpJob* __restrict__ jobs, int nvec)
 {
   const LerpJob job = jobs[blockIdx.x];
+  const float ca = job.ca, cb = job.cb;
   for (int i = threadIdx.x; i < nvec; i += kThreads)
   {
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -41,6 +41,9 @@ struct DynTables
   const DynRingEntry* ring;      // [nsrc][2 ears][R]
   const int* src_input;          // [nsrc] input id (X ring) of a source slot
   const int* src_parts;          // [nsrc] partitions of its delay line
+  const DynRingEntry* upd;       // [nsrc][2] the filters current in THIS block (= what the forward
+                                 //  kernel stores into ring[b]); read instead of ring[b], so that
+                                 //  nothing here depends on the forward kernel's ring update
   unsigned long long* stats;     // [2]: H partitions read, X partitions read (or null)
   int nsrc, R, Pmax;
 };
@@ -106,8 +109,17 @@ mac_kernel(const MacParams p)
   __shared__ const float4* s_h[kMacTile][MT];
   __shared__ float s_w[kMacTile];
   __shared__ int s_count;
+  // generated terms with the forward transform still running (head_bias): terms with
+  // p == 0 -- the only ones that read the spectrum it is producing -- are held back here
+  __shared__ const float4* s_lx[DYN ? kMacTile : 1];
+  __shared__ const float4* s_lh[DYN ? kMacTile : 1][MT];
+  __shared__ float s_lw[DYN ? kMacTile : 1];
+  __shared__ int s_late;
 
-  grid_dependency_wait();
+  const bool defer = DYN && p.head_bias != 0;
+  bool waited = !defer;
+  if (!defer) grid_dependency_wait();
+  if (DYN && threadIdx.x == 0) s_late = 0;
   const int t = threadIdx.x;
   const int lane = t & 31;
   const int nvec = p.B >> 1;  // float4 per partition
@@ -160,18 +172,42 @@ mac_kernel(const MacParams p)
     for (int v = 0; v < NV; ++v) acc[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
-  for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+  for (int tb = wk.x; ; tb += kMacTile)
   {
-    const int tile_n = min(kMacTile, wk.y - tb);
+    const bool last_pass = tb >= wk.y;   // generated terms: one more pass for the held-back terms
+    if (last_pass && !DYN) break;
+    const int tile_n = last_pass ? 0 : min(kMacTile, wk.y - tb);
     __syncthreads();  // previous tile fully consumed
-    if (t < 32)
+    if constexpr (DYN)
+    {
+      // (uniform over the CTA: s_late is only written between barriers)
+      if (!waited && (last_pass || s_late + tile_n > kMacTile))
+      {
+        grid_dependency_wait();          // the forward transform of this block is complete
+        waited = true;
+      }
+      if (last_pass)
+      {
+        const int n_late = s_late;
+        if (n_late == 0) break;
+        if (t < n_late)
+        {
+          s_x[t] = s_lx[t]; s_w[t] = s_lw[t];
+#pragma unroll
+          for (int j = 0; j < MT; ++j) s_h[t][j] = s_lh[t][j];
+        }
+        if (t == 0) s_count = n_late;
+      }
+    }
+    if (t < 32 && !last_pass)
     {
       // warp 0 stages the tile and compacts away terms with zero weight
       int count = 0;
+      int late_count = DYN ? s_late : 0;
       for (int base = 0; base < tile_n; base += 32)
       {
         const int i = base + lane;
-        bool ok = false;
+        bool ok = false, late = false;
         MacTermMeta m; float w = 0.f;
         const float4* hgen[2] = {nullptr, nullptr};
         if (i < tile_n)
@@ -188,13 +224,16 @@ mac_kernel(const MacParams p)
                 long long time = p.dyn.ctl->b - (kind == 1 ? 1 : 0) - m.p;
                 int slot = int(time % p.dyn.R);
                 if (slot < 0) slot += p.dyn.R;
+                const bool current = (kind != 1 && m.p == 0);   // ring[b] = this block's update
 #pragma unroll
                 for (int ear = 0; ear < 2; ++ear)
                 {
-                  const DynRingEntry en = p.dyn.ring[(size_t(src) * 2 + ear) * p.dyn.R + slot];
+                  const DynRingEntry en = current ? p.dyn.upd[size_t(src) * 2 + ear]
+                                                  : p.dyn.ring[(size_t(src) * 2 + ear) * p.dyn.R + slot];
                   if (en.base && m.p < en.nparts && (!en.flags || en.flags[m.p])) hgen[ear] = en.base + size_t(m.p) * nvec;
                 }
                 ok = hgen[0] || hgen[1];
+                late = ok && !waited && m.p == 0;
               }
             }
           }
@@ -205,20 +244,32 @@ mac_kernel(const MacParams p)
             ok = (w != 0.0f);
           }
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        const unsigned mask = __ballot_sync(0xffffffffu, ok && !late);
+        const unsigned mask_late = DYN ? __ballot_sync(0xffffffffu, late) : 0u;
         if (ok)
         {
-          const int pos = count + __popc(mask & ((1u << lane) - 1u));
           const int parts = p.xparts[m.input];
           int slot = p.heads[m.input] + p.head_bias - m.p;
           if (slot < 0) slot += parts;
           if (slot >= parts) slot -= parts;
-          s_x[pos] = p.xring[m.input] + size_t(slot) * nvec;
-          s_w[pos] = w;
+          const float4* xptr = p.xring[m.input] + size_t(slot) * nvec;
+          if (DYN && late)
+          {
+            const int lpos = late_count + __popc(mask_late & ((1u << lane) - 1u));
+            s_lx[lpos] = xptr;
+            s_lw[lpos] = w;
+            s_lh[lpos][0] = hgen[0] ? hgen[0] : p.zero;
+            s_lh[lpos][MT - 1] = hgen[1] ? hgen[1] : p.zero;
+          }
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          if (!late) { s_x[pos] = xptr; s_w[pos] = w; }
           if constexpr (DYN)
           {
-            s_h[pos][0] = hgen[0] ? hgen[0] : p.zero;
-            s_h[pos][1] = hgen[1] ? hgen[1] : p.zero;
+            if (!late)
+            {
+              s_h[pos][0] = hgen[0] ? hgen[0] : p.zero;
+              s_h[pos][1] = hgen[1] ? hgen[1] : p.zero;
+            }
           }
           else
           {
@@ -227,6 +278,7 @@ mac_kernel(const MacParams p)
           }
         }
         count += __popc(mask);
+        late_count += __popc(mask_late);
         if (DYN && p.dyn.stats && blockIdx.y == 0)
         {
           // traffic accounting: H and X partitions this CTA reads
@@ -236,11 +288,11 @@ mac_kernel(const MacParams p)
           {
             atomicAdd(p.dyn.stats, (unsigned long long)nh);
             // X[n, p] counts once: the old-state group re-reads it from L2
-            if (kind != 1) atomicAdd(p.dyn.stats + 1, (unsigned long long)__popc(mask));
+            if (kind != 1) atomicAdd(p.dyn.stats + 1, (unsigned long long)__popc(mask | mask_late));
           }
         }
       }
-      if (lane == 0) s_count = count;
+      if (lane == 0) { s_count = count; if (DYN) s_late = late_count; }
     }
     __syncthreads();
     const int n = s_count;
@@ -326,6 +378,7 @@ mac_kernel(const MacParams p)
     }
 #undef SSR_MAC_LOAD
 #undef SSR_MAC_FMA
+    if (last_pass) break;
   }
 
   // bin 0 holds (DC, Nyquist), both real products (convolver.h:510-541):

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,31 +26,6 @@ namespace ssr_b200
 using namespace ssrk;
 
 static constexpr int kGenericMT = 4;
-
-// SSR_B200_PROFILE_HOST=1: wall time of the host-side sections of a block,
-// printed when the renderer is destroyed (development aid)
-struct HostProfile
-{
-  bool on = std::getenv("SSR_B200_PROFILE_HOST") != nullptr;
-  double acc[8] = {0}; uint64_t n = 0;
-  std::chrono::steady_clock::time_point t;
-  void start() { if (on) t = std::chrono::steady_clock::now(); }
-  void lap(int i)
-  {
-    if (!on) return;
-    auto now = std::chrono::steady_clock::now();
-    acc[i] += std::chrono::duration<double, std::micro>(now - t).count();
-    t = now;
-  }
-  void report(const char* what)
-  {
-    if (!on || !n) return;
-    std::printf("[ssr_b200 host profile] %s: %llu blocks; us/block:", what, (unsigned long long)n);
-    for (int i = 0; i < 8; ++i) if (acc[i] > 0) std::printf(" s%d=%.1f", i, acc[i] / n);
-    std::printf("\n");
-  }
-};
-static HostProfile g_prof;
 
 Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   : e(e_), cfg(c)
@@ -94,13 +70,63 @@ Renderer::~Renderer()
   for (auto ev : ev_k) if (ev) cudaEventDestroy(ev);
   if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_out); }
   drop_graphs();
-  g_prof.report("s0 source logic, s1 plan, s2 inv+arena, s3 fwd table, s4 launches");
+  prof.report("s0 source logic, s1 plan, s2 inv+arena, s3 fwd table, s4 launches");
+}
+
+Renderer::Source* Renderer::find_or_null(int id)
+{
+  for (auto& s : sources) if (s->id == id) return s.get();
+  return nullptr;
 }
 
 Renderer::Source* Renderer::find(int id)
 {
-  for (auto& s : sources) if (s->id == id) return s.get();
+  if (Source* s = find_or_null(id)) return s;
   throw Error(SSR_ERR_INVALID, "ssr_b200: no such source");
+}
+
+bool ControlQueue::push(const Cmd& c)
+{
+  std::lock_guard<std::mutex> lock(producers);
+  for (int tries = 0; ; ++tries)
+  {
+    const uint32_t t = tail.load(std::memory_order_relaxed);
+    if (t - head.load(std::memory_order_acquire) < kCapacity)
+    {
+      ring[t % kCapacity] = c;
+      tail.store(t + 1, std::memory_order_release);
+      return true;
+    }
+    // "if the FIFO is full: retry, retry, ..." with usleep(50) (apf/apf/commandqueue.h:203-209)
+    if (tries > 4000) return false;
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+}
+
+// CommandQueue::process_commands() (apf/apf/commandqueue.h:141-153) at the start of the
+// audio block (apf/apf/mimoprocessor.h:374): the SetCommands execute in order
+void Renderer::apply_controls()
+{
+  ++blocks_started;
+  control.drain([this](const ControlQueue::Cmd& c)
+  {
+    Source* s = nullptr;
+    if (c.kind <= ControlQueue::SRC_MODEL && !(s = find_or_null(c.id))) return;  // removed meanwhile
+    switch (c.kind)
+    {
+      case ControlQueue::SRC_GAIN: s->gain = c.a; break;
+      case ControlQueue::SRC_MUTE: s->mute = c.a != 0.0f; break;
+      case ControlQueue::SRC_POSITION: s->px = c.a; s->py = c.b; break;
+      case ControlQueue::SRC_MODEL: s->plane = c.a != 0.0f; break;
+      case ControlQueue::REF_POSITION: ref_x = c.a; ref_y = c.b; break;
+      case ControlQueue::REF_ORIENTATION: ref_az = c.a; break;
+      case ControlQueue::OFF_POSITION: off_x = c.a; off_y = c.b; break;
+      case ControlQueue::OFF_ORIENTATION: off_az = c.a; break;
+      case ControlQueue::MASTER_VOLUME: master_volume = c.a; break;
+      case ControlQueue::PROCESSING: processing = c.a != 0.0f; break;
+      case ControlQueue::AMP_REF_DISTANCE: amplitude_reference_distance = c.a; break;
+    }
+  });
 }
 
 int Renderer::add_source(std::unique_ptr<FilterSet> irs, int channels)
@@ -365,7 +391,7 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   const int N = int(sources.size());
   const int B = e->B;
   const bool binaural = cfg.kind == SSR_RENDERER_BINAURAL;
-  g_prof.start();
+  prof.start();
 
   if (static_dirty)
   {
@@ -388,7 +414,12 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     }
     dyn_ring.resize(ring.size());
     SSR_CUDA(cudaMemcpy(dyn_ring.ptr, ring.data(), ring.size() * sizeof(DynRingEntry), cudaMemcpyHostToDevice));
+    // CTAs of the generated-terms MAC: what is resident at once -- next to the forward
+    // kernel's CTAs when that runs under the MAC (one CTA per source, each takes the
+    // registers of one MAC CTA on its SM)
     dyn_G = e->dyn_mac_slots();
+    if (e->fwd_overlap) dyn_G = std::max(e->sm_count, dyn_G - std::min(N, e->sm_count));
+    if (const char* v = std::getenv("SSR_B200_DYN_CTAS")) dyn_G = std::max(1, std::atoi(v));  // experiments
     e->ensure_partials(size_t(dyn_G) * 2);
     static_dirty = false;
     invalidate_inv();
@@ -416,6 +447,7 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   DynRingEntry* upd = reinterpret_cast<DynRingEntry*>(st + off_upd);
   std::memset(wtab, 0, size_t(3) * N * sizeof(float));
 
+  lerp_tab.host.clear();
   const long long b = ++dyn_b;   // block index of the state after this block's switch
   int nk[3] = {0, 0, 0};
   auto select = [&](int n, int kind, float w)
@@ -532,7 +564,7 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
               s.temp[i].emplace_back(new FilterSet(e, 1, partitions));
               tmp = s.temp[i].back().get();
             }
-            tmp->lerp_from(0, *hrtfs, hch, *neutral, 0, s.interp.get());
+            tmp->lerp_plan(0, *hrtfs, hch, *neutral, 0, s.interp.get(), lerp_tab.host);
             s.latest[i] = DynRingEntry{reinterpret_cast<const float4*>(tmp->part(0, 0)),
                 tmp->device_flags_row(0), tmp->partitions, 0};
           }
@@ -551,9 +583,18 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     if (mode == CONSTANT) select(n, 0, w.get());
     else if (mode == CHANGE || mode == FADE_IN) select(n, 2, w.get());
   }
+  if (!lerp_tab.host.empty())
+  {
+    // this block's Dirac interpolations (src/binauralrenderer.h:365-379) in ONE stream-ordered
+    // launch: preallocated pinned + device job table, no cudaMalloc / sync on the audio path
+    lerp_tab.upload(e->stream);
+    lerp_kernel<<<int(lerp_tab.host.size()), kThreads, 0, e->stream>>>(lerp_tab.device(), B / 2);
+    SSR_CUDA(cudaGetLastError());
+    e->count_launch();
+  }
   ctl->b = b;
   ctl->n[0] = nk[0]; ctl->n[1] = nk[1]; ctl->n[2] = nk[2]; ctl->pad = 0;
-  g_prof.lap(0);
+  prof.lap(0);
 
   SSR_CUDA(cudaMemcpyAsync(dyn_dev.ptr, st, total, cudaMemcpyHostToDevice, e->stream));
   SSR_CUDA(cudaEventRecord(dyn_copied[dyn_slot], e->stream));
@@ -562,11 +603,12 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   dyn_tables.src_input = reinterpret_cast<const int*>(dyn_dev.ptr + off_input);
   dyn_tables.src_parts = reinterpret_cast<const int*>(dyn_dev.ptr + off_parts);
   dyn_tables.ring = dyn_ring.ptr;
+  dyn_tables.upd = reinterpret_cast<const DynRingEntry*>(dyn_dev.ptr + off_upd);
   dyn_tables.stats = nullptr;
   dyn_tables.nsrc = N; dyn_tables.R = dyn_R; dyn_tables.Pmax = dyn_Pmax;
   dyn_wtab_dev = reinterpret_cast<const float*>(dyn_dev.ptr + off_w);
   dyn_upd_dev = reinterpret_cast<const DynRingEntry*>(dyn_dev.ptr + off_upd);
-  g_prof.lap(1);
+  prof.lap(1);
 
   // the inverse tables are static: one job per ear, one entry per accumulator kind
   if (inv_key != 1 || (inv.jobs.host.size() && inv.jobs.host[0].out != d_output))
@@ -581,10 +623,10 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     inv.upload(e->stream);
     inv_key = 1;
   }
-  g_prof.lap(2);
+  prof.lap(2);
 
   build_fwd(d_input);
-  g_prof.lap(3);
+  prof.lap(3);
   d.N = N;
   d.kind_mask = 1;
   // partitions read are counted by the kernel (Engine::d_dyn_stats); the
@@ -722,13 +764,14 @@ void Renderer::launch(const StepDesc& d)
   const bool dynamic = cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS;
   // Generic plans on the bulk-copy MAC: the forward transform runs UNDER the MAC (only the
   // p == 0 terms need its result); the ring heads are then committed by the inverse kernel
-  const bool overlap = e->fwd_overlap && cfg.kind == SSR_RENDERER_GENERIC && e->mac_tma()
-      && static_mac.MT == kGenericMT && d.N > 0;
+  // (Binaural / BRS: the generated-terms MAC does the same)
+  const bool overlap = e->fwd_overlap && d.N > 0
+      && (dynamic || (cfg.kind == SSR_RENDERER_GENERIC && e->mac_tma() && static_mac.MT == kGenericMT));
   if (dynamic && d.N > 0)
   {
     // the forward kernel's CTA n also records source n's current filters in the ring
     const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
-    e->launch_fwd(fwd->device(), d.N, &ru);
+    e->launch_fwd(fwd->device(), d.N, &ru, overlap);
   }
   else e->launch_fwd(fwd->device(), d.N, nullptr, overlap);
   e->stage_mark(1);
@@ -750,7 +793,7 @@ void Renderer::launch(const StepDesc& d)
     if (cfg.kind == SSR_RENDERER_PREFILTER_BANK) e->launch_mac(static_mac, 0, 0);
     else
     {
-      e->launch_mac_dyn(dyn_tables, dyn_G, dyn_wtab_dev);
+      e->launch_mac_dyn(dyn_tables, dyn_G, dyn_wtab_dev, overlap);
     }
     if (e->cur)
     {
@@ -761,7 +804,7 @@ void Renderer::launch(const StepDesc& d)
   e->stage_mark(2);
   const HeadCommit hc{overlap ? fwd->device() : nullptr, overlap ? d.N : 0};
   if (cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS)
-    e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G);
+    e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G, hc);
   else if (gather) e->launch_inv(inv, gather->next_block(), hc);
   else if (hostgather)
   {
@@ -780,12 +823,13 @@ void Renderer::step(const float* d_input, float* d_output)
   if (hostgather)
     throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: the device-buffer step delivers through the peer-memory gather "
         "(ssr_gather_*); a host-direct gather serves ssr_renderer_process");
+  apply_controls();
   cur_slot = 0;
   const StepDesc d = prepare(d_input, d_output);
-  g_prof.start();
+  prof.start();
   launch(d);
-  g_prof.lap(4);
-  g_prof.n++;
+  prof.lap(4);
+  prof.n++;
 }
 
 void Renderer::drop_graphs()
@@ -913,13 +957,19 @@ void Renderer::process_batch(int n, int nblocks, const float* const* in, float* 
   int t = 0;
   while (t < nblocks)
   {
+    // the commands queued so far take effect with this block (and then with none of
+    // the following ones of a batched run: a control thread that wants per-block control
+    // of an offline render calls this function block by block)
+    apply_controls();
     if (nblocks - t >= Input::kTimeBatch && batch_eligible())
     {
       run_batch(in + size_t(t) * N, out + size_t(t) * n_out);
+      blocks_started += Input::kTimeBatch - 1;
       t += Input::kTimeBatch;
     }
     else
     {
+      controls_applied = true;
       process(n, in + size_t(t) * N, out + size_t(t) * n_out);
       t += 1;
     }
@@ -952,6 +1002,8 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   // assert(n == block_size()) (apf/apf/pointer_policy.h:114)
   if (n != e->B) throw Error(SSR_ERR_INVALID, "ssr_b200: audio_callback: n != block size");
   if (outstanding >= 2) throw Error(SSR_ERR_STATE, "ssr_b200: at most 2 blocks may be in flight");
+  if (!controls_applied) apply_controls();
+  controls_applied = false;
   e->use_device();
   const int N = int(sources.size());
   const int B = e->B;
@@ -1043,7 +1095,7 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   if (use_graphs && d.graphable && !e->timing && d.kind_mask > 0 && d.kind_mask < 8)
   {
     GraphEntry& g = graphs[cur_slot][d.kind_mask];
-    const uint64_t epoch = g_layout_epoch.load();
+    const uint64_t epoch = e->graph_epoch();
     if (g.exec && g.epoch == epoch)
     {
       SSR_CUDA(cudaGraphLaunch(g.exec, e->stream));

@@ -15,6 +15,14 @@ sys.path.insert(0, ROOT)
 from oracle import ref  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# tests/test_gpu_dropin.py re-runs these scenarios with SSR_REF_LIB pointing at the build of
+# the same reference code on top of the GPU engine (one host thread per engine) and
+# --out elsewhere, then compares with the committed fixtures
+OUT = HERE
+
+
+def threads(n):
+    return 1 if os.environ.get("SSR_REF_LIB") else n
 
 
 def decaying(rng, frames, channels, gain):
@@ -55,7 +63,7 @@ def golden_level1():
     h1 = decaying(rng, L1, 1, 0.05)[:, 0]
     x1 = rng.uniform(-1, 1, T1 * B1).astype(np.float32)
     y1, _ = ref.static_convolver_run(B1, h1, x1)
-    np.savez_compressed(os.path.join(HERE, "level1.npz"), B=B, P=P, taps=tp, lens=lens, x=x, switch=switch,
+    np.savez_compressed(os.path.join(OUT, "level1.npz"), B=B, P=P, taps=tp, lens=lens, x=x, switch=switch,
                         weight=weight, y=y, queues_empty=qe, spectra=spectra,
                         cfg1_h=h1, cfg1_x=x1, cfg1_y=y1)
 
@@ -64,7 +72,7 @@ def golden_generic():
     rng = np.random.default_rng(777)
     B, L, N, M, T = 64, 200, 3, 4, 30
     irs = np.stack([decaying(rng, L, M, 0.1) for _ in range(N)])
-    r = ref.Renderer("generic", B, 48000, threads=2)
+    r = ref.Renderer("generic", B, 48000, threads=threads(2))
     r.add_outputs(M)
     ids = []
     for n in range(N):
@@ -85,7 +93,7 @@ def golden_generic():
                     r.set_state(what, v)
         y[t] = r.process(x[t])
     codes = {"gain": 0, "mute": 1, "master_volume": 2, "processing": 3}
-    np.savez_compressed(os.path.join(HERE, "generic.npz"), B=B, irs=irs, x=x, y=y,
+    np.savez_compressed(os.path.join(OUT, "generic.npz"), B=B, irs=irs, x=x, y=y,
                         script_block=np.array([a for a, _, _, _ in script]),
                         script_what=np.array([codes[b] for _, b, _, _ in script]),
                         script_source=np.array([c for _, _, c, _ in script]),
@@ -112,7 +120,7 @@ def golden_brs():
             a = -123.0
         az[t] = a
     y, _, _ = r.run(x, T, azimuth=az)
-    np.savez_compressed(os.path.join(HERE, "brs.npz"), B=B, brirs=brirs, x=x, az=az, y=y)
+    np.savez_compressed(os.path.join(OUT, "brs.npz"), B=B, brirs=brirs, x=x, az=az, y=y)
 
 
 def golden_binaural():
@@ -120,7 +128,7 @@ def golden_binaural():
     B, L, N, A, T = 256, 200, 2, 12, 40
     hrir = decaying(rng, L, 2 * A, 0.15)
     ref.register_sndfile("h", hrir, 48000)
-    r = ref.Renderer("binaural", B, 48000, threads=2, hrir_file="h")
+    r = ref.Renderer("binaural", B, 48000, threads=threads(2), hrir_file="h")
     r.load_reproduction_setup()
     ids = [r.add_source() for _ in range(N)]
     r.activate()
@@ -134,7 +142,7 @@ def golden_binaural():
         for n in range(N):
             r.set_source(ids[n], "position", float(pos[t, n, 0]), float(pos[t, n, 1]))
         y[t] = r.process(x[t])
-    np.savez_compressed(os.path.join(HERE, "binaural.npz"), B=B, hrir=hrir, x=x, pos=pos, y=y)
+    np.savez_compressed(os.path.join(OUT, "binaural.npz"), B=B, hrir=hrir, x=x, pos=pos, y=y)
 
 
 def golden_brs_dynamic():
@@ -181,7 +189,7 @@ def golden_brs_dynamic():
     pad = np.zeros((3, max(lengths), 2 * A), np.float32)
     for k, b in enumerate(brirs):
         pad[k, :b.shape[0]] = b
-    np.savez_compressed(os.path.join(HERE, "brs_dynamic.npz"), B=B, brirs=pad, lengths=np.array(lengths),
+    np.savez_compressed(os.path.join(OUT, "brs_dynamic.npz"), B=B, brirs=pad, lengths=np.array(lengths),
                         x=x, az=az, y=y, channel=channel)
 
 
@@ -230,7 +238,7 @@ def golden_binaural_multipartition():
         channel[t, :len(live)] = live
         y[t] = r.process(x[t, :r.n_in])
     ref.unregister_sndfile("gh")
-    np.savez_compressed(os.path.join(HERE, "binaural_multipartition.npz"), B=B, hrir=hrir, x=x, pos=pos, mute=mute,
+    np.savez_compressed(os.path.join(OUT, "binaural_multipartition.npz"), B=B, hrir=hrir, x=x, pos=pos, mute=mute,
                         az=ref_az, y=y, channel=channel)
 
 
@@ -246,18 +254,26 @@ def golden_hrirs_fabian():
     data = (raw[:, :4].astype(np.float32) / 32768.0)
     B = 512
     spectra = np.stack([ref.Filter(B, data[:, c]).get(0)[0] for c in range(4)])
-    np.savez_compressed(os.path.join(HERE, "hrirs_fabian_4ch.npz"), B=B, fs=fs, channels=ch, frames=n,
+    np.savez_compressed(os.path.join(OUT, "hrirs_fabian_4ch.npz"), B=B, fs=fs, channels=ch, frames=n,
                         data=data, spectra=spectra)
 
 
+SCENARIOS = {
+    "level1": golden_level1, "generic": golden_generic, "brs": golden_brs, "binaural": golden_binaural,
+    "brs_dynamic": golden_brs_dynamic, "binaural_multipartition": golden_binaural_multipartition,
+    "hrirs_fabian": golden_hrirs_fabian,
+}
+
 if __name__ == "__main__":
-    golden_level1()
-    golden_generic()
-    golden_brs()
-    golden_binaural()
-    golden_brs_dynamic()
-    golden_binaural_multipartition()
-    golden_hrirs_fabian()
-    for f in sorted(os.listdir(HERE)):
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=HERE)
+    ap.add_argument("scenarios", nargs="*", default=list(SCENARIOS))
+    a = ap.parse_args()
+    OUT = a.out
+    os.makedirs(OUT, exist_ok=True)
+    for name in a.scenarios:
+        SCENARIOS[name]()
+    for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
-            print(f, os.path.getsize(os.path.join(HERE, f)))
+            print(f, os.path.getsize(os.path.join(OUT, f)))

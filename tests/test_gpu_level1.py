@@ -278,3 +278,49 @@ def test_synthetic_ir_is_bit_identical_host_device(capi, engine_factory):
             a, _ = fs.download(c, p)
             b, _ = ref.download(0, p)
             assert np.array_equal(a, b)
+
+
+def test_filter_edited_in_place_after_binding_is_seen(capi, engine_factory):
+    """The reference reads fft_node::zero live in every _multiply_spectra
+    (apf/apf/convolver.h:556-561): a partition prepared AFTER the filter was bound
+    (StaticOutput) or set (Output) takes part from the next convolve() on, and one
+    that is zero-flagged in place stops doing so.  (the plan cache used to
+    snapshot the flags.)"""
+    B, P = 64, 3
+    e = engine_factory(B)
+    rng = np.random.default_rng(21)
+    taps = [rng.uniform(-1, 1, B).astype(np.float32) * 0.2 for _ in range(P)]
+    x = [rng.uniform(-1, 1, B).astype(np.float32) for _ in range(10)]
+
+    def direct(active):
+        h = np.zeros(P * B)
+        for p in active:
+            h[p * B:(p + 1) * B] = taps[p]
+        return np.convolve(np.concatenate(x).astype(np.float64), h)[:len(x) * B].reshape(len(x), B)
+
+    for dynamic in (False, True):
+        fs = capi.FilterSet(e, 1, P)                 # Filter(block, partitions): all zero-flagged
+        fs.set_partition_time(0, 0, taps[0])
+        inp = capi.Input(e, P)
+        if dynamic:
+            out = capi.Output(inp)
+            out.set_filter(fs)
+        else:
+            out = capi.StaticOutput(inp, fs=fs)
+        got = []
+        for t in range(len(x)):
+            if t == 3:
+                fs.set_partition_time(0, 2, taps[2])     # edited in place, already bound
+            if t == 7:
+                fs.set_partition_time(0, 0, taps[0][:0])  # chunk == 0 -> zero flag (convolver.h:218-221)
+            inp.add_block(x[t])
+            if dynamic and not out.queues_empty():
+                out.rotate_queues()
+            got.append(out.convolve(1.0))
+        got = np.stack(got)
+        # blocks 0-2: partition 0 only; 3-6: partitions 0 and 2; 7-: partition 2 only.  The
+        # delay line keeps the input, so each phase is the direct convolution with the
+        # partitions active in THAT block
+        want = np.stack([direct([0])[t] if t < 3 else (direct([0, 2])[t] if t < 7 else direct([2])[t])
+                         for t in range(len(x))])
+        assert np.abs(got - want).max() <= 1e-5, dynamic
