@@ -42,7 +42,7 @@ typedef enum ssr_status
   SSR_ERR_INVALID = -1,      /* bad argument / precondition (reference: assert) */
   SSR_ERR_BLOCK_SIZE = -2,   /* "Convolver: block size must be a multiple of 8!"
                                 (apf/apf/convolver.h:163-166) */
-  SSR_ERR_UNSUPPORTED = -3,  /* block size not a power of two in [8, 4096] */
+  SSR_ERR_UNSUPPORTED = -3,  /* block size above 4096 (every multiple of 8 up to there is accepted) */
   SSR_ERR_CUDA = -4,         /* CUDA runtime failure / no device */
   SSR_ERR_NOMEM = -5,
   SSR_ERR_STATE = -6,        /* call order violated */

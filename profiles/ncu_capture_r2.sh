@@ -32,4 +32,13 @@ run_pair mac_cfg4_gpus8 "mac_tma_kernel" 2 2 $BASE --workload cfg4 --outputs 8
 run_pair fft_cfg5 "fwd_fft_overlap_kernel|inv_fft_kernel" 4 4 $BASE --outputs 64
 run_pair cfg3 "mac_kernel|dyn_reduce_kernel|inv_fft_kernel|fwd_fft_overlap_kernel" 160 4 python bench.py --workload cfg3 --steps 6 --warmup 50 --no-cpu-baseline --no-parity
 run_pair cfg2 "mac_kernel|dyn_reduce_kernel|inv_fft_kernel|fwd_fft_overlap_kernel" 160 4 python bench.py --workload cfg2 --steps 6 --warmup 50 --no-cpu-baseline --no-parity
-ls -la $OUT/*.ncu-rep | tail -20
+# summaries are made here (gpurun brings back at most 64 MiB): raw CSV pages + the markdown
+# table of profiles/ncu_summary.py; only the two headline reports travel as .ncu-rep
+for rep in $OUT/r2_*.ncu-rep; do
+  ncu -i $rep --page raw --csv > ${rep%.ncu-rep}.raw.csv 2> /dev/null
+done
+python profiles/ncu_summary.py $OUT/r2_*.ncu-rep > $OUT/r2_ncu_kernels.md 2>&1
+ncu -i $OUT/r2_mac_cfg5_gpus8.ncu-rep --page source --csv > $OUT/r2_mac_cfg5_gpus8.source.csv 2> /dev/null
+mkdir -p $OUT/keep && mv $OUT/r2_mac_cfg5_gpus1.ncu-rep $OUT/r2_cfg3.ncu-rep $OUT/keep/ && rm -f $OUT/r2_*.ncu-rep && mv $OUT/keep/* $OUT/ && rmdir $OUT/keep
+ls -la $OUT | tail -30
+du -sh $OUT

@@ -88,8 +88,11 @@ static void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 }
 
 // ------------------------------------------------------------------ Engine
-static int mac_nv(int B) { return B >= 1024 ? 2 : 1; }
-static int mac_ktiles(int B) { return B > 1024 ? B / 1024 : 1; }
+// float4 per thread and 1024-bin tiles (gridDim.y) of the register-staged MAC for block
+// size B (B / 2 float4 per partition spectrum; any multiple of 8)
+static int mac_nv(int B) { return B / 2 > kThreads ? 2 : 1; }
+static int mac_ktiles(int B) { return std::max(1, (B / 2 + 2 * kThreads - 1) / (2 * kThreads)); }
+static bool is_pow2(int B) { return (B & (B - 1)) == 0; }
 
 template<int MT, int NV, int ST = 2, int MINB = 1>
 static void* mac_fn() { return (void*)mac_kernel<MT, NV, ST, MINB>; }
@@ -136,9 +139,8 @@ Engine::Engine(const ssr_engine_config& cfg)
   fft1024_always = fft_env && std::string(fft_env) == "fft1024";  // also for small launches (tests, A/B)
   if (B <= 0 || B % 8 != 0)
     throw Error(SSR_ERR_BLOCK_SIZE, "Convolver: block size must be a multiple of 8!");
-  if ((B & (B - 1)) != 0 || B > 4096)
-    throw Error(SSR_ERR_UNSUPPORTED,
-        "ssr_b200: block size must be a power of two in [8, 4096]");
+  if (B > 4096)
+    throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: block size must be a multiple of 8 in [8, 4096]");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess || ndev == 0)
@@ -206,6 +208,7 @@ Engine::Engine(const ssr_engine_config& cfg)
   if (const char* v = std::getenv("SSR_B200_PREREDUCE_MIN")) prereduce_min = std::max(1, std::atoi(v));
   fwd_overlap = fwd_overlap && pdl;
   if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
+  if (!is_pow2(B)) level1_fused = false;   // the fused Level-1 launch is instantiated for power-of-two spectra
   if (2 * fft_smem > 48 * 1024)
   {
     SSR_CUDA(cudaFuncSetAttribute(level1_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
@@ -261,7 +264,7 @@ void Engine::unregister_input(int id)
 }
 
 // bulk-copy (TMA) staged MAC for the four-row (Generic) plans at B >= 1024
-bool Engine::mac_tma() const { return (mac_variant == 0 || mac_variant == 6 || mac_variant == 7) && B >= 1024; }
+bool Engine::mac_tma() const { return (mac_variant == 0 || mac_variant == 6 || mac_variant == 7) && B >= 1024 && is_pow2(B); }
 
 // Fixed cost of a CTA in units of one term, for MacPlan::make_work: staging and the
 // partial spectra it writes (and the inverse kernel sums); the bulk-copy kernel also
@@ -282,7 +285,8 @@ int Engine::mac_slots(int MT) const
   return sm_count * occ;
 }
 
-void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ring_update, bool overlap)
+void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ring_update, bool overlap,
+                        const float* in_base)
 {
   if (njobs <= 0) return;
   FwdRingUpdate ru{nullptr, nullptr, nullptr, 0};
@@ -294,12 +298,12 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
     if (ring_update) { ru = *ring_update; ring_update = nullptr; }
     if (ru.ctl)
       launch_kernel(fwd_fft_overlap_kernel<1>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
-          d_jobs, B, static_cast<const float2*>(tw.ptr), ru);
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base);
     else
       launch_kernel(fwd_fft_overlap_kernel<0>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
-          d_jobs, B, static_cast<const float2*>(tw.ptr), ru);
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base);
   }
-  else if (fft1024 && (njobs >= kFft1024MinJobs || fft1024_always))
+  else if (fft1024 && !in_base && (njobs >= kFft1024MinJobs || fft1024_always))
   {
     const int ctas = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
     fwd_fft1024_kernel<<<ctas, kWarpsPerCta * 32, 0, stream>>>(d_jobs, njobs, tw.ptr);
@@ -308,7 +312,7 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
   {
     const size_t smem = size_t(4) * B * sizeof(float2);  // data + staged twiddles
     if (ring_update) { ru = *ring_update; ring_update = nullptr; }  // folded into this launch
-    fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr, ru);
+    fwd_fft_kernel<<<njobs, kThreads, smem, stream>>>(d_jobs, B, tw.ptr, ru, in_base);
   }
   SSR_CUDA(cudaGetLastError());
   count_launch();

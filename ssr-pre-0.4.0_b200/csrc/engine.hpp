@@ -227,7 +227,7 @@ struct Engine
   // loop and leaves the ring heads to be committed by the block's inverse kernel
   // (ssrk::HeadCommit), so that the MAC launched behind it may run concurrently
   void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs, const ssrk::FwdRingUpdate* ring_update = nullptr,
-                  bool overlap = false);
+                  bool overlap = false, const float* in_base = nullptr);
   void launch_fwd_batch(const ssrk::FwdBatch& batch, int nparts, int nchannels);
   void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr,
                   bool fwd_overlap = false);
@@ -677,6 +677,7 @@ struct Renderer
   {
     const float* d_input = nullptr; float* d_output = nullptr;
     int N = 0;
+    const float* in_base = nullptr;    // the caller's page-locked input array (device view), read in place
     int kind_mask = 0;                 // generic: accumulator kinds active (const / old / new)
     uint64_t hparts[3] = {0, 0, 0}, xparts[3] = {0, 0, 0};
     int nrows = 0;
@@ -693,6 +694,7 @@ struct Renderer
   GraphEntry graphs[2][8];             // [device-buffer slot][kind mask]
   bool use_graphs = true;
   bool zero_copy = true;               // process(): inverse kernel stores into the caller's pinned array
+  bool zero_copy_in = true;            // process(): forward kernel reads the caller's pinned input array
   uint64_t graph_launches = 0;
   void drop_graphs();
   // level meters

@@ -138,8 +138,11 @@ __device__ __forceinline__ float block_max(float v)
 }
 
 // ---------------------------------------------------------------- FFT core
-// Complex FFT of size m (power of two) in shared memory, Stockham autosort,
-// radix-4 stages plus one radix-2 stage when log2(m) is odd.  `a` holds the
+// Complex FFT of size m in shared memory, Stockham autosort: radix-4 stages, one radix-2
+// stage when the power of two in m is odd, then -- block sizes that are multiples of 8
+// but not powers of two (the reference accepts every B % 8 == 0, convolver.h:163-166) --
+// one generic radix-r stage per remaining odd prime factor r (direct r-point DFT per
+// butterfly: cheap for 3, 5, 7; correct for any r).  `a` holds the
 // input; the result ends up in the returned buffer (a or b).  tw[i] =
 // exp(-2 pi i * i / (2m)), i in [0, 2m); INVERSE conjugates the twiddles.
 // barrier `bar` over kThreads threads (0 = the whole CTA of a kThreads-thread kernel;
@@ -197,7 +200,7 @@ __device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
       }
       Ns <<= 2; rem >>= 2;
     }
-    else
+    else if ((rem & 1) == 0)
     {
       const int q = m >> 1;
       const int tstep = (2 * m) / (2 * Ns);
@@ -217,6 +220,36 @@ __device__ __forceinline__ float2* fft_smem(float2* a, float2* b, int m,
         dst[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
       }
       Ns <<= 1; rem >>= 1;
+    }
+    else
+    {
+      // smallest odd factor r of what is left (the powers of two are gone, so Ns may
+      // stop being a power of two from here on: % instead of &)
+      int r = 3;
+      while (rem % r) r += 2;
+      const int q = m / r;
+      const int tstep = (2 * m) / (r * Ns);   // e^{-2 pi i k / (r Ns)} = tw[k * tstep]
+      const int rstep = (2 * m) / r;          // e^{-2 pi i / r}        = tw[rstep]
+      for (int j = t; j < q; j += kThreads)
+      {
+        const int k = j % Ns;
+        const int j0 = (j - k) * r + k;
+        for (int pp = 0; pp < r; ++pp)
+        {
+          float2 acc = make_float2(0.f, 0.f);
+          for (int qq = 0; qq < r; ++qq)
+          {
+            int idx = qq * k * tstep + ((pp * qq) % r) * rstep;   // both exponents on the 2m-entry table
+            if (idx >= 2 * m) idx -= 2 * m;
+            float2 w = TWS ? tw[idx] : __ldg(&tw[idx]);
+            if (INVERSE) w.y = -w.y;
+            const float2 v = cmul(src[j + qq * q], w);
+            acc.x += v.x; acc.y += v.y;
+          }
+          dst[j0 + pp * Ns] = acc;
+        }
+      }
+      Ns *= r; rem /= r;
     }
     group_sync(bar);
     float2* tmp = src; src = dst; dst = tmp;
@@ -370,10 +403,16 @@ struct FwdRingUpdate
 };
 __device__ __forceinline__ void fwd_ring_update(const FwdRingUpdate& u, int source, int ear);
 
+// in_base != null: job i reads its new block from in_base + i * B instead of the address in
+// the job table -- the renderers pass the caller's page-locked input array (mapped host
+// memory) here, so that no H2D copy precedes the launch and, with the overlapped variant
+// below, the PCIe transfer itself runs under the MAC.
 __global__ void __launch_bounds__(kThreads)
-fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru)
+fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru,
+               const float* __restrict__ in_base)
 {
-  const FwdJob job = jobs[blockIdx.x];
+  FwdJob job = jobs[blockIdx.x];
+  if (in_base) job.second.ptr = in_base + size_t(blockIdx.x) * B;
   if (ru.ctl && threadIdx.x < 2) fwd_ring_update(ru, blockIdx.x, threadIdx.x);
   fwd_fft_body<true>(job, B, tw);
 }
@@ -389,11 +428,13 @@ fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict_
 // maximal shared-memory carve-out, 1 next to the generated-terms MAC under the default one)
 template<int VARIANT>
 __global__ void __launch_bounds__(kThreads)
-fwd_fft_overlap_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru)
+fwd_fft_overlap_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru,
+                       const float* __restrict__ in_base)
 {
   grid_dependency_wait();
   grid_launch_dependents();
-  const FwdJob job = jobs[blockIdx.x];
+  FwdJob job = jobs[blockIdx.x];
+  if (in_base) job.second.ptr = in_base + size_t(blockIdx.x) * B;
   if (ru.ctl && threadIdx.x < 2) fwd_ring_update(ru, blockIdx.x, threadIdx.x);
   fwd_fft_body<false, true>(job, B, tw);
 }

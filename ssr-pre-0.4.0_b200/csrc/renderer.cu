@@ -54,6 +54,7 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
   if (const char* v = std::getenv("SSR_B200_ZEROCOPY_OUT")) zero_copy = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SSR_B200_ZEROCOPY_IN")) zero_copy_in = std::atoi(v) != 0;
   static_mac.MT = kGenericMT;
   for (auto& d : d_out) d.resize(size_t(std::max(m_local, 1)) * e->B);
   h_out.resize(size_t(2) * std::max(m_local, 1) * e->B);
@@ -771,9 +772,9 @@ void Renderer::launch(const StepDesc& d)
   {
     // the forward kernel's CTA n also records source n's current filters in the ring
     const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
-    e->launch_fwd(fwd->device(), d.N, &ru, overlap);
+    e->launch_fwd(fwd->device(), d.N, &ru, overlap, d.in_base);
   }
-  else e->launch_fwd(fwd->device(), d.N, nullptr, overlap);
+  else e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base);
   e->stage_mark(1);
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
@@ -1035,7 +1036,7 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
   if (hostgather && pipelined) throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: submit()/wait() with a host-direct gather: use process()");
   if (hostgather && hostgather->is_root()) hostgather->publish_consumed(hostgather->epoch);
   const float* hin = nullptr;
-  if (direct_out && N > 0 && contiguous_pinned(e, in, N, B)) hin = in[0];
+  if (!pipelined && N > 0 && contiguous_pinned(e, in, N, B)) hin = in[0];  // synchronous call: used in place
   else
   {
     float* stage = h_in.ptr + size_t(slot) * in_floats;
@@ -1071,7 +1072,24 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
     else { cudaGetLastError(); zero_copy_out = false; }
   }
 
-  const StepDesc d = prepare(din, dout);
+  StepDesc d = prepare(din, dout);
+  // Synchronous call with the caller's page-locked input array: the forward kernel reads the
+  // blocks straight from it (mapped host memory) -- no H2D copy in front of the block, and
+  // with the forward transform running under the MAC the PCIe transfer is off the critical
+  // path as well.  (Every sample still crosses the bus once: the kernel keeps the block as
+  // the next block's first half in device memory.)
+  bool direct_in = zero_copy_in && !pipelined && N > 0 && hin == in[0] && e->pdl
+      && !(e->fft1024 && N >= Engine::kFft1024MinJobs);
+  if (direct_in)
+  {
+    void* mapped = nullptr;
+    if (cudaHostGetDevicePointer(&mapped, const_cast<float*>(hin), 0) == cudaSuccess && mapped)
+    {
+      d.in_base = static_cast<const float*>(mapped);
+      d.graphable = false;   // the array's address is a kernel argument of this block
+    }
+    else { cudaGetLastError(); direct_in = false; }
+  }
   if (pipelined)
   {
     // H2D on the copy-in stream, once the kernels of block t-2 (readers of this
@@ -1084,7 +1102,7 @@ void Renderer::submit_block(int n, const float* const* in, float* const* direct_
     SSR_CUDA(cudaStreamWaitEvent(e->stream, ev_in[slot], 0));
     if (slot_used[slot]) SSR_CUDA(cudaStreamWaitEvent(e->stream, done[slot], 0));
   }
-  else if (N > 0)
+  else if (N > 0 && !direct_in)
     SSR_CUDA(cudaMemcpyAsync(din, hin, size_t(N) * B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   // Steady state (no table moved or resized since the last blocks): the kernel
   // sequence {forward FFT, MAC passes, [partial reduce], inverse FFT} is replayed

@@ -129,12 +129,17 @@ def test_block_size_errors(capi):
         capi.Engine(12)
     assert ei.value.code == capi.SSR_ERR_BLOCK_SIZE
     assert "multiple of 8" in ei.value.msg
+    capi.Engine(24).close()   # every multiple of 8 is a block size, like the reference's
     with pytest.raises(capi.SsrError) as ei:
-        capi.Engine(24)  # multiple of 8 but not a power of two: documented deviation
+        capi.Engine(8192)     # the engine's own upper limit
     assert ei.value.code == capi.SSR_ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("B,L", [(8, 16), (16, 50), (64, 200), (256, 1000), (1024, 8192), (2048, 5000), (4096, 9000)])
+@pytest.mark.parametrize("B,L", [(8, 16), (16, 50), (64, 200), (256, 1000), (1024, 8192), (2048, 5000), (4096, 9000),
+                                 # multiples of 8 that are not powers of two (convolver.h:163-166 accepts them):
+                                 # odd factors 3, 5, 7, 11, 5^3, 3 * 43 and 3 * 5^3 go through the generic-radix stage
+                                 (24, 100), (40, 90), (56, 300), (88, 200), (120, 500), (1000, 3000), (1032, 2500),
+                                 (3000, 7000)])
 def test_filter_and_input_spectra_match_oracle(capi, co, engine_factory, B, L):
     rng = np.random.default_rng(B + L)
     e = engine_factory(B)
@@ -324,3 +329,40 @@ def test_filter_edited_in_place_after_binding_is_seen(capi, engine_factory):
         want = np.stack([direct([0])[t] if t < 3 else (direct([0, 2])[t] if t < 7 else direct([2])[t])
                          for t in range(len(x))])
         assert np.abs(got - want).max() <= 1e-5, dynamic
+
+
+@pytest.mark.parametrize("B", [24, 48, 120, 200, 1000, 1536])
+def test_block_sizes_that_are_not_powers_of_two(capi, co, engine_factory, B):
+    """apf::conv accepts every block size that is a multiple of 8 (convolver.h:163-166);
+    so does the engine (generic-radix FFT stages for the odd factors): StaticConvolver and a
+    dynamic Output with a staggered switch against the oracle, plus float64 direct convolution."""
+    rng = np.random.default_rng(B)
+    e = engine_factory(B)
+    L = 3 * B + B // 2
+    h = (rng.uniform(-1, 1, L) * np.exp(-6.9 * np.arange(L) / L)).astype(np.float32) * 0.2
+    h2 = (rng.uniform(-1, 1, L) * np.exp(-6.9 * np.arange(L) / L)).astype(np.float32) * 0.2
+    P = capi.min_partitions(B, L)
+    inp = capi.Input(e, P)
+    so = capi.StaticOutput(inp, taps=h)
+    dyn = capi.Output(inp)
+    f1, f2 = capi.FilterSet.from_time(e, h[:, None], P), capi.FilterSet.from_time(e, h2[:, None], P)
+    dyn.set_filter(f1)
+    oin = co.Input(B, P)
+    oso = co.StaticOutput(oin, taps=h)
+    odyn = co.Output(oin)
+    of1, of2 = co.Filter(B, h, P), co.Filter(B, h2, P)
+    odyn.set_filter(of1)
+    T = 10
+    x = rng.uniform(-1, 1, (T, B)).astype(np.float32)
+    ys = []
+    for t in range(T):
+        inp.add_block(x[t]); oin.add_block(x[t])
+        if not dyn.queues_empty():
+            dyn.rotate_queues(); odyn.rotate_queues()
+        if t == 5:
+            dyn.set_filter(f2); odyn.set_filter(of2)
+        ys.append(so.convolve(0.8))
+        assert np.abs(ys[-1] - oso.convolve(0.8)).max() <= 1e-5
+        assert np.abs(dyn.convolve(1.0) - odyn.convolve(1.0)).max() <= 1e-5
+    direct = 0.8 * np.convolve(x.reshape(-1).astype(np.float64), h.astype(np.float64))[:T * B]
+    assert np.abs(np.concatenate(ys) - direct).max() <= 1e-5
