@@ -883,11 +883,18 @@ def main_ours(args):
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
     mac_ms = st["ms_mac"]
     achieved = (st["mac_bytes"] / 1e9) / (mac_ms * 1e-3) if mac_ms > 0 else 0.0
-    traffic = None
+    # DRAM traffic of the MAC launch from the committed ncu capture of the SAME plan: the entry is
+    # used only when its grid equals the grid this run launched (profiles/mac_traffic.json)
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not reduced:
         try:
-            traffic = json.load(open(tpath)).get(f"{args.workload}_gpus{world}")
+            ent = json.load(open(tpath)).get(f"{args.workload}_gpus{world}")
+            if ent and int(ent["grid"]) == int(st.get("last_mac_grid", -1)):
+                traffic = float(ent["bytes"])
+                traffic_source = f"{ent['capture']} at commit {ent['commit']} (grid {ent['grid']})"
+            elif ent:
+                traffic_source = f"capture on file is for grid {ent['grid']}, this run launched {st.get('last_mac_grid')}: omitted"
         except Exception:
             traffic = None
     roofline = {
@@ -895,7 +902,8 @@ def main_ours(args):
                                     else f"MAC variant {args.mac_variant} (profiles/r1_mac_variants.md)")
                                    if w.kind == "generic"
                                    else "ssrk::mac_kernel<2,2,2,2,true> (terms generated on the device)"), "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
+        "mac_grid": int(st.get("last_mac_grid", 0)),
         "bytes_per_launch": st["mac_bytes"] / max(1, st["mac_launches"]),
         "ms_per_launch": mac_ms / max(1, st["mac_launches"]),
         "mac_share_of_step": mac_ms / max(1e-9, st["ms_total"]),

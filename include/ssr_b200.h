@@ -103,7 +103,8 @@ typedef struct ssr_engine_stats
   int timing_enabled;
   int timing_every;          /* every timing_every-th block step carries the stage events */
   uint64_t launches_total;   /* every kernel the engine launched (timed or not, graph replays included) */
-  int reserved[4];
+  int last_mac_grid;         /* CTAs of the most recent MAC launch (ties ncu captures to the plan that ran) */
+  int reserved[3];
 } ssr_engine_stats;
 
 /* Per-stage CUDA events.  enabled = 0: off; 1: every block step; k > 1: every k-th

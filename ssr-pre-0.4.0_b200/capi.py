@@ -33,7 +33,7 @@ class EngineStats(C.Structure):
                 ("mac_bytes", C.c_uint64), ("mac_terms", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("timing_enabled", C.c_int), ("timing_every", C.c_int),
-                ("launches_total", C.c_uint64), ("reserved", C.c_int * 4)]
+                ("launches_total", C.c_uint64), ("last_mac_grid", C.c_int), ("reserved", C.c_int * 3)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

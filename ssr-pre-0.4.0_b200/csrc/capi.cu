@@ -84,7 +84,7 @@ int ssr_engine_get_stats(ssr_engine* e, ssr_engine_stats* out, int reset)
     *out = e->impl.stats;
     out->timing_enabled = e->impl.timing ? 1 : 0;
     out->timing_every = e->impl.timing_every;
-    if (reset) e->impl.stats = ssr_engine_stats{};
+    if (reset) { const int grid = e->impl.stats.last_mac_grid; e->impl.stats = ssr_engine_stats{}; e->impl.stats.last_mac_grid = grid; }
   });
 }
 

@@ -406,6 +406,7 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   p.l2_hints = (mac_variant == 3) ? 0 : 1;
   void* args[] = { &p };
   dim3 grid(nwork, mac_ktiles(B), 1);
+  stats.last_mac_grid = nwork * mac_ktiles(B);
   if (mac_tma() && plan.MT == 4)
   {
     const bool five = mac_variant != 6;
@@ -519,6 +520,7 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights, b
   void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 2, true> : (void*)mac_kernel<2, 1, 2, 2, true>;
   void* args[] = { &p };
   dim3 grid(G, mac_ktiles(B), 1);
+  stats.last_mac_grid = G * mac_ktiles(B);
   launch_mac_fn(fn, grid, args);
   count_launch();
   if (cur) cur->mac_launches++;

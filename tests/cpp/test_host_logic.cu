@@ -13,7 +13,9 @@
 //  * ssrk::dyn_split: the CTA ranges of the three accumulator groups.
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <set>
+#include <thread>
 #include <vector>
 
 #include "../../ssr-pre-0.4.0_b200/csrc/engine.hpp"
@@ -334,8 +336,35 @@ static void test_cfg5_split()
   CHECK(longest == 651);                 // 96 256 terms / 148 (round 1: 6016 / 9 = 669)
 }
 
+// ControlQueue = apf::CommandQueue for the control setters (apf/apf/commandqueue.h:141-153,185-210):
+// commands come out in the order they went in, a full ring is reported (not overwritten), and
+// a producer thread racing the consumer loses nothing.
+static void test_control_queue()
+{
+  auto q = std::unique_ptr<ControlQueue>(new ControlQueue);
+  for (int i = 0; i < 10; ++i) CHECK(q->push(ControlQueue::Cmd{ControlQueue::REF_ORIENTATION, i, float(i), 0.f}));
+  int seen = 0; bool ordered = true;
+  q->drain([&](const ControlQueue::Cmd& c) { ordered = ordered && c.id == seen && c.a == float(seen); ++seen; });
+  CHECK(seen == 10 && ordered);
+  q->drain([&](const ControlQueue::Cmd&) { ++seen; });
+  CHECK(seen == 10);   // empty now
+  for (uint32_t i = 0; i < ControlQueue::kCapacity; ++i) CHECK(q->push(ControlQueue::Cmd{0, int(i), 0.f, 0.f}));
+  CHECK(!q->push(ControlQueue::Cmd{0, -1, 0.f, 0.f}));   // full: reported after the retries, nothing overwritten
+  seen = 0; ordered = true;
+  q->drain([&](const ControlQueue::Cmd& c) { ordered = ordered && c.id == seen; ++seen; });
+  CHECK(seen == int(ControlQueue::kCapacity) && ordered);
+  // producer thread vs consumer: 200 000 commands through a 4096-slot ring
+  const int total = 200000;
+  std::thread producer([&] { for (int i = 0; i < total; ++i) while (!q->push(ControlQueue::Cmd{1, i, 0.f, 0.f})) {} });
+  int next = 0; ordered = true;
+  while (next < total) q->drain([&](const ControlQueue::Cmd& c) { ordered = ordered && c.id == next; ++next; });
+  producer.join();
+  CHECK(ordered && next == total);
+}
+
 int main()
 {
+  test_control_queue();
   test_cfg5_split();
   test_ptr_table();
   test_make_work();
