@@ -113,6 +113,10 @@ typedef struct ssr_engine_stats
  * the per-kind launch counts then describe the sampled steps only). */
 int ssr_engine_set_timing(ssr_engine* e, int enabled);
 int ssr_engine_get_stats(ssr_engine* e, ssr_engine_stats* out, int reset);
+/* Development aid (engines that run the bulk-copy MAC, B >= 1024, else SSR_ERR_STATE): per
+ * CTA of the most recent MAC launch {start, first data, end, busy time accumulated since the
+ * last share calibration} in %globaltimer nanoseconds; out holds 4 * max_ctas values. */
+int ssr_engine_debug_mac_trace(ssr_engine* e, uint64_t* out, int max_ctas);
 
 /* ------------------------------------------------------------- filter sets */
 

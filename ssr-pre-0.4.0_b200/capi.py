@@ -77,6 +77,7 @@ SIGNATURES = {
     "ssr_engine_synchronize": (C.c_int, [C.c_void_p]),
     "ssr_engine_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ssr_engine_get_stats": (C.c_int, [C.c_void_p, C.POINTER(EngineStats), C.c_int]),
+    "ssr_engine_debug_mac_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "ssr_filterset_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ssr_filterset_destroy": (None, [C.c_void_p]),
     "ssr_filterset_channels": (C.c_int, [C.c_void_p]),
@@ -232,6 +233,13 @@ class Engine:
     def set_timing(self, on, every: int = 1):
         """Per-stage CUDA events on every `every`-th block step (0 / False: off)."""
         _check(lib().ssr_engine_set_timing(self.h, (max(1, int(every)) if on else 0)))
+
+    def mac_trace(self, ctas: int) -> np.ndarray:
+        """(ctas, 4) uint64: start / first data / end of every CTA of the last bulk-copy MAC launch
+        (engine created under SSR_B200_MAC_TRACE=1)."""
+        out = np.zeros((ctas, 4), np.uint64)
+        _check(lib().ssr_engine_debug_mac_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), ctas))
+        return out
 
     def stats(self, reset: bool = False) -> dict:
         st = EngineStats()

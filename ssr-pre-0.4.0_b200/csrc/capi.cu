@@ -88,6 +88,19 @@ int ssr_engine_get_stats(ssr_engine* e, ssr_engine_stats* out, int reset)
   });
 }
 
+int ssr_engine_debug_mac_trace(ssr_engine* e, uint64_t* out, int max_ctas)
+{
+  return guarded([&] {
+    require(e && out && max_ctas > 0, "debug_mac_trace: bad argument");
+    Engine& E = e->impl;
+    if (!E.mac_trace.ptr) throw Error(SSR_ERR_STATE, "ssr_b200: this engine does not run the bulk-copy MAC (B < 1024)");
+    E.use_device();
+    E.sync();
+    const size_t n = std::min<size_t>(size_t(max_ctas) * 4, E.mac_trace.count);
+    SSR_CUDA(cudaMemcpy(out, E.mac_trace.ptr, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  });
+}
+
 /* ------------------------------------------------------------- filter sets */
 
 int ssr_filterset_create(ssr_engine* e, int channels, int partitions, ssr_filterset** out)

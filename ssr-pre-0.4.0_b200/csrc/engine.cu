@@ -12,7 +12,7 @@ namespace ssr_b200
 using namespace ssrk;
 
 // ------------------------------------------------------------------ MacPlan
-void MacPlan::make_work(int slots, int fixed_cost, int waves)
+void MacPlan::make_work(int slots, int fixed_cost, int waves, const std::vector<double>* weights)
 {
   work.host.clear();
   cta_first.host.clear();
@@ -31,9 +31,25 @@ void MacPlan::make_work(int slots, int fixed_cost, int waves)
   std::vector<int4> segs;
   std::vector<int> first;
   size_t g = 0;
+  // share boundaries: equal, or proportional to the calibrated speed of each CTA
+  std::vector<long> bound(size_t(C) + 1);
+  if (weights && long(weights->size()) == C)
+  {
+    double sum = 0.0, run = 0.0;
+    for (double w : *weights) sum += std::max(w, 1e-9);
+    bound[0] = 0;
+    for (long c = 0; c < C; ++c)
+    {
+      run += std::max((*weights)[size_t(c)], 1e-9);
+      bound[size_t(c) + 1] = std::max(bound[size_t(c)], std::min<long>(total, long(double(total) * run / sum + 0.5)));
+    }
+    bound[size_t(C)] = total;
+  }
+  else
+    for (long c = 0; c <= C; ++c) bound[size_t(c)] = total * c / C;
   for (long c = 0; c < C; ++c)
   {
-    const long b = total * c / C, e = total * (c + 1) / C;   // share of CTA c in the term table
+    const long b = bound[size_t(c)], e = bound[size_t(c) + 1];   // share of CTA c in the term table
     first.push_back(int(segs.size()));
     long pos = b;
     while (pos < e)
@@ -206,6 +222,12 @@ Engine::Engine(const ssr_engine_config& cfg)
   if (const char* v = std::getenv("SSR_B200_FWD_OVERLAP")) fwd_overlap = std::atoi(v) != 0;
   if (const char* v = std::getenv("SSR_B200_MAC_WAVES")) mac_waves = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("SSR_B200_PREREDUCE_MIN")) prereduce_min = std::max(1, std::atoi(v));
+  if (const char* v = std::getenv("SSR_B200_MAC_CALIBRATE")) mac_calibrate = std::atoi(v) != 0;
+  if (mac_tma())
+  {
+    mac_trace.resize(4096 * 4);
+    SSR_CUDA(cudaMemset(mac_trace.ptr, 0, mac_trace.count * sizeof(unsigned long long)));
+  }
   fwd_overlap = fwd_overlap && pdl;
   if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
   if (!is_pow2(B)) level1_fused = false;   // the fused Level-1 launch is instantiated for power-of-two spectra
@@ -395,6 +417,7 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   p.work = plan.work.device();
   p.cta_first = plan.cta_first.device();
   p.head_bias = overlap ? 1 : 0;
+  if (mac_trace.ptr) p.trace = mac_trace.ptr;
   p.wtab = weights ? weights : wtab.device();
   p.xring = d_xring.ptr;
   p.xparts = d_xparts.ptr;

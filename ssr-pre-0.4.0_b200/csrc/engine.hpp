@@ -169,7 +169,9 @@ struct MacPlan
   void end_group() { groups.back().term_end = int(meta.host.size()); }
   // `slots` = CTAs resident at once; `fixed_cost` = cost of one more CTA in units of one
   // term (pipeline fill, partials); `waves` > 0 forces waves x slots CTAs (experiments)
-  void make_work(int slots, int fixed_cost = 2, int waves = 0);
+  // `weights` (one per CTA of the resulting plan, or null): relative speed of each CTA -- its share of
+  // the term table is proportional to it (Renderer::calibrate)
+  void make_work(int slots, int fixed_cost = 2, int waves = 0, const std::vector<double>* weights = nullptr);
   void upload(cudaStream_t s) { meta.upload(s); hptr.upload(s); work.upload(s); cta_first.upload(s); }
 };
 
@@ -235,6 +237,8 @@ struct Engine
                   const ssrk::HeadCommit& hc = ssrk::HeadCommit{});
   bool fwd_overlap = true;         // forward transform under the MAC (SSR_B200_FWD_OVERLAP=0: off)
   int mac_waves = 0;               // SSR_B200_MAC_WAVES: CTAs of a MAC launch = waves x resident CTAs
+  DeviceArray<unsigned long long> mac_trace;   // per-CTA timestamps / busy time of the bulk-copy MAC launches
+  bool mac_calibrate = false;                  // SSR_B200_MAC_CALIBRATE=1: re-cut the shares by measured CTA rates
   int prereduce_min = 16;          // partials per accumulator from which a separate reduction launch pays
   // dynamic renderers: terms generated on the device (ssrk::DynTables), static launch shapes
   void launch_mac_dyn(const ssrk::DynTables& dyn, int G, const float* weights, bool fwd_overlap = false);
@@ -637,6 +641,24 @@ struct Renderer
   // per-block plans
   MacPlan static_mac;           // generic: built when the source list changes
   bool static_dirty = true;
+  // Share calibration of the bulk-copy MAC (experiment, OFF by default: SSR_B200_MAC_CALIBRATE=1).
+  // With one equal share per SM the CTAs of one launch finish up to 7 % apart (scripts/mac_trace.py:
+  // 420 .. 475 us on the per-GPU shard of the 8-GPU run; the same CTAs are slow launch after launch).
+  // The kernel accumulates each CTA's busy time; after a few steady blocks the shares are re-cut in
+  // proportion to the measured rates, twice.  Measured: the spread barely shrinks (a CTA's rate depends
+  // on what its neighbours do, not on its share alone) and the block gets 1 - 2 % faster at best, because
+  // the CTAs still running keep HBM saturated during the tail anyway (profiles/r2_mac_balance.md).  Not
+  // worth results that differ from run to run in the last bits, hence off.
+  struct Calibration
+  {
+    int state = 0;                 // 0 counting steady blocks, 1 measuring, 2 read-back queued, 3 done
+    int steady = 0, measured = 0, rounds = 0;
+    std::vector<double> weights;   // per CTA; empty = equal shares
+    PinnedArray<unsigned long long> host;
+    cudaEvent_t ev = nullptr;
+    void reset() { state = 0; steady = 0; measured = 0; rounds = 0; weights.clear(); }
+  } calib;
+  void calibrate(int kind_mask);
   InvPlan inv_plans[2];         // inverse tables per output buffer (pipelined submit() alternates)
   int inv_keys[2] = {-1, -1};
   int cur_slot = 0;

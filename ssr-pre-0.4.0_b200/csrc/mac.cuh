@@ -90,6 +90,8 @@ struct MacParams
   int partial_offset;                // added to work.z
   int l2_hints;                      // 1: evict-first for H, evict-last for X
   const float4* zero;                // an all-zero partition
+  unsigned long long* trace;         // per CTA {start, first data, end, accumulated busy time} in %globaltimer ns, or
+                                     //  null (bulk-copy MAC): feeds the share calibration (Renderer::calibrate)
   int head_bias;                     // 1: the forward transform of this block runs CONCURRENTLY (it has not
                                      //  published the ring heads yet): newest slot = heads[] + 1, and terms with
                                      //  p == 0 are issued last, behind griddepcontrol.wait (mac_tma_kernel)
@@ -557,6 +559,7 @@ mac_tma_kernel(const MacParams p)
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (p.trace) { unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now)); p.trace[size_t(blockIdx.x) * 4] = now; }
   }
   __syncthreads();
   // head_bias: this block's forward transform may still be running (programmatic dependent
@@ -651,11 +654,25 @@ mac_tma_kernel(const MacParams p)
   const int tt = tile_off + t;
   int s = 0;
   unsigned phase = 0;
+  bool first_stage = true;
   while (true)
   {
     mbar_wait(full + s, phase);
+    if (p.trace && t == 0 && first_stage)
+    { unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now)); p.trace[size_t(blockIdx.x) * 4 + 1] = now; }
+    first_stage = false;
     const int kind = stage_kind[s];
-    if (kind == kStageDone) break;
+    if (kind == kStageDone)
+    {
+      if (p.trace && t == 0)
+      {
+        unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        unsigned long long* tr = p.trace + size_t(blockIdx.x) * 4;
+        tr[2] = now;
+        tr[3] += now - tr[0];   // only this CTA writes its slot
+      }
+      break;
+    }
     if (kind == kStageFlush)
     {
       // end of a segment: the accumulators go to its partial spectra

@@ -65,6 +65,7 @@ Renderer::~Renderer()
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (auto ev : done) if (ev) cudaEventDestroy(ev);
+  if (calib.ev) cudaEventDestroy(calib.ev);
   for (auto ev : dyn_copied) if (ev) cudaEventDestroy(ev);
   if (s_in) { cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_out); }
   for (auto ev : ev_in) if (ev) cudaEventDestroy(ev);
@@ -274,6 +275,71 @@ static Mode mode_from_weight(const BlockParameter<float>& f)
   return CHANGE;
 }
 
+// Share calibration of the bulk-copy MAC (see Renderer::Calibration).  Called once per block
+// of the Generic renderer, before the block's kernels are queued.
+void Renderer::calibrate(int kind_mask)
+{
+  constexpr int kSettle = 8, kMeasure = 16, kRounds = 2;
+  if (!e->mac_calibrate || !e->mac_tma() || static_mac.MT != kGenericMT || static_mac.ncta < 2
+      || !e->mac_trace.ptr || static_mac.ncta > int(e->mac_trace.count / 4) || calib.state == 3)
+    return;
+  const bool steady = kind_mask == 1;   // one MAC launch per block, constant weights
+  if (calib.state == 2)
+  {
+    if (cudaEventQuery(calib.ev) != cudaSuccess) { cudaGetLastError(); return; }
+    // rates: terms of the share / busy time accumulated over the measured launches
+    const int C = static_mac.ncta;
+    std::vector<double> rate(size_t(C), 0.0);
+    bool ok = true;
+    for (int c = 0; c < C && ok; ++c)
+    {
+      long terms = 0;
+      for (int i = static_mac.cta_first.host[size_t(c)]; i < static_mac.cta_first.host[size_t(c) + 1]; ++i)
+        terms += static_mac.work.host[size_t(i)].y - static_mac.work.host[size_t(i)].x;
+      const double busy = double(calib.host.ptr[size_t(c) * 4 + 3]);
+      ok = terms > 0 && busy > 0.0;
+      if (ok) rate[size_t(c)] = double(terms) / busy;
+    }
+    double mean = 0.0;
+    for (double r : rate) mean += r / double(C);
+    for (int c = 0; c < C && ok; ++c) ok = rate[size_t(c)] > 0.5 * mean && rate[size_t(c)] < 2.0 * mean;  // sane
+    if (ok)
+    {
+      e->sync();   // kernels in flight still read the old work tables
+      calib.weights = rate;
+      static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT), e->mac_waves, &calib.weights);
+      static_mac.upload(e->stream);
+      e->ensure_partials(size_t(3) * static_mac.npartials * static_mac.MT);
+      invalidate_inv();
+      inv_batch_key = -1;
+      ++calib.rounds;
+    }
+    calib.state = (calib.rounds >= kRounds || !ok) ? 3 : 0;
+    calib.steady = 0;
+    return;
+  }
+  if (!steady) { if (calib.state == 1) calib.state = 0; calib.steady = 0; return; }
+  if (calib.state == 0)
+  {
+    if (++calib.steady < kSettle) return;
+    // start measuring with this block's launch: clear the accumulated busy times (stream-ordered)
+    SSR_CUDA(cudaMemsetAsync(e->mac_trace.ptr, 0, size_t(static_mac.ncta) * 4 * sizeof(unsigned long long), e->stream));
+    calib.state = 1;
+    calib.measured = 0;
+    return;
+  }
+  if (calib.state == 1 && ++calib.measured > kMeasure)
+  {
+    // the launches of the last kMeasure blocks are queued before this copy
+    if (calib.host.count < size_t(static_mac.ncta) * 4) calib.host.resize(size_t(static_mac.ncta) * 4);
+    if (!calib.ev) SSR_CUDA(cudaEventCreateWithFlags(&calib.ev, cudaEventDisableTiming));
+    SSR_CUDA(cudaMemcpyAsync(calib.host.ptr, e->mac_trace.ptr, size_t(static_mac.ncta) * 4 * sizeof(unsigned long long),
+          cudaMemcpyDeviceToHost, e->stream));
+    SSR_CUDA(cudaEventRecord(calib.ev, e->stream));
+    calib.state = 2;
+  }
+}
+
 Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_output)
 {
   InvPlan& inv = inv_plans[cur_slot];   // one set of inverse tables per output buffer
@@ -302,28 +368,52 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
     e->sync();
     static_mac.clear();
     const float4* zero = reinterpret_cast<const float4*>(e->zero_part.ptr);
+    // order of a group's (source, partition) terms in the table (a CTA's share is a contiguous
+    // run of it): 0 = source-major, 1 = partition-major, 2 = pseudo-random (experiments)
+    int term_order = 0;
+    if (const char* v = std::getenv("SSR_B200_TERM_ORDER")) term_order = std::atoi(v);
+    std::vector<std::pair<int, int>> np_list;
+    int Pmax = 0;
+    for (int n = 0; n < N; ++n) Pmax = std::max(Pmax, sources[n]->irs->partitions);
+    if (term_order == 1)
+    {
+      for (int p = 0; p < Pmax; ++p)
+        for (int n = 0; n < N; ++n) if (p < sources[n]->irs->partitions) np_list.emplace_back(n, p);
+    }
+    else
+    {
+      for (int n = 0; n < N; ++n)
+        for (int p = 0; p < sources[n]->irs->partitions; ++p) np_list.emplace_back(n, p);
+      if (term_order == 2)
+      {
+        uint64_t st = 0x9E3779B97F4A7C15ull;
+        for (size_t i = np_list.size(); i > 1; --i)
+        {
+          st = st * 6364136223846793005ull + 1442695040888963407ull;
+          std::swap(np_list[i - 1], np_list[size_t((st >> 33) % i)]);
+        }
+      }
+    }
     for (int m0 = 0; m0 < m_local; m0 += kGenericMT)
     {
       static_mac.begin_group();
-      for (int n = 0; n < N; ++n)
+      for (auto& np : np_list)
       {
+        const int n = np.first, p = np.second;
         Source& s = *sources[n];
-        const int P = s.irs->partitions;
-        for (int p = 0; p < P; ++p)
+        const float4* h[kGenericMT];
+        bool any = false;
+        for (int j = 0; j < kGenericMT; ++j)
         {
-          const float4* h[kGenericMT];
-          bool any = false;
-          for (int j = 0; j < kGenericMT; ++j)
-          {
-            const float2* ptr = (m0 + j < m_local) ? s.irs->part_or_null(m0 + j, p) : nullptr;
-            h[j] = ptr ? reinterpret_cast<const float4*>(ptr) : zero;
-            any |= (ptr != nullptr);
-          }
-          if (any) static_mac.add_term(s.input->id, p, n, h);
+          const float2* ptr = (m0 + j < m_local) ? s.irs->part_or_null(m0 + j, p) : nullptr;
+          h[j] = ptr ? reinterpret_cast<const float4*>(ptr) : zero;
+          any |= (ptr != nullptr);
         }
+        if (any) static_mac.add_term(s.input->id, p, n, h);
       }
       static_mac.end_group();
     }
+    calib.reset();
     static_mac.make_work(e->mac_slots(static_mac.MT), e->split_cost(static_mac.MT), e->mac_waves);
     static_mac.upload(e->stream);
     e->ensure_partials(size_t(3) * static_mac.npartials * static_mac.MT);
@@ -332,6 +422,7 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
   }
 
   const int key = (kind_active[0] ? 1 : 0) | (kind_active[1] ? 2 : 0) | (kind_active[2] ? 4 : 0);
+  calibrate(key);   // may re-cut the MAC shares (then the inverse tables below are rebuilt)
   if (key != inv_key || (inv.jobs.host.size() && inv.jobs.host[0].out != d_output))
   {
     inv.clear();
