@@ -280,7 +280,7 @@ def port_sample(w, steps: int, warmup: int):
 
 
 def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, rotate: bool = True,
-                     repeats: int = 1):
+                     repeats: int = 1, bounded: bool = False):
     """Runs the reference CPU arm on a bounded sample of workload `w`: `repeats` runs of
     `steps` blocks, the MEDIAN run is reported (one noisy run used to move the number by
     tens of percent).  Returns (full-workload ms per block, per-block ms scaled, cores
@@ -289,7 +289,8 @@ def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, 
     if not ref.available():
         return port_sample(w, steps, warmup)
     if w.kind == "generic":
-        shard, why = reference_plan(w, steps, warmup, budget_s, threads, repeats)
+        shard, why = reference_plan(w, steps, warmup, budget_s, threads, repeats,
+                                    max_shard=(max(min(threads, w.outputs), w.outputs // 8) if bounded else w.outputs))
         used = max(1, min(threads, shard))  # items are spread round-robin over outputs
         secs_all, times = run_reference_renderer(w, shard, steps, warmup, used, repeats)
         factor = w.outputs / shard
@@ -297,7 +298,7 @@ def reference_sample(w, steps: int, warmup: int, budget_s: float, threads: int, 
     else:
         # cost ~ sources * 2 ears * partitions * (1 or 2 evaluations)
         per_src = 2 * w.partitions * (2 if rotate else 1) * 1.6e-6 * 1.6
-        nsrc = w.sources
+        nsrc = max(1, w.sources // 8) if bounded else w.sources
         while nsrc > 1 and (per_src * nsrc / max(1, min(threads, nsrc)) * (steps + warmup) * repeats > budget_s
                             or nsrc * w.channels * (w.partitions * 8 * w.block + 4 * w.taps) > 0.5 * host_ram_available()):
             nsrc //= 2
@@ -330,7 +331,8 @@ def host_ram_available() -> float:
         return 32e9
 
 
-def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int, repeats: int = 1):
+def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int, repeats: int = 1,
+                   max_shard: int = 0):
     """Pick the output shard of a Generic workload: the FULL shape when it fits in host
     memory and (steps + warmup) x repeats blocks fit the time budget,
     else the largest multiple of the thread count that does.  The per-block cost is
@@ -349,6 +351,10 @@ def reference_plan(w, steps: int, warmup: int, budget_s: float, threads: int, re
     rounds = max(1, int(budget_s / (max(1, repeats) * (steps + warmup) * per_round)))
     time_shard = rounds * probe_out
     shard = min(w.outputs, mem_shard, time_shard)
+    if max_shard and shard > max_shard:
+        # the cpu_baseline leg of the GPU arm: a BOUNDED sample (loading the full 25 GB shape alone
+        # takes minutes); the reference arm (--impl reference) runs the full shape
+        return max_shard, "bounded sample of the GPU arm's cpu_baseline leg"
     if shard >= w.outputs:
         return w.outputs, "full shape"
     shard = max(probe_out if shard >= probe_out else 1, (shard // probe_out) * probe_out)
@@ -386,7 +392,7 @@ def main_reference(args):
     steps, warmup = args.steps, args.warmup
     rotate = w.kind != "generic" and not args.static_head
     full_ms, times, threads_used, sample, kind = reference_sample(w, steps, warmup, args.reference_budget_s, threads,
-                                                                  rotate=rotate, repeats=3)
+                                                                  rotate=rotate, repeats=5)
     value = (w.block / w.fs) / (full_ms * 1e-3)
     config, _ = make_config(w, reduced, max(1, args.gpus), rotate)
     line = {
@@ -961,7 +967,8 @@ def main_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             threads = os.cpu_count() or 1
-            full_ms, _, used, sample, kind = reference_sample(w, 40, 5, args.cpu_seconds, threads, rotate=rotate)
+            full_ms, _, used, sample, kind = reference_sample(w, 20, 3, args.cpu_seconds, threads, rotate=rotate,
+                                                              repeats=3, bounded=True)
             line["cpu_baseline"] = {
                 "value": (B / w.fs) / (full_ms * 1e-3), "unit": UNIT, "cores": used, "kind": kind,
                 "sample": sample}
