@@ -447,6 +447,56 @@ int ssr_hostgather_total_outputs(const ssr_hostgather* g);
 int ssr_hostgather_slot(ssr_hostgather* g, int slot /* 0 | 1 */, float** host_blocks);
 int ssr_hostgather_next_slot(const ssr_hostgather* g);
 
+/* ------------------------------------------------- non-uniform partitioning */
+/* SURVEY 8(f) row 4 -- NOT in the reference (its manual only notes the trade-off of the
+ * partition size, doc/manual/renderers.tex:199-204): a GenericRenderer whose impulse
+ * responses are cut into LEVELS of growing partition size.  Level 0 has `level_partitions[0]`
+ * partitions of the block size B and is the reference's algorithm unchanged
+ * (apf/apf/convolver.h:324-375,435-465; src/genericrenderer.h:122-203); level l > 0 has
+ * `level_partitions[l]` partitions of level_mult[l] * B samples, rendered by the same engine at
+ * that block size every level_mult[l] blocks, its outputs spread over the blocks of a period
+ * (csrc/nonuniform.cu).  Zero added latency, the same output within rounding for constant
+ * source weights; a weight change reaches a tail level at that level's block rate.  The
+ * filter bytes read per block fall from P to sum_l level_partitions[l] partitions' worth.
+ * Rules (SSR_ERR_INVALID otherwise): level_mult[0] = 1; level_mult increasing powers of two
+ * with level_mult[l] * B <= 4096; level l > 0 starts (sum of the lower levels' taps) at a
+ * multiple of its partition size and at least two of its partitions into the response.
+ * Sources are added before the first block. */
+typedef struct ssr_nu ssr_nu;
+typedef struct ssr_nu_config
+{
+  int device, block_size, sample_rate;
+  int outputs;                       /* loudspeakers M (total) */
+  int output_first, output_count;    /* output shard of this engine; count = 0: all */
+  int levels;                        /* 1..4 */
+  int level_mult[4];
+  int level_partitions[4];
+  float master_volume_correction_db;
+  int reserved[8];
+} ssr_nu_config;
+int ssr_nu_create(const ssr_nu_config* cfg, ssr_nu** out);
+void ssr_nu_destroy(ssr_nu* r);
+/* as ssr_renderer_add_source / _synthetic for the Generic renderer; frames (taps) must not
+ * exceed ssr_nu_taps_covered() */
+int ssr_nu_add_source(ssr_nu* r, const float* ir, long frames, int channels, int* id);
+int ssr_nu_add_source_synthetic(ssr_nu* r, long taps, int channels, uint64_t seed, uint64_t channel_id_offset,
+                                const float* envelope, float scale, int* id);
+int ssr_nu_source_set_gain(ssr_nu* r, int id, float gain);
+int ssr_nu_source_set_mute(ssr_nu* r, int id, int mute);
+int ssr_nu_set_master_volume(ssr_nu* r, float volume);
+int ssr_nu_sources(const ssr_nu* r);
+int ssr_nu_local_outputs(const ssr_nu* r);
+long ssr_nu_taps_covered(const ssr_nu* r);
+/* one block: host channel pointers, n = frames = the block size (= ssr_renderer_process,
+ * apf/apf/pointer_policy.h:112-122) / device arrays [sources][B] -> [local outputs][B],
+ * asynchronous on ssr_nu_stream() */
+int ssr_nu_process(ssr_nu* r, int n, const float* const* in, float* const* out);
+int ssr_nu_process_device(ssr_nu* r, const float* d_in, float* d_out);
+int ssr_nu_synchronize(ssr_nu* r);
+void* ssr_nu_stream(ssr_nu* r);
+/* ALGORITHMIC bytes (SURVEY 8d formula per MAC launch, summed) of block `block_index` */
+int ssr_nu_block_mac_bytes(ssr_nu* r, uint64_t block_index, uint64_t* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,13 @@ class RendererConfig(C.Structure):
                 ("reserved", C.c_int * 8)]
 
 
+class NuConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("block_size", C.c_int), ("sample_rate", C.c_int), ("outputs", C.c_int),
+                ("output_first", C.c_int), ("output_count", C.c_int), ("levels", C.c_int),
+                ("level_mult", C.c_int * 4), ("level_partitions", C.c_int * 4),
+                ("master_volume_correction_db", C.c_float), ("reserved", C.c_int * 8)]
+
+
 class RendererState(C.Structure):
     _fields_ = [("reference_x", C.c_float), ("reference_y", C.c_float), ("reference_azimuth", C.c_float),
                 ("reference_offset_x", C.c_float), ("reference_offset_y", C.c_float),
@@ -150,6 +157,21 @@ SIGNATURES = {
     "ssr_hostgather_total_outputs": (C.c_int, [C.c_void_p]),
     "ssr_hostgather_slot": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_f32p)]),
     "ssr_hostgather_next_slot": (C.c_int, [C.c_void_p]),
+    "ssr_nu_create": (C.c_int, [C.POINTER(NuConfig), C.POINTER(C.c_void_p)]),
+    "ssr_nu_destroy": (None, [C.c_void_p]),
+    "ssr_nu_add_source": (C.c_int, [C.c_void_p, _f32p, C.c_long, C.c_int, C.POINTER(C.c_int)]),
+    "ssr_nu_add_source_synthetic": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_uint64, C.c_uint64, _f32p, C.c_float, C.POINTER(C.c_int)]),
+    "ssr_nu_source_set_gain": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
+    "ssr_nu_source_set_mute": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ssr_nu_set_master_volume": (C.c_int, [C.c_void_p, C.c_float]),
+    "ssr_nu_sources": (C.c_int, [C.c_void_p]),
+    "ssr_nu_local_outputs": (C.c_int, [C.c_void_p]),
+    "ssr_nu_taps_covered": (C.c_long, [C.c_void_p]),
+    "ssr_nu_process": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p)]),
+    "ssr_nu_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_nu_synchronize": (C.c_int, [C.c_void_p]),
+    "ssr_nu_stream": (C.c_void_p, [C.c_void_p]),
+    "ssr_nu_block_mac_bytes": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 GATHER_HANDLE_BYTES = 64
 
@@ -666,3 +688,86 @@ class Renderer:
 
     def __del__(self):
         self.close()
+
+
+class NuRenderer:
+    """Non-uniformly partitioned Generic renderer (ssr_nu_*; not in the reference).
+    levels: [(block multiple, partitions), ...], first multiple 1."""
+
+    def __init__(self, block_size: int, outputs: int, levels: Sequence, sample_rate: int = 48000, device: int = 0,
+                 output_first: int = 0, output_count: int = 0, master_volume_correction_db: float = 0.0):
+        cfg = NuConfig(device=device, block_size=block_size, sample_rate=sample_rate, outputs=outputs,
+                       output_first=output_first, output_count=output_count, levels=len(levels),
+                       master_volume_correction_db=master_volume_correction_db)
+        for i, (k, p) in enumerate(levels):
+            cfg.level_mult[i] = int(k)
+            cfg.level_partitions[i] = int(p)
+        self.block_size = block_size
+        h = C.c_void_p()
+        _check(lib().ssr_nu_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    @property
+    def local_outputs(self) -> int:
+        return lib().ssr_nu_local_outputs(self.h)
+
+    @property
+    def n_sources(self) -> int:
+        return lib().ssr_nu_sources(self.h)
+
+    @property
+    def taps_covered(self) -> int:
+        return int(lib().ssr_nu_taps_covered(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().ssr_nu_stream(self.h) or 0)
+
+    def add_source(self, ir) -> int:
+        sid = C.c_int()
+        a = _f32(ir)
+        _check(lib().ssr_nu_add_source(self.h, _ptr(a), a.shape[0], a.shape[1], C.byref(sid)))
+        return sid.value
+
+    def add_source_synthetic(self, taps: int, channels: int, seed: int, channel_id_offset: int = 0,
+                             envelope=None, scale: float = 1.0) -> int:
+        sid = C.c_int()
+        env = None if envelope is None else _f32(envelope)
+        _check(lib().ssr_nu_add_source_synthetic(self.h, taps, channels, seed, channel_id_offset,
+                                                 _ptr(env), scale, C.byref(sid)))
+        return sid.value
+
+    def set_gain(self, sid, v): _check(lib().ssr_nu_source_set_gain(self.h, sid, v))
+    def set_mute(self, sid, v): _check(lib().ssr_nu_source_set_mute(self.h, sid, int(v)))
+    def set_master_volume(self, v): _check(lib().ssr_nu_set_master_volume(self.h, v))
+
+    def process(self, x) -> np.ndarray:
+        B = self.block_size
+        x = _f32(x).reshape(-1, B)
+        y = np.empty((self.local_outputs, B), np.float32)
+        ins = (_f32p * max(1, x.shape[0]))(*[x[i].ctypes.data_as(_f32p) for i in range(x.shape[0])])
+        outs = (_f32p * max(1, y.shape[0]))(*[y[i].ctypes.data_as(_f32p) for i in range(y.shape[0])])
+        _check(lib().ssr_nu_process(self.h, B, ins, outs))
+        return y
+
+    def process_device(self, d_in_ptr: int, d_out_ptr: int):
+        _check(lib().ssr_nu_process_device(self.h, d_in_ptr, d_out_ptr))
+
+    def synchronize(self):
+        _check(lib().ssr_nu_synchronize(self.h))
+
+    def block_mac_bytes(self, block_index: int) -> int:
+        v = C.c_uint64(0)
+        _check(lib().ssr_nu_block_mac_bytes(self.h, block_index, C.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if self.h:
+            lib().ssr_nu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -16,6 +16,7 @@ void MacPlan::make_work(int slots, int fixed_cost, int waves, const std::vector<
 {
   work.host.clear();
   cta_first.host.clear();
+  cta_head.host.clear();
   npartials = 0; ncta = 0;
   long total = 0;
   for (auto& g : groups) { total += g.term_end - g.term_begin; g.partial_first = 0; g.nsplit = 0; }
@@ -82,6 +83,12 @@ void MacPlan::make_work(int slots, int fixed_cost, int waves, const std::vector<
   }
   work.host = segs;
   cta_first.host = first;
+  for (long c = 0; c < C; ++c)
+  {
+    const int lo = first[size_t(c)], hi = first[size_t(c) + 1];
+    cta_head.host.push_back(make_int4(lo, hi, 0, 0));
+    cta_head.host.push_back(lo < hi ? segs[size_t(lo)] : make_int4(0, 0, 0, 0));
+  }
   ncta = int(C);
 }
 
@@ -100,6 +107,23 @@ static void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
+  SSR_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
+// the same with thread-block clusters of `cluster` CTAs along x (grid.x is a multiple of it)
+template<typename... KArgs, typename... Args>
+static void launch_cluster_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, int cluster, size_t smem,
+                                  cudaStream_t stream, bool pdl, Args&&... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(cluster); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
   SSR_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
@@ -212,6 +236,38 @@ Engine::Engine(const ssr_engine_config& cfg)
     SSR_CUDA(cudaFuncSetAttribute(mac_tma_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
           int(mac_tma_smem_bytes<4, 5>())));
   }
+  if (const char* v = std::getenv("SSR_B200_DYN_TMA")) dyn_tma_enabled = std::atoi(v) != 0;   // A/B experiments
+  if (dyn_tma())
+  {
+    SSR_CUDA(cudaFuncSetAttribute(mac_dyn_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          int(mac_dyn_tma_smem_bytes<5>())));
+    SSR_CUDA(cudaFuncSetAttribute(inv_dyn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem * 4)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+          int(cudaSharedmemCarveoutMaxShared)));
+    if (2 * fft_smem > 48 * 1024)
+      SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    // cluster size of the inverse kernel: 16 CTAs (non-portable) when the device schedules them, else 8
+    dyn_cluster = 8;
+    if (cudaFuncSetAttribute(inv_dyn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)
+    {
+      cudaLaunchConfig_t qc{};
+      qc.gridDim = dim3(32); qc.blockDim = dim3(kThreads * 3); qc.dynamicSmemBytes = fft_smem * 4;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, inv_dyn_cluster_kernel, &qc) == cudaSuccess && nclusters >= 2)
+        dyn_cluster = 16;
+    }
+    (void)cudaGetLastError();
+    if (const char* v = std::getenv("SSR_B200_DYN_CLUSTER"))
+    {
+      const int c = std::atoi(v);
+      if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) dyn_cluster = c;
+    }
+    while (dyn_cluster > 1 && (B / 2) % dyn_cluster != 0) dyn_cluster /= 2;
+  }
   // the overlapped forward kernel shares its SM with a MAC CTA (205 KiB of shared memory):
   // both must run under the same (maximal) shared-memory carve-out to be co-resident
   SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -223,6 +279,8 @@ Engine::Engine(const ssr_engine_config& cfg)
   if (const char* v = std::getenv("SSR_B200_MAC_WAVES")) mac_waves = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("SSR_B200_PREREDUCE_MIN")) prereduce_min = std::max(1, std::atoi(v));
   if (const char* v = std::getenv("SSR_B200_MAC_CALIBRATE")) mac_calibrate = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SSR_B200_EARLY_TRIGGER")) early_trigger = std::atoi(v) != 0;   // A/B experiments (profiles/r2_ab)
+  if (const char* v = std::getenv("SSR_B200_TRACE_ISSUE")) trace_mode = std::atoi(v) != 0 ? 1 : 0;   // scripts/mac_trace.py
   if (mac_tma())
   {
     mac_trace.resize(4096 * 4);
@@ -299,7 +357,9 @@ int Engine::split_cost(int MT) const
 
 int Engine::mac_slots(int MT) const
 {
-  if (mac_tma() && MT == 4) return sm_count;  // one CTA per SM (shared-memory bound)
+  // one CTA per SM (shared-memory bound); B > 1024: every share runs as mac_ktiles(B) CTAs, one per
+  // 1024-bin tile of the spectrum, so fewer shares fill the same single wave
+  if (mac_tma() && MT == 4) return std::max(1, sm_count / mac_ktiles(B));
   int occ = 0;
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
       &occ, mac_kernel_ptr(MT, mac_nv(B), mac_variant), kThreads, 0);
@@ -318,7 +378,10 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
   if (overlap)
   {
     if (ring_update) { ru = *ring_update; ring_update = nullptr; }
-    if (ru.ctl)
+    if (ru.ctl && dyn_tma())
+      launch_kernel(fwd_fft_overlap_kernel<2>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base);
+    else if (ru.ctl)
       launch_kernel(fwd_fft_overlap_kernel<1>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
           d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base);
     else
@@ -416,8 +479,11 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   p.term_h = plan.hptr.device();
   p.work = plan.work.device();
   p.cta_first = plan.cta_first.device();
+  p.cta_head = plan.cta_head.device();
   p.head_bias = overlap ? 1 : 0;
   if (mac_trace.ptr) p.trace = mac_trace.ptr;
+  p.trace_mode = trace_mode;
+  p.early_trigger = early_trigger ? 1 : 0;
   p.wtab = weights ? weights : wtab.device();
   p.xring = d_xring.ptr;
   p.xparts = d_xparts.ptr;
@@ -446,8 +512,13 @@ void Engine::launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset
   if (cur) cur->mac_launches++;
 }
 
+// generated-terms MAC on the bulk-copy ring + cluster inverse (Binaural / BRS at B = 1024 / 2048: three
+// inverse groups side by side must fit the shared memory)
+bool Engine::dyn_tma() const { return dyn_tma_enabled && B >= 1024 && is_pow2(B) && inv_groups(3) == 3; }
+
 int Engine::dyn_mac_slots() const
 {
+  if (dyn_tma()) return sm_count;   // one CTA per SM (shared-memory bound)
   int occ = 0;
   void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 2, true> : (void*)mac_kernel<2, 1, 2, 2, true>;
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0);
@@ -540,11 +611,19 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights, b
   p.zero = reinterpret_cast<const float4*>(zero_part.ptr);
   p.dyn = dyn;
   p.dyn.stats = cur ? d_dyn_stats.ptr : nullptr;
-  void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 2, true> : (void*)mac_kernel<2, 1, 2, 2, true>;
+  p.trace_mode = trace_mode;
+  p.early_trigger = early_trigger ? 1 : 0;
+  if (dyn_tma() && trace_mode == 1 && mac_trace.ptr && size_t(G) * 4 <= mac_trace.count) p.trace = mac_trace.ptr;
   void* args[] = { &p };
   dim3 grid(G, mac_ktiles(B), 1);
   stats.last_mac_grid = G * mac_ktiles(B);
-  launch_mac_fn(fn, grid, args);
+  if (dyn_tma())
+    launch_mac_fn((void*)mac_dyn_tma_kernel<5>, grid, args, kTmaThreads, mac_dyn_tma_smem_bytes<5>());
+  else
+  {
+    void* fn = mac_nv(B) == 2 ? (void*)mac_kernel<2, 2, 2, 2, true> : (void*)mac_kernel<2, 1, 2, 2, true>;
+    launch_mac_fn(fn, grid, args);
+  }
   count_launch();
   if (cur) cur->mac_launches++;
 }
@@ -554,6 +633,18 @@ void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, in
 {
   const int njobs = int(plan.jobs.uploaded);
   if (njobs == 0) return;
+  if (dyn_tma())
+  {
+    // one cluster per ear sums the [G][kind][ear] partial spectra and transforms (no reduction launch)
+    launch_cluster_kernel(inv_dyn_cluster_kernel, dim3(njobs * dyn_cluster), dim3(kThreads * 3), dyn_cluster,
+        size_t(2) * B * sizeof(float2) * 4, stream, pdl, plan.jobs.device(), plan.entries.device(),
+        reinterpret_cast<const float2*>(partials.ptr), G, B, static_cast<const float2*>(tw.ptr),
+        static_cast<const float*>(fade_out.ptr), static_cast<const float*>(fade_in.ptr), ctl->n, hc,
+        (trace_mode == 1 && mac_trace.ptr) ? mac_trace.ptr + 8192 : static_cast<unsigned long long*>(nullptr));
+    count_launch();
+    if (cur) cur->ifft_launches++;
+    return;
+  }
   const size_t need = size_t(6) * (B / 2);
   if (need > reduced.count) { sync(); reduced.resize(need); }
   dim3 grid(6, (B / 2 + 31) / 32, 1);
@@ -801,7 +892,7 @@ void FilterSet::set_partition_time(int ch, int p, const float* taps, int n)
 }
 
 void FilterSet::generate(int first_channel, int nch, long taps, uint64_t seed, uint64_t id_offset,
-                         const float* envelope, float scale)
+                         const float* envelope, float scale, uint64_t tap_offset)
 {
   if (first_channel < 0 || nch <= 0 || first_channel + nch > channels || taps <= 0)
     throw Error(SSR_ERR_INVALID, "ssr_b200: filterset_generate: bad arguments");
@@ -823,7 +914,10 @@ void FilterSet::generate(int first_channel, int nch, long taps, uint64_t seed, u
     touch_flags();
   }
   FwdBatch batch{};
-  batch.time = d_env.ptr;
+  // (tap t of the slice is tap tap_offset + t of the generated impulse response; the envelope table
+  // passed in covers the slice, the kernels index it by the absolute tap)
+  batch.time = d_env.ptr ? d_env.ptr - tap_offset : nullptr;
+  batch.tap_offset = tap_offset;
   batch.frame_stride = 1; batch.channel_stride = 0;
   batch.frames = taps;
   batch.set = data.ptr; batch.partitions = partitions; batch.first_channel = first_channel;

@@ -154,12 +154,13 @@ struct MacPlan
   // [cta_first[c], cta_first[c + 1]) -- its longest one first.
   Table<int4> work;            // x = term_begin, y = term_end, z = partial index
   Table<int> cta_first;        // [ncta + 1]
+  Table<int4> cta_head;        // [ncta][2]: {cta_first[c], cta_first[c + 1], 0, 0}, work[cta_first[c]] (bulk-copy MAC)
   int ncta = 0;
   int npartials = 0;           // partial spectra groups written per launch (= segments)
   struct Group { int term_begin, term_end, partial_first, nsplit; };
   std::vector<Group> groups;
   void clear()
-  { meta.host.clear(); hptr.host.clear(); work.host.clear(); cta_first.host.clear(); groups.clear(); npartials = 0; ncta = 0; }
+  { meta.host.clear(); hptr.host.clear(); work.host.clear(); cta_first.host.clear(); cta_head.host.clear(); groups.clear(); npartials = 0; ncta = 0; }
   int begin_group() { groups.push_back({int(meta.host.size()), 0, 0, 0}); return int(groups.size()) - 1; }
   void add_term(int input, int p, int wslot, const float4* const* h)
   {
@@ -172,7 +173,7 @@ struct MacPlan
   // `weights` (one per CTA of the resulting plan, or null): relative speed of each CTA -- its share of
   // the term table is proportional to it (Renderer::calibrate)
   void make_work(int slots, int fixed_cost = 2, int waves = 0, const std::vector<double>* weights = nullptr);
-  void upload(cudaStream_t s) { meta.upload(s); hptr.upload(s); work.upload(s); cta_first.upload(s); }
+  void upload(cudaStream_t s) { meta.upload(s); hptr.upload(s); work.upload(s); cta_first.upload(s); cta_head.upload(s); }
 };
 
 struct InvPlan
@@ -238,6 +239,9 @@ struct Engine
   bool fwd_overlap = true;         // forward transform under the MAC (SSR_B200_FWD_OVERLAP=0: off)
   int mac_waves = 0;               // SSR_B200_MAC_WAVES: CTAs of a MAC launch = waves x resident CTAs
   DeviceArray<unsigned long long> mac_trace;   // per-CTA timestamps / busy time of the bulk-copy MAC launches
+  bool early_trigger = false;                  // SSR_B200_EARLY_TRIGGER=1: the bulk-copy MACs let their dependent kernel launch at once
+                                               //  (measured: the block gets 5 us SLOWER on cfg4, profiles/r2_ab; off)
+  int trace_mode = 0;                          // SSR_B200_TRACE_ISSUE=1: trace[3] = first bulk copy (see MacParams)
   bool mac_calibrate = false;                  // SSR_B200_MAC_CALIBRATE=1: re-cut the shares by measured CTA rates
   int prereduce_min = 16;          // partials per accumulator from which a separate reduction launch pays
   // dynamic renderers: terms generated on the device (ssrk::DynTables), static launch shapes
@@ -247,6 +251,9 @@ struct Engine
   void launch_dyn_ring_update(const ssrk::DynCtl* ctl, const ssrk::DynRingEntry* upd,
                               ssrk::DynRingEntry* ring, int rows, int R);
   int dyn_mac_slots() const;
+  bool dyn_tma_enabled = true;     // SSR_B200_DYN_TMA=0: the register-staged generated-terms MAC + dyn_reduce_kernel
+  bool dyn_tma() const;            // Binaural / BRS on mac_dyn_tma_kernel + inv_dyn_cluster_kernel
+  int dyn_cluster = 8;             // CTAs per cluster of inv_dyn_cluster_kernel
   int inv_groups(int max_entries) const;
   void launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const float2* red,
                          const ssrk::GatherArgs& ga, const int* kind_counts,
@@ -309,8 +316,10 @@ struct FilterSet
   void load_time(int first_channel, int nch, const float* data, long frames,
                  long frame_stride, long channel_stride);
   void set_partition_time(int ch, int p, const float* taps, int n);
+  // tap_offset: the set holds taps [tap_offset, tap_offset + taps) of the generated responses (a level of
+  // the non-uniformly partitioned renderer); `envelope` then points at that slice's first entry
   void generate(int first_channel, int nch, long taps, uint64_t seed, uint64_t id_offset,
-                const float* envelope, float scale);
+                const float* envelope, float scale, uint64_t tap_offset = 0);
   void lerp_from(int dch, const FilterSet& a, int ach, const FilterSet& b, int bch, float t);
   // host half of lerp_from: zero flags + one job per partition appended to `jobs`; the caller
   // launches ssrk::lerp_kernel over them (the renderers batch a block's interpolations
@@ -606,6 +615,7 @@ struct Renderer
     // generic
     std::unique_ptr<FilterSet> irs;
     BlockParameter<float> w{0.0f};
+    bool primed = false;       // tail_level: the first block's "old" weight has been set
     // brs / binaural
     int angles = 0;
     std::unique_ptr<FilterSet> brtf;
@@ -625,6 +635,8 @@ struct Renderer
 
   Engine* e;
   ssr_renderer_config cfg;
+  bool tail_level = false;     // a tail level of the non-uniformly partitioned renderer (nonuniform.cu): new
+                               //  sources start at their weight instead of fading in from 0
   int M_total, m_first, m_local;
   std::vector<std::unique_ptr<Source>> sources;
   int next_id = 1;

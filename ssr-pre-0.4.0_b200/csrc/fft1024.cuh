@@ -228,7 +228,7 @@ fwd_fft1024_batch_kernel(const FwdBatch batch, int nparts, long ntransforms, con
     job.first.ptr = batch.time;
     job.first.stride = 1;
     job.first.key = synth_key(batch.seed, batch.id_offset + uint64_t(c));
-    job.first.first_index = uint64_t(first_tap);
+    job.first.first_index = batch.tap_offset + uint64_t(first_tap);
   }
   else
   {

@@ -2,6 +2,8 @@
 // (part of the kernel set of kernels.cuh; included from there, in this order)
 #pragma once
 
+#include <cooperative_groups.h>
+
 namespace ssrk
 {
 
@@ -236,14 +238,24 @@ __global__ void dyn_ring_update_kernel(const DynCtl* __restrict__ ctl, const Dyn
 // other; group 0 adds the faded results and stores the block.
 constexpr int kInvMaxGroups = 3;
 
-template<int GROUPS>
-__global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 4 : 1)
-inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
-               const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
-               const float2* __restrict__ tw,
-               const float* __restrict__ fade_out, const float* __restrict__ fade_in,
-               const GatherArgs ga, const int* __restrict__ kind_counts, const HeadCommit hc)
+// CLUSTER (generated-terms MAC, mac_dyn_tma_kernel): one thread-block cluster per output block.  The
+// partial spectra [CTA][kind][ear][B] of the MAC launch are summed by the whole cluster -- CTA r takes
+// the r-th slice of the bins, group g the accumulator kind g -- straight into the leader CTA's
+// shared memory over DSMEM; the leader then transforms as usual.  This replaces the separate
+// dyn_reduce_kernel launch (9 us of a 47 us BRS block).
+template<int GROUPS, bool CLUSTER>
+__device__ __forceinline__ void
+inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
+             const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
+             const float2* __restrict__ tw,
+             const float* __restrict__ fade_out, const float* __restrict__ fade_in,
+             const GatherArgs& ga, const int* __restrict__ kind_counts, const HeadCommit& hc, int dyn_G,
+             unsigned long long* dbg = nullptr)
 {
+  // (development: per-CTA time stamps of the cluster variant, scripts/mac_trace2.py)
+#define SSR_INV_STAMP(i) \
+  if constexpr (CLUSTER) { if (dbg && threadIdx.x == 0) dbg[size_t(blockIdx.x) * 8 + (i)] = globaltimer_ns(); }
+  SSR_INV_STAMP(0)
   extern __shared__ float2 smem[];
   __shared__ float s_max[kThreads / 32];
   __shared__ int s_slot_ok;
@@ -252,12 +264,94 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
   constexpr int ngroups = GROUPS;
   float2* a = smem + size_t(g) * 2 * B;
   float2* b = a + B;
-  const InvJob job = jobs[blockIdx.x];
+  unsigned crank = 0, csize = 1;
+  if constexpr (CLUSTER)
+  {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  }
+  const InvJob job = jobs[CLUSTER ? blockIdx.x / csize : blockIdx.x];
   const int half = B >> 1;
   // twiddle table -> shared memory, once for all groups
   float2* stw = smem + size_t(GROUPS) * 2 * B;
-  stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);  // constants: may overlap the predecessor's tail
+  if (crank == 0)
+    stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);  // constants: may overlap the predecessor's tail
+  // (CLUSTER: static tables and the block's control word -- uploaded before the block's first kernel --
+  // are read ahead of the wait; they are the head of the dependent chain to the partial spectra)
+  InvEntry cen{};
+  int ckind_count = 0;
+  if constexpr (CLUSTER)
+  {
+    if (g < job.n_entries)
+    {
+      cen = entries[job.first_entry + g];
+      ckind_count = kind_counts[cen.fade];
+    }
+  }
   grid_dependency_wait();
+  SSR_INV_STAMP(1)
+  if constexpr (CLUSTER)
+  {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();   // every CTA of the cluster is running: the leader's shared memory may be written
+    SSR_INV_STAMP(2)
+    if (g < job.n_entries)
+    {
+      const InvEntry en = cen;
+      if (ckind_count != 0)
+      {
+        const int nvec = B >> 1;
+        const int nslice = nvec / int(csize);   // float4 per CTA of the cluster
+        float4* dst = reinterpret_cast<float4*>(cluster.map_shared_rank(smem + size_t(g) * 2 * B, 0))
+            + size_t(crank) * nslice;
+        const float4* base = reinterpret_cast<const float4*>(partials)
+            + (size_t(en.fade) * 2 + en.part_row) * nvec + size_t(crank) * nslice;
+        const size_t cstride = size_t(6) * nvec;   // partials: [CTA][kind][ear][B]
+        // A warp reads one CTA's whole slice row (32 lanes x float4 = 512 contiguous bytes) per load;
+        // the 8 warps of the group split the CTAs, each with its loads of a batch all in flight before
+        // the first add (the phase is L2 latency: two round trips for 148 partial sets); the warps'
+        // sums meet in the group's spare transform buffer.  Fixed order: deterministic.
+        constexpr int UNR = 10, NW = kThreads / 32;
+        const int warp = t >> 5, lane = t & 31;
+        float4* scratch = reinterpret_cast<float4*>(b);
+        for (int r0 = 0; r0 < nslice; r0 += 32)
+        {
+          const int v = r0 + lane;
+          float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c0 = warp; c0 < dyn_G; c0 += NW * UNR)
+          {
+            float4 q[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+            {
+              const int c = c0 + u * NW;
+              q[u] = (v < nslice && c < dyn_G) ? __ldcs(base + size_t(c) * cstride + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) { s0.x += q[u].x; s0.y += q[u].y; s0.z += q[u].z; s0.w += q[u].w; }
+          }
+          scratch[warp * 32 + lane] = s0;
+          group_sync(g + 1);
+          if (warp == 0)
+          {
+#pragma unroll
+            for (int w2 = 1; w2 < NW; ++w2)
+            {
+              const float4 o = scratch[w2 * 32 + lane];
+              s0.x += o.x; s0.y += o.y; s0.z += o.z; s0.w += o.w;
+            }
+            if (v < nslice) dst[v] = s0;
+          }
+          group_sync(g + 1);
+        }
+      }
+    }
+    SSR_INV_STAMP(3)
+    cluster.sync();   // (release / acquire: the slices are visible in the leader's shared memory)
+    SSR_INV_STAMP(4)
+    if (crank != 0) return;
+  }
   if (hc.n && blockIdx.x == 0)
     for (int i = threadIdx.x; i < hc.n; i += kThreads * GROUPS)
     {
@@ -284,7 +378,11 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
     // A[k] = sum over split partials
     // (float4 = two bins per thread; the loop over partials is unrolled so that
     // 8 independent loads are in flight per thread)
-    if (reduced)
+    if constexpr (CLUSTER)
+    {
+      // a[] already holds the sum (written by the cluster above)
+    }
+    else if (reduced)
     {
       const float4* r = reinterpret_cast<const float4*>(reduced) + size_t(job.first_entry + e) * (B >> 1);
       for (int k = t; k < (B >> 1); k += kThreads) reinterpret_cast<float4*>(a)[k] = __ldcs(r + k);
@@ -360,6 +458,7 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
     group_sync(g + 1);  // z (smem) is rewritten by the group's next entry / the hand-over below
   }
 
+  SSR_INV_STAMP(5)
   // groups 1.. hand their faded blocks to group 0 through their own smem region
   if (ngroups > 1)
   {
@@ -420,6 +519,8 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
       }
     }
   }
+  SSR_INV_STAMP(6)
+#undef SSR_INV_STAMP
   if (ga.arrived)
   {
     // all stores of this CTA (peer memory, over NVLink) -> fence -> arrival count
@@ -448,6 +549,28 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
       }
     }
   }
+}
+
+template<int GROUPS>
+__global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 4 : 1)
+inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
+               const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
+               const float2* __restrict__ tw,
+               const float* __restrict__ fade_out, const float* __restrict__ fade_in,
+               const GatherArgs ga, const int* __restrict__ kind_counts, const HeadCommit hc)
+{
+  inv_fft_body<GROUPS, false>(jobs, entries, partials, reduced, B, tw, fade_out, fade_in, ga, kind_counts, hc, 0);
+}
+
+// Binaural / BRS behind mac_dyn_tma_kernel: grid = outputs x cluster size (launch attribute), three
+// kThreads-thread groups = the three accumulator kinds; `partials` = [dyn_G][kind][ear][B]
+__global__ void __launch_bounds__(kThreads * 3, 1)
+inv_dyn_cluster_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
+                       const float2* __restrict__ partials, int dyn_G, int B, const float2* __restrict__ tw,
+                       const float* __restrict__ fade_out, const float* __restrict__ fade_in,
+                       const int* __restrict__ kind_counts, const HeadCommit hc, unsigned long long* dbg)
+{
+  inv_fft_body<3, true>(jobs, entries, partials, nullptr, B, tw, fade_out, fade_in, GatherArgs{}, kind_counts, hc, dyn_G, dbg);
 }
 
 }  // namespace ssrk

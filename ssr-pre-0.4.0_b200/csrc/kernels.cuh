@@ -453,6 +453,7 @@ struct FwdBatch
   int synth;               // 1: generate u(seed, id_offset + c, tap) * envelope[tap] * scale
   float scale;
   uint64_t seed, id_offset;
+  uint64_t tap_offset;     // synth: the set holds taps [tap_offset, tap_offset + frames) of the generated responses
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -472,7 +473,7 @@ fwd_fft_batch_kernel(const FwdBatch batch, int B, const float2* __restrict__ tw)
     job.first.ptr = batch.time;   // envelope (indexed by first_index + i) or null
     job.first.stride = 1;
     job.first.key = synth_key(batch.seed, batch.id_offset + uint64_t(c));
-    job.first.first_index = uint64_t(first_tap);
+    job.first.first_index = batch.tap_offset + uint64_t(first_tap);
   }
   else
   {

@@ -80,6 +80,9 @@ struct MacParams
   const int* cta_first;              // [CTAs + 1]: CTA c works through segments [cta_first[c], cta_first[c + 1])
                                      //  (usually one; two or more where its share of the term list straddles
                                      //  a group boundary -- that is what lets 16 groups fill all 148 SMs)
+  const int4* cta_head;              // bulk-copy MAC: per CTA {first segment, end segment, 0, 0} and a copy of its
+                                     //  first segment (work[first]) -- ONE load level from blockIdx to the first
+                                     //  term tile instead of two (the start-up chain of a 25 - 50 us launch)
   const float* wtab;                 // weights by slot
   const float4* const* xring;        // per input: ring base
   const int* xparts;                 // per input: ring length
@@ -92,6 +95,9 @@ struct MacParams
   const float4* zero;                // an all-zero partition
   unsigned long long* trace;         // per CTA {start, first data, end, accumulated busy time} in %globaltimer ns, or
                                      //  null (bulk-copy MAC): feeds the share calibration (Renderer::calibrate)
+  int early_trigger;                 // 1: griddepcontrol.launch_dependents at the start of the bulk-copy MACs
+  int trace_mode;                    // 0: trace[3] accumulates the CTA's busy time (share calibration);
+                                     //  1: trace[3] = time of the producer's first bulk copy (scripts/mac_trace.py)
   int head_bias;                     // 1: the forward transform of this block runs CONCURRENTLY (it has not
                                      //  published the ring heads yet): newest slot = heads[] + 1, and terms with
                                      //  p == 0 are issued last, behind griddepcontrol.wait (mac_tma_kernel)
@@ -567,13 +573,21 @@ mac_tma_kernel(const MacParams p)
   // slots of EARLIER blocks, the filter spectra -- may be read already.  Only the producer
   // warp reads global memory; it waits before its first p == 0 term.
   if (!p.head_bias) grid_dependency_wait();
-  const int seg_first = p.cta_first[blockIdx.x], seg_last = p.cta_first[blockIdx.x + 1];
+  // the kernel behind this one (the block's inverse transform, or the next accumulator kind's MAC)
+  // may move into SMs as they free up: its launch latency and prologue hide under our tail
+  if (p.early_trigger) grid_launch_dependents();
 
   if (t >= kThreads)
   {
-    // ---- producer warp: resolve the terms tile by tile, then one lane feeds the ring
+    // ---- producer warp: resolve the terms tile by tile, then one lane feeds the ring.
+    // Start-up latency is what a 25 - 50 us launch pays for most (profiles/r2_mac_balance.md: first data
+    // after 4 - 10 us): the dependent loads from blockIdx to the first bulk copy are kept to three levels
+    // (CTA head -> term records -> weights / ring heads), and the records of the NEXT tile are
+    // fetched before the current one is fed, so that later tiles cost one level.
     const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
     const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const int4 hd = p.cta_head[2 * blockIdx.x];
+    const int seg_first = hd.x, seg_last = hd.y;
     int s = 0;
     unsigned phase = 0;
     bool waited = !p.head_bias;
@@ -590,10 +604,15 @@ mac_tma_kernel(const MacParams p)
         bulk_copy_g2s(dst + size_t(1 + j) * kTmaTileVec, h[j] + tile_off, kTmaTileBytes, full + s, pol_h);
       if (++s == STAGES) { s = 0; phase ^= 1u; }
     };
+    bool first_issue = p.trace != nullptr && p.trace_mode == 1;
     auto feed = [&](int count)
     {
       if (lane == 0)
+      {
+        if (first_issue && count > 0)
+        { unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now)); p.trace[size_t(blockIdx.x) * 4 + 3] = now; first_issue = false; }
         for (int i = 0; i < count; ++i) issue(q_x[i][0], q_h[i], q_w[i]);
+      }
       __syncwarp();
     };
     auto marker = [&](int kind, int aux)
@@ -622,20 +641,116 @@ mac_tma_kernel(const MacParams p)
       __syncwarp();
       deferred = 0;
     };
-    for (int seg = seg_first; seg < seg_last; ++seg)
+    // a tile's term records, two per lane (first load level of a tile)
+    struct TileRegs { MacTermMeta m[2]; const float4* h[2][MT]; };
+    auto fetch = [&](int tb, int tile_n, TileRegs& r)
     {
-      const int4 wk = p.work[seg];
-      for (int tb = wk.x; tb < wk.y; tb += kMacTile)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
       {
-        const int tile_n = min(kMacTile, wk.y - tb);
-        if (!waited && deferred + tile_n > kMacDeferCap) release_deferred();
-        const int count = waited
-            ? mac_tma_resolve_tile<MT, 1>(p, tb, tile_n, lane, nvec, q_x, q_h, q_w)
-            : mac_tma_resolve_tile<MT, 1>(p, tb, tile_n, lane, nvec, q_x, q_h, q_w, &deferred, d_x, d_h, d_w);
-        feed(count);
+        const int i = rr * 32 + lane;
+        if (i < tile_n)
+        {
+          r.m[rr] = p.term_meta[tb + i];
+#pragma unroll
+          for (int j = 0; j < MT; ++j) r.h[rr][j] = p.term_h[size_t(tb + i) * MT + j];
+        }
       }
-      if (!waited) release_deferred();               // the side list belongs to this segment's accumulators
-      marker(kStageFlush, wk.z + p.partial_offset);
+    };
+    // second level (weights, ring heads), then the records go to the staging lists; terms with
+    // zero weight are dropped (a muted source costs no traffic)
+    auto finish = [&](const TileRegs& r, int tile_n) -> int
+    {
+      float w[2]; int parts[2], head[2]; const float4* xr[2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+      {
+        w[rr] = 0.f; parts[rr] = 1; head[rr] = 0; xr[rr] = nullptr;
+        if (rr * 32 + lane < tile_n)
+        {
+          w[rr] = p.wtab[r.m[rr].wslot + p.wtab_offset];
+          parts[rr] = p.xparts[r.m[rr].input];
+          head[rr] = p.heads[r.m[rr].input];
+          xr[rr] = p.xring[r.m[rr].input];
+        }
+      }
+      int count = 0;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+      {
+        const bool ok = (rr * 32 + lane < tile_n) && w[rr] != 0.0f;
+        const bool late = ok && !waited && r.m[rr].p == 0;
+        const unsigned mask_late = __ballot_sync(0xffffffffu, late);
+        const unsigned mask = __ballot_sync(0xffffffffu, ok && !late);
+        if (ok)
+        {
+          int slot = head[rr] + p.head_bias - r.m[rr].p;
+          while (slot < 0) slot += parts[rr];
+          if (slot >= parts[rr]) slot -= parts[rr];
+          const float4* xp = xr[rr] + size_t(slot) * nvec;
+          if (late)
+          {
+            const int pos = deferred + __popc(mask_late & ((1u << lane) - 1u));
+            d_x[pos] = xp; d_w[pos] = w[rr];
+#pragma unroll
+            for (int j = 0; j < MT; ++j) d_h[pos][j] = r.h[rr][j];
+          }
+          else
+          {
+            const int pos = count + __popc(mask & ((1u << lane) - 1u));
+            q_x[pos][0] = xp; q_w[pos] = w[rr];
+#pragma unroll
+            for (int j = 0; j < MT; ++j) q_h[pos][j] = r.h[rr][j];
+          }
+        }
+        count += __popc(mask);
+        deferred += __popc(mask_late);
+      }
+      __syncwarp();
+      return count;
+    };
+    // the CTA's segments beyond the first, one per lane (a CTA rarely has more than two or three)
+    int4 seg_pref = make_int4(0, 0, 0, 0);
+    if (seg_first + 1 + lane < seg_last) seg_pref = p.work[seg_first + 1 + lane];
+    auto load_seg = [&](int sg) -> int4
+    {
+      const int k = sg - seg_first - 1;
+      if (k >= 32) return p.work[sg];
+      return make_int4(__shfl_sync(0xffffffffu, seg_pref.x, k), __shfl_sync(0xffffffffu, seg_pref.y, k),
+                       __shfl_sync(0xffffffffu, seg_pref.z, k), 0);
+    };
+
+    int seg = seg_first;
+    int4 wk = p.cta_head[2 * blockIdx.x + 1];
+    int tb = wk.x;
+    bool have = seg < seg_last;
+    TileRegs cur;
+    if (have) fetch(tb, min(kMacTile, wk.y - tb), cur);
+    while (have)
+    {
+      const int tile_n = max(0, min(kMacTile, wk.y - tb));
+      if (!waited && deferred + tile_n > kMacDeferCap) release_deferred();
+      const int count = finish(cur, tile_n);
+      const bool seg_end = tb + kMacTile >= wk.y;
+      // the next tile's records are requested before this one is fed
+      int nseg = seg, ntb = tb + kMacTile;
+      int4 nwk = wk;
+      if (seg_end)
+      {
+        nseg = seg + 1;
+        if (nseg < seg_last) { nwk = load_seg(nseg); ntb = nwk.x; }
+      }
+      const bool nhave = nseg < seg_last;
+      TileRegs nxt;
+      if (nhave) fetch(ntb, min(kMacTile, nwk.y - ntb), nxt);
+      feed(count);
+      if (seg_end)
+      {
+        if (!waited) release_deferred();             // the side list belongs to this segment's accumulators
+        marker(kStageFlush, wk.z + p.partial_offset);
+      }
+      seg = nseg; wk = nwk; tb = ntb; have = nhave;
+      if (have) cur = nxt;
     }
     marker(kStageDone, 0);
     return;
@@ -669,7 +784,7 @@ mac_tma_kernel(const MacParams p)
         unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
         unsigned long long* tr = p.trace + size_t(blockIdx.x) * 4;
         tr[2] = now;
-        tr[3] += now - tr[0];   // only this CTA writes its slot
+        if (p.trace_mode == 0) tr[3] += now - tr[0];   // only this CTA writes its slot
       }
       break;
     }
@@ -725,6 +840,301 @@ mac_tma_kernel(const MacParams p)
     if (lane == 0) mbar_arrive(empty + s);            // this warp is done with the stage
     if (++s == STAGES) { s = 0; phase ^= 1u; }
   }
+}
+
+// ---------------------------------------------------------------- MAC, generated terms, bulk-copy staged
+// Binaural / BRS at B >= 1024 (round 2; replaces mac_kernel<2, NV, 2, 2, true> there, which stays for
+// smaller blocks).  Same producer / consumer ring as mac_tma_kernel, but the work is cut by
+// (source, partition) SLOT, independent of the block's control data: CTA c owns slots
+// [T c / G, T (c + 1) / G) of T = sources x Pmax.  A slot is evaluated for every accumulator kind its
+// source takes part in this block -- constant, or old and / or new around a filter switch or weight change
+// (src/brsrenderer.h:141-210, src/binauralrenderer.h:316-343) -- from ONE copy of X[n, p]: a stage holds
+// the X tile and up to four H tiles (old L/R, new L/R), the consumers keep 3 kinds x 2 ears of accumulators.
+// What that buys over the kind-major split of mac_kernel<DYN>:
+//   * the path from blockIdx to the first bulk copy is three load levels (control block + per-source
+//     weights -> filter-ring entries + delay-line heads -> zero flags, usually absent) instead of five,
+//     resolved by 32 lanes at once, and 160 KiB stay in flight per SM whatever the consumers do;
+//   * X[n, p] is read once per slot, not once per kind;
+//   * every CTA writes ONE set of partial spectra [CTA][kind][ear][B], which the cluster variant of the
+//     inverse kernel sums itself (no separate reduction launch).
+struct DynStage { float wa, wb; int ka; unsigned mask; };   // mask: bit j = H tile j present (0,1: kind ka; 2,3: new)
+constexpr int kDynTiles = 5;                                // X + 4 H tiles per stage
+constexpr int kDynRound = 32;                               // slots resolved per round (one per producer lane)
+
+template<int STAGES>
+constexpr size_t mac_dyn_tma_smem_bytes()
+{
+  return size_t(STAGES) * kDynTiles * kTmaTileBytes + size_t(STAGES) * (8 + 8 + 4 + sizeof(DynStage)) + 128;
+}
+
+struct DynSlot { const float4* x; const float4* h[4]; DynStage st; };
+
+template<int STAGES>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+mac_dyn_tma_kernel(const MacParams p)
+{
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ DynSlot q[kDynRound];               // producer-private staging of a round of slots
+  __shared__ DynSlot dq[kMacDeferCap];           // p == 0 slots held back until the forward transform is done
+  float4* buf = reinterpret_cast<float4*>(tma_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tma_smem + size_t(STAGES) * kDynTiles * kTmaTileBytes);
+  uint64_t* empty = full + STAGES;
+  volatile int* stage_kind = reinterpret_cast<volatile int*>(empty + STAGES);
+  volatile DynStage* stage_info = reinterpret_cast<volatile DynStage*>(const_cast<int*>(stage_kind) + STAGES);
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int nvec = p.B >> 1;
+  const int tile_off = blockIdx.y * kTmaTileVec;   // B > 1024: blockIdx.y selects a 1024-bin tile
+
+  if (t == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (p.trace) { unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now)); p.trace[size_t(blockIdx.x) * 4] = now; }
+  }
+  __syncthreads();
+  if (!p.head_bias) grid_dependency_wait();
+  if (p.early_trigger) grid_launch_dependents();   // the inverse kernel's CTAs may move in as SMs free up
+
+  if (t >= kThreads)
+  {
+    const uint64_t pol_h = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t pol_x = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    int s = 0;
+    unsigned phase = 0;
+    bool waited = !p.head_bias;
+    auto issue = [&](const DynSlot& sl)
+    {
+      mbar_wait(empty + s, phase ^ 1u);
+      stage_info[s].wa = sl.st.wa; stage_info[s].wb = sl.st.wb;
+      stage_info[s].ka = sl.st.ka; stage_info[s].mask = sl.st.mask;
+      stage_kind[s] = kStageData;
+      mbar_arrive_expect_tx(full + s, unsigned(1 + __popc(sl.st.mask)) * kTmaTileBytes);
+      float4* dst = buf + size_t(s) * kDynTiles * kTmaTileVec;
+      bulk_copy_g2s(dst, sl.x + tile_off, kTmaTileBytes, full + s, pol_x);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (sl.st.mask & (1u << j))
+          bulk_copy_g2s(dst + size_t(1 + j) * kTmaTileVec, sl.h[j] + tile_off, kTmaTileBytes, full + s, pol_h);
+      if (++s == STAGES) { s = 0; phase ^= 1u; }
+    };
+    int deferred = 0;
+    auto release_deferred = [&]()
+    {
+      grid_dependency_wait();                        // the forward transform of this block is complete
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      waited = true;
+      if (lane == 0)
+        for (int i = 0; i < deferred; ++i) issue(dq[i]);
+      __syncwarp();
+      deferred = 0;
+    };
+
+    bool first_issue = p.trace != nullptr;
+    const DynTables& d = p.dyn;
+    const long long T = (long long)d.nsrc * d.Pmax;
+    const int s0 = int(T * blockIdx.x / gridDim.x), s1 = int(T * (blockIdx.x + 1) / gridDim.x);
+    unsigned long long n_h = 0, n_x = 0;
+    for (int base = s0; base < s1; base += kDynRound)
+    {
+      const int i = base + lane;
+      const bool in = i < s1;
+      const int n = in ? i / d.Pmax : 0;
+      const int pp = in ? i % d.Pmax : 0;
+      // level 1: the block's control word and everything indexed by the source alone
+      const long long b = d.ctl->b;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+      int input = 0, sparts = 0;
+      if (in)
+      {
+        w0 = p.wtab[n]; w1 = p.wtab[d.nsrc + n]; w2 = p.wtab[2 * d.nsrc + n];
+        input = d.src_input[n]; sparts = d.src_parts[n];
+      }
+      bool alive = in && pp < sparts && (w0 != 0.0f || w1 != 0.0f || w2 != 0.0f);
+      // constant sources carry kind 0 alone; the others kind 1 (old state) and / or kind 2 (new state)
+      DynSlot sl;
+      sl.st.ka = w0 != 0.0f ? 0 : (w1 != 0.0f ? 1 : 2);
+      sl.st.wa = w0 != 0.0f ? w0 : (w1 != 0.0f ? w1 : w2);
+      const bool second = w0 == 0.0f && w1 != 0.0f && w2 != 0.0f;
+      sl.st.wb = second ? w2 : 0.0f;
+      sl.st.mask = 0;
+      // level 2: the filters current in block b - p (state after this block's switch) / b - 1 - p
+      // (state before it), per ear; and the delay-line slot
+      DynRingEntry en[4];
+      int xparts = 1, head = 0;
+      const float4* xr = nullptr;
+      if (alive)
+      {
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2)
+        {
+          const int kind = k2 == 0 ? sl.st.ka : 2;
+          const bool want = k2 == 0 || second;
+          long long time = b - (kind == 1 ? 1 : 0) - pp;
+          int slot = int(time % d.R);
+          if (slot < 0) slot += d.R;
+          const bool current = (kind != 1 && pp == 0);   // ring[b] = this block's update
+#pragma unroll
+          for (int ear = 0; ear < 2; ++ear)
+          {
+            if (want)
+              en[k2 * 2 + ear] = current ? d.upd[size_t(n) * 2 + ear]
+                                         : d.ring[(size_t(n) * 2 + ear) * d.R + slot];
+            else en[k2 * 2 + ear] = DynRingEntry{nullptr, nullptr, 0, 0};
+          }
+        }
+        xparts = p.xparts[input]; head = p.heads[input]; xr = p.xring[input];
+      }
+      // level 3: zero flags (null for filters without zero-flagged partitions)
+      if (alive)
+      {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          sl.h[j] = nullptr;
+          if (en[j].base && pp < en[j].nparts && (!en[j].flags || en[j].flags[pp]))
+          {
+            sl.h[j] = en[j].base + size_t(pp) * nvec;
+            sl.st.mask |= 1u << j;
+          }
+        }
+        alive = sl.st.mask != 0;
+        int slot = head + p.head_bias - pp;
+        while (slot < 0) slot += xparts;
+        if (slot >= xparts) slot -= xparts;
+        sl.x = xr + size_t(slot) * nvec;
+      }
+      const bool late = alive && !waited && pp == 0;
+      const unsigned m_now = __ballot_sync(0xffffffffu, alive && !late);
+      const unsigned m_late = __ballot_sync(0xffffffffu, late);
+      if (!waited && deferred + __popc(m_late) > kMacDeferCap) release_deferred();   // (then these go out behind them)
+      if (alive)
+      {
+        if (late && !waited) dq[deferred + __popc(m_late & ((1u << lane) - 1u))] = sl;
+        else q[__popc((waited ? (m_now | m_late) : m_now) & ((1u << lane) - 1u))] = sl;
+        n_h += __popc(sl.st.mask); n_x += 1;
+      }
+      const int count = waited ? __popc(m_now | m_late) : __popc(m_now);
+      if (!waited) deferred += __popc(m_late);
+      __syncwarp();
+      if (lane == 0)
+      {
+        if (first_issue && count > 0)
+        { unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now)); p.trace[size_t(blockIdx.x) * 4 + 3] = now; first_issue = false; }
+        for (int k = 0; k < count; ++k) issue(q[k]);
+      }
+      __syncwarp();
+    }
+    if (!waited) release_deferred();     // (every CTA waits once: MAC complete implies forward transform complete)
+    if (lane == 0)
+    {
+      mbar_wait(empty + s, phase ^ 1u);
+      stage_kind[s] = kStageDone;
+      mbar_arrive(full + s);
+    }
+    if (d.stats && blockIdx.y == 0)
+    {
+      // traffic accounting: H and X partitions this CTA read
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        n_h += __shfl_xor_sync(0xffffffffu, n_h, o);
+        n_x += __shfl_xor_sync(0xffffffffu, n_x, o);
+      }
+      if (lane == 0 && n_h) { atomicAdd(d.stats, n_h); atomicAdd(d.stats + 1, n_x); }
+    }
+    return;
+  }
+
+  // ---- consumer warps: acc[kind][ear][2 float4]
+  float4 acc[3][2][2];
+  float nyq[3][2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+    {
+      nyq[k][j] = 0.0f;
+      acc[k][j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[k][j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  const int tt = tile_off + t;
+  int s = 0;
+  unsigned phase = 0;
+  // (kinds without sources this block are not written; read now, not in the tail)
+  const int n0 = p.dyn.ctl->n[0], n1 = p.dyn.ctl->n[1], n2 = p.dyn.ctl->n[2];
+
+#define SSR_DYN_CMAC(A, NQ, X, H) \
+  { \
+    A.x = fmaf(X.x, H.x, A.x); A.x = fmaf(-X.y, H.y, A.x); \
+    A.y = fmaf(X.x, H.y, A.y); A.y = fmaf(X.y, H.x, A.y); \
+    A.z = fmaf(X.z, H.z, A.z); A.z = fmaf(-X.w, H.w, A.z); \
+    A.w = fmaf(X.z, H.w, A.w); A.w = fmaf(X.w, H.z, A.w); \
+    if (v == 0 && tt == 0) NQ = fmaf(X.y, H.y, NQ); \
+  }
+#define SSR_DYN_KIND(K, X, ROW0, BIT0) \
+  { \
+    _Pragma("unroll") for (int j = 0; j < 2; ++j) \
+      if (mask & (1u << (BIT0 + j))) \
+      { \
+        const float4 h = sb[size_t(ROW0 + j) * kTmaTileVec + t + v * kThreads]; \
+        SSR_DYN_CMAC(acc[K][j][v], nyq[K][j], X, h) \
+      } \
+  }
+
+  bool first_stage = p.trace != nullptr && t == 0;
+  while (true)
+  {
+    mbar_wait(full + s, phase);
+    if (first_stage)
+    { unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now)); p.trace[size_t(blockIdx.x) * 4 + 1] = now; first_stage = false; }
+    if (stage_kind[s] == kStageDone) break;
+    const float wa = stage_info[s].wa, wb = stage_info[s].wb;
+    const int ka = stage_info[s].ka;
+    const unsigned mask = stage_info[s].mask;
+    const float4* sb = buf + size_t(s) * kDynTiles * kTmaTileVec;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+    {
+      const float4 x = sb[t + v * kThreads];
+      const float4 xa = make_float4(x.x * wa, x.y * wa, x.z * wa, x.w * wa);
+      if (ka == 0) SSR_DYN_KIND(0, xa, 1, 0)
+      else if (ka == 1) SSR_DYN_KIND(1, xa, 1, 0)
+      else SSR_DYN_KIND(2, xa, 1, 0)
+      if (mask & 12u)
+      {
+        const float4 xb = make_float4(x.x * wb, x.y * wb, x.z * wb, x.w * wb);
+        SSR_DYN_KIND(2, xb, 3, 2)
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    if (++s == STAGES) { s = 0; phase ^= 1u; }
+  }
+#undef SSR_DYN_KIND
+#undef SSR_DYN_CMAC
+
+  // one set of partial spectra per CTA: [CTA][kind][ear][B]; kinds without sources this block are
+  // skipped (the inverse kernel skips them too); bin 0 holds (DC, Nyquist), both real products
+  // (convolver.h:510-541)
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    if ((k == 0 ? n0 : (k == 1 ? n1 : n2)) == 0) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+    {
+      if (tt == 0) { acc[k][j][0].x += nyq[k][j]; acc[k][j][0].y = nyq[k][j]; }
+      float4* out = p.partials + ((size_t(blockIdx.x) * 3 + k) * 2 + j) * nvec;
+      out[tt] = acc[k][j][0];
+      out[tt + kThreads] = acc[k][j][1];
+    }
+  }
+  if (p.trace && t == 0)
+  { unsigned long long now; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now)); p.trace[size_t(blockIdx.x) * 4 + 2] = now; }
 }
 
 // ---------------------------------------------------------------- MAC, time-batched (offline)

@@ -354,6 +354,14 @@ Renderer::StepDesc Renderer::prepare_generic(const float* d_input, float* d_outp
   for (int n = 0; n < N; ++n)
   {
     Source& s = *sources[n];
+    if (tail_level && !s.primed)
+    {
+      // (non-uniform partitioning, tail level: what this renderer adds sounds 2 K blocks after the
+      // source started, when the reference's initial fade-in is long over)
+      base_weight(s);
+      s.w.assign(s.weighting_factor.get());
+      s.primed = true;
+    }
     base_weight(s);
     s.w.assign(s.weighting_factor.get());  // src/genericrenderer.h:124
     s.mode = mode_from_weight(s.w);
@@ -510,9 +518,13 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
     // kernel's CTAs when that runs under the MAC (one CTA per source, each takes the
     // registers of one MAC CTA on its SM)
     dyn_G = e->dyn_mac_slots();
-    if (e->fwd_overlap) dyn_G = std::max(e->sm_count, dyn_G - std::min(N, e->sm_count));
+    if (e->dyn_tma())
+      // one CTA per SM, each with an equal run of (source, partition) slots and ONE set of
+      // [kind][ear] partial spectra (mac_dyn_tma_kernel)
+      dyn_G = int(std::max<long long>(1, std::min<long long>(e->sm_count, (long long)N * dyn_Pmax)));
+    else if (e->fwd_overlap) dyn_G = std::max(e->sm_count, dyn_G - std::min(N, e->sm_count));
     if (const char* v = std::getenv("SSR_B200_DYN_CTAS")) dyn_G = std::max(1, std::atoi(v));  // experiments
-    e->ensure_partials(size_t(dyn_G) * 2);
+    e->ensure_partials(size_t(dyn_G) * (e->dyn_tma() ? 6 : 2));
     static_dirty = false;
     invalidate_inv();
   }

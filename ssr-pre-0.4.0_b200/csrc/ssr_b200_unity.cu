@@ -5,3 +5,4 @@
 #include "hostgather.cu"
 #include "renderer.cu"
 #include "capi.cu"
+#include "nonuniform.cu"
