@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--reference-budget-s", type=float, default=150.0,
                     help="--impl reference: time budget of the measured blocks (3 repeats)")
+    ap.add_argument("--nonuniform", default="",
+                    help="Generic workloads on the non-uniformly partitioned renderer (ssr_nu_*; reported separately "
+                         "from the headline): level layout 'KxP,...' = block multiple x partitions, e.g. 1x8,4x10")
     ap.add_argument("--mac-variant", type=int, default=0)
     ap.add_argument("--static-head", action="store_true", help="Binaural/BRS: no head rotation")
     ap.add_argument("--stage-timing-every", type=int, default=8,
@@ -463,6 +466,22 @@ def main_ours(args):
 
     w, reduced = get_workload(args)
     B = w.block
+    if args.nonuniform:
+        import types
+        import ssr_b200.nubench as nubench
+
+        def hbm_peak():
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(peaks_path):
+                return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return 6650.0, "fallback (B200_PROFILING.md)"
+        nubench.run(args, w, reduced, types.SimpleNamespace(
+            parity_truth=parity_truth, ClockSampler=ClockSampler, PARITY_TOL=PARITY_TOL,
+            make_config=lambda *a: make_config(*a)[0], hbm_peak=hbm_peak))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     if w.kind == "generic":
         m_first, m_local = mg.shard_outputs(w.outputs, world, rank)
     else:

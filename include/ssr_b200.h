@@ -494,6 +494,8 @@ int ssr_nu_process(ssr_nu* r, int n, const float* const* in, float* const* out);
 int ssr_nu_process_device(ssr_nu* r, const float* d_in, float* d_out);
 int ssr_nu_synchronize(ssr_nu* r);
 void* ssr_nu_stream(ssr_nu* r);
+/* kernels launched so far (all levels' engines + the mixer) */
+int ssr_nu_launches(ssr_nu* r, uint64_t* launches);
 /* ALGORITHMIC bytes (SURVEY 8d formula per MAC launch, summed) of block `block_index` */
 int ssr_nu_block_mac_bytes(ssr_nu* r, uint64_t block_index, uint64_t* bytes);
 

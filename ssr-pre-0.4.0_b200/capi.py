@@ -171,6 +171,7 @@ SIGNATURES = {
     "ssr_nu_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_nu_synchronize": (C.c_int, [C.c_void_p]),
     "ssr_nu_stream": (C.c_void_p, [C.c_void_p]),
+    "ssr_nu_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ssr_nu_block_mac_bytes": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 GATHER_HANDLE_BYTES = 64
@@ -755,6 +756,12 @@ class NuRenderer:
 
     def synchronize(self):
         _check(lib().ssr_nu_synchronize(self.h))
+
+    @property
+    def launches(self) -> int:
+        v = C.c_uint64(0)
+        _check(lib().ssr_nu_launches(self.h, C.byref(v)))
+        return int(v.value)
 
     def block_mac_bytes(self, block_index: int) -> int:
         v = C.c_uint64(0)

@@ -77,6 +77,7 @@ struct NuRenderer
   std::vector<std::unique_ptr<Level>> levels;
   int n_sources = 0;
   uint64_t block = 0;          // blocks rendered so far
+  uint64_t mix_launches = 0;
   DeviceArray<float> d_in, d_out;
   PinnedArray<float> h_in, h_out;
   std::vector<int> ids;        // source ids (the same in every sub-renderer)
@@ -256,6 +257,7 @@ struct NuRenderer
     {
       nu_mix_kernel<<<m_local, 256, 0, stream>>>(d_output, mix, B);
       SSR_CUDA(cudaGetLastError());
+      mix_launches++;
     }
     block++;
   }
@@ -362,6 +364,17 @@ int ssr_nu_synchronize(ssr_nu* r)
 }
 
 void* ssr_nu_stream(ssr_nu* r) { return r ? static_cast<void*>(r->impl.stream) : nullptr; }
+
+// kernels launched so far by all levels' engines and the mixer
+int ssr_nu_launches(ssr_nu* r, uint64_t* launches)
+{
+  return guarded([&] {
+    if (!r || !launches) throw Error(SSR_ERR_INVALID, "ssr_b200: null argument");
+    uint64_t total = r->impl.mix_launches;
+    for (auto& L : r->impl.levels) total += L->eng->stats.launches_total;
+    *launches = total;
+  });
+}
 
 // ALGORITHMIC bytes of the MAC launches of block `block_index` (SURVEY 8d formula per launch, summed):
 // level 0 every block, level l's sub-renderer `block mod K` from the second period on.
