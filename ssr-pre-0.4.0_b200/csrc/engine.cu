@@ -629,7 +629,16 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights, b
 }
 
 // reduce the generated-terms partials per (ear, kind), then one inverse CTA per ear
-void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, int G, const HeadCommit& hc)
+void Engine::launch_ctl_upload(const void* src_host, void* dst, int n16, unsigned long long* counter,
+                               unsigned long long* ack)
+{
+  launch_kernel(ctl_upload_kernel, dim3(1), dim3(kThreads), 0, stream, pdl, static_cast<const uint4*>(src_host),
+      static_cast<uint4*>(dst), n16, counter, static_cast<volatile unsigned long long*>(ack));
+  count_launch();
+}
+
+void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, int G, const HeadCommit& hc,
+                            bool early_trigger)
 {
   const int njobs = int(plan.jobs.uploaded);
   if (njobs == 0) return;
@@ -640,7 +649,8 @@ void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, in
         size_t(2) * B * sizeof(float2) * 4, stream, pdl, plan.jobs.device(), plan.entries.device(),
         reinterpret_cast<const float2*>(partials.ptr), G, B, static_cast<const float2*>(tw.ptr),
         static_cast<const float*>(fade_out.ptr), static_cast<const float*>(fade_in.ptr), ctl->n, hc,
-        (trace_mode == 1 && mac_trace.ptr) ? mac_trace.ptr + 8192 : static_cast<unsigned long long*>(nullptr));
+        (trace_mode == 1 && mac_trace.ptr) ? mac_trace.ptr + 8192 : static_cast<unsigned long long*>(nullptr),
+        early_trigger ? 1 : 0);
     count_launch();
     if (cur) cur->ifft_launches++;
     return;

@@ -247,7 +247,9 @@ struct Engine
   // dynamic renderers: terms generated on the device (ssrk::DynTables), static launch shapes
   void launch_mac_dyn(const ssrk::DynTables& dyn, int G, const float* weights, bool fwd_overlap = false);
   void launch_inv_dyn(const InvPlan& plan, const ssrk::DynCtl* ctl, int Pmax, int G,
-                      const ssrk::HeadCommit& hc = ssrk::HeadCommit{});
+                      const ssrk::HeadCommit& hc = ssrk::HeadCommit{}, bool early_trigger = false);
+  void launch_ctl_upload(const void* src_host, void* dst, int n16, unsigned long long* counter,
+                         unsigned long long* ack);
   void launch_dyn_ring_update(const ssrk::DynCtl* ctl, const ssrk::DynRingEntry* upd,
                               ssrk::DynRingEntry* ring, int rows, int R);
   int dyn_mac_slots() const;
@@ -679,10 +681,16 @@ struct Renderer
   long long dyn_b = 0;                   // block counter
   int dyn_Pmax = 1, dyn_R = 2, dyn_G = 0;
   DeviceArray<ssrk::DynRingEntry> dyn_ring;   // [sources][2 ears][R]
-  DeviceArray<unsigned char> dyn_dev;    // this block's control data (one small upload)
+  // this block's control data: staged in page-locked memory, brought over by ctl_upload_kernel (or, with
+  // SSR_B200_CTL_UPLOAD=copy, a stream-ordered copy); staging slot and device buffer alternate by block
+  DeviceArray<unsigned char> dyn_dev[2];
   PinnedArray<unsigned char> dyn_stage[2];
   cudaEvent_t dyn_copied[2] = {nullptr, nullptr};
   int dyn_slot = 0;
+  bool ctl_by_kernel = true;
+  DeviceArray<unsigned long long> dyn_upload_count;      // [2] uploads done per staging slot (device)
+  PinnedArray<unsigned long long> dyn_ack;               // [2] the same, as the host sees it
+  unsigned long long dyn_uploads_issued[2] = {0, 0};
   ssrk::DynTables dyn_tables{};
   const float* dyn_wtab_dev = nullptr;
   const ssrk::DynRingEntry* dyn_upd_dev = nullptr;
@@ -716,6 +724,8 @@ struct Renderer
     uint64_t hparts[3] = {0, 0, 0}, xparts[3] = {0, 0, 0};
     int nrows = 0;
     bool graphable = false;
+    // Binaural / BRS: control upload done by the block's first kernel (ctl_upload_kernel)
+    const void* ctl_src = nullptr; void* ctl_dst = nullptr; int ctl_n16 = 0; int ctl_slot = 0;
   };
   StepDesc prepare(const float* d_input, float* d_output);
   void launch(const StepDesc& d);

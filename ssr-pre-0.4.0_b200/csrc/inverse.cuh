@@ -221,6 +221,38 @@ __device__ __forceinline__ void fwd_ring_update(const FwdRingUpdate& u, int sour
   u.ring[size_t(row) * u.R + slot] = u.upd[row];
 }
 
+// Binaural / BRS: this block's control data (DynCtl + lists + weights + filter updates, a few KB)
+// goes from the renderer's page-locked staging buffer to the device with a KERNEL instead of a copy
+// in front of the block: as the first link of the block's programmatic-dependent-launch chain it is
+// scheduled while the previous block's inverse transform still runs (which triggers its dependents at
+// once, InvFlags::early_trigger), reads the host buffer over PCIe meanwhile, and only then waits for
+// that inverse kernel -- so neither the transfer nor a launch latency sits between two blocks (a
+// stream-ordered cudaMemcpyAsync costs ~5 us there, 10 % of a BRS block).  Two device buffers
+// alternate by block parity (the previous block's kernels still read theirs).  `ack`: mapped host
+// word that receives the number of uploads done from this staging slot, so that the host knows when
+// it may refill it without an event in the stream.
+__global__ void __launch_bounds__(kThreads)
+ctl_upload_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, int n16,
+                  unsigned long long* counter, volatile unsigned long long* ack)
+{
+  grid_launch_dependents();
+  for (int i = threadIdx.x; i < n16; i += kThreads)
+  {
+    uint4 v;
+    asm volatile("ld.global.cv.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src_host + i));
+    dst[i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned long long c = *counter + 1;
+    *counter = c;
+    *ack = c;
+    __threadfence_system();
+  }
+  grid_dependency_wait();   // completion of this kernel implies completion of the previous block
+}
+
 // ring[(source, ear)][b mod R] = the filter that is current in block b
 __global__ void dyn_ring_update_kernel(const DynCtl* __restrict__ ctl, const DynRingEntry* __restrict__ upd,
                                        DynRingEntry* __restrict__ ring, int rows, int R)
@@ -568,8 +600,11 @@ __global__ void __launch_bounds__(kThreads * 3, 1)
 inv_dyn_cluster_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
                        const float2* __restrict__ partials, int dyn_G, int B, const float2* __restrict__ tw,
                        const float* __restrict__ fade_out, const float* __restrict__ fade_in,
-                       const int* __restrict__ kind_counts, const HeadCommit hc, unsigned long long* dbg)
+                       const int* __restrict__ kind_counts, const HeadCommit hc, unsigned long long* dbg,
+                       int early_trigger)
 {
+  // the next block's control upload (ctl_upload_kernel) does not depend on this kernel: let it in
+  if (early_trigger) grid_launch_dependents();
   inv_fft_body<3, true>(jobs, entries, partials, nullptr, B, tw, fade_out, fade_in, GatherArgs{}, kind_counts, hc, dyn_G, dbg);
 }
 

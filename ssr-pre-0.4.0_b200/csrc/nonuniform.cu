@@ -268,13 +268,26 @@ struct NuRenderer
     if (n != B) throw Error(SSR_ERR_INVALID, "ssr_b200: process(): n must equal the block size");
     const int nin = n_sources;
     SSR_CUDA(cudaSetDevice(cfg.device));
-    for (int i = 0; i < nin; ++i) std::memcpy(h_in.ptr + size_t(i) * B, in[i], size_t(B) * sizeof(float));
+    // channel blocks that form one contiguous page-locked array are used in place by the copy engines
+    // (the layout a driver with its own pinned I/O buffers passes); anything else is staged
+    Engine* e0 = levels[0]->eng.get();
+    auto contiguous_pinned = [&](const float* const* ptrs, int count) {
+      if (count <= 0 || !ptrs || !ptrs[0]) return false;
+      for (int i = 1; i < count; ++i) if (ptrs[i] != ptrs[0] + size_t(i) * B) return false;
+      return e0->is_pinned(ptrs[0], size_t(count) * B * sizeof(float));
+    };
+    const float* src = h_in.ptr;
+    if (contiguous_pinned(in, nin)) src = in[0];
+    else for (int i = 0; i < nin; ++i) std::memcpy(h_in.ptr + size_t(i) * B, in[i], size_t(B) * sizeof(float));
     if (nin > 0)
-      SSR_CUDA(cudaMemcpyAsync(d_in.ptr, h_in.ptr, size_t(nin) * B * sizeof(float), cudaMemcpyHostToDevice, stream));
+      SSR_CUDA(cudaMemcpyAsync(d_in.ptr, src, size_t(nin) * B * sizeof(float), cudaMemcpyHostToDevice, stream));
     step(d_in.ptr, d_out.ptr);
-    SSR_CUDA(cudaMemcpyAsync(h_out.ptr, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    const bool direct_out = contiguous_pinned(out, m_local);
+    float* dst = direct_out ? out[0] : h_out.ptr;
+    SSR_CUDA(cudaMemcpyAsync(dst, d_out.ptr, size_t(m_local) * B * sizeof(float), cudaMemcpyDeviceToHost, stream));
     SSR_CUDA(cudaStreamSynchronize(stream));
-    for (int m = 0; m < m_local; ++m) std::memcpy(out[m], h_out.ptr + size_t(m) * B, size_t(B) * sizeof(float));
+    if (!direct_out)
+      for (int m = 0; m < m_local; ++m) std::memcpy(out[m], h_out.ptr + size_t(m) * B, size_t(B) * sizeof(float));
   }
 };
 

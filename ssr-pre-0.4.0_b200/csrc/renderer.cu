@@ -53,6 +53,7 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   // apf::math::dB2linear (src/rendererbase.h:234-235)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
+  if (const char* v = std::getenv("SSR_B200_CTL_UPLOAD")) ctl_by_kernel = std::string(v) != "copy";   // A/B
   if (const char* v = std::getenv("SSR_B200_ZEROCOPY_OUT")) zero_copy = std::atoi(v) != 0;
   if (const char* v = std::getenv("SSR_B200_ZEROCOPY_IN")) zero_copy_in = std::atoi(v) != 0;
   static_mac.MT = kGenericMT;
@@ -538,10 +539,37 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   off_upd = (off_upd + 15) & ~size_t(15);
   const size_t total = off_upd + size_t(2) * N * sizeof(DynRingEntry);
   dyn_slot ^= 1;
-  if (dyn_copied[dyn_slot]) SSR_CUDA(cudaEventSynchronize(dyn_copied[dyn_slot]));
-  else SSR_CUDA(cudaEventCreateWithFlags(&dyn_copied[dyn_slot], cudaEventDisableTiming));
-  if (dyn_stage[dyn_slot].count < total) dyn_stage[dyn_slot].resize(total + total / 2 + 256);
-  if (dyn_dev.count < total) { e->sync(); dyn_dev.resize(total + total / 2 + 256); }
+  if (ctl_by_kernel)
+  {
+    if (!dyn_ack.ptr)
+    {
+      dyn_ack.resize(2); dyn_ack.ptr[0] = dyn_ack.ptr[1] = 0;
+      dyn_upload_count.resize(2);
+      SSR_CUDA(cudaMemsetAsync(dyn_upload_count.ptr, 0, 2 * sizeof(unsigned long long), e->stream));
+    }
+    // the upload kernel that last read this staging slot has run (normally long ago)
+    const volatile unsigned long long* ack = dyn_ack.ptr + dyn_slot;
+    if (*ack < dyn_uploads_issued[dyn_slot])
+    {
+      const auto t0 = std::chrono::steady_clock::now();
+      while (*ack < dyn_uploads_issued[dyn_slot])
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
+          throw Error(SSR_ERR_STATE, "ssr_b200: control upload of an earlier block never ran");
+    }
+  }
+  else
+  {
+    if (dyn_copied[dyn_slot]) SSR_CUDA(cudaEventSynchronize(dyn_copied[dyn_slot]));
+    else SSR_CUDA(cudaEventCreateWithFlags(&dyn_copied[dyn_slot], cudaEventDisableTiming));
+  }
+  if (dyn_stage[dyn_slot].count < total + 16)
+  {
+    // (a slot that grows may still be read by an upload in flight)
+    if (ctl_by_kernel) e->sync();
+    dyn_stage[dyn_slot].resize(total + total / 2 + 256);
+  }
+  DeviceArray<unsigned char>& dyn_dev_cur = dyn_dev[dyn_slot];
+  if (dyn_dev_cur.count < total + 16) { e->sync(); dyn_dev_cur.resize(total + total / 2 + 256); }
   unsigned char* st = dyn_stage[dyn_slot].ptr;
   DynCtl* ctl = reinterpret_cast<DynCtl*>(st);
   int* lists = reinterpret_cast<int*>(st + off_lists);
@@ -700,18 +728,29 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   ctl->n[0] = nk[0]; ctl->n[1] = nk[1]; ctl->n[2] = nk[2]; ctl->pad = 0;
   prof.lap(0);
 
-  SSR_CUDA(cudaMemcpyAsync(dyn_dev.ptr, st, total, cudaMemcpyHostToDevice, e->stream));
-  SSR_CUDA(cudaEventRecord(dyn_copied[dyn_slot], e->stream));
-  dyn_tables.ctl = reinterpret_cast<const DynCtl*>(dyn_dev.ptr);
-  dyn_tables.lists = reinterpret_cast<const int*>(dyn_dev.ptr + off_lists);
-  dyn_tables.src_input = reinterpret_cast<const int*>(dyn_dev.ptr + off_input);
-  dyn_tables.src_parts = reinterpret_cast<const int*>(dyn_dev.ptr + off_parts);
+  unsigned char* dev_ctl = dyn_dev_cur.ptr;
+  if (ctl_by_kernel)
+  {
+    void* mapped = nullptr;   // the device's view of the staging slot (the same address under UVA)
+    SSR_CUDA(cudaHostGetDevicePointer(&mapped, st, 0));
+    d.ctl_src = mapped; d.ctl_dst = dev_ctl; d.ctl_n16 = int((total + 15) / 16); d.ctl_slot = dyn_slot;
+    dyn_uploads_issued[dyn_slot]++;   // (the launch itself may be a replayed graph node)
+  }
+  else
+  {
+    SSR_CUDA(cudaMemcpyAsync(dev_ctl, st, total, cudaMemcpyHostToDevice, e->stream));
+    SSR_CUDA(cudaEventRecord(dyn_copied[dyn_slot], e->stream));
+  }
+  dyn_tables.ctl = reinterpret_cast<const DynCtl*>(dev_ctl);
+  dyn_tables.lists = reinterpret_cast<const int*>(dev_ctl + off_lists);
+  dyn_tables.src_input = reinterpret_cast<const int*>(dev_ctl + off_input);
+  dyn_tables.src_parts = reinterpret_cast<const int*>(dev_ctl + off_parts);
   dyn_tables.ring = dyn_ring.ptr;
-  dyn_tables.upd = reinterpret_cast<const DynRingEntry*>(dyn_dev.ptr + off_upd);
+  dyn_tables.upd = reinterpret_cast<const DynRingEntry*>(dev_ctl + off_upd);
   dyn_tables.stats = nullptr;
   dyn_tables.nsrc = N; dyn_tables.R = dyn_R; dyn_tables.Pmax = dyn_Pmax;
-  dyn_wtab_dev = reinterpret_cast<const float*>(dyn_dev.ptr + off_w);
-  dyn_upd_dev = reinterpret_cast<const DynRingEntry*>(dyn_dev.ptr + off_upd);
+  dyn_wtab_dev = reinterpret_cast<const float*>(dev_ctl + off_w);
+  dyn_upd_dev = reinterpret_cast<const DynRingEntry*>(dev_ctl + off_upd);
   prof.lap(1);
 
   // the inverse tables are static: one job per ear, one entry per accumulator kind
@@ -732,7 +771,7 @@ Renderer::StepDesc Renderer::prepare_dynamic(const float* d_input, float* d_outp
   build_fwd(d_input);
   prof.lap(3);
   d.N = N;
-  d.kind_mask = 1;
+  d.kind_mask = 1 + 2 * dyn_slot;   // (graph key: the control buffers of the two parities have different addresses)
   // partitions read are counted by the kernel (Engine::d_dyn_stats); the
   // accumulators written per output are known here
   d.nrows = 2 * ((nk[0] > 0) + (nk[1] > 0) + (nk[2] > 0));
@@ -871,6 +910,10 @@ void Renderer::launch(const StepDesc& d)
   // (Binaural / BRS: the generated-terms MAC does the same)
   const bool overlap = e->fwd_overlap && d.N > 0
       && (dynamic || (cfg.kind == SSR_RENDERER_GENERIC && e->mac_tma() && static_mac.MT == kGenericMT));
+  if (d.ctl_n16 > 0)
+  {
+    e->launch_ctl_upload(d.ctl_src, d.ctl_dst, d.ctl_n16, dyn_upload_count.ptr + d.ctl_slot, dyn_ack.ptr + d.ctl_slot);
+  }
   if (dynamic && d.N > 0)
   {
     // the forward kernel's CTA n also records source n's current filters in the ring
@@ -908,7 +951,7 @@ void Renderer::launch(const StepDesc& d)
   e->stage_mark(2);
   const HeadCommit hc{overlap ? fwd->device() : nullptr, overlap ? d.N : 0};
   if (cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS)
-    e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G, hc);
+    e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G, hc, ctl_by_kernel && e->pdl);
   else if (gather) e->launch_inv(inv, gather->next_block(), hc);
   else if (hostgather)
   {

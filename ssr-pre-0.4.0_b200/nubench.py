@@ -65,7 +65,8 @@ def run(args, w, reduced, helpers):
         host_in[t] = torch.from_numpy(wl.signal_block(w, t))
     dev_in = host_in.to(dev)
     d_out = torch.zeros((m_local, B), dtype=torch.float32, device=dev)
-    host_out = np.empty((m_local, B), np.float32)
+    host_out_t = torch.empty((m_local, B), dtype=torch.float32).pin_memory()
+    host_out = host_out_t.numpy()
     f32p = ctypes.POINTER(ctypes.c_float)
     in_ptr_sets = []
     for t in range(nring):
