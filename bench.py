@@ -922,11 +922,29 @@ def main_ours(args):
                 traffic_source = f"capture on file is for grid {ent['grid']}, this run launched {st.get('last_mac_grid')}: omitted"
         except Exception:
             traffic = None
+    dyn_tma = B in (1024, 2048) and os.environ.get("SSR_B200_DYN_TMA", "1") != "0"
+    # device-clock span of the LAST MAC launch (first CTA start -> last CTA end, %globaltimer inside the kernel):
+    # the CUDA-event figure above also holds the launch latency on both sides, which is a fifth of a 20 us launch
+    device_clock = None
+    try:
+        grid = int(st.get("last_mac_grid", 0))
+        if grid > 0 and B >= 1024 and args.mac_variant in (0, 6, 7) and (w.kind == "generic" or dyn_tma):
+            tr = eng.mac_trace(grid).astype(np.int64)
+            tr = tr[(tr[:, 0] > 0) & (tr[:, 2] > 0)]
+            if len(tr):
+                span_ms = float(tr[:, 2].max() - tr[:, 0].min()) * 1e-6
+                bpl = st["mac_bytes"] / max(1, st["mac_launches"])
+                device_clock = {"ms": span_ms, "gbs": bpl / 1e9 / (span_ms * 1e-3), "frac": bpl / 1e9 / (span_ms * 1e-3) / peak,
+                                "ctas": int(len(tr)), "what": "last MAC launch of the run, first CTA start to last CTA end"}
+    except Exception:
+        device_clock = None
     roofline = {
         "bound": "hbm", "kernel": (("ssrk::mac_tma_kernel<4,5> (cp.async.bulk staged)" if args.mac_variant in (0, 7) and B >= 1024
                                     else f"MAC variant {args.mac_variant} (profiles/r1_mac_variants.md)")
                                    if w.kind == "generic"
-                                   else "ssrk::mac_kernel<2,2,2,2,true> (terms generated on the device)"), "achieved": achieved, "peak": peak,
+                                   else ("ssrk::mac_dyn_tma_kernel<5> (terms generated on the device, cp.async.bulk staged)" if dyn_tma
+                                         else "ssrk::mac_kernel<2,2,2,2,true> (terms generated on the device)")),
+        "achieved": achieved, "peak": peak, "device_clock": device_clock,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
         "mac_grid": int(st.get("last_mac_grid", 0)),
         "bytes_per_launch": st["mac_bytes"] / max(1, st["mac_launches"]),

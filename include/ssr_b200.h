@@ -42,7 +42,7 @@ typedef enum ssr_status
   SSR_ERR_INVALID = -1,      /* bad argument / precondition (reference: assert) */
   SSR_ERR_BLOCK_SIZE = -2,   /* "Convolver: block size must be a multiple of 8!"
                                 (apf/apf/convolver.h:163-166) */
-  SSR_ERR_UNSUPPORTED = -3,  /* block size above 4096 (every multiple of 8 up to there is accepted) */
+  SSR_ERR_UNSUPPORTED = -3,  /* block size above 8192 (every multiple of 8 up to there is accepted) */
   SSR_ERR_CUDA = -4,         /* CUDA runtime failure / no device */
   SSR_ERR_NOMEM = -5,
   SSR_ERR_STATE = -6,        /* call order violated */
@@ -459,7 +459,7 @@ int ssr_hostgather_next_slot(const ssr_hostgather* g);
  * source weights; a weight change reaches a tail level at that level's block rate.  The
  * filter bytes read per block fall from P to sum_l level_partitions[l] partitions' worth.
  * Rules (SSR_ERR_INVALID otherwise): level_mult[0] = 1; level_mult increasing powers of two
- * with level_mult[l] * B <= 4096; level l > 0 starts (sum of the lower levels' taps) at a
+ * with level_mult[l] * B <= 8192; level l > 0 starts (sum of the lower levels' taps) at a
  * multiple of its partition size and at least two of its partitions into the response.
  * Sources are added before the first block. */
 typedef struct ssr_nu ssr_nu;

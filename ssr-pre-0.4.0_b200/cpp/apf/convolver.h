@@ -17,7 +17,7 @@
 //    use (src/binauralrenderer.h:372-377) -- runs as a kernel; any other binary
 //    host callable works too, through a host round trip of the spectra (it is
 //    host code; a load-time operation in the reference as well).
-//  * block sizes must be powers of two in [8, 4096]; other multiples of 8 throw
+//  * block sizes must be powers of two in [8, 8192]; other multiples of 8 throw
 //    std::logic_error with a different message.
 //  * One engine per (device, block size) is created lazily; the device ordinal
 //    comes from the environment variable SSR_B200_DEVICE (default 0).

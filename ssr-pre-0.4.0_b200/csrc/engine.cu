@@ -179,8 +179,8 @@ Engine::Engine(const ssr_engine_config& cfg)
   fft1024_always = fft_env && std::string(fft_env) == "fft1024";  // also for small launches (tests, A/B)
   if (B <= 0 || B % 8 != 0)
     throw Error(SSR_ERR_BLOCK_SIZE, "Convolver: block size must be a multiple of 8!");
-  if (B > 4096)
-    throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: block size must be a multiple of 8 in [8, 4096]");
+  if (B > kMaxBlock)
+    throw Error(SSR_ERR_UNSUPPORTED, "ssr_b200: block size must be a multiple of 8 in [8, 8192]");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess || ndev == 0)
@@ -279,6 +279,7 @@ Engine::Engine(const ssr_engine_config& cfg)
   if (const char* v = std::getenv("SSR_B200_MAC_WAVES")) mac_waves = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("SSR_B200_PREREDUCE_MIN")) prereduce_min = std::max(1, std::atoi(v));
   if (const char* v = std::getenv("SSR_B200_MAC_CALIBRATE")) mac_calibrate = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SSR_B200_INV_TRIGGER")) inv_trigger = std::atoi(v) != 0;   // A/B experiments
   if (const char* v = std::getenv("SSR_B200_EARLY_TRIGGER")) early_trigger = std::atoi(v) != 0;   // A/B experiments (profiles/r2_ab)
   if (const char* v = std::getenv("SSR_B200_TRACE_ISSUE")) trace_mode = std::atoi(v) != 0 ? 1 : 0;   // scripts/mac_trace.py
   if (mac_tma())
@@ -289,7 +290,18 @@ Engine::Engine(const ssr_engine_config& cfg)
   fwd_overlap = fwd_overlap && pdl;
   if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
   if (!is_pow2(B)) level1_fused = false;   // the fused Level-1 launch is instantiated for power-of-two spectra
-  if (2 * fft_smem > 48 * 1024)
+  // 4096 < B <= 8192: the two transform buffers take 128 KiB; kernels that also stage the twiddle table or
+  // run several transforms side by side have "large" variants without (fwd_fft_large_kernel, inv_fft_large_kernel)
+  if (large()) level1_fused = false;
+  if (large())
+  {
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(inv_fft_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+    SSR_CUDA(cudaFuncSetAttribute(fwd_fft_overlap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem)));
+  }
+  else if (2 * fft_smem > 48 * 1024)
   {
     SSR_CUDA(cudaFuncSetAttribute(level1_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
     SSR_CUDA(cudaFuncSetAttribute(level1_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * fft_smem)));
@@ -301,7 +313,8 @@ Engine::Engine(const ssr_engine_config& cfg)
   // the inverse kernel runs up to kInvMaxGroups transforms side by side (3 x 16 KiB
   // at B = 1024, which with its static shared memory already exceeds 48 KiB)
   // (+ one staged twiddle table per CTA)
-  SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem * 2)));
+  if (!large())
+    SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem * 2)));
   if (inv_groups(2) == 2)
     SSR_CUDA(cudaFuncSetAttribute(inv_fft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fft_smem * 3)));
   if (inv_groups(3) == 3)
@@ -392,6 +405,11 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
   {
     const int ctas = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
     fwd_fft1024_kernel<<<ctas, kWarpsPerCta * 32, 0, stream>>>(d_jobs, njobs, tw.ptr);
+  }
+  else if (large())
+  {
+    if (ring_update) { ru = *ring_update; ring_update = nullptr; }
+    fwd_fft_large_kernel<<<njobs, kThreads, size_t(2) * B * sizeof(float2), stream>>>(d_jobs, B, tw.ptr, ru, in_base);
   }
   else
   {
@@ -531,6 +549,7 @@ int Engine::dyn_mac_slots() const
 int Engine::inv_groups(int max_entries) const
 {
   const size_t per_group = size_t(2) * B * sizeof(float2);  // the twiddle table takes as much again
+  if (large()) return 1;
   int g = std::max(1, std::min(max_entries, kInvMaxGroups));
   while (g > 1 && per_group * (g + 1) > size_t(200) * 1024) --g;
   return g;
@@ -541,7 +560,10 @@ void Engine::launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const
 {
   const size_t smem = size_t(2) * B * sizeof(float2) * (groups + 1);
   const float2* part = reinterpret_cast<const float2*>(partials.ptr);
-  if (groups == 3)
+  if (large())
+    launch_kernel(inv_fft_large_kernel, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
+        plan.jobs.device(), plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts, hc);
+  else if (groups == 3)
     launch_kernel(inv_fft_kernel<3>, dim3(njobs), dim3(kThreads * 3), smem, stream, pdl, plan.jobs.device(),
         plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts, hc);
   else if (groups == 2)
@@ -613,7 +635,7 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights, b
   p.dyn.stats = cur ? d_dyn_stats.ptr : nullptr;
   p.trace_mode = trace_mode;
   p.early_trigger = early_trigger ? 1 : 0;
-  if (dyn_tma() && trace_mode == 1 && mac_trace.ptr && size_t(G) * 4 <= mac_trace.count) p.trace = mac_trace.ptr;
+  if (dyn_tma() && mac_trace.ptr && size_t(G) * 4 <= mac_trace.count) p.trace = mac_trace.ptr;
   void* args[] = { &p };
   dim3 grid(G, mac_ktiles(B), 1);
   stats.last_mac_grid = G * mac_ktiles(B);

@@ -193,6 +193,8 @@ struct Engine
   ~Engine();
 
   int device, B, sample_rate, sm_count, mac_variant;
+  static constexpr int kMaxBlock = 8192;
+  bool large() const { return B > 4096; }   // transform buffers of 128 KiB: kernels without staged twiddles
   bool fft1024 = false;            // B == 1024: register/shuffle FFT kernels (fft1024.cuh)
   bool fft1024_always = false;
   bool pdl = true;                 // programmatic dependent launch of the MAC / reduce / inverse kernels
@@ -241,6 +243,7 @@ struct Engine
   DeviceArray<unsigned long long> mac_trace;   // per-CTA timestamps / busy time of the bulk-copy MAC launches
   bool early_trigger = false;                  // SSR_B200_EARLY_TRIGGER=1: the bulk-copy MACs let their dependent kernel launch at once
                                                //  (measured: the block gets 5 us SLOWER on cfg4, profiles/r2_ab; off)
+  bool inv_trigger = false;                    // SSR_B200_INV_TRIGGER=1: see ssrk::HeadCommit::early_trigger
   int trace_mode = 0;                          // SSR_B200_TRACE_ISSUE=1: trace[3] = first bulk copy (see MacParams)
   bool mac_calibrate = false;                  // SSR_B200_MAC_CALIBRATE=1: re-cut the shares by measured CTA rates
   int prereduce_min = 16;          // partials per accumulator from which a separate reduction launch pays

@@ -26,7 +26,8 @@ struct InvJob
   float* level;     // if non-null: max |out| (src/rendererbase.h:468-472)
 };
 
-constexpr int kInvMaxRes = 8;  // B <= 4096: (B/2 float2) / 256 threads
+constexpr int kInvMaxRes = 8;        // B <= 4096: (B/2 float2) / 256 threads
+constexpr int kInvMaxResLarge = 16;  // B <= 8192 (inv_fft_large_kernel)
 
 // Multi-GPU output gather fused into the inverse kernel: the output
 // blocks of a rank are stored straight into the host-facing rank's gather buffer
@@ -58,6 +59,8 @@ struct HeadCommit
 {
   const FwdJob* jobs;   // the forward launch's job table (head pointer + ring length per input)
   int n;                // 0: nothing to commit
+  int early_trigger;    // 1: the kernel lets its dependents (the next block's forward transform, which waits for
+                        //  this kernel's completion itself) be scheduled at once (SSR_B200_INV_TRIGGER=1, experiment)
 };
 
 constexpr unsigned long long kGatherTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
@@ -275,7 +278,9 @@ constexpr int kInvMaxGroups = 3;
 // the r-th slice of the bins, group g the accumulator kind g -- straight into the leader CTA's
 // shared memory over DSMEM; the leader then transforms as usual.  This replaces the separate
 // dyn_reduce_kernel launch (9 us of a 47 us BRS block).
-template<int GROUPS, bool CLUSTER>
+// MAXRES: output pairs per thread (B / 2 / kThreads); TWS: twiddle table staged in shared memory (B <= 4096;
+// above that the transform buffers take the shared memory and the twiddles come from L1 / L2)
+template<int GROUPS, bool CLUSTER, int MAXRES = kInvMaxRes, bool TWS = true>
 __device__ __forceinline__ void
 inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
              const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
@@ -306,7 +311,7 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
   const int half = B >> 1;
   // twiddle table -> shared memory, once for all groups
   float2* stw = smem + size_t(GROUPS) * 2 * B;
-  if (crank == 0)
+  if (TWS && crank == 0)
     stage_twiddles(stw, tw, B, threadIdx.x, kThreads * GROUPS);  // constants: may overlap the predecessor's tail
   // (CLUSTER: static tables and the block's control word -- uploaded before the block's first kernel --
   // are read ahead of the wait; they are the head of the dependent chain to the partial spectra)
@@ -397,9 +402,9 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
   // read out by the root (checked by one thread while the others start loading)
   if (ga.consumed && threadIdx.x == 0) s_slot_ok = gather_wait_ge(ga.consumed, ga.need_consumed, ga.error, ga.timeout_ns) ? 1 : 0;
 
-  float2 res[kInvMaxRes];
+  float2 res[MAXRES];
 #pragma unroll
-  for (int q = 0; q < kInvMaxRes; ++q) res[q] = make_float2(0.f, 0.f);
+  for (int q = 0; q < MAXRES; ++q) res[q] = make_float2(0.f, 0.f);
 
   // entries beyond the launched groups are handled by the last group in turn
   for (int e = g; e < job.n_entries; e += ngroups)
@@ -463,7 +468,7 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
         const float2 xk = a[k], xk2 = a[k2];
         const float er = xk.x + xk2.x, ei = xk.y - xk2.y;
         const float dr = xk.x - xk2.x, di = xk.y + xk2.y;
-        float2 w = stw[k];
+        float2 w = TWS ? stw[k] : __ldg(&tw[k]);
         w.y = -w.y;  // w^{-k}
         const float tr = -(dr * w.y + di * w.x), ti = dr * w.x - di * w.y;
         b[k] = make_float2(er + tr, ei + ti);
@@ -471,10 +476,10 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
       }
     }
     group_sync(g + 1);
-    const float2* z = fft_smem<true, true>(b, a, B, stw, t, g + 1);
+    const float2* z = TWS ? fft_smem<true, true>(b, a, B, stw, t, g + 1) : fft_smem<true, false>(b, a, B, tw, t, g + 1);
     // keep the second half: time index i = 2j, 2j+1 with j >= B/2
 #pragma unroll
-    for (int q = 0; q < kInvMaxRes; ++q)
+    for (int q = 0; q < MAXRES; ++q)
     {
       const int jj = t + q * kThreads;  // j - half
       if (jj < half)
@@ -497,7 +502,7 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
     if (g > 0)
     {
 #pragma unroll
-      for (int q = 0; q < kInvMaxRes; ++q)
+      for (int q = 0; q < MAXRES; ++q)
       {
         const int jj = t + q * kThreads;
         if (jj < half) a[jj] = res[q];
@@ -509,7 +514,7 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
       {
         const float2* other = smem + size_t(gg) * 2 * B;
 #pragma unroll
-        for (int q = 0; q < kInvMaxRes; ++q)
+        for (int q = 0; q < MAXRES; ++q)
         {
           const int jj = t + q * kThreads;
           if (jj < half) { const float2 v = other[jj]; res[q].x += v.x; res[q].y += v.y; }
@@ -527,7 +532,7 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
     float m = 0.0f;
     float2* out = reinterpret_cast<float2*>(job.out + ga.out_offset);
 #pragma unroll
-    for (int q = 0; q < kInvMaxRes; ++q)
+    for (int q = 0; q < MAXRES; ++q)
     {
       const int jj = t + q * kThreads;
       if (jj < half)
@@ -591,7 +596,19 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
                const float* __restrict__ fade_out, const float* __restrict__ fade_in,
                const GatherArgs ga, const int* __restrict__ kind_counts, const HeadCommit hc)
 {
+  if (hc.early_trigger) grid_launch_dependents();
   inv_fft_body<GROUPS, false>(jobs, entries, partials, reduced, B, tw, fade_out, fade_in, ga, kind_counts, hc, 0);
+}
+
+// 4096 < B <= 8192 (a tail level of the non-uniformly partitioned renderer): one entry group, no staged twiddles
+__global__ void __launch_bounds__(kThreads, 1)
+inv_fft_large_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entries,
+                     const float2* __restrict__ partials, const float2* __restrict__ reduced, int B,
+                     const float2* __restrict__ tw,
+                     const float* __restrict__ fade_out, const float* __restrict__ fade_in,
+                     const GatherArgs ga, const int* __restrict__ kind_counts, const HeadCommit hc)
+{
+  inv_fft_body<1, false, kInvMaxResLarge, false>(jobs, entries, partials, reduced, B, tw, fade_out, fade_in, ga, kind_counts, hc, 0);
 }
 
 // Binaural / BRS behind mac_dyn_tma_kernel: grid = outputs x cluster size (launch attribute), three

@@ -417,6 +417,17 @@ fwd_fft_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict_
   fwd_fft_body<true>(job, B, tw);
 }
 
+// B > 4096: the two transform buffers take 128 KiB of shared memory; the twiddles stay in global memory
+__global__ void __launch_bounds__(kThreads)
+fwd_fft_large_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru,
+                     const float* __restrict__ in_base)
+{
+  FwdJob job = jobs[blockIdx.x];
+  if (in_base) job.second.ptr = in_base + size_t(blockIdx.x) * B;
+  if (ru.ctl && threadIdx.x < 2) fwd_ring_update(ru, blockIdx.x, threadIdx.x);
+  fwd_fft_body<false>(job, B, tw);
+}
+
 // The block loop's forward launch when the MAC behind it overlaps it (Engine::fwd_overlap):
 // part of the programmatic-dependent-launch chain inverse(t-1) -> forward(t) -> MAC(t).
 // It waits for the previous block's inverse kernel (which commits the ring heads and is

@@ -949,7 +949,7 @@ void Renderer::launch(const StepDesc& d)
     }
   }
   e->stage_mark(2);
-  const HeadCommit hc{overlap ? fwd->device() : nullptr, overlap ? d.N : 0};
+  const HeadCommit hc{overlap ? fwd->device() : nullptr, overlap ? d.N : 0, (e->inv_trigger && e->pdl) ? 1 : 0};
   if (cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS)
     e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G, hc, ctl_by_kernel && e->pdl);
   else if (gather) e->launch_inv(inv, gather->next_block(), hc);

@@ -131,11 +131,12 @@ def test_block_size_errors(capi):
     assert "multiple of 8" in ei.value.msg
     capi.Engine(24).close()   # every multiple of 8 is a block size, like the reference's
     with pytest.raises(capi.SsrError) as ei:
-        capi.Engine(8192)     # the engine's own upper limit
+        capi.Engine(16384)    # the engine's own upper limit is 8192
     assert ei.value.code == capi.SSR_ERR_UNSUPPORTED
 
 
 @pytest.mark.parametrize("B,L", [(8, 16), (16, 50), (64, 200), (256, 1000), (1024, 8192), (2048, 5000), (4096, 9000),
+                                 (8192, 20000),   # above 4096: the kernels without staged twiddles
                                  # multiples of 8 that are not powers of two (convolver.h:163-166 accepts them):
                                  # odd factors 3, 5, 7, 11, 5^3, 3 * 43 and 3 * 5^3 go through the generic-radix stage
                                  (24, 100), (40, 90), (56, 300), (88, 200), (120, 500), (1000, 3000), (1032, 2500),

@@ -40,6 +40,7 @@ def _ir(rng, taps, M, scale):
     (128, [(1, 8), (4, 3)], 1300, 3, 2),            # IR ends inside the first tail partition
     (128, [(1, 8), (4, 3)], 1000, 3, 2),            # IR ends before the tail level (silent tail)
     (1024, [(1, 8), (4, 2)], 14000, 4, 2),          # the bulk-copy MAC at both levels (B = 1024 / 4096)
+    (1024, [(1, 4), (2, 2), (4, 2), (8, 2)], 30000, 8, 2),   # four levels up to 8192-sample partitions
 ])
 def test_nonuniform_equals_direct_convolution(capi, B, levels, taps, M, N):
     rng = np.random.default_rng(B + taps)
