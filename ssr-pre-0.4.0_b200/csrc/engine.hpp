@@ -614,7 +614,7 @@ struct Renderer
   struct Source
   {
     int id;
-    std::unique_ptr<Input> input;
+    std::shared_ptr<Input> input;   // (shared by the sub-renderers of a tail level of the non-uniform renderer)
     float gain = 1.0f; bool mute = false; float px = 0, py = 0; bool plane = false;
     BlockParameter<float> weighting_factor{0.0f};
     // generic
@@ -640,6 +640,8 @@ struct Renderer
 
   Engine* e;
   ssr_renderer_config cfg;
+  bool skip_forward = false;   // the delay lines (Source::input) belong to another renderer of the same engine, which
+                               //  has already transformed this block (non-uniform renderer: sub-renderers 1.. of a level)
   bool tail_level = false;     // a tail level of the non-uniformly partitioned renderer (nonuniform.cu): new
                                //  sources start at their weight instead of fading in from 0
   int M_total, m_first, m_local;

@@ -78,6 +78,7 @@ struct NuRenderer
   int n_sources = 0;
   uint64_t block = 0;          // blocks rendered so far
   uint64_t mix_launches = 0;
+  bool share_inputs = std::getenv("SSR_B200_NU_SHARE_INPUTS") == nullptr || std::atoi(std::getenv("SSR_B200_NU_SHARE_INPUTS")) != 0;
   DeviceArray<float> d_in, d_out;
   PinnedArray<float> h_in, h_out;
   std::vector<int> ids;        // source ids (the same in every sub-renderer)
@@ -200,6 +201,15 @@ struct NuRenderer
         const int id = R.add_source(std::move(fs), channels);
         if (sid < 0) sid = id;
         else if (id != sid) throw Error(SSR_ERR_STATE, "ssr_b200: nonuniform: source ids of the levels diverged");
+        // ONE delay line per (level, source): sub-renderer 0 transforms the level's input segment in its phase,
+        // the others (later phases of the same period) multiply against the same spectra
+        if (share_inputs && &R != L.subs[0].get())
+        {
+          if (R.sources.back()->input->P != L.subs[0]->sources.back()->input->P)
+            throw Error(SSR_ERR_STATE, "ssr_b200: nonuniform: partition counts of a level's sub-renderers differ");
+          R.sources.back()->input = L.subs[0]->sources.back()->input;
+          R.skip_forward = true;
+        }
       }
     }
     ids.push_back(sid);

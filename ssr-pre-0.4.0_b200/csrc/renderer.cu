@@ -908,7 +908,7 @@ void Renderer::launch(const StepDesc& d)
   // Generic plans on the bulk-copy MAC: the forward transform runs UNDER the MAC (only the
   // p == 0 terms need its result); the ring heads are then committed by the inverse kernel
   // (Binaural / BRS: the generated-terms MAC does the same)
-  const bool overlap = e->fwd_overlap && d.N > 0
+  const bool overlap = e->fwd_overlap && d.N > 0 && !skip_forward
       && (dynamic || (cfg.kind == SSR_RENDERER_GENERIC && e->mac_tma() && static_mac.MT == kGenericMT));
   if (d.ctl_n16 > 0)
   {
@@ -920,7 +920,7 @@ void Renderer::launch(const StepDesc& d)
     const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
     e->launch_fwd(fwd->device(), d.N, &ru, overlap, d.in_base);
   }
-  else e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base);
+  else if (!skip_forward) e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base);
   e->stage_mark(1);
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
