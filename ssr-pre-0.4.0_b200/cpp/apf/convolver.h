@@ -17,8 +17,8 @@
 //    use (src/binauralrenderer.h:372-377) -- runs as a kernel; any other binary
 //    host callable works too, through a host round trip of the spectra (it is
 //    host code; a load-time operation in the reference as well).
-//  * block sizes must be powers of two in [8, 8192]; other multiples of 8 throw
-//    std::logic_error with a different message.
+//  * block sizes: every multiple of 8 up to 8192 (the reference has no upper
+//    bound); larger ones throw std::logic_error with the engine's message.
 //  * One engine per (device, block size) is created lazily; the device ordinal
 //    comes from the environment variable SSR_B200_DEVICE (default 0).
 #ifndef SSR_B200_APF_CONVOLVER_H
