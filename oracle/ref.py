@@ -82,6 +82,8 @@ def lib():
         "ref_fade_table": (None, [i, _f32p, _f32p]),
         "ref_static_convolver_run": (d, [i, _f32p, l, _f32p, l, _f32p, i]),
         "ref_renderer_new": (vp, [s, i, i, i, s, l]),
+        "ref_renderer_new_wfs": (vp, [i, i, i, s, l, l]),
+        "ref_renderer_add_loudspeaker": (i, [vp, f, f, f, i]),
         "ref_renderer_delete": (None, [vp]),
         "ref_renderer_load_reproduction_setup": (i, [vp]),
         "ref_renderer_add_outputs": (i, [vp, i]),
@@ -263,21 +265,30 @@ def static_convolver_run(block: int, taps, x, repeat: int = 1, want_output: bool
 
 
 class Renderer:
-    """kind in {"generic", "binaural", "brs"} -- the reference's renderer classes
+    """kind in {"generic", "binaural", "brs", "wfs"} -- the reference's renderer classes
     under apf::pointer_policy<float*> + apf::posix_thread_policy."""
 
     def __init__(self, kind: str, block: int, sample_rate: int, threads: int = 1,
-                 hrir_file: str = "", hrir_size: int = 0):
+                 hrir_file: str = "", hrir_size: int = 0, prefilter_file: str = "",
+                 delayline_size: int = 0, initial_delay: int = 0):
         self.kind = kind
         self.block = block
-        self.h = _nonnull(lib().ref_renderer_new(kind.encode(), block, sample_rate, threads,
-                                                 hrir_file.encode(), hrir_size))
+        if kind == "wfs":  # src/wfsrenderer.h:60-88: pre-filter file, delay line size / initial delay in samples
+            self.h = _nonnull(lib().ref_renderer_new_wfs(block, sample_rate, threads, prefilter_file.encode(),
+                                                         delayline_size, initial_delay))
+        else:
+            self.h = _nonnull(lib().ref_renderer_new(kind.encode(), block, sample_rate, threads,
+                                                     hrir_file.encode(), hrir_size))
 
     def load_reproduction_setup(self):
         _check(lib().ref_renderer_load_reproduction_setup(self.h))
 
     def add_outputs(self, m: int):
         _check(lib().ref_renderer_add_outputs(self.h, m))
+
+    def add_loudspeaker(self, x: float, y: float, azimuth: float, subwoofer: bool = False):
+        """An Output of a loudspeaker-based renderer (src/loudspeakerrenderer.h:49-58) without the XML loader."""
+        _check(lib().ref_renderer_add_loudspeaker(self.h, float(x), float(y), float(azimuth), int(subwoofer)))
 
     def add_source(self, properties_file: str = "") -> int:
         sid = lib().ref_renderer_add_source(self.h, properties_file.encode())

@@ -2,7 +2,7 @@
  *
  * TEST INFRASTRUCTURE ONLY.  This file compiles the reference's own
  * apf/apf/convolver.h, apf/apf/combine_channels.h and
- * src/{generic,binaural,brs}renderer.h from where they lie under
+ * src/{generic,binaural,brs,wfs}renderer.h from where they lie under
  * /root/reference (see oracle/Makefile) into oracle/_ref/libssr_ref.so.
  * Nothing under the product package links or loads it; only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
@@ -26,6 +26,8 @@
 #include "genericrenderer.h"
 #include "binauralrenderer.h"
 #include "brsrenderer.h"
+#include "ssr_global.h"    // ssr::c_inverse, which wfsrenderer.h uses without including it (the application gets it through src/controller.h:45)
+#include "wfsrenderer.h"   // its pre-filter apf::conv::StaticConvolver per input (src/wfsrenderer.h:104-123)
 
 #include <chrono>
 #include <cstdio>
@@ -63,6 +65,7 @@ struct IRenderer
   virtual ~IRenderer() {}
   virtual void load_reproduction_setup() = 0;
   virtual void add_output() = 0;
+  virtual void add_loudspeaker(float x, float y, float azimuth, int subwoofer) = 0;
   virtual int add_source(const std::string& file) = 0;
   virtual void rem_source(int id) = 0;
   virtual void activate() = 0;
@@ -77,6 +80,25 @@ struct IRenderer
 template<typename R> struct add_output_helper
 {
   static void add(R& r) { r.add(typename R::Output::Params()); }
+};
+
+// Loudspeaker-based renderers (src/loudspeakerrenderer.h:49-58): an output is a Loudspeaker with
+// position, orientation and model; the XML loader is replaced by explicit calls.
+template<typename R> struct loudspeaker_helper
+{
+  static void add(R&, float, float, float, int)
+  { throw std::logic_error("ref_harness: this renderer has no loudspeakers"); }
+};
+template<> struct loudspeaker_helper<ssr::WfsRenderer>
+{
+  static void add(ssr::WfsRenderer& r, float x, float y, float azimuth, int subwoofer)
+  {
+    ssr::WfsRenderer::Output::Params p;
+    p.position = Position(x, y);
+    p.orientation = Orientation(azimuth);
+    p.model = subwoofer ? Loudspeaker::subwoofer : Loudspeaker::normal;
+    r.add(p);
+  }
 };
 
 // GenericRenderer::load_reproduction_setup() is LoudspeakerRenderer's XML loader
@@ -95,6 +117,15 @@ template<> struct setup_helper<ssr::GenericRenderer>
   }
 };
 
+template<> struct setup_helper<ssr::WfsRenderer>
+{
+  static void load(ssr::WfsRenderer&)
+  {
+    throw std::logic_error("ref_harness: WfsRenderer reproduction setup "
+        "needs libxml2; use ref_renderer_add_loudspeaker()");
+  }
+};
+
 template<typename R>
 struct RendererWrap : IRenderer
 {
@@ -102,6 +133,8 @@ struct RendererWrap : IRenderer
 
   void load_reproduction_setup() override { setup_helper<R>::load(r); }
   void add_output() override { add_output_helper<R>::add(r); }
+  void add_loudspeaker(float x, float y, float azimuth, int subwoofer) override
+  { loudspeaker_helper<R>::add(r, x, y, azimuth, subwoofer); }
 
   int add_source(const std::string& file) override
   {
@@ -397,6 +430,32 @@ void* ref_renderer_new(const char* kind, int block, int sample_rate
   });
   if (rc) { delete h; return nullptr; }
   return h;
+}
+
+/* WfsRenderer (src/wfsrenderer.h:60-88): pre-filter from `prefilter_file` (one channel), the
+ * delay line's size and initial delay in samples (src/configuration.h:62-66). */
+void* ref_renderer_new_wfs(int block, int sample_rate, int threads, const char* prefilter_file
+    , long delayline_size, long initial_delay)
+{
+  auto* h = new RendererHandle;
+  int rc = guarded([&] {
+    apf::parameter_map p;
+    p.set("block_size", block);
+    p.set("sample_rate", sample_rate);
+    p.set("threads", threads);
+    p.set("prefilter_file", std::string(prefilter_file));
+    p.set("delayline_size", delayline_size);
+    p.set("initial_delay", initial_delay);
+    h->impl.reset(new RendererWrap<ssr::WfsRenderer>(p));
+  });
+  if (rc) { delete h; return nullptr; }
+  return h;
+}
+
+int ref_renderer_add_loudspeaker(void* r, float x, float y, float azimuth, int subwoofer)
+{
+  return guarded([&] {
+      static_cast<RendererHandle*>(r)->impl->add_loudspeaker(x, y, azimuth, subwoofer); });
 }
 
 void ref_renderer_delete(void* r) { delete static_cast<RendererHandle*>(r); }

@@ -242,6 +242,50 @@ def golden_binaural_multipartition():
                         az=ref_az, y=y, channel=channel)
 
 
+def golden_wfs():
+    """WfsRenderer (src/wfsrenderer.h): the fourth in-tree caller of apf::conv -- one pre-filter
+    StaticConvolver per input (src/wfsrenderer.h:104-123), whose output feeds the delay line the
+    loudspeaker weights / delays read from.  Linear array of 8 loudspeakers + a subwoofer (added
+    with explicit positions instead of the XML setup), a point source that moves and a plane
+    wave that turns, a 3-partition pre-filter."""
+    rng = np.random.default_rng(1313)
+    B, L, T = 64, 150, 40
+    pre = (rng.uniform(-1, 1, L) * np.exp(-np.arange(L) / 30.0) * 0.3).astype(np.float32)
+    ref.register_sndfile("wfs_prefilter", pre[:, None], 48000)
+    r = ref.Renderer("wfs", B, 48000, threads=threads(2), prefilter_file="wfs_prefilter",
+                     delayline_size=4096, initial_delay=512)
+    speakers = [(-1.75 + 0.5 * k, 2.0, -90.0, 0) for k in range(8)] + [(0.0, 2.5, -90.0, 1)]
+    for (px, py, az, sub) in speakers:
+        r.add_loudspeaker(px, py, az, bool(sub))
+    ids = [r.add_source(), r.add_source()]
+    r.activate()
+    r.set_source(ids[0], "position", 0.3, 4.0)
+    r.set_source(ids[1], "position", 0.0, 0.0)
+    r.set_source(ids[1], "model", 1.0)          # plane wave
+    r.set_source(ids[1], "orientation", -80.0)   # travelling towards -y: it drives the array
+    x = (rng.uniform(-1, 1, (T, 2, B)) * 0.5).astype(np.float32)
+    # control script: (block, what, source index, a, b)
+    script = [(6, "position", 0, -0.6, 3.0), (11, "gain", 1, 0.5, 0.0), (15, "orientation", 1, -100.0, 0.0),
+              (19, "mute", 0, 1.0, 0.0), (23, "mute", 0, 0.0, 0.0), (27, "position", 0, 0.2, 1.0),
+              (31, "master_volume", -1, 0.8, 0.0), (35, "reference_position", -1, 0.1, -0.2)]
+    y = np.zeros((T, len(speakers), B), np.float32)
+    for t in range(T):
+        for (tb, what, n, a, b) in script:
+            if tb == t:
+                if n >= 0:
+                    r.set_source(ids[n], what, a, b)
+                else:
+                    r.set_state(what, a, b)
+        y[t] = r.process(x[t])
+    np.savez_compressed(os.path.join(OUT, "wfs.npz"), B=B, prefilter=pre, x=x, y=y,
+                        speakers=np.array(speakers, np.float32),
+                        script_block=np.array([c[0] for c in script]),
+                        script_what=np.array([c[1] for c in script]),
+                        script_source=np.array([c[2] for c in script]),
+                        script_a=np.array([c[3] for c in script], np.float32),
+                        script_b=np.array([c[4] for c in script], np.float32))
+
+
 def golden_hrirs_fabian():
     """Real-data fixture: the reference's shipped HRIR set
     (data/impulse_responses/hrirs/hrirs_fabian.wav, 720 ch x 512 frames, 44.1 kHz,
@@ -261,7 +305,7 @@ def golden_hrirs_fabian():
 SCENARIOS = {
     "level1": golden_level1, "generic": golden_generic, "brs": golden_brs, "binaural": golden_binaural,
     "brs_dynamic": golden_brs_dynamic, "binaural_multipartition": golden_binaural_multipartition,
-    "hrirs_fabian": golden_hrirs_fabian,
+    "wfs": golden_wfs, "hrirs_fabian": golden_hrirs_fabian,
 }
 
 if __name__ == "__main__":

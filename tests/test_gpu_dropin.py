@@ -3,8 +3,9 @@ BrsRenderer and GenericRenderer call it as a drop-in").
 
 oracle/Makefile compiles, from the unmodified sources under /root/reference,
   * apf/unit_tests/test_convolver.cpp (the reference's Catch test of the path), and
-  * src/{generic,binaural,brs}renderer.h + apf::MimoProcessor behind the same C harness
-    that produced the golden fixtures,
+  * src/{generic,binaural,brs,wfs}renderer.h + apf::MimoProcessor behind the same C harness
+    that produced the golden fixtures (wfs: the fourth in-tree caller of apf::conv, one pre-filter
+    StaticConvolver per input, src/wfsrenderer.h:104-123),
 against ssr-pre-0.4.0_b200/cpp/apf/convolver.h -- the GPU engine's facade of the
 apf::conv class API -- placed ahead of the reference's apf/ on the include path, and
 links them to libssr_b200.so.  Every apf::conv::Input / Output / Filter those programs
@@ -48,6 +49,7 @@ def test_reference_unit_test_of_the_convolver_passes_on_the_gpu_engine():
     ("binaural", ["y"]),
     ("brs_dynamic", ["y"]),
     ("binaural_multipartition", ["y"]),
+    ("wfs", ["y"]),
 ])
 def test_reference_renderers_on_the_gpu_engine_reproduce_the_golden_fixtures(tmp_path, scenario, keys):
     """The scenario script of tests/golden/make_golden.py, run on the build of the

@@ -451,3 +451,51 @@ def test_reference_zero_skip_defect_is_reproduced_and_switchable():
     truth = co.direct_convolution_f64(x, h)
     assert np.abs(run(False) - truth).max() <= TOL
     assert np.abs(run(True) - truth).max() > 1e-2
+
+
+@needs_ref
+def test_live_wfs_prefilter_stage_is_the_oracles_static_convolver():
+    """The fourth in-tree caller of apf::conv: WfsRenderer runs one pre-filter StaticConvolver per
+    input and writes its result into the delay line the loudspeakers read from
+    (src/wfsrenderer.h:104-123).  For a plane wave with constant parameters every loudspeaker signal
+    is therefore  w * u[n - d]  with u = the pre-filtered input, an integer delay d and a weight w
+    (src/wfsrenderer.h:463-520): u from the numpy oracle's StaticConvolver reproduces the reference's
+    WFS output for every loudspeaker."""
+    rng = np.random.default_rng(77)
+    B, L, T = 64, 150, 40
+    pre = (rng.uniform(-1, 1, L) * np.exp(-np.arange(L) / 30.0) * 0.3).astype(np.float32)
+    ref.register_sndfile("wfs_pre_live", pre[:, None], 48000)
+    r = ref.Renderer("wfs", B, 48000, threads=1, prefilter_file="wfs_pre_live", delayline_size=4096, initial_delay=512)
+    for k in range(4):
+        r.add_loudspeaker(-0.75 + 0.5 * k, 2.0, -90.0)
+    r.add_loudspeaker(0.0, 2.5, -90.0, subwoofer=True)
+    sid = r.add_source()
+    r.activate()
+    r.set_source(sid, "model", 1.0)            # plane wave
+    r.set_source(sid, "position", 0.0, 0.0)
+    r.set_source(sid, "orientation", -75.0)
+    x = (rng.uniform(-1, 1, (T, 1, B)) * 0.5).astype(np.float32)
+    y = np.stack([r.process(x[t]) for t in range(T)])          # (T, 5, B)
+    conv = co.StaticConvolver(B, taps=pre)
+    u = []
+    for t in range(T):
+        conv.add_block(x[t, 0])
+        u.append(np.array(conv.convolve(), np.float32))
+    u = np.concatenate(u).astype(np.float64)
+    # steady state: skip the initial fade-in (rendererbase.h:379) and the delay line's fill
+    first = 12 * B
+    matched = 0
+    for m in range(y.shape[1]):
+        ym = y[:, m, :].reshape(-1).astype(np.float64)
+        if np.abs(ym[first:]).max() < 1e-6:
+            continue          # a loudspeaker this plane wave does not drive
+        best = None
+        for d in range(0, first):
+            seg_u = u[first - d:len(u) - d]
+            w = float(seg_u @ ym[first:]) / float(seg_u @ seg_u)
+            err = float(np.abs(ym[first:] - w * seg_u).max())
+            if best is None or err < best[0]:
+                best = (err, d, w)
+        assert best[0] <= 2e-6, (m, best)
+        matched += 1
+    assert matched >= 3
