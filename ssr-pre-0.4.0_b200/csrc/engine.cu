@@ -288,6 +288,9 @@ Engine::Engine(const ssr_engine_config& cfg)
     SSR_CUDA(cudaMemset(mac_trace.ptr, 0, mac_trace.count * sizeof(unsigned long long)));
   }
   fwd_overlap = fwd_overlap && pdl;
+  if (const char* v = std::getenv("SSR_B200_BLOCK_OVERLAP")) block_overlap = std::atoi(v) != 0;   // A/B (profiles/r2c_ab)
+  // the inverse kernel may only commit the ring heads first if the MAC in front of it is complete when it starts
+  block_overlap = block_overlap && fwd_overlap && !early_trigger;
   if (const char* v = std::getenv("SSR_B200_LEVEL1")) level1_fused = std::string(v) != "unfused";  // A/B experiments
   if (!is_pow2(B)) level1_fused = false;   // the fused Level-1 launch is instantiated for power-of-two spectra
   // 4096 < B <= 8192: the two transform buffers take 128 KiB; kernels that also stage the twiddle table or
@@ -381,7 +384,7 @@ int Engine::mac_slots(int MT) const
 }
 
 void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ring_update, bool overlap,
-                        const float* in_base)
+                        const float* in_base, bool late_wait)
 {
   if (njobs <= 0) return;
   FwdRingUpdate ru{nullptr, nullptr, nullptr, 0};
@@ -393,13 +396,13 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
     if (ring_update) { ru = *ring_update; ring_update = nullptr; }
     if (ru.ctl && dyn_tma())
       launch_kernel(fwd_fft_overlap_kernel<2>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
-          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base);
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base, 0);
     else if (ru.ctl)
       launch_kernel(fwd_fft_overlap_kernel<1>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
-          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base);
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base, 0);
     else
       launch_kernel(fwd_fft_overlap_kernel<0>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
-          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base);
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base, late_wait ? 1 : 0);
   }
   else if (fft1024 && !in_base && (njobs >= kFft1024MinJobs || fft1024_always))
   {
@@ -560,6 +563,7 @@ void Engine::launch_inv_kernel(int groups, int njobs, const InvPlan& plan, const
 {
   const size_t smem = size_t(2) * B * sizeof(float2) * (groups + 1);
   const float2* part = reinterpret_cast<const float2*>(partials.ptr);
+  if (hc.early_trigger == 2) njobs += 1;   // the CTA that commits the ring heads (ssrk::inv_prologue)
   if (large())
     launch_kernel(inv_fft_large_kernel, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
         plan.jobs.device(), plan.entries.device(), part, red, B, tw.ptr, fade_out.ptr, fade_in.ptr, ga, kind_counts, hc);

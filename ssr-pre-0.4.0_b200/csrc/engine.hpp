@@ -231,14 +231,23 @@ struct Engine
   // overlap: the launch takes part in the programmatic-dependent-launch chain of a block
   // loop and leaves the ring heads to be committed by the block's inverse kernel
   // (ssrk::HeadCommit), so that the MAC launched behind it may run concurrently
+  // late_wait: see fwd_fft_overlap_kernel (block overlap; only with `overlap`)
   void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs, const ssrk::FwdRingUpdate* ring_update = nullptr,
-                  bool overlap = false, const float* in_base = nullptr);
+                  bool overlap = false, const float* in_base = nullptr, bool late_wait = false);
   void launch_fwd_batch(const ssrk::FwdBatch& batch, int nparts, int nchannels);
   void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr,
                   bool fwd_overlap = false);
   void launch_inv(const InvPlan& plan, const ssrk::GatherArgs& ga = ssrk::GatherArgs{},
                   const ssrk::HeadCommit& hc = ssrk::HeadCommit{});
   bool fwd_overlap = true;         // forward transform under the MAC (SSR_B200_FWD_OVERLAP=0: off)
+  // Block overlap (SSR_B200_BLOCK_OVERLAP): in a loop of device-resident blocks the NEXT block's forward transform
+  // and the p != 0 terms of its MAC run under THIS block's inverse transform (and, on the root of a sharded
+  // renderer, under the gather's wait / release helpers).  The inverse kernel commits the ring heads before it
+  // lets its dependents in (HeadCommit::early_trigger == 2), the forward kernel passes the trigger on at once and
+  // waits at its end (late_wait); the MAC's p == 0 terms and its first partial-spectra store still wait for the
+  // forward kernel's completion, i.e. for the previous block's inverse transform.  Generic plans on the
+  // bulk-copy MAC; a synchronous host call (one block at a time) is unaffected.
+  bool block_overlap = true;
   int mac_waves = 0;               // SSR_B200_MAC_WAVES: CTAs of a MAC launch = waves x resident CTAs
   DeviceArray<unsigned long long> mac_trace;   // per-CTA timestamps / busy time of the bulk-copy MAC launches
   bool early_trigger = false;                  // SSR_B200_EARLY_TRIGGER=1: the bulk-copy MACs let their dependent kernel launch at once

@@ -61,7 +61,38 @@ struct HeadCommit
   int n;                // 0: nothing to commit
   int early_trigger;    // 1: the kernel lets its dependents (the next block's forward transform, which waits for
                         //  this kernel's completion itself) be scheduled at once (SSR_B200_INV_TRIGGER=1, experiment)
+                        // 2: BLOCK OVERLAP (Engine::block_overlap): an extra CTA commits the heads FIRST -- the MAC,
+                        //  their last reader, is complete when this kernel starts -- and only then has the whole
+                        //  grid let its dependents in; the next block's forward transform (late_wait) passes the trigger on at
+                        //  once, so the next block's MAC streams its p != 0 terms while this kernel still runs
 };
+
+// Start of every inverse kernel of the block loop (before anything that waits); true: this CTA is done.
+// early_trigger == 2: the launch carries ONE EXTRA CTA (the last one) that only commits the heads, so that the
+// dependent load -> store -> fence (1.5 - 2 us) is on no output block's path.
+__device__ __forceinline__ bool inv_prologue(const HeadCommit& hc, int nthreads)
+{
+  if (hc.early_trigger == 2)
+  {
+    if (blockIdx.x == gridDim.x - 1)
+    {
+      for (int i = threadIdx.x; i < hc.n; i += nthreads)
+      {
+        int* head = hc.jobs[i].head;
+        int h = *head + 1;
+        if (h >= hc.jobs[i].parts) h = 0;
+        *head = h;
+      }
+      __threadfence();     // the new heads are at device scope before this CTA's trigger
+      __syncthreads();
+      grid_launch_dependents();
+      return true;
+    }
+    grid_launch_dependents();
+  }
+  else if (hc.early_trigger) grid_launch_dependents();
+  return false;
+}
 
 constexpr unsigned long long kGatherTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
@@ -119,8 +150,8 @@ __global__ void gather_wait_kernel(GatherWaitArgs a)
 {
   // (programmatic dependent launch: the root's own inverse kernel -- whose blocks go to the
   // same slot -- must be complete when this kernel is)
+  grid_launch_dependents();   // the kernels behind (release, the next block's chain) wait for our completion themselves
   grid_dependency_wait();
-  grid_launch_dependents();
   const int g = threadIdx.x;
   if (g < a.world && a.ctas[g] > 0)
     gather_wait_ge(a.arrived + size_t(g) * kGatherCounterStride,
@@ -130,6 +161,7 @@ __global__ void gather_wait_kernel(GatherWaitArgs a)
 // root: block `epoch` has been read out of its slot -> peers may overwrite it
 __global__ void gather_release_kernel(unsigned long long* consumed, unsigned long long value)
 {
+  grid_launch_dependents();
   grid_dependency_wait();   // everything queued before (the readers of the slot) is complete
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(consumed), "l"(value) : "memory");
 }
@@ -389,7 +421,7 @@ inv_fft_body(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ entri
     SSR_INV_STAMP(4)
     if (crank != 0) return;
   }
-  if (hc.n && blockIdx.x == 0)
+  if (hc.n && hc.early_trigger != 2 && blockIdx.x == 0)
     for (int i = threadIdx.x; i < hc.n; i += kThreads * GROUPS)
     {
       int* head = hc.jobs[i].head;
@@ -596,7 +628,7 @@ inv_fft_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict__ ent
                const float* __restrict__ fade_out, const float* __restrict__ fade_in,
                const GatherArgs ga, const int* __restrict__ kind_counts, const HeadCommit hc)
 {
-  if (hc.early_trigger) grid_launch_dependents();
+  if (inv_prologue(hc, kThreads * GROUPS)) return;
   inv_fft_body<GROUPS, false>(jobs, entries, partials, reduced, B, tw, fade_out, fade_in, ga, kind_counts, hc, 0);
 }
 
@@ -608,6 +640,7 @@ inv_fft_large_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restrict
                      const float* __restrict__ fade_out, const float* __restrict__ fade_in,
                      const GatherArgs ga, const int* __restrict__ kind_counts, const HeadCommit hc)
 {
+  if (inv_prologue(hc, kThreads)) return;
   inv_fft_body<1, false, kInvMaxResLarge, false>(jobs, entries, partials, reduced, B, tw, fade_out, fade_in, ga, kind_counts, hc, 0);
 }
 

@@ -326,7 +326,8 @@ __device__ __forceinline__ void fwd_fft_body(const FwdJob& job, int B, const flo
   int new_head = 0;
   if (!job.dst)
   {
-    new_head = *job.head + 1;
+    // (volatile: with Engine::block_overlap the head was committed by a kernel that may still be running)
+    new_head = *reinterpret_cast<volatile int*>(job.head) + 1;
     if (new_head >= job.parts) new_head = 0;
   }
 
@@ -437,17 +438,23 @@ fwd_fft_large_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __res
 // spectrum while we compute it.  The ring heads stay untouched (DEFER_HEAD).
 // (VARIANT only separates the function attributes: 0 runs next to the bulk-copy MAC under the
 // maximal shared-memory carve-out, 1 next to the generated-terms MAC under the default one)
+// late_wait (Engine::block_overlap): the previous block's inverse kernel has committed the heads BEFORE it let
+// us in (HeadCommit::early_trigger == 2) and nothing we touch -- the input block, `prev`, the ring slot
+// head + 1 -- is read by it, so the trigger is passed on at once and the MAC of this block starts while that
+// inverse kernel still runs.  We wait for it at our END instead: our completion (which the MAC waits for in
+// front of its p == 0 terms and of its first partial-spectra store) still implies the previous block's.
 template<int VARIANT>
 __global__ void __launch_bounds__(kThreads)
 fwd_fft_overlap_kernel(const FwdJob* __restrict__ jobs, int B, const float2* __restrict__ tw, const FwdRingUpdate ru,
-                       const float* __restrict__ in_base)
+                       const float* __restrict__ in_base, int late_wait)
 {
-  grid_dependency_wait();
+  if (!late_wait) grid_dependency_wait();
   grid_launch_dependents();
   FwdJob job = jobs[blockIdx.x];
   if (in_base) job.second.ptr = in_base + size_t(blockIdx.x) * B;
   if (ru.ctl && threadIdx.x < 2) fwd_ring_update(ru, blockIdx.x, threadIdx.x);
   fwd_fft_body<false, true>(job, B, tw);
+  if (late_wait) grid_dependency_wait();
 }
 
 // Filter-set loading: one launch transforms `channels x nvalid` partitions described

@@ -670,7 +670,7 @@ mac_tma_kernel(const MacParams p)
         {
           w[rr] = p.wtab[r.m[rr].wslot + p.wtab_offset];
           parts[rr] = p.xparts[r.m[rr].input];
-          head[rr] = p.heads[r.m[rr].input];
+          head[rr] = *reinterpret_cast<const volatile int*>(p.heads + r.m[rr].input);   // (see fwd_fft_body)
           xr[rr] = p.xring[r.m[rr].input];
         }
       }

@@ -910,6 +910,9 @@ void Renderer::launch(const StepDesc& d)
   // (Binaural / BRS: the generated-terms MAC does the same)
   const bool overlap = e->fwd_overlap && d.N > 0 && !skip_forward
       && (dynamic || (cfg.kind == SSR_RENDERER_GENERIC && e->mac_tma() && static_mac.MT == kGenericMT));
+  // block overlap (Engine::block_overlap): this block's forward transform and the p != 0 terms of its MAC may
+  // run under the PREVIOUS block's inverse transform; the inverse kernel then commits the heads first
+  const bool block_overlap = overlap && !dynamic && e->block_overlap && e->pdl;
   if (d.ctl_n16 > 0)
   {
     e->launch_ctl_upload(d.ctl_src, d.ctl_dst, d.ctl_n16, dyn_upload_count.ptr + d.ctl_slot, dyn_ack.ptr + d.ctl_slot);
@@ -920,7 +923,7 @@ void Renderer::launch(const StepDesc& d)
     const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
     e->launch_fwd(fwd->device(), d.N, &ru, overlap, d.in_base);
   }
-  else if (!skip_forward) e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base);
+  else if (!skip_forward) e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base, block_overlap);
   e->stage_mark(1);
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
@@ -949,7 +952,8 @@ void Renderer::launch(const StepDesc& d)
     }
   }
   e->stage_mark(2);
-  const HeadCommit hc{overlap ? fwd->device() : nullptr, overlap ? d.N : 0, (e->inv_trigger && e->pdl) ? 1 : 0};
+  const HeadCommit hc{overlap ? fwd->device() : nullptr, overlap ? d.N : 0,
+                      block_overlap ? 2 : ((e->inv_trigger && e->pdl) ? 1 : 0)};
   if (cfg.kind == SSR_RENDERER_BINAURAL || cfg.kind == SSR_RENDERER_BRS)
     e->launch_inv_dyn(inv, dyn_tables.ctl, dyn_Pmax, dyn_G, hc, ctl_by_kernel && e->pdl);
   else if (gather) e->launch_inv(inv, gather->next_block(), hc);

@@ -673,3 +673,55 @@ def test_offline_time_batched_blocks_equal_block_by_block(capi, co, engine_facto
     worst_truth = max(float(np.abs(g - w).max()) for g, w in zip(got, truth))
     assert worst <= 2e-6, worst
     assert worst_truth <= TOL, worst_truth
+
+
+@pytest.mark.parametrize("B,M", [(1024, 8), (1024, 64), (2048, 6)])
+def test_device_resident_blocks_queued_back_to_back_equal_synchronous_blocks(capi, co, engine_factory, B, M):
+    """Block overlap (Engine::block_overlap): in a loop of ssr_renderer_process_device calls with nothing in
+    between, block t + 1's forward transform and the p != 0 terms of its MAC run under block t's inverse
+    transform (the inverse kernel commits the ring heads before it lets its dependents in, the forward kernel
+    waits at its end).  50 blocks queued without a synchronisation -- every block into its own output array, gain
+    changes and a mute on the way (several MAC launches per block) -- are bit-identical to the same blocks
+    rendered one synchronous host call at a time, and equal the oracle."""
+    import torch
+    L, N, T = 5 * B + 77, 6, 50
+    rng = np.random.default_rng(B + M)
+    irs = [decaying(rng, L, M, 0.5 / np.sqrt(N * L / 6.9)) for _ in range(N)]
+    r1 = capi.Renderer(engine_factory(B), capi.GENERIC, outputs=M)
+    e2 = engine_factory(B)
+    r2 = capi.Renderer(e2, capi.GENERIC, outputs=M)
+    o = co.GenericRendererOracle(B, M)
+    for ir in irs:
+        r1.add_source(ir); r2.add_source(ir); o.add_source(ir)
+    x = rng.uniform(-1, 1, (T, N, B)).astype(np.float32)
+
+    def script(t, r):
+        if t == 9:
+            r.set_gain(2, 0.3)
+        if t == 17:
+            r.set_mute(1, True)
+        if t == 18:
+            r.set_gain(3, 0.7)
+        if t == 30:
+            r.set_mute(1, False)
+
+    class OracleControls:
+        def set_gain(self, sid, g): o.sources[sid - 1].gain = g
+        def set_mute(self, sid, m): o.sources[sid - 1].mute = m
+
+    want, truth = [], []
+    for t in range(T):
+        script(t, r1); script(t, OracleControls())
+        want.append(r1.process(x[t]))
+        truth.append(o.process(x[t]))
+    x_dev = torch.from_numpy(x).cuda()
+    y_dev = torch.zeros((T, M, B), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for t in range(T):
+        script(t, r2)
+        r2.process_device(x_dev[t].data_ptr(), y_dev[t].data_ptr())
+    e2.synchronize()
+    got = y_dev.cpu().numpy()
+    want = np.stack(want)
+    assert np.array_equal(got, want), float(np.abs(got - want).max())
+    assert maxerr(got, np.stack(truth)) <= TOL
