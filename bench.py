@@ -969,6 +969,11 @@ def main_ours(args):
                                          f"inside the timed region, every {args.stage_timing_every}th step"),
                         "filter_load_s": load_s,
                         "forward_under_mac": os.environ.get("SSR_B200_FWD_OVERLAP", "1") != "0",
+                        # device-resident loop: the next block's forward transform and p != 0 MAC terms run under
+                        # this block's inverse transform (Engine::block_overlap)
+                        "block_overlap": (os.environ.get("SSR_B200_BLOCK_OVERLAP", "1") != "0"
+                                          and os.environ.get("SSR_B200_FWD_OVERLAP", "1") != "0"
+                                          and os.environ.get("SSR_B200_PDL", "1") != "0"),
                         "env": {k: v for k, v in os.environ.items() if k.startswith("SSR_B200_")}},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": w.sources * B * 4 * world,
