@@ -950,6 +950,9 @@ def main_ours(args):
         "bytes_per_launch": st["mac_bytes"] / max(1, st["mac_launches"]),
         "ms_per_launch": mac_ms / max(1, st["mac_launches"]),
         "mac_share_of_step": mac_ms / max(1e-9, st["ms_total"]),
+        # the same against the TIMED loop: the stage events of the line above serialise the kernels of the steps
+        # that carry them, the timed loop overlaps them (forward under the MAC, block overlap)
+        "mac_share_of_timed_step": (mac_ms / max(1, st["blocks"])) / max(1e-9, ms_per_step),
         "fft_ms_per_step": st["ms_fft"] / max(1, st["blocks"]),
         "ifft_ms_per_step": st["ms_ifft"] / max(1, st["blocks"]),
         "fft_gflops": (w.sources * 56320 / 1e9) / max(1e-12, st["ms_fft"] / max(1, st["blocks"]) * 1e-3),
