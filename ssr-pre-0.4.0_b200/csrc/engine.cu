@@ -384,7 +384,7 @@ int Engine::mac_slots(int MT) const
 }
 
 void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ring_update, bool overlap,
-                        const float* in_base, bool late_wait)
+                        const float* in_base, bool late_wait, bool dyn_variant)
 {
   if (njobs <= 0) return;
   FwdRingUpdate ru{nullptr, nullptr, nullptr, 0};
@@ -394,9 +394,9 @@ void Engine::launch_fwd(const FwdJob* d_jobs, int njobs, const FwdRingUpdate* ri
   if (overlap)
   {
     if (ring_update) { ru = *ring_update; ring_update = nullptr; }
-    if (ru.ctl && dyn_tma())
+    if ((ru.ctl || dyn_variant) && dyn_tma())
       launch_kernel(fwd_fft_overlap_kernel<2>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
-          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base, 0);
+          d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base, late_wait ? 1 : 0);
     else if (ru.ctl)
       launch_kernel(fwd_fft_overlap_kernel<1>, dim3(njobs), dim3(kThreads), size_t(2) * B * sizeof(float2), stream, pdl,
           d_jobs, B, static_cast<const float2*>(tw.ptr), ru, in_base, 0);
@@ -656,10 +656,12 @@ void Engine::launch_mac_dyn(const DynTables& dyn, int G, const float* weights, b
 
 // reduce the generated-terms partials per (ear, kind), then one inverse CTA per ear
 void Engine::launch_ctl_upload(const void* src_host, void* dst, int n16, unsigned long long* counter,
-                               unsigned long long* ack)
+                               unsigned long long* ack, const FwdRingUpdate* ring_update, int ring_rows)
 {
+  const FwdRingUpdate ru = ring_update ? *ring_update : FwdRingUpdate{nullptr, nullptr, nullptr, 0};
   launch_kernel(ctl_upload_kernel, dim3(1), dim3(kThreads), 0, stream, pdl, static_cast<const uint4*>(src_host),
-      static_cast<uint4*>(dst), n16, counter, static_cast<volatile unsigned long long*>(ack));
+      static_cast<uint4*>(dst), n16, counter, static_cast<volatile unsigned long long*>(ack), ru, ring_rows,
+      ring_update ? 1 : 0);
   count_launch();
 }
 
@@ -671,12 +673,13 @@ void Engine::launch_inv_dyn(const InvPlan& plan, const DynCtl* ctl, int Pmax, in
   if (dyn_tma())
   {
     // one cluster per ear sums the [G][kind][ear] partial spectra and transforms (no reduction launch)
-    launch_cluster_kernel(inv_dyn_cluster_kernel, dim3(njobs * dyn_cluster), dim3(kThreads * 3), dyn_cluster,
+    // (block overlap: one extra cluster commits the ring heads first, see the kernel)
+    launch_cluster_kernel(inv_dyn_cluster_kernel, dim3((njobs + (hc.early_trigger == 2 ? 1 : 0)) * dyn_cluster), dim3(kThreads * 3), dyn_cluster,
         size_t(2) * B * sizeof(float2) * 4, stream, pdl, plan.jobs.device(), plan.entries.device(),
         reinterpret_cast<const float2*>(partials.ptr), G, B, static_cast<const float2*>(tw.ptr),
         static_cast<const float*>(fade_out.ptr), static_cast<const float*>(fade_in.ptr), ctl->n, hc,
         (trace_mode == 1 && mac_trace.ptr) ? mac_trace.ptr + 8192 : static_cast<unsigned long long*>(nullptr),
-        early_trigger ? 1 : 0);
+        hc.early_trigger == 2 ? 2 : (early_trigger ? 1 : 0));
     count_launch();
     if (cur) cur->ifft_launches++;
     return;

@@ -232,8 +232,11 @@ struct Engine
   // loop and leaves the ring heads to be committed by the block's inverse kernel
   // (ssrk::HeadCommit), so that the MAC launched behind it may run concurrently
   // late_wait: see fwd_fft_overlap_kernel (block overlap; only with `overlap`)
+  // dyn_variant: the function variant that runs next to the generated-terms bulk-copy MAC, without a ring update
+  // (block overlap of the Binaural / BRS chain: the update moved into ctl_upload_kernel)
   void launch_fwd(const ssrk::FwdJob* d_jobs, int njobs, const ssrk::FwdRingUpdate* ring_update = nullptr,
-                  bool overlap = false, const float* in_base = nullptr, bool late_wait = false);
+                  bool overlap = false, const float* in_base = nullptr, bool late_wait = false,
+                  bool dyn_variant = false);
   void launch_fwd_batch(const ssrk::FwdBatch& batch, int nparts, int nchannels);
   void launch_mac(const MacPlan& plan, int wtab_offset, int partial_offset, const float* weights = nullptr,
                   bool fwd_overlap = false);
@@ -260,8 +263,9 @@ struct Engine
   void launch_mac_dyn(const ssrk::DynTables& dyn, int G, const float* weights, bool fwd_overlap = false);
   void launch_inv_dyn(const InvPlan& plan, const ssrk::DynCtl* ctl, int Pmax, int G,
                       const ssrk::HeadCommit& hc = ssrk::HeadCommit{}, bool early_trigger = false);
+  // ring_update != null: late-trigger mode (behind the forward transform, see ctl_upload_kernel)
   void launch_ctl_upload(const void* src_host, void* dst, int n16, unsigned long long* counter,
-                         unsigned long long* ack);
+                         unsigned long long* ack, const ssrk::FwdRingUpdate* ring_update = nullptr, int ring_rows = 0);
   void launch_dyn_ring_update(const ssrk::DynCtl* ctl, const ssrk::DynRingEntry* upd,
                               ssrk::DynRingEntry* ring, int rows, int R);
   int dyn_mac_slots() const;
@@ -702,6 +706,8 @@ struct Renderer
   cudaEvent_t dyn_copied[2] = {nullptr, nullptr};
   int dyn_slot = 0;
   bool ctl_by_kernel = true;
+  bool dyn_block_overlap = true;   // Binaural / BRS: block overlap with the chain forward -> control upload -> MAC
+                                   //  (SSR_B200_DYN_BLOCK_OVERLAP=0: the chain control upload -> forward -> MAC)
   DeviceArray<unsigned long long> dyn_upload_count;      // [2] uploads done per staging slot (device)
   PinnedArray<unsigned long long> dyn_ack;               // [2] the same, as the host sees it
   unsigned long long dyn_uploads_issued[2] = {0, 0};

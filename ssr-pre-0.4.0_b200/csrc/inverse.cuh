@@ -266,16 +266,33 @@ __device__ __forceinline__ void fwd_ring_update(const FwdRingUpdate& u, int sour
 // alternate by block parity (the previous block's kernels still read theirs).  `ack`: mapped host
 // word that receives the number of uploads done from this staging slot, so that the host knows when
 // it may refill it without an event in the stream.
+// late_trigger (block overlap of the Binaural / BRS chain, Engine::block_overlap): the kernel sits BEHIND the
+// block's forward transform (which no longer needs the control data: the filter-ring update moved here) and in
+// front of the MAC; it lets the MAC in as soon as the copy is complete and fenced, so the MAC resolves its slots
+// and streams its p != 0 terms while this kernel finishes and the forward transform -- and, in a loop of
+// device-resident blocks, the previous block's inverse transform -- still run.  Its wait at the end makes its
+// completion imply the forward kernel's, which implies the previous block's.
 __global__ void __launch_bounds__(kThreads)
 ctl_upload_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, int n16,
-                  unsigned long long* counter, volatile unsigned long long* ack)
+                  unsigned long long* counter, volatile unsigned long long* ack,
+                  const FwdRingUpdate ru, int ring_rows, int late_trigger)
 {
-  grid_launch_dependents();
+  if (!late_trigger) grid_launch_dependents();
   for (int i = threadIdx.x; i < n16; i += kThreads)
   {
     uint4 v;
     asm volatile("ld.global.cv.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src_host + i));
     dst[i] = v;
+  }
+  if (late_trigger)
+  {
+    __threadfence();      // the device copy is at device scope before the MAC is let in
+    __syncthreads();
+    grid_launch_dependents();
+    // ring[(source, ear)][b mod R] = the filters current in this block (read by LATER blocks only; the MAC of
+    // this block takes them from the control data; the last reader of that ring slot was the previous block's MAC)
+    if (ru.ctl)
+      for (int row = threadIdx.x; row < ring_rows; row += kThreads) fwd_ring_update(ru, row >> 1, row & 1);
   }
   __syncthreads();
   if (threadIdx.x == 0)
@@ -285,7 +302,7 @@ ctl_upload_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, i
     *ack = c;
     __threadfence_system();
   }
-  grid_dependency_wait();   // completion of this kernel implies completion of the previous block
+  grid_dependency_wait();   // completion of this kernel implies completion of everything in front of it
 }
 
 // ring[(source, ear)][b mod R] = the filter that is current in block b
@@ -654,7 +671,34 @@ inv_dyn_cluster_kernel(const InvJob* __restrict__ jobs, const InvEntry* __restri
                        int early_trigger)
 {
   // the next block's control upload (ctl_upload_kernel) does not depend on this kernel: let it in
-  if (early_trigger) grid_launch_dependents();
+  // early_trigger == 2 (block overlap): the launch carries one EXTRA CLUSTER whose leader commits the ring heads
+  // first (the MAC, their last reader, is complete when this kernel starts); only then has the whole grid
+  // triggered, and the next block's forward transform / control upload / MAC may run under this kernel
+  if (early_trigger == 2)
+  {
+    unsigned crank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    if (blockIdx.x / csize == gridDim.x / csize - 1)
+    {
+      if (crank == 0)
+      {
+        for (int i = threadIdx.x; i < hc.n; i += kThreads * 3)
+        {
+          int* head = hc.jobs[i].head;
+          int h = *head + 1;
+          if (h >= hc.jobs[i].parts) h = 0;
+          *head = h;
+        }
+        __threadfence();
+        __syncthreads();
+      }
+      grid_launch_dependents();
+      return;
+    }
+    grid_launch_dependents();
+  }
+  else if (early_trigger) grid_launch_dependents();
   inv_fft_body<3, true>(jobs, entries, partials, nullptr, B, tw, fade_out, fade_in, GatherArgs{}, kind_counts, hc, dyn_G, dbg);
 }
 

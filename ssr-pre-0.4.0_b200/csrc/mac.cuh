@@ -986,7 +986,7 @@ mac_dyn_tma_kernel(const MacParams p)
             else en[k2 * 2 + ear] = DynRingEntry{nullptr, nullptr, 0, 0};
           }
         }
-        xparts = p.xparts[input]; head = p.heads[input]; xr = p.xring[input];
+        xparts = p.xparts[input]; head = *reinterpret_cast<const volatile int*>(p.heads + input); xr = p.xring[input];   // (see fwd_fft_body)
       }
       // level 3: zero flags (null for filters without zero-flagged partitions)
       if (alive)

@@ -54,6 +54,7 @@ Renderer::Renderer(Engine* e_, const ssr_renderer_config& c)
   mvc = float(std::pow(10.0, double(cfg.master_volume_correction_db) / 20.0));
   if (std::getenv("SSR_B200_NO_GRAPHS")) use_graphs = false;  // experiments
   if (const char* v = std::getenv("SSR_B200_CTL_UPLOAD")) ctl_by_kernel = std::string(v) != "copy";   // A/B
+  if (const char* v = std::getenv("SSR_B200_DYN_BLOCK_OVERLAP")) dyn_block_overlap = std::atoi(v) != 0;   // A/B
   if (const char* v = std::getenv("SSR_B200_ZEROCOPY_OUT")) zero_copy = std::atoi(v) != 0;
   if (const char* v = std::getenv("SSR_B200_ZEROCOPY_IN")) zero_copy_in = std::atoi(v) != 0;
   static_mac.MT = kGenericMT;
@@ -912,18 +913,34 @@ void Renderer::launch(const StepDesc& d)
       && (dynamic || (cfg.kind == SSR_RENDERER_GENERIC && e->mac_tma() && static_mac.MT == kGenericMT));
   // block overlap (Engine::block_overlap): this block's forward transform and the p != 0 terms of its MAC may
   // run under the PREVIOUS block's inverse transform; the inverse kernel then commits the heads first
-  const bool block_overlap = overlap && !dynamic && e->block_overlap && e->pdl;
-  if (d.ctl_n16 > 0)
+  // (Binaural / BRS: needs the control upload by kernel and the bulk-copy generated-terms MAC; the chain becomes
+  //  forward -> control upload -> MAC, see ctl_upload_kernel.  Not when the forward kernel fetches its input from
+  //  the caller's page-locked array (the synchronous host call): 256 KB of input reads on the PCIe link in front
+  //  of the control data's 5 KB delay the MAC's start by more than the reordering gives -- measured, cfg3:
+  //  55.5 -> 61.7 us per call; the upload-first chain keeps the link free for the control data there.)
+  const bool block_overlap = overlap && e->block_overlap && e->pdl
+      && (!dynamic || (d.ctl_n16 > 0 && e->dyn_tma() && dyn_block_overlap && !d.in_base));
+  if (dynamic && block_overlap)
   {
-    e->launch_ctl_upload(d.ctl_src, d.ctl_dst, d.ctl_n16, dyn_upload_count.ptr + d.ctl_slot, dyn_ack.ptr + d.ctl_slot);
-  }
-  if (dynamic && d.N > 0)
-  {
-    // the forward kernel's CTA n also records source n's current filters in the ring
     const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
-    e->launch_fwd(fwd->device(), d.N, &ru, overlap, d.in_base);
+    e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base, true, true);
+    e->launch_ctl_upload(d.ctl_src, d.ctl_dst, d.ctl_n16, dyn_upload_count.ptr + d.ctl_slot, dyn_ack.ptr + d.ctl_slot,
+        &ru, 2 * d.N);
   }
-  else if (!skip_forward) e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base, block_overlap);
+  else
+  {
+    if (d.ctl_n16 > 0)
+    {
+      e->launch_ctl_upload(d.ctl_src, d.ctl_dst, d.ctl_n16, dyn_upload_count.ptr + d.ctl_slot, dyn_ack.ptr + d.ctl_slot);
+    }
+    if (dynamic && d.N > 0)
+    {
+      // the forward kernel's CTA n also records source n's current filters in the ring
+      const FwdRingUpdate ru{dyn_tables.ctl, dyn_upd_dev, dyn_ring.ptr, dyn_R};
+      e->launch_fwd(fwd->device(), d.N, &ru, overlap, d.in_base);
+    }
+    else if (!skip_forward) e->launch_fwd(fwd->device(), d.N, nullptr, overlap, d.in_base, block_overlap);
+  }
   e->stage_mark(1);
   if (cfg.kind == SSR_RENDERER_GENERIC)
   {
