@@ -349,7 +349,14 @@ int ssr_renderer_batched_blocks(const ssr_renderer* r, uint64_t* blocks);
 
 /* Same step on DEVICE buffers, asynchronous on the engine's stream: d_in is
  * sources x B floats, d_out is local_outputs x B floats (both contiguous).
- * Used by the multi-GPU driver, which owns the buffers and the NCCL gather. */
+ * Used by the multi-GPU driver, which owns the buffers and the NCCL gather.
+ * Calls queued back to back with nothing else on the stream in between overlap:
+ * the forward transform of block t + 1 and the part of its multiply-accumulate
+ * that does not need it run while block t's inverse transform still does
+ * (results are bit-identical to one call at a time; every block must get its own
+ * d_out if the caller reads them later, and d_in must stay valid until the block
+ * has run).  Anything the caller queues on the stream between two calls -- a
+ * copy, an event, a kernel -- simply keeps the blocks apart as before. */
 int ssr_renderer_process_device(ssr_renderer* r, const float* d_in, float* d_out);
 
 /* Pipelined host variant: queues the block and returns immediately; the result
