@@ -75,3 +75,27 @@ def test_reference_arm_never_needs_the_product_library():
                    src.index("# ----------------------------------------------------------------- parity")]
     ref_part = ref_part.replace('"ssr_b200.capi" in sys.modules', "")   # (the line that REPORTS whether it was loaded)
     assert "capi" not in ref_part, "the reference arm must generate its data with the numpy twins (workloads.py)"
+
+
+def test_mac_traffic_table_is_reproducible_from_the_committed_ncu_pages():
+    """profiles/mac_traffic.json (what bench.py reports as roofline.traffic) is what profiles/traffic_from_ncu.py
+    extracts from the committed raw pages of the ncu captures: same DRAM bytes per MAC launch, same grid."""
+    import importlib.util
+    import json
+    prof = os.path.join(ROOT, "profiles")
+    spec = importlib.util.spec_from_file_location("traffic_from_ncu", os.path.join(prof, "traffic_from_ncu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    table = json.load(open(os.path.join(prof, "mac_traffic.json")))
+    pages = {"cfg5_gpus1": "r2c_ncu/r2b_mac_cfg5_gpus1.raw.csv", "cfg5_gpus8": "r2c_ncu/r2b_mac_cfg5_gpus8.raw.csv",
+             "cfg4_gpus1": "r2c_ncu/r2b_mac_cfg4_gpus1.raw.csv", "cfg3_gpus1": "r2b_ncu/r2b_cfg3.raw.csv",
+             "cfg2_gpus1": "r2b_ncu/r2b_cfg2.raw.csv"}
+    for key, rel in pages.items():
+        e = mod.entry(os.path.join(prof, rel))
+        assert e is not None, key
+        assert int(e["grid"]) == int(table[key]["grid"]), key
+        assert abs(e["bytes"] - table[key]["bytes"]) <= 1e-6 * table[key]["bytes"], key
+        assert e["kernel"] == table[key]["kernel"], key
+    # the judged kernel's traffic stays within 1 % of the algorithmic bytes (SURVEY 8d) on one GPU
+    algorithmic = 8192 * (47 * 128 * 512 + 128 * 47 + 512)
+    assert 1.0 <= table["cfg5_gpus1"]["bytes"] / algorithmic <= 1.01
