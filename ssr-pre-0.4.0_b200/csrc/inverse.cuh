@@ -278,6 +278,10 @@ ctl_upload_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, i
                   const FwdRingUpdate ru, int ring_rows, int late_trigger)
 {
   if (!late_trigger) grid_launch_dependents();
+  // (the upload count is fetched while the copy's loads are in flight: this kernel's whole duration is on the path
+  //  of a synchronous block, whose forward transform waits for its completion)
+  unsigned long long count = 0;
+  if (threadIdx.x == 0) count = *counter + 1;
   for (int i = threadIdx.x; i < n16; i += kThreads)
   {
     uint4 v;
@@ -297,10 +301,13 @@ ctl_upload_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, i
   __syncthreads();
   if (threadIdx.x == 0)
   {
-    const unsigned long long c = *counter + 1;
-    *counter = c;
-    *ack = c;
-    __threadfence_system();
+    // every load of the staging slot has returned: the host may refill it.  Upload-first chain (a synchronous
+    // block: this kernel's duration is on its path, and the kernel ends at once): a posted write, no fence.
+    // Late-trigger chain (a loop of queued blocks): the kernel now lingers until the forward transform and the
+    // previous block are through, and the host -- two blocks ahead -- is waiting for exactly this word.
+    *counter = count;
+    *ack = count;
+    if (late_trigger) __threadfence_system();
   }
   grid_dependency_wait();   // completion of this kernel implies completion of everything in front of it
 }
